@@ -1,0 +1,197 @@
+/*
+ * arc_rad.h -- C ABI of the B200-native RRTMG SW/LW radiation hot path
+ * (drop-in for the WRF-Chem ARC "clean atmosphere" patched RRTMG of
+ *  douglowe/WRFChem-ARC-Interactions, v3.9.1).
+ *
+ * Every entry point replaces one Fortran entry point of the reference; the
+ * struct members carry exactly the reference's dummy arguments (same names,
+ * same units, same WRF memory order).  Citations are into
+ * WRF-Chem_code/v3.9.1/phys/ of the reference:
+ *
+ *   arc_rad_init      <- rrtmg_swinit  module_ra_rrtmg_sw.F:11211-11236
+ *                        rrtmg_lwinit  module_ra_rrtmg_lw.F:12845-12876
+ *   arc_rad_sw        <- RRTMG_SWRAD   module_ra_rrtmg_sw.F:9901-11207
+ *   arc_rad_lw        <- RRTMG_LWRAD   module_ra_rrtmg_lw.F:11451-12700
+ *   arc_rad_finalize  <- (nothing; the reference never frees its module tables)
+ *   arc_rad_last_error<- wrf_error_fatal / stop messages (SW: 40 sites, LW: 30)
+ *
+ * Array conventions (module_radiation_driver.F:1528-1577, 1944-2001):
+ *   3-D  REAL(4) (ims:ime, kms:kme, jms:jme)   i contiguous, then k, then j
+ *   2-D  REAL(4) (ims:ime, jms:jme)
+ *   flux profiles (ims:ime, kms:kme+2, jms:jme)
+ *   4-D  (ims:ime, kms:kme, jms:jme, n)
+ * Only the tile its:ite, kts:kte, jts:jte is read / written; halo cells are
+ * never touched.  Each OPTIONAL Fortran dummy is a nullable pointer; each F_Qx
+ * LOGICAL is an int flag.  The caller owns every array; nothing is retained
+ * after return.
+ *
+ * New relative to the reference: `memspace` (pointers are host or device
+ * memory) and `variant_mask`, which hands the whole tile over once with a
+ * call-variant axis instead of the reference's two internal solver calls.
+ */
+#ifndef ARC_RAD_H
+#define ARC_RAD_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARC_OK                 0
+#define ARC_ERR_NOT_INIT       1
+#define ARC_ERR_BAD_ARG        2
+#define ARC_ERR_IO             3   /* table file missing / malformed record        */
+#define ARC_ERR_MISSING_FIELD  4   /* 'missing fields required for aerosol radiation' SW:10288-10305 */
+#define ARC_ERR_NEG_AOD        5   /* 'Negative total optical depth'  SW:11031, LW:12613 */
+#define ARC_ERR_RADIUS         6   /* effective radius / dge out of table bounds SW:2164,2281 LW:2844,2893 */
+#define ARC_ERR_CUDA           7
+#define ARC_ERR_CONFIG         8   /* clean_atm_diag>0 needs aer_ra_feedback>0, chemics_init.F:406-408 */
+#define ARC_ERR_UNSUPPORTED    9
+
+#define ARC_MEM_HOST   0
+#define ARC_MEM_DEVICE 1
+
+/* call variants (Ghan 2012 decomposition streams) */
+#define ARC_VAR_FULL       1   /* clouds + aerosol          -> SWUPT ...        */
+#define ARC_VAR_CLEAR      2   /* no clouds, with aerosol   -> SWUPTC ...       */
+#define ARC_VAR_CLEAN      4   /* clouds, no aerosol        -> SWUPTCLN ...     */
+#define ARC_VAR_CLEANCLEAR 8   /* no clouds, no aerosol (computed and discarded by the reference,
+                                  SW:9466, LW:11026; exposed here as an option) */
+
+/* the 18 WRF index integers, in the reference's order */
+typedef struct ArcDims {
+  int ids, ide, jds, jde, kds, kde;
+  int ims, ime, jms, jme, kms, kme;
+  int its, ite, jts, jte, kts, kte;
+} ArcDims;
+
+/* init-time configuration (rrtmg_swinit/rrtmg_lwinit arguments + module_model_constants) */
+typedef struct ArcConfig {
+  float cp;        /* specific heat of dry air, module_model_constants cp = 7*287/2 = 1004.5 */
+  float p_top;     /* model top pressure (Pa); LW nlayers = kme + nint(p_top*0.01/4) - 1  LW:12861 */
+  int   kme;       /* memory upper k bound used for nlayers                                 */
+  int   device;    /* CUDA device ordinal (-1: current)                                     */
+  const char *inline_tables; /* path of rrtmg_inline_tables.bin (NULL: $ARC_RAD_TABLES or package default) */
+} ArcConfig;
+
+/* --------------------------------------------------------------------------------------------
+ * RRTMG_SWRAD  (SW:9901-9945 argument list; declarations SW:9949-10102)                        */
+typedef struct ArcSwIn {
+  int memspace;            /* ARC_MEM_HOST / ARC_MEM_DEVICE */
+  int variant_mask;        /* 0: FULL|CLEAR (+CLEAN when clean_atm_diag>0)                     */
+  /* scalars */
+  float radt, degrad, declin, solcon, xtime, gmt, r, g, julian;
+  int julday, icloud, warm_rain, is_cammgmp_used;
+  int has_reqc, has_reqi, has_reqs;
+  int o3input, aer_opt, no_src, sf_surface_physics, mp_physics;
+  int aer_ra_feedback, progn, clean_atm_diag;
+  int f_qv, f_qc, f_qr, f_qi, f_qs, f_qg, f_qndrop;   /* -1 = argument not present */
+  /* 3-D (i,k,j) */
+  const float *t3d, *t8w, *p3d, *p8w, *pi3d, *rho3d, *dz8w;
+  const float *cldfra3d, *lradius, *iradius;
+  const float *qv3d, *qc3d, *qr3d, *qi3d, *qs3d, *qg3d, *qndrop3d;
+  const float *o33d;
+  const float *re_cloud, *re_ice, *re_snow;
+  const float *f_ice_phy, *f_rain_phy;
+  const float *tauaer300, *tauaer400, *tauaer600, *tauaer999;
+  const float *gaer300, *gaer400, *gaer600, *gaer999;
+  const float *waer300, *waer400, *waer600, *waer999;
+  const float *aerod;                                   /* (i,k,j,no_src), aer_opt=1: unsupported */
+  const float *tauaer3d_sw, *ssaaer3d_sw, *asyaer3d_sw; /* (i,k,j,14) pointers, aer_opt=2,3  */
+  /* 2-D (i,j) */
+  const float *xcoszen, *albedo, *tsk, *xland, *xice, *snow;
+  const float *alswvisdir, *alswvisdif, *alswnirdir, *alswnirdif;
+  const float *xlat, *xlong;                            /* unused by the reference body */
+} ArcSwIn;
+
+typedef struct ArcSwOut {
+  float *rthratensw;                                    /* (i,k,j) written only where coszen>0 */
+  float *gsw, *swcf, *coszr;                            /* (i,j) */
+  float *swupt, *swuptc, *swuptcln, *swdnt, *swdntc, *swdntcln;
+  float *swupb, *swupbc, *swupbcln, *swdnb, *swdnbc, *swdnbcln;
+  float *swvisdir, *swvisdif, *swnirdir, *swnirdif;
+  float *swddir, *swddni, *swddif;
+  float *swupflx, *swupflxc, *swupflxcln;               /* (i, kms:kme+2, j), optional */
+  float *swdnflx, *swdnflxc, *swdnflxcln;
+  /* extension: the 4th (clean + clear) stream, TOA/surface, optional */
+  float *swuptclnc, *swdntclnc, *swupbclnc, *swdnbclnc;
+} ArcSwOut;
+
+/* --------------------------------------------------------------------------------------------
+ * RRTMG_LWRAD  (LW:11451-11486 argument list; declarations LW:11493-11604)                     */
+typedef struct ArcLwIn {
+  int memspace;
+  int variant_mask;
+  float r, g, julian;
+  int yr;
+  int icloud, warm_rain, is_cammgmp_used;
+  int has_reqc, has_reqi, has_reqs;
+  int o3input, mp_physics;
+  int aer_ra_feedback, progn, clean_atm_diag;
+  int f_qv, f_qc, f_qr, f_qi, f_qs, f_qg, f_qndrop;
+  const float *p8w, *p3d, *pi3d, *dz8w, *t3d, *t8w, *rho3d;
+  const float *cldfra3d, *lradius, *iradius;
+  const float *qv3d, *qc3d, *qr3d, *qi3d, *qs3d, *qg3d, *qndrop3d;
+  const float *o33d;
+  const float *re_cloud, *re_ice, *re_snow;
+  const float *f_ice_phy, *f_rain_phy;
+  const float *tauaerlw[16];                            /* tauaerlw1 .. tauaerlw16 */
+  const float *emiss, *tsk, *xland, *xice, *snow;       /* (i,j) */
+} ArcLwIn;
+
+typedef struct ArcLwOut {
+  float *rthratenlw;                                    /* (i,k,j) */
+  float *glw, *olr, *lwcf;                              /* (i,j) */
+  float *lwupt, *lwuptc, *lwuptcln, *lwdnt, *lwdntc, *lwdntcln;
+  float *lwupb, *lwupbc, *lwupbcln, *lwdnb, *lwdnbc, *lwdnbcln;
+  float *lwupflx, *lwupflxc, *lwupflxcln;               /* (i, kms:kme+2, j), optional */
+  float *lwdnflx, *lwdnflxc, *lwdnflxcln;
+  float *lwuptclnc, *lwdntclnc, *lwupbclnc, *lwdnbclnc; /* extension, optional */
+} ArcLwOut;
+
+/* --------------------------------------------------------------------------------------------
+ * Optional intermediate taps used by the parity tests (all pointers nullable, always HOST
+ * memory).  Column index c = (j-jts)*(ite-its+1) + (i-its).  Layer index 0 = surface.
+ * nlay = kte-kts+2 (SW) or nlayers (LW).                                                      */
+typedef struct ArcDebug {
+  int   *laytrop;      /* [ncol]                                  */
+  int   *jp, *jt, *jt1, *indfor, *indself;   /* [ncol][nlay]       */
+  int   *indminor;     /* LW only [ncol][nlay]                    */
+  float *fac00, *fac01, *fac10, *fac11;      /* [ncol][nlay]       */
+  unsigned char *cldmask;  /* McICA mask [ncol][nlay][ngpt] 0/1     */
+  float *taug;         /* [ncol][nlay][ngpt]                      */
+  float *taur;         /* SW [ncol][nlay][ngpt]; LW: fracs         */
+  float *sfluxzen;     /* SW [ncol][ngpt]                         */
+  float *taucmc;       /* [ncol][nlay][ngpt] cloud optical depth (SW delta-scaled) */
+  float *hr;           /* heating rate K/day [ncol][nlay], full    */
+} ArcDebug;
+
+int  arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_data_path);
+int  arc_rad_sw(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out);
+int  arc_rad_lw(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out);
+/* same as above with intermediate taps (tests only) */
+int  arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebug *dbg);
+int  arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebug *dbg);
+void arc_rad_finalize(void);
+const char *arc_rad_last_error(void);
+int  arc_rad_lw_nlayers(void);                 /* LW:12861 value fixed at init */
+
+/* bookkeeping done by radiation_driver around the two calls
+ * (module_radiation_driver.F:1692-1702, 2180-2194, 2308-2377):
+ *   rthratenlw = rthraten(after LW); rthraten += sw; rthratensw = rthraten - rthratenlw;
+ *   swdown = gsw/(1-albedo); and time accumulation ac* += flux*dt.                          */
+int  arc_rad_driver_post(const ArcDims *d, int memspace,
+                         const float *rthratenlw, const float *rthratensw, float *rthraten,
+                         const float *gsw, const float *albedo, float *swdown);
+
+/* Kernel launch counter (number of this library's CUDA kernels launched since init) */
+long long arc_rad_launch_count(void);
+/* CUDA stream used for all work (cudaStream_t as void*), for event timing by the caller */
+void *arc_rad_stream(void);
+/* time (ms, CUDA events on the library stream) spent in the named kernel class during the last call:
+ * "sw_solver", "sw_taumol", "lw_rtrnmc", ...; returns <0 if unknown */
+float arc_rad_last_kernel_ms(const char *name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARC_RAD_H */

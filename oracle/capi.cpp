@@ -1,0 +1,97 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.hpp).  C entry points for ctypes.
+#include <cstring>
+#include <string>
+#include <vector>
+#include <thread>
+
+#include "../include/arc_rad.h"
+#include "oracle.hpp"
+
+namespace orc {
+int oracle_swrad(const ArcDims &d, const ArcSwIn &in, ArcSwOut &out, ArcDebug *dbg, std::string &err);
+int oracle_lwrad(const ArcDims &d, const ArcLwIn &in, ArcLwOut &out, ArcDebug *dbg, std::string &err);
+}
+
+static std::string g_err;
+
+extern "C" {
+
+int arc_oracle_init(const ArcConfig *cfg, const char *sw_path, const char *lw_path) {
+  if (!cfg || !cfg->inline_tables || !sw_path || !lw_path) { g_err = "arc_oracle_init: null argument"; return ARC_ERR_BAD_ARG; }
+  return orc::init_tables(cfg->inline_tables, sw_path, lw_path, cfg->cp, cfg->p_top, cfg->kme, g_err);
+}
+
+const char *arc_oracle_last_error(void) { return g_err.c_str(); }
+int arc_oracle_lw_nlayers(void) { return orc::tables().lw_nlayers; }
+
+int arc_oracle_sw(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebug *dbg) {
+  return orc::oracle_swrad(*d, *in, *out, dbg, g_err);
+}
+int arc_oracle_lw(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebug *dbg) {
+  return orc::oracle_lwrad(*d, *in, *out, dbg, g_err);
+}
+
+// Threads over j-rows, mimicking radiation_driver's "!$OMP PARALLEL DO" over tiles
+// (module_radiation_driver.F:975-978) with a static schedule.  nthreads <= 0: all hardware threads.
+} // extern C
+template <class F>
+static int run_tiles(const ArcDims *d, int nthreads, F fn) {
+  int nj = d->jte - d->jts + 1;
+  int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > nj) nt = nj;
+  std::vector<std::thread> th;
+  std::vector<int> rcs(nt, 0);
+  std::vector<std::string> errs(nt);
+  for (int t = 0; t < nt; t++) {
+    th.emplace_back([&, t]() {
+      int j0 = d->jts + (int)((long long)nj * t / nt), j1 = d->jts + (int)((long long)nj * (t + 1) / nt) - 1;
+      if (j1 < j0) return;
+      ArcDims tile = *d; tile.jts = j0; tile.jte = j1;
+      rcs[t] = fn(tile, errs[t]);
+    });
+  }
+  for (auto &x : th) x.join();
+  for (int t = 0; t < nt; t++) if (rcs[t]) { g_err = errs[t]; return rcs[t]; }
+  return 0;
+}
+extern "C" {
+int arc_oracle_sw_omp(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, int nthreads) {
+  // debug column index is tile-relative, so no taps here
+  return run_tiles(d, nthreads, [&](const ArcDims &t, std::string &e) { return orc::oracle_swrad(t, *in, *out, nullptr, e); });
+}
+int arc_oracle_lw_omp(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, int nthreads) {
+  return run_tiles(d, nthreads, [&](const ArcDims &t, std::string &e) { return orc::oracle_lwrad(t, *in, *out, nullptr, e); });
+}
+int arc_oracle_max_threads(void) { int n = (int)std::thread::hardware_concurrency(); return n > 0 ? n : 1; }
+
+// Reduced-table taps so tests can compare the product's init against this restatement.
+// kind: 0 = SW, 1 = LW; name: "absa","absb","selfref","forref","sfluxref"/"fracrefa","fracrefb", ...
+int arc_oracle_table(int kind, int band /*1-based within kind*/, const char *name, float *buf, int cap) {
+  const orc::Tables &T = orc::tables();
+  const orc::FArr *a = nullptr;
+  std::string n(name);
+  if (kind == 0) {
+    const orc::SwBand &B = T.sw[band - 1];
+    if (n == "absa") a = &B.absa; else if (n == "absb") a = &B.absb; else if (n == "selfref") a = &B.selfref;
+    else if (n == "forref") a = &B.forref; else if (n == "sfluxref") a = &B.sfluxref; else if (n == "raylg") a = &B.raylg;
+    else if (n == "rayla") a = &B.rayla; else if (n == "raylb") a = &B.raylb; else if (n == "abso3a") a = &B.abso3a;
+    else if (n == "abso3b") a = &B.abso3b; else if (n == "absch4") a = &B.absch4; else if (n == "absh2o") a = &B.absh2o;
+    else if (n == "absco2") a = &B.absco2;
+  } else {
+    const orc::LwBand &B = T.lw[band - 1];
+    if (n == "absa") a = &B.absa; else if (n == "absb") a = &B.absb; else if (n == "selfref") a = &B.selfref;
+    else if (n == "forref") a = &B.forref; else if (n == "fracrefa") a = &B.fracrefa; else if (n == "fracrefb") a = &B.fracrefb;
+    else if (n == "ka_mn2") a = &B.ka_mn2; else if (n == "kb_mn2") a = &B.kb_mn2; else if (n == "ka_mn2o") a = &B.ka_mn2o;
+    else if (n == "kb_mn2o") a = &B.kb_mn2o; else if (n == "ka_mo3") a = &B.ka_mo3; else if (n == "kb_mo3") a = &B.kb_mo3;
+    else if (n == "ka_mco2") a = &B.ka_mco2; else if (n == "kb_mco2") a = &B.kb_mco2; else if (n == "ka_mco") a = &B.ka_mco;
+    else if (n == "ka_mo2") a = &B.ka_mo2; else if (n == "kb_mo2") a = &B.kb_mo2; else if (n == "ccl4") a = &B.ccl4;
+    else if (n == "cfc11adj") a = &B.cfc11adj; else if (n == "cfc12") a = &B.cfc12; else if (n == "cfc22adj") a = &B.cfc22adj;
+  }
+  if (!a) return -1;
+  int cnt = (int)a->size();
+  if (buf && cap >= cnt) memcpy(buf, a->v.data(), (size_t)cnt * 4);
+  return cnt;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+"""Host-side mirror of the reference's operator interface for the radiation hot path.
+
+Same entry-point names and argument meaning as the Fortran the reference patches:
+
+    rrtmg_swinit / rrtmg_lwinit   module_ra_rrtmg_sw.F:11211, module_ra_rrtmg_lw.F:12845
+    RRTMG_SWRAD                   module_ra_rrtmg_sw.F:9901
+    RRTMG_LWRAD                   module_ra_rrtmg_lw.F:11451
+
+Arguments are keyword arguments named exactly like the Fortran dummies; arrays are numpy
+float32 arrays in WRF memory order (host) or torch CUDA tensors (device, zero-copy).
+A non-zero status raises RadiationError (the reference calls wrf_error_fatal / stop).
+
+All arithmetic happens in libarcrad.so (csrc/, hand-written CUDA for sm_100a).  There is
+no CPU fallback: if the library is missing this module fails loudly at import of the
+library handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libarcrad.so")
+INLINE_TABLES = os.path.join(_HERE, "data", "rrtmg_inline_tables.bin")
+
+
+class RadiationError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("arc_rad status %d: %s" % (code, msg))
+        self.code = code
+
+
+def _is_device(a):
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return abi.fptr(int(a.data_ptr()))
+    return abi.fptr(a)
+
+
+class RadLib:
+    """Thin binding of a shared library exporting the arc_rad C ABI (prefix selects the symbol family)."""
+
+    def __init__(self, path, prefix="arc_rad_"):
+        if not os.path.exists(path):
+            raise ImportError("native library %s not found: run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        L = self.lib
+        g = lambda n: getattr(L, prefix + n)
+        self._init = g("init"); self._init.restype = C.c_int
+        self._init.argtypes = [C.POINTER(abi.ArcConfig), C.c_char_p, C.c_char_p]
+        self._err = g("last_error"); self._err.restype = C.c_char_p
+        self._nlay = g("lw_nlayers"); self._nlay.restype = C.c_int
+        if prefix == "arc_rad_":
+            self._sw = L.arc_rad_sw_debug; self._lw = L.arc_rad_lw_debug
+        else:
+            self._sw = g("sw"); self._lw = g("lw")
+        self._sw.restype = C.c_int; self._lw.restype = C.c_int
+        self._sw.argtypes = [C.POINTER(abi.ArcDims), C.POINTER(abi.ArcSwIn), C.POINTER(abi.ArcSwOut), C.POINTER(abi.ArcDebug)]
+        self._lw.argtypes = [C.POINTER(abi.ArcDims), C.POINTER(abi.ArcLwIn), C.POINTER(abi.ArcLwOut), C.POINTER(abi.ArcDebug)]
+        self.initialised = False
+
+    def last_error(self):
+        return (self._err() or b"").decode(errors="replace")
+
+    def check(self, rc):
+        if rc != 0:
+            raise RadiationError(rc, self.last_error())
+
+    # rrtmg_swinit + rrtmg_lwinit
+    def init(self, p_top, kme, sw_data, lw_data, cp=1004.5, device=-1, inline_tables=None):
+        cfg = abi.ArcConfig(cp=float(cp), p_top=float(p_top), kme=int(kme), device=int(device),
+                            inline_tables=(inline_tables or INLINE_TABLES).encode())
+        self.check(self._init(C.byref(cfg), sw_data.encode(), lw_data.encode()))
+        self.initialised = True
+        return self
+
+    def lw_nlayers(self):
+        return int(self._nlay())
+
+    @staticmethod
+    def _fill(struct, names, kw, used):
+        for n in names:
+            v = kw.get(n)
+            used.add(n)
+            setattr(struct, n, _ptr(v))
+
+    def RRTMG_SWRAD(self, dims, debug=None, **kw):
+        """kw: Fortran dummy names -> arrays / scalars.  F_Qx flags: True/False or omitted (= not PRESENT)."""
+        d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        si, so = abi.ArcSwIn(), abi.ArcSwOut()
+        used = set()
+        dev = [_is_device(v) for v in kw.values() if v is not None and (hasattr(v, "data_ptr") or isinstance(v, np.ndarray))]
+        if dev and any(dev) and not all(dev):
+            raise ValueError("mix of host and device arrays")
+        si.memspace = abi.ARC_MEM_DEVICE if (dev and dev[0]) else abi.ARC_MEM_HOST
+        si.variant_mask = int(kw.get("variant_mask", 0)); used.add("variant_mask")
+        for n in abi.SW_IN_SCALARS_F:
+            setattr(si, n, float(kw.get(n, 0.0))); used.add(n)
+        for n in abi.SW_IN_SCALARS_I:
+            dflt = -1 if n.startswith("f_q") else 0
+            v = kw.get(n, dflt)
+            setattr(si, n, int(v) if v is not None else dflt); used.add(n)
+        self._fill(si, abi.SW_IN_3D + abi.SW_IN_2D, kw, used)
+        self._fill(so, abi.SW_OUT_3D + abi.SW_OUT_2D + abi.SW_OUT_PROF + abi.SW_OUT_EXT, kw, used)
+        unknown = set(kw) - used
+        if unknown:
+            raise TypeError("RRTMG_SWRAD: unknown arguments %s" % sorted(unknown))
+        for req in ("rthratensw", "gsw", "swcf", "coszr", "swddir", "swddni", "swddif", "xcoszen", "albedo", "t3d", "t8w",
+                    "p3d", "p8w", "pi3d", "qv3d", "tsk", "xland", "xice", "snow"):
+            if kw.get(req) is None:
+                raise TypeError("RRTMG_SWRAD: required argument %s missing" % req)
+        self.check(self._sw(C.byref(d), C.byref(si), C.byref(so), C.byref(debug) if debug is not None else None))
+
+    def RRTMG_LWRAD(self, dims, debug=None, **kw):
+        d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        li, lo = abi.ArcLwIn(), abi.ArcLwOut()
+        used = set()
+        dev = [_is_device(v) for v in kw.values() if v is not None and (hasattr(v, "data_ptr") or isinstance(v, np.ndarray))]
+        if dev and any(dev) and not all(dev):
+            raise ValueError("mix of host and device arrays")
+        li.memspace = abi.ARC_MEM_DEVICE if (dev and dev[0]) else abi.ARC_MEM_HOST
+        li.variant_mask = int(kw.get("variant_mask", 0)); used.add("variant_mask")
+        for n in abi.LW_IN_SCALARS_F:
+            setattr(li, n, float(kw.get(n, 0.0))); used.add(n)
+        for n in abi.LW_IN_SCALARS_I:
+            dflt = -1 if n.startswith("f_q") else 0
+            v = kw.get(n, dflt)
+            setattr(li, n, int(v) if v is not None else dflt); used.add(n)
+        self._fill(li, abi.LW_IN_3D + abi.LW_IN_2D, kw, used)
+        for b in range(16):
+            n = "tauaerlw%d" % (b + 1)
+            li.tauaerlw[b] = _ptr(kw.get(n)); used.add(n)
+        self._fill(lo, abi.LW_OUT_3D + abi.LW_OUT_2D + abi.LW_OUT_PROF + abi.LW_OUT_EXT, kw, used)
+        unknown = set(kw) - used
+        if unknown:
+            raise TypeError("RRTMG_LWRAD: unknown arguments %s" % sorted(unknown))
+        for req in ("rthratenlw", "glw", "olr", "lwcf", "emiss", "t3d", "t8w", "p3d", "p8w", "pi3d", "qv3d", "tsk",
+                    "xland", "xice", "snow"):
+            if kw.get(req) is None:
+                raise TypeError("RRTMG_LWRAD: required argument %s missing" % req)
+        self.check(self._lw(C.byref(d), C.byref(li), C.byref(lo), C.byref(debug) if debug is not None else None))
+
+
+_LIB = None
+
+
+def lib() -> RadLib:
+    """The product library (CUDA).  Raises ImportError when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        _LIB = RadLib(LIB_PATH, "arc_rad_")
+        L = _LIB.lib
+        L.arc_rad_launch_count.restype = C.c_longlong
+        L.arc_rad_stream.restype = C.c_void_p
+        L.arc_rad_last_kernel_ms.restype = C.c_float
+        L.arc_rad_last_kernel_ms.argtypes = [C.c_char_p]
+        L.arc_rad_finalize.restype = None
+    return _LIB
+
+
+def rrtmg_init(p_top, kme, sw_data, lw_data, cp=1004.5, device=-1):
+    """rrtmg_swinit + rrtmg_lwinit (SW:11211, LW:12845): read + reduce tables, upload to the GPU."""
+    return lib().init(p_top, kme, sw_data, lw_data, cp=cp, device=device)
+
+
+def RRTMG_SWRAD(dims, **kw):
+    return lib().RRTMG_SWRAD(dims, **kw)
+
+
+def RRTMG_LWRAD(dims, **kw):
+    return lib().RRTMG_LWRAD(dims, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# convenience used by tests / bench: run one ARC radiation step on a synthetic domain dict
+
+SW_FIELDS_3D = ("t3d", "t8w", "p3d", "p8w", "pi3d", "rho3d", "dz8w", "cldfra3d", "qv3d", "qc3d", "qr3d", "qi3d", "qs3d",
+                "qg3d", "re_cloud", "re_ice", "re_snow",
+                "tauaer300", "tauaer400", "tauaer600", "tauaer999", "gaer300", "gaer400", "gaer600", "gaer999",
+                "waer300", "waer400", "waer600", "waer999")
+SW_FIELDS_2D = ("xcoszen", "albedo", "tsk", "xland", "xice", "snow")
+LW_FIELDS_3D = ("p8w", "p3d", "pi3d", "dz8w", "t3d", "t8w", "rho3d", "cldfra3d", "qv3d", "qc3d", "qr3d", "qi3d", "qs3d",
+                "qg3d", "re_cloud", "re_ice", "re_snow") + tuple("tauaerlw%d" % (b + 1) for b in range(16))
+LW_FIELDS_2D = ("emiss", "tsk", "xland", "xice", "snow")
+
+
+def common_flags(dom, clean_atm_diag=1, aer_ra_feedback=1):
+    has_re = "re_cloud" in dom
+    return dict(icloud=1, warm_rain=0, is_cammgmp_used=0, has_reqc=int(has_re), has_reqi=int(has_re), has_reqs=int(has_re),
+                o3input=0, mp_physics=0, aer_ra_feedback=aer_ra_feedback, progn=0, clean_atm_diag=clean_atm_diag,
+                f_qv=1, f_qc=1, f_qr=1, f_qi=1, f_qs=1, f_qg=1, r=float(dom["r"]), g=float(dom["g"]))
+
+
+def alloc_outputs(dom, which, xp=None, like=None):
+    """Allocate output arrays (numpy, or torch on like.device) for 'sw' or 'lw'."""
+    nj, ni = dom["xcoszen"].shape[-2:] if like is None else like.shape[-2:]
+    nkm = dom["t3d"].shape[-2]
+    names3 = abi.SW_OUT_3D if which == "sw" else abi.LW_OUT_3D
+    names2 = (abi.SW_OUT_2D + abi.SW_OUT_EXT) if which == "sw" else (abi.LW_OUT_2D + abi.LW_OUT_EXT)
+    namesp = abi.SW_OUT_PROF if which == "sw" else abi.LW_OUT_PROF
+    out = {}
+    if like is not None:
+        import torch
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=like.device)
+    else:
+        z = lambda *s: np.zeros(s, np.float32)
+    for n in names3:
+        out[n] = z(nj, nkm, ni)
+    for n in names2:
+        out[n] = z(nj, ni)
+    for n in namesp:
+        out[n] = z(nj, nkm + 2, ni)
+    return out
+
+
+def sw_kwargs(dom, outs, **flags):
+    kw = {k: dom[k] for k in SW_FIELDS_3D + SW_FIELDS_2D if k in dom}
+    kw.update(outs)
+    kw.update(dict(solcon=float(dom["solcon"]), aer_opt=0, sf_surface_physics=0))
+    kw.update(flags)
+    return kw
+
+
+def lw_kwargs(dom, outs, **flags):
+    kw = {k: dom[k] for k in LW_FIELDS_3D + LW_FIELDS_2D if k in dom}
+    kw.update(outs)
+    kw.update(flags)
+    return kw
