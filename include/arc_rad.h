@@ -163,6 +163,10 @@ typedef struct ArcDebug {
   float *sfluxzen;     /* SW [ncol][ngpt]                         */
   float *taucmc;       /* [ncol][nlay][ngpt] cloud optical depth (SW delta-scaled) */
   float *hr;           /* heating rate K/day [ncol][nlay], full    */
+  float *sw_cond;      /* SW, filled by the oracle only [ncol]: min over (g, layer, stream) of |1 - (k*mu0)^2| in
+                          reftra_sw.  At k*mu0 = 1 the reference's two-stream solution is a table-quantised 0/0
+                          (SW:2629-2660): its own output there is rounding noise, so parity tests exclude columns
+                          whose conditioning is below a stated threshold and report how many. */
 } ArcDebug;
 
 int  arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_data_path);

@@ -574,6 +574,8 @@ int cldprmc_sw(const Tables &T, int nlayers, int inflag, int iceflag, int liqfla
   return 0;
 }
 
+static thread_local float g_min_cond = 1.f;   // conditioning diagnostic, see ArcDebug.sw_cond
+
 // ---- reftra_sw SW:2422-2701 (kmodts = 2) -------------------------------------------------------------
 void reftra_sw(const Tables &T, int nlayers, const bool *lrtchk, const float *pgg, float prmuz, const float *ptau,
                const float *pw, float *pref, float *prefd, float *ptra, float *ptrad) {
@@ -612,6 +614,7 @@ void reftra_sw(const Tables &T, int nlayers, const bool *lrtchk, const float *pg
         float zrp = zrk * prmuz;
         float zrp1 = 1.f + zrp, zrm1 = 1.f - zrp, zrk2 = 2.f * zrk;
         float zrpp = 1.f - zrp * zrp;
+        if (fabsf(zrpp) < g_min_cond) g_min_cond = fabsf(zrpp);
         float zrkg = zrk + zgamma1;
         float zr1 = zrm1 * (za2 + zrk * zgamma3);
         float zr2 = zrp1 * (za2 - zrk * zgamma3);
@@ -1020,6 +1023,7 @@ int oracle_swrad(const ArcDims &d, const ArcSwIn &in, ArcSwOut &out, ArcDebug *d
           }
         }
         SwColumnOut co;
+        g_min_cond = 1.f;
         int rc = rrtmg_sw_column(T, nlay, play, plev, tlay, h2ovmr, o3vmr, co2, ch4, n2o, o2, asdir, asdif, aldir, aldif, coszrs,
                                  1.0f, 0, in.solcon, inflgsw, iceflgsw, liqflgsw, clean, W, co, err);
         if (rc) return rc;
@@ -1053,6 +1057,7 @@ int oracle_swrad(const ArcDims &d, const ArcSwIn &in, ArcSwOut &out, ArcDebug *d
         }
         if (dbg) {
           if (dbg->laytrop) dbg->laytrop[c] = W.coef.laytrop;
+          if (dbg->sw_cond) dbg->sw_cond[c] = g_min_cond;
           for (int l = 1; l <= nlay; l++) {
             size_t q = c * nlay + (l - 1);
             if (dbg->jp) dbg->jp[q] = W.coef.jp[l];

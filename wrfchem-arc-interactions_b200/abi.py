@@ -85,7 +85,7 @@ class ArcLwOut(C.Structure):
 
 DBG_I = ("laytrop", "jp", "jt", "jt1", "indfor", "indself", "indminor")
 DBG_F1 = ("fac00", "fac01", "fac10", "fac11")
-DBG_F2 = ("taug", "taur", "sfluxzen", "taucmc", "hr")
+DBG_F2 = ("taug", "taur", "sfluxzen", "taucmc", "hr", "sw_cond")
 
 
 class ArcDebug(C.Structure):
@@ -119,6 +119,7 @@ def alloc_debug(ncol, nlay, ngpt, lw=False):
         "sfluxzen": np.zeros((ncol, ngpt), np.float32),
         "taucmc": np.zeros((ncol, nlay, ngpt), np.float32),
         "hr": np.zeros((ncol, nlay), np.float32),
+        "sw_cond": np.ones(ncol, np.float32),
     }
     dbg = ArcDebug()
     for k in DBG_I:

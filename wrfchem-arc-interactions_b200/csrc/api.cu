@@ -1,0 +1,725 @@
+// C ABI of the B200 radiation path (include/arc_rad.h): table upload, workspace / staging management, chunked
+// kernel pipelines for RRTMG_SWRAD and RRTMG_LWRAD, error reporting.
+//
+//   arc_rad_init  <- rrtmg_swinit SW:11211 + rrtmg_lwinit LW:12845
+//   arc_rad_sw    <- RRTMG_SWRAD  SW:9901        arc_rad_lw <- RRTMG_LWRAD LW:11451
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/arc_rad.h"
+#include "args.h"
+
+using namespace arc;
+
+namespace {
+
+struct EvPair { std::string name; cudaEvent_t a, b; };
+
+struct Ctx {
+  bool ready = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  HostTables H;
+  DevTables D;
+  std::vector<void *> table_allocs;
+  int *d_status = nullptr, *d_count = nullptr;
+  int *d_cols = nullptr; size_t cols_cap = 0;
+  // workspaces (grow-only)
+  SwWs sw{}; size_t sw_bytes = 0; void *sw_arena = nullptr;
+  LwWs lw{}; size_t lw_bytes = 0; void *lw_arena = nullptr;
+  // host<->device staging pool (grow-only)
+  struct Slot { void *d = nullptr; size_t bytes = 0; };
+  std::vector<Slot> pool; size_t pool_next = 0;
+  struct Back { void *host; void *dev; size_t bytes; };
+  std::vector<Back> backs;
+  // timing
+  std::vector<EvPair> evs; size_t ev_next = 0;
+  std::map<std::string, float> last_ms;
+  std::string err;
+};
+Ctx g;
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      g.err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;                   \
+      return ARC_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+template <class T>
+int upload(const T *h, size_t n, const T **d) {
+  void *p = nullptr;
+  CK(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
+  CK(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  g.table_allocs.push_back(p);
+  *d = (const T *)p;
+  return 0;
+}
+int upload_vec(const std::vector<float> &v, const float **d) { return upload(v.data(), v.size(), d); }
+
+size_t chunk_cap_default() {
+  const char *e = getenv("ARC_RAD_CHUNK");
+  long v = e ? atol(e) : 65536;
+  if (v < 256) v = 256;
+  return (size_t)((v + 255) / 256 * 256);
+}
+
+struct Carver {
+  char *base; size_t off = 0;
+  template <class T> T *take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? (T *)(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+void carve_sw(SwWs &w, char *base, size_t &bytes) {
+  Carver c{base};
+  const size_t cap = w.cap, nl = w.nlay;
+  w.coef = c.take<float>((size_t)SWC_N * nl * cap);
+  w.aer = c.take<float>((size_t)NBSW * 3 * nl * cap);
+  w.cld = c.take<float>((size_t)NBSW * 4 * nl * cap);
+  w.mask = c.take<uint32_t>((size_t)NGSW * w.W * cap);
+  w.anyc = c.take<uint32_t>((size_t)w.W * cap);
+  w.laytrop = c.take<int>(cap);
+  w.laysol = c.take<int>((size_t)NBSW * cap);
+  w.colf = c.take<float>((size_t)SWF_N * cap);
+  w.part = c.take<float>((size_t)NGSW * (nl + 1) * NKIND * cap);
+  w.dirs = c.take<float>((size_t)NGSW * cap);
+  bytes = c.off;
+}
+void carve_lw(LwWs &w, char *base, size_t &bytes) {
+  Carver c{base};
+  const size_t cap = w.cap, nl = w.nlay;
+  w.coef = c.take<float>((size_t)LWC_N * nl * cap);
+  w.aer = c.take<float>((size_t)NBLW * nl * cap);
+  w.cld = c.take<float>((size_t)NBLW * nl * cap);
+  w.mask = c.take<uint32_t>((size_t)NGLW * w.W * cap);
+  w.anyc = c.take<uint32_t>((size_t)w.W * cap);
+  w.laytrop = c.take<int>(cap);
+  w.colf = c.take<float>((size_t)LWF_N * cap);
+  w.secdiff = c.take<float>((size_t)NBLW * cap);
+  w.part = c.take<float>((size_t)NGLW * (nl + 1) * NKIND * cap);
+  bytes = c.off;
+}
+
+int ensure_sw_ws(int nlay, size_t cap) {
+  SwWs w{}; w.cap = (int)cap; w.nlay = nlay; w.W = (nlay + 31) / 32;
+  size_t need; carve_sw(w, nullptr, need);
+  if (need > g.sw_bytes) {
+    if (g.sw_arena) cudaFree(g.sw_arena);
+    g.sw_arena = nullptr; g.sw_bytes = 0;
+    CK(cudaMalloc(&g.sw_arena, need));
+    g.sw_bytes = need;
+  }
+  carve_sw(w, (char *)g.sw_arena, need);
+  g.sw = w;
+  return 0;
+}
+int ensure_lw_ws(int nlay, size_t cap) {
+  LwWs w{}; w.cap = (int)cap; w.nlay = nlay; w.W = (nlay + 31) / 32;
+  size_t need; carve_lw(w, nullptr, need);
+  if (need > g.lw_bytes) {
+    if (g.lw_arena) cudaFree(g.lw_arena);
+    g.lw_arena = nullptr; g.lw_bytes = 0;
+    CK(cudaMalloc(&g.lw_arena, need));
+    g.lw_bytes = need;
+  }
+  carve_lw(w, (char *)g.lw_arena, need);
+  g.lw = w;
+  return 0;
+}
+
+// ---- staging -------------------------------------------------------------------------------------------
+int stage_slot(size_t bytes, void **d) {
+  if (g.pool_next >= g.pool.size()) g.pool.push_back({});
+  Ctx::Slot &s = g.pool[g.pool_next++];
+  if (s.bytes < bytes) {
+    if (s.d) cudaFree(s.d);
+    s.d = nullptr; s.bytes = 0;
+    CK(cudaMalloc(&s.d, bytes));
+    s.bytes = bytes;
+  }
+  *d = s.d;
+  return 0;
+}
+// input array: returns the device pointer to use
+int in_arr(int memspace, const float *p, size_t n, const float **out) {
+  *out = nullptr;
+  if (!p) return 0;
+  if (memspace == ARC_MEM_DEVICE) { *out = p; return 0; }
+  void *d;
+  int rc = stage_slot(n * 4, &d);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d, p, n * 4, cudaMemcpyHostToDevice, g.stream));
+  *out = (const float *)d;
+  return 0;
+}
+// output array (INOUT semantics: cells outside the tile / night columns keep the caller's values)
+int out_arr(int memspace, float *p, size_t n, float **out) {
+  *out = nullptr;
+  if (!p) return 0;
+  if (memspace == ARC_MEM_DEVICE) { *out = p; return 0; }
+  void *d;
+  int rc = stage_slot(n * 4, &d);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d, p, n * 4, cudaMemcpyHostToDevice, g.stream));
+  g.backs.push_back({p, d, n * 4});
+  *out = (float *)d;
+  return 0;
+}
+int copy_back() {
+  for (auto &b : g.backs) CK(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, g.stream));
+  g.backs.clear();
+  return 0;
+}
+
+// ---- timing ----------------------------------------------------------------------------------------------
+struct Timed {
+  EvPair *e;
+  explicit Timed(const char *name) {
+    if (g.ev_next >= g.evs.size()) {
+      EvPair p; p.name = name;
+      cudaEventCreate(&p.a); cudaEventCreate(&p.b);
+      g.evs.push_back(p);
+    }
+    e = &g.evs[g.ev_next++];
+    e->name = name;
+    cudaEventRecord(e->a, g.stream);
+  }
+  ~Timed() { cudaEventRecord(e->b, g.stream); }
+};
+void collect_times() {
+  for (size_t i = 0; i < g.ev_next; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g.evs[i].a, g.evs[i].b) == cudaSuccess) g.last_ms[g.evs[i].name] += ms;
+  }
+  g.ev_next = 0;
+}
+
+const char *code_msg(int code) {
+  switch (code) {
+    case ARC_ERR_NEG_AOD: return "ERROR: Negative total optical depth";
+    case ARC_ERR_RADIUS: return "ERROR: cloud particle effective size / fdelta out of table bounds";
+    case ARC_ERR_UNSUPPORTED: return "unsupported option (iceflag < 3)";
+    default: return "device-side error";
+  }
+}
+
+Geo make_geo(const ArcDims &d) {
+  Geo G;
+  G.ims = d.ims; G.ime = d.ime; G.kms = d.kms; G.kme = d.kme; G.jms = d.jms; G.jme = d.jme;
+  G.its = d.its; G.ite = d.ite; G.jts = d.jts; G.jte = d.jte; G.kts = d.kts; G.kte = d.kte;
+  G.ni = d.ime - d.ims + 1; G.nk = d.kme - d.kms + 1;
+  G.nci = d.ite - d.its + 1; G.ncol_tile = G.nci * (d.jte - d.jts + 1);
+  return G;
+}
+int check_dims(const ArcDims &d) {
+  if (d.its < d.ims || d.ite > d.ime || d.jts < d.jms || d.jte > d.jme || d.kts < d.kms || d.kte + 1 > d.kme ||
+      d.ite < d.its || d.jte < d.jts || d.kte - d.kts + 1 < 4) {
+    g.err = "bad dimensions: tile must lie inside memory bounds, kte+1 <= kme, at least 4 layers";
+    return ARC_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+template <class T> int dbg_alloc(T *host, size_t n, T **dev, std::vector<std::pair<void *, std::pair<void *, size_t>>> &list) {
+  *dev = nullptr;
+  if (!host) return 0;
+  void *d;
+  int rc = stage_slot(n * sizeof(T), &d);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(d, 0, n * sizeof(T), g.stream));
+  list.push_back({host, {d, n * sizeof(T)}});
+  *dev = (T *)d;
+  return 0;
+}
+
+__global__ void k_unpack_mask(const uint32_t *__restrict__ mask, const int *__restrict__ cols, int col0, int ncols, int cap, int W,
+                              int nlay, int ngpt, unsigned char *__restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  const int tc = cols ? cols[c] : col0 + c;
+  for (int gq = 0; gq < ngpt; gq++)
+    for (int l = 0; l < nlay; l++) {
+      const uint32_t w = mask[((size_t)gq * W + (l >> 5)) * cap + c];
+      out[((size_t)tc * nlay + l) * ngpt + gq] = (w >> (l & 31)) & 1u;
+    }
+}
+
+int setup_debug(ArcDebug *dbg, size_t ncol, int nlay, int ngpt, DebugTaps &t,
+                std::vector<std::pair<void *, std::pair<void *, size_t>>> &list) {
+  memset(&t, 0, sizeof(t));
+  if (!dbg) return 0;
+  int rc = 0;
+  const size_t nl = ncol * nlay, ng = nl * ngpt;
+  if ((rc = dbg_alloc(dbg->laytrop, ncol, &t.laytrop, list))) return rc;
+  // the index taps are written together: require all-or-none
+  const bool idx = dbg->jp && dbg->jt && dbg->jt1 && dbg->indfor && dbg->indself && dbg->fac00 && dbg->fac01 && dbg->fac10 && dbg->fac11;
+  if (idx) {
+    if ((rc = dbg_alloc(dbg->jp, nl, &t.jp, list))) return rc;
+    if ((rc = dbg_alloc(dbg->jt, nl, &t.jt, list))) return rc;
+    if ((rc = dbg_alloc(dbg->jt1, nl, &t.jt1, list))) return rc;
+    if ((rc = dbg_alloc(dbg->indfor, nl, &t.indfor, list))) return rc;
+    if ((rc = dbg_alloc(dbg->indself, nl, &t.indself, list))) return rc;
+    if ((rc = dbg_alloc(dbg->indminor, nl, &t.indminor, list))) return rc;
+    if ((rc = dbg_alloc(dbg->fac00, nl, &t.fac00, list))) return rc;
+    if ((rc = dbg_alloc(dbg->fac01, nl, &t.fac01, list))) return rc;
+    if ((rc = dbg_alloc(dbg->fac10, nl, &t.fac10, list))) return rc;
+    if ((rc = dbg_alloc(dbg->fac11, nl, &t.fac11, list))) return rc;
+    if (!t.indminor) {   // kernels write indminor unconditionally with jp: give LW a scratch target
+      void *d; if ((rc = stage_slot(nl * 4, &d))) return rc; t.indminor = (int *)d;
+    }
+  }
+  if ((rc = dbg_alloc(dbg->cldmask, ng, &t.cldmask, list))) return rc;
+  if (dbg->taug && dbg->taur) {
+    if ((rc = dbg_alloc(dbg->taug, ng, &t.taug, list))) return rc;
+    if ((rc = dbg_alloc(dbg->taur, ng, &t.taur, list))) return rc;
+  }
+  if ((rc = dbg_alloc(dbg->sfluxzen, ncol * ngpt, &t.sfluxzen, list))) return rc;
+  if ((rc = dbg_alloc(dbg->taucmc, ng, &t.taucmc, list))) return rc;
+  if ((rc = dbg_alloc(dbg->hr, nl, &t.hr, list))) return rc;
+  return 0;
+}
+
+int finish_call(std::vector<std::pair<void *, std::pair<void *, size_t>>> &dbglist) {
+  for (auto &e : dbglist) CK(cudaMemcpyAsync(e.first, e.second.first, e.second.second, cudaMemcpyDeviceToHost, g.stream));
+  int rc = copy_back();
+  if (rc) return rc;
+  int status = 0;
+  CK(cudaMemcpyAsync(&status, g.d_status, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  collect_times();
+  if (status) { g.err = code_msg(status); return status; }
+  return 0;
+}
+
+void fill_cloud(CloudFields &cf, int memspace, int &rc, int icloud, int warm_rain, int is_cammgmp_used, int has_reqc, int has_reqi,
+                int has_reqs, int progn, const int fq[7], float gacc, const float *const p3[18], const float *const p2[3],
+                size_t n3, size_t n2) {
+  cf.icloud = icloud; cf.warm_rain = warm_rain; cf.is_cammgmp_used = is_cammgmp_used;
+  cf.has_reqc = has_reqc; cf.has_reqi = has_reqi; cf.has_reqs = has_reqs; cf.progn = progn;
+  cf.f_qv = fq[0]; cf.f_qc = fq[1]; cf.f_qr = fq[2]; cf.f_qi = fq[3]; cf.f_qs = fq[4]; cf.f_qg = fq[5]; cf.f_qndrop = fq[6];
+  cf.g = gacc;
+  const float **dst3[18] = {&cf.t3d, &cf.cldfra3d, &cf.lradius, &cf.iradius, &cf.qv3d, &cf.qc3d, &cf.qr3d, &cf.qi3d, &cf.qs3d,
+                            &cf.qg3d, &cf.qndrop3d, &cf.re_cloud, &cf.re_ice, &cf.re_snow, &cf.f_ice_phy, nullptr, nullptr, nullptr};
+  for (int q = 0; q < 15 && !rc; q++) rc = in_arr(memspace, p3[q], n3, dst3[q]);
+  const float **dst2[3] = {&cf.xland, &cf.xice, &cf.snow};
+  for (int q = 0; q < 3 && !rc; q++) rc = in_arr(memspace, p2[q], n2, dst2[q]);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *arc_rad_last_error(void) { return g.err.c_str(); }
+int arc_rad_lw_nlayers(void) { return g.ready ? g.H.lw_nlayers : 0; }
+long long arc_rad_launch_count(void) { return launch_count(); }
+void *arc_rad_stream(void) { return (void *)g.stream; }
+float arc_rad_last_kernel_ms(const char *name) {
+  auto it = g.last_ms.find(name ? name : "");
+  return it == g.last_ms.end() ? -1.f : it->second;
+}
+
+void arc_rad_finalize(void) {
+  if (!g.ready) return;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.stream);
+  for (void *p : g.table_allocs) cudaFree(p);
+  g.table_allocs.clear();
+  if (g.sw_arena) cudaFree(g.sw_arena);
+  if (g.lw_arena) cudaFree(g.lw_arena);
+  g.sw_arena = g.lw_arena = nullptr; g.sw_bytes = g.lw_bytes = 0;
+  for (auto &s : g.pool) if (s.d) cudaFree(s.d);
+  g.pool.clear();
+  if (g.d_cols) cudaFree(g.d_cols);
+  g.d_cols = nullptr; g.cols_cap = 0;
+  if (g.d_status) cudaFree(g.d_status);
+  if (g.d_count) cudaFree(g.d_count);
+  g.d_status = g.d_count = nullptr;
+  for (auto &e : g.evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  g.evs.clear();
+  if (g.stream) cudaStreamDestroy(g.stream);
+  g.stream = nullptr;
+  g.ready = false;
+}
+
+int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_data_path) {
+  if (!cfg || !sw_data_path || !lw_data_path) { g.err = "arc_rad_init: null argument"; return ARC_ERR_BAD_ARG; }
+  if (g.ready) arc_rad_finalize();
+  std::string inl;
+  if (cfg->inline_tables) inl = cfg->inline_tables;
+  else if (getenv("ARC_RAD_TABLES")) inl = getenv("ARC_RAD_TABLES");
+  else { g.err = "arc_rad_init: inline table path missing (ArcConfig.inline_tables or $ARC_RAD_TABLES)"; return ARC_ERR_BAD_ARG; }
+  int rc = build_host_tables(inl, sw_data_path, lw_data_path, cfg->cp, cfg->p_top, cfg->kme, g.H, g.err);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g.err = "arc_rad_init: no CUDA device available (this library has no CPU fallback)";
+    return ARC_ERR_CUDA;
+  }
+  if (cfg->device >= 0) { CK(cudaSetDevice(cfg->device)); g.device = cfg->device; }
+  else CK(cudaGetDevice(&g.device));
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&g.d_status, sizeof(int)));
+  CK(cudaMalloc(&g.d_count, sizeof(int)));
+
+  const HostTables &H = g.H;
+  DevTables &D = g.D;
+  memset(&D, 0, sizeof(D));
+  if ((rc = upload_vec(H.sw_buf, &D.sw_tab))) return rc;
+  if ((rc = upload_vec(H.lw_buf, &D.lw_tab))) return rc;
+  {
+    std::vector<float> e(10004, 0.f);
+    for (int i = 0; i < NTBL; i++) e[i] = H.sw_exp_tbl[i];
+    if ((rc = upload_vec(e, &D.sw_exp))) return rc;
+    std::vector<float> et(2 * 10002, 0.f);
+    for (int i = 0; i < NTBL; i++) { et[2 * i] = H.lw_exp_tbl[i]; et[2 * i + 1] = H.lw_tfn_tbl[i]; }
+    if ((rc = upload_vec(et, &D.lw_exptfn))) return rc;
+  }
+  if ((rc = upload_vec(H.get("sw_extliq1"), &D.sw_extliq1))) return rc;
+  if ((rc = upload_vec(H.get("sw_ssaliq1"), &D.sw_ssaliq1))) return rc;
+  if ((rc = upload_vec(H.get("sw_asyliq1"), &D.sw_asyliq1))) return rc;
+  if ((rc = upload_vec(H.get("sw_extice3"), &D.sw_extice3))) return rc;
+  if ((rc = upload_vec(H.get("sw_ssaice3"), &D.sw_ssaice3))) return rc;
+  if ((rc = upload_vec(H.get("sw_asyice3"), &D.sw_asyice3))) return rc;
+  if ((rc = upload_vec(H.get("sw_fdlice3"), &D.sw_fdlice3))) return rc;
+  if ((rc = upload_vec(H.get("lw_absliq1"), &D.lw_absliq1))) return rc;
+  if ((rc = upload_vec(H.get("lw_absice3"), &D.lw_absice3))) return rc;
+  if ((rc = upload_vec(H.get("sw_preflog"), &D.sw_preflog))) return rc;
+  if ((rc = upload_vec(H.get("sw_tref"), &D.sw_tref))) return rc;
+  if ((rc = upload_vec(H.get("lw_preflog"), &D.lw_preflog))) return rc;
+  if ((rc = upload_vec(H.get("lw_tref"), &D.lw_tref))) return rc;
+  if ((rc = upload_vec(H.get("lw_chi_mls"), &D.chi_mls))) return rc;
+  {
+    const std::vector<float> &tp = H.get("lw_totplnk");   // (181,16)
+    std::vector<float> pad(184 * 16, 0.f);
+    for (int b = 0; b < 16; b++) for (int i = 0; i < 181; i++) pad[184 * b + i] = tp[i + 181 * b];
+    if ((rc = upload_vec(pad, &D.totplnk))) return rc;
+  }
+  {
+    // annual-mean ozone profile and half-level pressures, o3data LW:12773-12798 (column independent)
+    const std::vector<float> &o3sum = H.get("lw_o3sum"), &ppsum = H.get("lw_ppsum"), &o3win = H.get("lw_o3win"), &ppwin = H.get("lw_ppwin");
+    std::vector<float> o3ann(31), ppwrkh(32);
+    o3ann[0] = 0.5f * (o3sum[0] + o3win[0]);
+    for (int k = 1; k < 31; k++) o3ann[k] = o3win[k - 1] + (o3win[k] - o3win[k - 1]) / (ppwin[k] - ppwin[k - 1]) * (ppsum[k] - ppwin[k - 1]);
+    for (int k = 1; k < 31; k++) o3ann[k] = 0.5f * (o3ann[k] + o3sum[k]);
+    ppwrkh[0] = 1100.f;
+    for (int k = 1; k < 31; k++) ppwrkh[k] = (ppsum[k] + ppsum[k - 1]) / 2.f;
+    ppwrkh[31] = 0.f;
+    if ((rc = upload_vec(o3ann, &D.o3wrk))) return rc;
+    if ((rc = upload_vec(ppwrkh, &D.ppwrkh))) return rc;
+  }
+  if ((rc = upload_vec(H.get("lw_retab"), &D.retab))) return rc;
+  if ((rc = upload_vec(H.get("lw_pprof"), &D.pprof))) return rc;
+  if ((rc = upload_vec(H.get("lw_tprof"), &D.tprof))) return rc;
+  D.heatfac = H.heatfac; D.fluxfac = H.fluxfac; D.oneminus = H.oneminus; D.bpade = H.bpade;
+  {
+    const std::vector<float> &wmin = H.get("sw_wavemin"), &wmax = H.get("sw_wavemax");
+    for (int b = 0; b < 14; b++) D.wavemid[b] = 0.5f * (wmin[b] + wmax[b]);
+    const std::vector<float> &a0 = H.get("lw_a0"), &a1 = H.get("lw_a1"), &a2 = H.get("lw_a2");
+    for (int b = 0; b < 16; b++) { D.a0[b] = a0[b]; D.a1[b] = a1[b]; D.a2[b] = a2[b]; D.delwave[b] = H.lw_delwave[b]; }
+  }
+  D.lw_nlayers = H.lw_nlayers;
+  upload_band_descs(H);
+  CK(cudaDeviceSynchronize());
+  g.ready = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebug *dbg) {
+  if (!g.ready) { g.err = "arc_rad_sw: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !in || !out) { g.err = "arc_rad_sw: null argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  // argument checks of the reference (SW:10288-10305, chemics_init.F:406-408)
+  if (in->aer_ra_feedback == 1 &&
+      !(in->tauaer300 && in->tauaer400 && in->tauaer600 && in->tauaer999 && in->gaer300 && in->gaer400 && in->gaer600 &&
+        in->gaer999 && in->waer300 && in->waer400 && in->waer600 && in->waer999)) {
+    g.err = "Warning: missing fields required for aerosol radiation"; return ARC_ERR_MISSING_FIELD;
+  }
+  if (in->clean_atm_diag > 0 && in->aer_ra_feedback <= 0) {
+    g.err = "clean_atm_diag > 0 requires aer_ra_feedback > 0 (chemics_init.F:406-408)"; return ARC_ERR_CONFIG;
+  }
+  if (in->aer_opt == 1) { g.err = "aer_opt=1 (Tegen climatology, iaer=6) not supported"; return ARC_ERR_UNSUPPORTED; }
+  if (!in->xcoszen || !in->albedo || !in->t3d || !in->t8w || !in->p3d || !in->p8w || !in->pi3d || !in->qv3d || !in->xland ||
+      !in->xice || !in->snow || !out->rthratensw || !out->gsw || !out->swcf || !out->coszr || !out->swddir || !out->swddni ||
+      !out->swddif) {
+    g.err = "arc_rad_sw: required array missing"; return ARC_ERR_BAD_ARG;
+  }
+  if (in->icloud != 0 && ((in->has_reqc && !in->re_cloud) || (in->has_reqi && !in->re_ice) || (in->has_reqs && !in->re_snow))) {
+    g.err = "arc_rad_sw: has_req* set but re_* array missing"; return ARC_ERR_BAD_ARG;
+  }
+  if (in->sf_surface_physics == 8 && !(in->alswvisdir && in->alswvisdif && in->alswnirdir && in->alswnirdif)) {
+    g.err = "arc_rad_sw: SSiB albedos missing"; return ARC_ERR_BAD_ARG;
+  }
+  if ((out->swupflx || out->swupflxc || out->swupflxcln || out->swdnflx || out->swdnflxc || out->swdnflxcln) &&
+      !(out->swupflx && out->swupflxc && out->swupflxcln && out->swdnflx && out->swdnflxc && out->swdnflxcln)) {
+    g.err = "arc_rad_sw: flux profile outputs must be passed all together"; return ARC_ERR_BAD_ARG;
+  }
+  if (out->swupt && !(out->swuptc && out->swuptcln && out->swdnt && out->swdntc && out->swdntcln && out->swupb && out->swupbc &&
+                      out->swupbcln && out->swdnb && out->swdnbc && out->swdnbcln && out->swvisdir && out->swvisdif &&
+                      out->swnirdir && out->swnirdif)) {
+    g.err = "arc_rad_sw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG;
+  }
+  CK(cudaSetDevice(g.device));
+  g.last_ms.clear();
+  g.pool_next = 0; g.backs.clear();
+  const int ms = in->memspace;
+  SwArgs a{};
+  a.geo = make_geo(*d);
+  a.tb = g.D;
+  const Geo &G = a.geo;
+  const size_t n3 = G.n3(), n2 = G.n2(), np = G.np();
+  const int nz = d->kte - d->kts + 1, nlay = nz + 1;
+  if (nlay > 159) { g.err = "arc_rad_sw: too many layers (max 158 model layers)"; return ARC_ERR_BAD_ARG; }
+
+  CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
+  {
+    const int fq[7] = {in->f_qv, in->f_qc, in->f_qr, in->f_qi, in->f_qs, in->f_qg, in->f_qndrop};
+    const float *const p3[18] = {in->t3d, in->cldfra3d, in->lradius, in->iradius, in->qv3d, in->qc3d, in->qr3d, in->qi3d, in->qs3d,
+                                 in->qg3d, in->qndrop3d, in->re_cloud, in->re_ice, in->re_snow, in->f_ice_phy, 0, 0, 0};
+    const float *const p2[3] = {in->xland, in->xice, in->snow};
+    fill_cloud(a.cf, ms, rc, in->icloud, in->warm_rain, in->is_cammgmp_used, in->has_reqc, in->has_reqi, in->has_reqs, in->progn, fq,
+               in->g, p3, p2, n3, n2);
+    if (rc) return rc;
+  }
+  a.o3input = in->o3input; a.aer_ra_feedback = in->aer_ra_feedback; a.sf_surface_physics = in->sf_surface_physics;
+  a.solcon = in->solcon;
+#define IN3(f) if ((rc = in_arr(ms, in->f, n3, &a.f))) return rc
+#define IN2(f) if ((rc = in_arr(ms, in->f, n2, &a.f))) return rc
+  IN3(t8w); IN3(p3d); IN3(p8w); IN3(pi3d); IN3(o33d);
+  IN2(tsk);
+  if (in->aer_ra_feedback == 1) { IN3(tauaer300); IN3(tauaer400); IN3(tauaer600); IN3(tauaer999); IN3(gaer400); IN3(gaer600); IN3(waer400); IN3(waer600); }
+  if (in->tauaer3d_sw && in->ssaaer3d_sw && in->asyaer3d_sw) {
+    if ((rc = in_arr(ms, in->tauaer3d_sw, n3 * 14, &a.tauaer3d_sw))) return rc;
+    if ((rc = in_arr(ms, in->ssaaer3d_sw, n3 * 14, &a.ssaaer3d_sw))) return rc;
+    if ((rc = in_arr(ms, in->asyaer3d_sw, n3 * 14, &a.asyaer3d_sw))) return rc;
+  }
+  IN2(xcoszen); IN2(albedo);
+  if (in->sf_surface_physics == 8) { IN2(alswvisdir); IN2(alswvisdif); IN2(alswnirdir); IN2(alswnirdif); }
+#undef IN3
+#undef IN2
+#define OUT3(f) if ((rc = out_arr(ms, out->f, n3, &a.f))) return rc
+#define OUT2(f) if ((rc = out_arr(ms, out->f, n2, &a.f))) return rc
+#define OUTP(f) if ((rc = out_arr(ms, out->f, np, &a.f))) return rc
+  OUT3(rthratensw); OUT2(gsw); OUT2(swcf); OUT2(coszr);
+  OUT2(swupt); OUT2(swuptc); OUT2(swuptcln); OUT2(swdnt); OUT2(swdntc); OUT2(swdntcln);
+  OUT2(swupb); OUT2(swupbc); OUT2(swupbcln); OUT2(swdnb); OUT2(swdnbc); OUT2(swdnbcln);
+  OUT2(swvisdir); OUT2(swvisdif); OUT2(swnirdir); OUT2(swnirdif); OUT2(swddir); OUT2(swddni); OUT2(swddif);
+  OUTP(swupflx); OUTP(swupflxc); OUTP(swupflxcln); OUTP(swdnflx); OUTP(swdnflxc); OUTP(swdnflxcln);
+  const bool ext = out->swuptclnc && out->swdntclnc && out->swupbclnc && out->swdnbclnc;
+  if (ext) { OUT2(swuptclnc); OUT2(swdntclnc); OUT2(swupbclnc); OUT2(swdnbclnc); }
+#undef OUT3
+#undef OUT2
+#undef OUTP
+  int variants = in->variant_mask;
+  if (variants == 0) variants = ARC_VAR_FULL | ARC_VAR_CLEAR | (in->clean_atm_diag > 0 ? ARC_VAR_CLEAN : 0);
+  variants |= ARC_VAR_FULL | ARC_VAR_CLEAR;
+  if (in->clean_atm_diag <= 0) variants &= ~(ARC_VAR_CLEAN | ARC_VAR_CLEANCLEAR);
+  if (ext && (variants & ARC_VAR_CLEAN)) variants |= ARC_VAR_CLEANCLEAR;
+  if (!ext) variants &= ~ARC_VAR_CLEANCLEAR;
+  a.variants = variants;
+  a.status = g.d_status;
+
+  std::vector<std::pair<void *, std::pair<void *, size_t>>> dbglist;
+  if ((rc = setup_debug(dbg, (size_t)G.ncol_tile, nlay, NGSW, a.dbg, dbglist))) return rc;
+
+  // sunlit compaction
+  if ((size_t)G.ncol_tile > g.cols_cap) {
+    if (g.d_cols) cudaFree(g.d_cols);
+    g.d_cols = nullptr; g.cols_cap = 0;
+    CK(cudaMalloc(&g.d_cols, sizeof(int) * (size_t)G.ncol_tile));
+    g.cols_cap = (size_t)G.ncol_tile;
+  }
+  int nsun = 0;
+  {
+    Timed t("sw_compact");
+    launch_compact_sunlit(G, a.xcoszen, g.d_cols, g.d_count, g.stream);
+    launch_sw_night(a, g.stream);
+  }
+  CK(cudaMemcpyAsync(&nsun, g.d_count, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  if (nsun > 0) {
+    const size_t cap = std::min(chunk_cap_default(), (size_t)((nsun + 255) / 256 * 256));
+    if ((rc = ensure_sw_ws(nlay, cap))) return rc;
+    for (int c0 = 0; c0 < nsun; c0 += (int)cap) {
+      const int nc = std::min((int)cap, nsun - c0);
+      a.ws = g.sw;
+      a.ws.cols = g.d_cols + c0;
+      a.ncols = nc;
+      McicaArgs m{};
+      m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGSW; m.permuteseed = 1; m.ncols = nc; m.W = a.ws.W; m.icloud = in->icloud;
+      m.cap = (int)cap; m.col0 = 0; m.lw_buffer = 0; m.cols = a.ws.cols; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
+      m.mask = a.ws.mask; m.anyc = a.ws.anyc;
+      { Timed t("sw_mcica"); launch_mcica(m, g.stream); }
+      { Timed t("sw_prep"); launch_sw_prep(a, g.stream); }
+      { Timed t("sw_solve"); launch_sw_solve(a, g.stream); }
+      { Timed t("sw_reduce"); launch_sw_reduce(a, g.stream); }
+      if (a.dbg.cldmask) {
+        k_unpack_mask<<<(nc + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, a.ws.cols, 0, nc, (int)cap, a.ws.W, nlay, NGSW, a.dbg.cldmask);
+        count_launch();
+      }
+    }
+  }
+  return finish_call(dbglist);
+}
+
+int arc_rad_sw(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out) { return arc_rad_sw_debug(d, in, out, nullptr); }
+
+// ---------------------------------------------------------------------------------------------------------
+int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebug *dbg) {
+  if (!g.ready) { g.err = "arc_rad_lw: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !in || !out) { g.err = "arc_rad_lw: null argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if (in->aer_ra_feedback == 1)
+    for (int b = 0; b < 16; b++)
+      if (!in->tauaerlw[b]) { g.err = "Warning: missing fields required for aerosol radiation"; return ARC_ERR_MISSING_FIELD; }
+  if (in->clean_atm_diag > 0 && in->aer_ra_feedback <= 0) {
+    g.err = "clean_atm_diag > 0 requires aer_ra_feedback > 0 (chemics_init.F:406-408)"; return ARC_ERR_CONFIG;
+  }
+  if (!in->emiss || !in->t3d || !in->t8w || !in->p3d || !in->p8w || !in->pi3d || !in->qv3d || !in->tsk || !in->xland || !in->xice ||
+      !in->snow || !out->rthratenlw || !out->glw || !out->olr || !out->lwcf) {
+    g.err = "arc_rad_lw: required array missing"; return ARC_ERR_BAD_ARG;
+  }
+  if (in->icloud != 0 && ((in->has_reqc && !in->re_cloud) || (in->has_reqi && !in->re_ice) || (in->has_reqs && !in->re_snow))) {
+    g.err = "arc_rad_lw: has_req* set but re_* array missing"; return ARC_ERR_BAD_ARG;
+  }
+  if ((out->lwupflx || out->lwupflxc || out->lwupflxcln || out->lwdnflx || out->lwdnflxc || out->lwdnflxcln) &&
+      !(out->lwupflx && out->lwupflxc && out->lwupflxcln && out->lwdnflx && out->lwdnflxc && out->lwdnflxcln)) {
+    g.err = "arc_rad_lw: flux profile outputs must be passed all together"; return ARC_ERR_BAD_ARG;
+  }
+  if (out->lwupt && !(out->lwuptc && out->lwuptcln && out->lwdnt && out->lwdntc && out->lwdntcln && out->lwupb && out->lwupbc &&
+                      out->lwupbcln && out->lwdnb && out->lwdnbc && out->lwdnbcln)) {
+    g.err = "arc_rad_lw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG;
+  }
+  CK(cudaSetDevice(g.device));
+  g.last_ms.clear();
+  g.pool_next = 0; g.backs.clear();
+  const int ms = in->memspace;
+  LwArgs a{};
+  a.geo = make_geo(*d);
+  a.tb = g.D;
+  const Geo &G = a.geo;
+  const size_t n3 = G.n3(), n2 = G.n2(), np = G.np();
+  const int nz = d->kte - d->kts + 1;
+  const int nlay = g.H.lw_nlayers - d->kts + 1;
+  if (nlay > 159 || nlay < nz + 1) { g.err = "arc_rad_lw: bad LW layer count (nlayers from init vs kte)"; return ARC_ERR_BAD_ARG; }
+
+  CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
+  {
+    const int fq[7] = {in->f_qv, in->f_qc, in->f_qr, in->f_qi, in->f_qs, in->f_qg, in->f_qndrop};
+    const float *const p3[18] = {in->t3d, in->cldfra3d, in->lradius, in->iradius, in->qv3d, in->qc3d, in->qr3d, in->qi3d, in->qs3d,
+                                 in->qg3d, in->qndrop3d, in->re_cloud, in->re_ice, in->re_snow, in->f_ice_phy, 0, 0, 0};
+    const float *const p2[3] = {in->xland, in->xice, in->snow};
+    fill_cloud(a.cf, ms, rc, in->icloud, in->warm_rain, in->is_cammgmp_used, in->has_reqc, in->has_reqi, in->has_reqs, in->progn, fq,
+               in->g, p3, p2, n3, n2);
+    if (rc) return rc;
+  }
+  a.o3input = in->o3input; a.aer_ra_feedback = in->aer_ra_feedback;
+#define IN3(f) if ((rc = in_arr(ms, in->f, n3, &a.f))) return rc
+#define IN2(f) if ((rc = in_arr(ms, in->f, n2, &a.f))) return rc
+  IN3(t8w); IN3(p3d); IN3(p8w); IN3(pi3d); IN3(o33d);
+  IN2(tsk); IN2(emiss);
+  if (in->aer_ra_feedback == 1)
+    for (int b = 0; b < 16; b++) if ((rc = in_arr(ms, in->tauaerlw[b], n3, &a.tauaerlw[b]))) return rc;
+#undef IN3
+#undef IN2
+#define OUT3(f) if ((rc = out_arr(ms, out->f, n3, &a.f))) return rc
+#define OUT2(f) if ((rc = out_arr(ms, out->f, n2, &a.f))) return rc
+#define OUTP(f) if ((rc = out_arr(ms, out->f, np, &a.f))) return rc
+  OUT3(rthratenlw); OUT2(glw); OUT2(olr); OUT2(lwcf);
+  OUT2(lwupt); OUT2(lwuptc); OUT2(lwuptcln); OUT2(lwdnt); OUT2(lwdntc); OUT2(lwdntcln);
+  OUT2(lwupb); OUT2(lwupbc); OUT2(lwupbcln); OUT2(lwdnb); OUT2(lwdnbc); OUT2(lwdnbcln);
+  OUTP(lwupflx); OUTP(lwupflxc); OUTP(lwupflxcln); OUTP(lwdnflx); OUTP(lwdnflxc); OUTP(lwdnflxcln);
+  const bool ext = out->lwuptclnc && out->lwdntclnc && out->lwupbclnc && out->lwdnbclnc;
+  if (ext) { OUT2(lwuptclnc); OUT2(lwdntclnc); OUT2(lwupbclnc); OUT2(lwdnbclnc); }
+#undef OUT3
+#undef OUT2
+#undef OUTP
+  int variants = ARC_VAR_FULL | ARC_VAR_CLEAR;
+  if (in->clean_atm_diag > 0) variants |= ARC_VAR_CLEAN | ARC_VAR_CLEANCLEAR;   // the clean call yields both (LW:11022-11027)
+  a.variants = variants;
+  a.status = g.d_status;
+
+  std::vector<std::pair<void *, std::pair<void *, size_t>>> dbglist;
+  if ((rc = setup_debug(dbg, (size_t)G.ncol_tile, nlay, NGLW, a.dbg, dbglist))) return rc;
+
+  const int ncol = G.ncol_tile;
+  const size_t cap = std::min(chunk_cap_default(), (size_t)((ncol + 255) / 256 * 256));
+  if ((rc = ensure_lw_ws(nlay, cap))) return rc;
+  for (int c0 = 0; c0 < ncol; c0 += (int)cap) {
+    const int nc = std::min((int)cap, ncol - c0);
+    a.ws = g.lw;
+    a.ws.cols = nullptr;
+    a.col0 = c0;
+    a.ncols = nc;
+    McicaArgs m{};
+    m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGLW; m.permuteseed = 150; m.ncols = nc; m.W = a.ws.W; m.icloud = in->icloud;
+    m.cap = (int)cap; m.col0 = c0; m.lw_buffer = 1; m.cols = nullptr; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
+    m.mask = a.ws.mask; m.anyc = a.ws.anyc;
+    { Timed t("lw_mcica"); launch_mcica(m, g.stream); }
+    { Timed t("lw_prep"); launch_lw_prep(a, g.stream); }
+    { Timed t("lw_solve"); launch_lw_solve(a, g.stream); }
+    { Timed t("lw_reduce"); launch_lw_reduce(a, g.stream); }
+    if (a.dbg.cldmask) {
+      k_unpack_mask<<<(nc + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, nullptr, c0, nc, (int)cap, a.ws.W, nlay, NGLW, a.dbg.cldmask);
+      count_launch();
+    }
+  }
+  return finish_call(dbglist);
+}
+
+int arc_rad_lw(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out) { return arc_rad_lw_debug(d, in, out, nullptr); }
+
+// ---------------------------------------------------------------------------------------------------------
+// radiation_driver bookkeeping around the two calls (module_radiation_driver.F:1692-1702, 2180-2194)
+__global__ void k_driver_post(Geo G, const float *__restrict__ lw, const float *__restrict__ sw, float *__restrict__ rthraten,
+                              const float *__restrict__ gsw, const float *__restrict__ albedo, float *__restrict__ swdown) {
+  const int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tc >= G.ncol_tile) return;
+  int i, j; G.ij(tc, i, j);
+  if (rthraten)
+    for (int k = G.kts; k <= G.kte; k++) { const size_t q = G.at3(i, k, j); rthraten[q] = lw[q] + sw[q]; }
+  if (swdown) { const size_t ij = G.at2(i, j); swdown[ij] = gsw[ij] / (1.f - albedo[ij]); }
+}
+
+int arc_rad_driver_post(const ArcDims *d, int memspace, const float *rthratenlw, const float *rthratensw, float *rthraten,
+                        const float *gsw, const float *albedo, float *swdown) {
+  if (!g.ready) { g.err = "arc_rad_driver_post: not initialised"; return ARC_ERR_NOT_INIT; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if ((rthraten && !(rthratenlw && rthratensw)) || (swdown && !(gsw && albedo))) { g.err = "arc_rad_driver_post: missing input"; return ARC_ERR_BAD_ARG; }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const float *lw, *sw, *gs, *al; float *rt, *sd;
+  if ((rc = in_arr(memspace, rthratenlw, G.n3(), &lw))) return rc;
+  if ((rc = in_arr(memspace, rthratensw, G.n3(), &sw))) return rc;
+  if ((rc = in_arr(memspace, gsw, G.n2(), &gs))) return rc;
+  if ((rc = in_arr(memspace, albedo, G.n2(), &al))) return rc;
+  if ((rc = out_arr(memspace, rthraten, G.n3(), &rt))) return rc;
+  if ((rc = out_arr(memspace, swdown, G.n2(), &sd))) return rc;
+  k_driver_post<<<(G.ncol_tile + 255) / 256, 256, 0, g.stream>>>(G, lw, sw, rt, gs, al, sd);
+  count_launch();
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

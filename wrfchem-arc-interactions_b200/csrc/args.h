@@ -1,4 +1,4 @@
-// Kernel argument blocks (device pointers in WRF memory order) shared by api.cu and the kernels.
+// Kernel argument blocks (device pointers in WRF memory order), per-chunk workspaces and launchers.
 #pragma once
 #include <stdint.h>
 
@@ -14,10 +14,14 @@ struct Geo {
   __host__ __device__ size_t at3(int i, int k, int j) const { return (size_t)(i - ims) + (size_t)ni * ((size_t)(k - kms) + (size_t)nk * (size_t)(j - jms)); }
   __host__ __device__ size_t at2(int i, int j) const { return (size_t)(i - ims) + (size_t)ni * (size_t)(j - jms); }
   __host__ __device__ size_t atp(int i, int k, int j) const { return (size_t)(i - ims) + (size_t)ni * ((size_t)(k - kms) + (size_t)(nk + 2) * (size_t)(j - jms)); }
+  __host__ __device__ size_t n2() const { return (size_t)ni * (size_t)(jme - jms + 1); }
   __host__ __device__ size_t n3() const { return (size_t)ni * nk * (size_t)(jme - jms + 1); }
+  __host__ __device__ size_t np() const { return (size_t)ni * (nk + 2) * (size_t)(jme - jms + 1); }
+  // tile column id -> (i, j)
+  __host__ __device__ void ij(int tc, int &i, int &j) const { j = jts + tc / nci; i = its + tc % nci; }
 };
 
-struct DebugTaps {     // device pointers (nullable)
+struct DebugTaps {     // device pointers (nullable); column index = tile column id
   int *laytrop, *jp, *jt, *jt1, *indfor, *indself, *indminor;
   float *fac00, *fac01, *fac10, *fac11;
   unsigned char *cldmask;
@@ -33,15 +37,38 @@ struct CloudFields {
   const float *re_cloud, *re_ice, *re_snow, *f_ice_phy, *xland, *xice, *snow;
 };
 
+// flux "kinds" in the partial buffer: full up/down, clear up/down, clean up/down, clean-clear up/down
+enum { K_FU = 0, K_FD, K_CU, K_CD, K_NU, K_ND, K_XU, K_XD, NKIND };
+
+// ---- SW workspace fields [field][lay][c] -------------------------------------------------------------
+enum { SWC_FAC00 = 0, SWC_FAC01, SWC_FAC10, SWC_FAC11, SWC_H2O, SWC_CO2, SWC_O3, SWC_CH4, SWC_O2, SWC_MOL,
+       SWC_SELFFAC, SWC_SELFFRAC, SWC_FORFAC, SWC_FORFRAC, SWC_IDX, SWC_N };
+// per-column floats [field][c]
+enum { SWF_MU0 = 0, SWF_ALBDIR_NIR, SWF_ALBDIF_NIR, SWF_ALBDIR_UV, SWF_ALBDIF_UV, SWF_ADJFLUX, SWF_N };
+
+struct SwWs {
+  int cap;                 // column stride (chunk capacity)
+  int nlay;                // kte-kts+2
+  int W;                   // mask words per (g, column)
+  int *cols;               // [cap] tile column id of each chunk column
+  float *coef;             // [SWC_N][nlay][cap]
+  float *aer;              // [14][3][nlay][cap]   tau, ssa, asy
+  float *cld;              // [14][4][nlay][cap]   taucmc, ssacmc, asmcmc, taormc
+  uint32_t *mask;          // [NGSW][W][cap]       McICA bits, bit (lay%32) of word lay/32
+  uint32_t *anyc;          // [W][cap]             OR over g of the mask
+  int *laytrop;            // [cap]
+  int *laysol;             // [14][cap]            layer (0-based) where sfluxzen is taken, -1 = never
+  float *colf;             // [SWF_N][cap]
+  float *part;             // [NGSW][nlay+1][NKIND][cap]
+  float *dirs;             // [NGSW][cap]          surface direct beam without delta scaling (x incident flux)
+};
+
 struct SwArgs {
   Geo geo;
   DevTables tb;
   CloudFields cf;
-  int nlay;                 // kte-kts+2
-  int ncols;                // sunlit columns to process
-  const int *cols;          // tile column ids (c = (j-jts)*nci + (i-its)) of the sunlit columns
-  const uint32_t *mask;     // McICA bits [(g*W + w)*ncols + ci]
-  int W;
+  SwWs ws;
+  int ncols;                // columns in this chunk
   int variants;             // ARC_VAR_* mask
   int o3input, aer_ra_feedback, sf_surface_physics;
   float solcon;
@@ -50,7 +77,7 @@ struct SwArgs {
   const float *tauaer3d_sw, *ssaaer3d_sw, *asyaer3d_sw;
   const float *xcoszen, *albedo, *alswvisdir, *alswvisdif, *alswnirdir, *alswnirdif;
   // outputs
-  float *rthratensw, *gsw, *swcf;
+  float *rthratensw, *gsw, *swcf, *coszr;
   float *swupt, *swuptc, *swuptcln, *swdnt, *swdntc, *swdntcln, *swupb, *swupbc, *swupbcln, *swdnb, *swdnbc, *swdnbcln;
   float *swvisdir, *swvisdif, *swnirdir, *swnirdif, *swddir, *swddni, *swddif;
   float *swupflx, *swupflxc, *swupflxcln, *swdnflx, *swdnflxc, *swdnflxcln;
@@ -59,14 +86,33 @@ struct SwArgs {
   DebugTaps dbg;
 };
 
+// ---- LW workspace ------------------------------------------------------------------------------------------
+enum { LWC_FAC00 = 0, LWC_FAC01, LWC_FAC10, LWC_FAC11, LWC_H2O, LWC_CO2, LWC_O3, LWC_N2O, LWC_CO, LWC_CH4, LWC_O2, LWC_BRD,
+       LWC_SELFFAC, LWC_SELFFRAC, LWC_FORFAC, LWC_FORFRAC, LWC_MINORFRAC, LWC_SCALEMINOR, LWC_SCALEMINORN2,
+       LWC_PAVEL, LWC_COLDRY, LWC_TAVEL, LWC_TZ, LWC_IDX, LWC_N };
+enum { LWF_TZ0 = 0, LWF_TBOUND, LWF_EMISS, LWF_N };
+
+struct LwWs {
+  int cap, nlay, W;
+  int *cols;               // nullable (identity)
+  float *coef;             // [LWC_N][nlay][cap]
+  float *aer;              // [16][nlay][cap]
+  float *cld;              // [16][nlay][cap]  taucmc
+  uint32_t *mask;          // [NGLW][W][cap]
+  uint32_t *anyc;          // [W][cap]
+  int *laytrop;            // [cap]
+  float *colf;             // [LWF_N][cap]
+  float *secdiff;          // [16][cap]
+  float *part;             // [NGLW][nlay+1][NKIND][cap]
+};
+
 struct LwArgs {
   Geo geo;
   DevTables tb;
   CloudFields cf;
-  int nlay;                 // LW nlayers
+  LwWs ws;
+  int col0;                 // first tile column of this chunk
   int ncols;
-  const uint32_t *mask;
-  int W;
   int variants;
   int o3input, aer_ra_feedback;
   const float *t8w, *p3d, *p8w, *pi3d, *o33d, *tsk, *emiss;
@@ -81,18 +127,26 @@ struct LwArgs {
 
 struct McicaArgs {
   Geo geo;
-  int nlay, ngpt, permuteseed, ncols, W, icloud;
-  const int *cols;          // nullable: identity
-  const float *p3d, *cldfra3d;
-  uint32_t *mask;
+  int nlay, nz, ngpt, permuteseed, ncols, W, icloud, cap, col0;
+  int lw_buffer;            // 1: LW layering above the model top (4-hPa buffer layers), 0: SW single extra layer
+  const int *cols;          // nullable: tile column = col0 + c
+  const float *p3d, *p8w, *cldfra3d;
+  uint32_t *mask;           // [ngpt][W][cap]
+  uint32_t *anyc;           // [W][cap]
 };
 
-// launchers (defined in the .cu files)
+// launchers (defined in the .cu files); every launcher bumps the launch counter
+void launch_compact_sunlit(const Geo &g, const float *xcoszen, int *cols, int *count, cudaStream_t s);
+void launch_sw_night(const SwArgs &a, cudaStream_t s);
 void launch_mcica(const McicaArgs &a, cudaStream_t s);
-void launch_sw(const SwArgs &a, int nblocks, cudaStream_t s);
-void launch_lw(const LwArgs &a, int nblocks, cudaStream_t s);
+void launch_sw_prep(const SwArgs &a, cudaStream_t s);
+void launch_sw_solve(const SwArgs &a, cudaStream_t s);
+void launch_sw_reduce(const SwArgs &a, cudaStream_t s);
+void launch_lw_prep(const LwArgs &a, cudaStream_t s);
+void launch_lw_solve(const LwArgs &a, cudaStream_t s);
+void launch_lw_reduce(const LwArgs &a, cudaStream_t s);
 void upload_band_descs(const HostTables &T);
-int sw_smem_bytes();
-int lw_smem_bytes();
+void count_launch(int n = 1);
+long long launch_count();
 
 }  // namespace arc

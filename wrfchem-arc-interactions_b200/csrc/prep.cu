@@ -1,0 +1,752 @@
+// Column preparation kernels: sunlit-column compaction, McICA sub-column masks, and the
+// WRF->RRTMG adapter + inatm + setcoef + aerosol/cloud band optics, one thread per column, writing
+// the [field][layer][column] workspace the spectral solvers read.
+//
+// Compiled with -fmad=false: jp/jt/jt1/indfor/indself/indminor/laytrop and the McICA masks must be
+// bit-identical to the reference's unfused arithmetic.
+//
+// Reference (module_ra_rrtmg_sw.F = SW, module_ra_rrtmg_lw.F = LW, v3.9.1):
+//   RRTMG_SWRAD SW:10320-11071, inatm_sw SW:9520-9873, setcoef_sw SW:2734-2990, cldprmc_sw SW:1969-2390,
+//   mcica_subcol_sw/generate_stochastic_clouds_sw/kissvec SW:1392-1932 (LW twins LW:2089-2618),
+//   RRTMG_LWRAD LW:11877-12629, inatm LW:11067-11403, setcoef LW:3444-3809, cldprmc LW:2653-2914,
+//   taumol_sw's laysolfr selection SW:3293-4538.
+#include "adapter.cuh"
+#include "../../include/arc_rad.h"
+
+namespace arc {
+
+static __constant__ SwBandDesc c_sw[14];
+
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+
+void upload_band_descs_sw(const HostTables &T);   // sw_solve.cu
+void upload_band_descs_lw(const HostTables &T);   // lw_solve.cu
+void upload_band_descs(const HostTables &T) {
+  cudaMemcpyToSymbol(c_sw, T.sw, sizeof(SwBandDesc) * 14);
+  upload_band_descs_sw(T);
+  upload_band_descs_lw(T);
+}
+
+__device__ __forceinline__ void set_status(int *status, int code) {
+  if (code) atomicCAS(status, 0, code);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Sunlit compaction (SW:10336 "if (coszrs.le.0.0) dorrsw = .false.").  Order-preserving: one block scans
+// a 1024-column segment, segment offsets come from a first counting pass, so the chunk-local ordering (and
+// with it every memory address) is deterministic.
+__global__ void k_count_sunlit(Geo G, const float *__restrict__ xcoszen, int *__restrict__ segcount) {
+  int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  bool sun = false;
+  if (tc < G.ncol_tile) { int i, j; G.ij(tc, i, j); sun = !(xcoszen[G.at2(i, j)] <= 0.0f); }
+  int n = __syncthreads_count(sun);
+  if (threadIdx.x == 0) segcount[blockIdx.x] = n;
+}
+__global__ void k_scan_segments(int nseg, int *__restrict__ segcount, int *__restrict__ total) {
+  // single thread block; nseg is small (ncol/1024)
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nseg; base += blockDim.x) {
+    int idx = base + threadIdx.x;
+    int v = idx < nseg ? segcount[idx] : 0;
+    // inclusive scan in shared memory (Hillis-Steele)
+    __shared__ int buf[1024];
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < blockDim.x; off <<= 1) {
+      int t = threadIdx.x >= off ? buf[threadIdx.x - off] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (idx < nseg) segcount[idx] = carry + buf[threadIdx.x] - v;   // exclusive offset
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += buf[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void k_fill_sunlit(Geo G, const float *__restrict__ xcoszen, const int *__restrict__ segoff, int *__restrict__ cols) {
+  int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  bool sun = false;
+  if (tc < G.ncol_tile) { int i, j; G.ij(tc, i, j); sun = !(xcoszen[G.at2(i, j)] <= 0.0f); }
+  __shared__ int wcount[32];
+  unsigned b = __ballot_sync(0xffffffffu, sun);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) wcount[w] = __popc(b);
+  __syncthreads();
+  int off = segoff[blockIdx.x];
+  for (int q = 0; q < w; q++) off += wcount[q];
+  if (sun) cols[off + __popc(b & ((1u << lane) - 1u))] = tc;
+}
+
+static int *g_seg = nullptr; static int g_seg_cap = 0;
+void launch_compact_sunlit(const Geo &g, const float *xcoszen, int *cols, int *count, cudaStream_t s) {
+  int nseg = (g.ncol_tile + 1023) / 1024;
+  if (nseg > g_seg_cap) { if (g_seg) cudaFree(g_seg); cudaMalloc(&g_seg, sizeof(int) * nseg); g_seg_cap = nseg; }
+  k_count_sunlit<<<nseg, 1024, 0, s>>>(g, xcoszen, g_seg);
+  k_scan_segments<<<1, 1024, 0, s>>>(nseg, g_seg, count);
+  k_fill_sunlit<<<nseg, 1024, 0, s>>>(g, xcoszen, g_seg, cols);
+  count_launch(3);
+}
+
+// Night columns and coszr: SW:10332, 11173-11199.  One thread per tile column.
+__global__ void k_sw_night(SwArgs a) {
+  int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tc >= a.geo.ncol_tile) return;
+  int i, j; a.geo.ij(tc, i, j);
+  size_t ij = a.geo.at2(i, j);
+  float cz = a.xcoszen[ij];
+  a.coszr[ij] = cz;
+  if (cz <= 0.0f) {
+    if (a.swupt) {
+      a.swupt[ij] = 0.f; a.swuptc[ij] = 0.f; a.swuptcln[ij] = 0.f; a.swdnt[ij] = 0.f; a.swdntc[ij] = 0.f; a.swdntcln[ij] = 0.f;
+      a.swupb[ij] = 0.f; a.swupbc[ij] = 0.f; a.swupbcln[ij] = 0.f; a.swdnb[ij] = 0.f; a.swdnbc[ij] = 0.f; a.swdnbcln[ij] = 0.f;
+      a.swvisdir[ij] = 0.f; a.swvisdif[ij] = 0.f; a.swnirdir[ij] = 0.f; a.swnirdif[ij] = 0.f;
+    }
+    if (a.swuptclnc) { a.swuptclnc[ij] = 0.f; a.swdntclnc[ij] = 0.f; a.swupbclnc[ij] = 0.f; a.swdnbclnc[ij] = 0.f; }
+    a.swddir[ij] = 0.f; a.swddni[ij] = 0.f; a.swddif[ij] = 0.f; a.swcf[ij] = 0.f;
+    if (a.dbg.laytrop) a.dbg.laytrop[tc] = -1;
+  }
+}
+void launch_sw_night(const SwArgs &a, cudaStream_t s) {
+  k_sw_night<<<(a.geo.ncol_tile + 255) / 256, 256, 0, s>>>(a);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// McICA masks: generate_stochastic_clouds(_sw) with icld = 2 (maximum-random), irng = 0 (kissvec).
+// One thread per column runs the serial KISS chain (sub-column major, layer minor: SW:1745-1750) and applies
+// the maximum-random overlap rescale (SW:1762-1772) on the fly -- the rescale of layer l only needs the final
+// value of layer l-1 of the same sub-column, which precedes it in the chain.
+constexpr int MCICA_MAXLAY = 160;
+
+__global__ void __launch_bounds__(128) k_mcica(McicaArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncols) return;
+  const int tc = a.cols ? a.cols[c] : a.col0 + c;
+  int i, j; a.geo.ij(tc, i, j);
+  const int kts = a.geo.kts;
+  float omc[MCICA_MAXLAY];      // 1 - cldf(l)
+  for (int l = 0; l < a.nlay; l++) {
+    float cf = 0.f;
+    if (l < a.nz && a.icloud != 0 && a.cldfra3d) cf = a.cldfra3d[a.geo.at3(i, kts + l, j)];
+    if (cf < 1.0e-20f) cf = 0.f;
+    omc[l] = 1.0f - cf;
+  }
+  Kiss K;
+  {
+    float pm[4];
+    for (int l = 0; l < 4; l++) {
+      float play = a.p3d[a.geo.at3(i, kts + l, j)] / 100.f;       // p1d = p3d/100 ; play = p1d
+      pm[l] = play * 1.e2f;                                        // pmid = play*1.e2
+    }
+    K.s1 = (uint32_t)(int32_t)((pm[0] - (float)(int)pm[0]) * 1000000000.f);
+    K.s2 = (uint32_t)(int32_t)((pm[1] - (float)(int)pm[1]) * 1000000000.f);
+    K.s3 = (uint32_t)(int32_t)((pm[2] - (float)(int)pm[2]) * 1000000000.f);
+    K.s4 = (uint32_t)(int32_t)((pm[3] - (float)(int)pm[3]) * 1000000000.f);
+  }
+  for (int q = 0; q < a.permuteseed; q++) (void)K.next();
+  uint32_t any[MCICA_MAXLAY / 32];
+  for (int w = 0; w < a.W; w++) any[w] = 0u;
+  for (int g = 0; g < a.ngpt; g++) {
+    float prev = 0.f;
+    uint32_t word = 0u;
+    for (int l = 0; l < a.nlay; l++) {
+      float x = K.next();
+      if (l > 0) {
+        if (prev > omc[l - 1]) x = prev; else x = x * omc[l - 1];
+      }
+      prev = x;
+      if (x >= omc[l]) word |= 1u << (l & 31);
+      if ((l & 31) == 31 || l == a.nlay - 1) {
+        a.mask[((size_t)g * a.W + (l >> 5)) * a.cap + c] = word;
+        any[l >> 5] |= word;
+        word = 0u;
+      }
+    }
+  }
+  for (int w = 0; w < a.W; w++) a.anyc[(size_t)w * a.cap + c] = any[w];
+}
+void launch_mcica(const McicaArgs &a, cudaStream_t s) {
+  k_mcica<<<(a.ncols + 127) / 128, 128, 0, s>>>(a);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Cloud optical properties of one (layer, band): cldprmc_sw SW:2100-2390, inflag >= 2 path.
+// Returns an ARC_ERR_* code.  Inputs are the in-cloud paths / sizes of the layer.
+__device__ inline int sw_cloud_optics(const DevTables &tb, int ib /*0..13*/, int iceflag, int liqflag, float ciwp, float clwp,
+                                      float cswp, float radice, float radliq, float radsno, float &taucmc, float &ssacmc,
+                                      float &asmcmc, float &taormc) {
+  const float cldmin = 1.e-20f;
+  float extcoice = 0.f, ssacoice = 0.f, gice = 0.f, forwice = 0.f;
+  float extcosno = 0.f, ssacosno = 0.f, gsno = 0.f, forwsno = 0.f;
+  float extcoliq = 0.f, ssacoliq = 0.f, gliq = 0.f, forwliq = 0.f;
+  if ((ciwp + cswp) == 0.0f) {
+  } else if (iceflag >= 3) {
+    if (radice < 5.0f || radice > 140.0f) return ARC_ERR_RADIUS;
+    float factor = (radice - 2.f) / 3.f;
+    int index = (int)factor;
+    if (index == 46) index = 45;
+    float fint = factor - (float)index;
+    const int o = (index - 1) + 46 * ib;
+    extcoice = tb.sw_extice3[o] + fint * (tb.sw_extice3[o + 1] - tb.sw_extice3[o]);
+    ssacoice = tb.sw_ssaice3[o] + fint * (tb.sw_ssaice3[o + 1] - tb.sw_ssaice3[o]);
+    gice = tb.sw_asyice3[o] + fint * (tb.sw_asyice3[o + 1] - tb.sw_asyice3[o]);
+    float fdelta = tb.sw_fdlice3[o] + fint * (tb.sw_fdlice3[o + 1] - tb.sw_fdlice3[o]);
+    if (fdelta < 0.0f || fdelta > 1.0f) return ARC_ERR_RADIUS;
+    forwice = fdelta + 0.5f / ssacoice;
+    if (forwice > gice) forwice = gice;
+  } else {
+    return ARC_ERR_UNSUPPORTED;
+  }
+  if (cswp > 0.0f && iceflag == 5) {
+    if (radsno < 5.0f || radsno > 140.0f) return ARC_ERR_RADIUS;
+    float factor = (radsno - 2.f) / 3.f;
+    int index = (int)factor;
+    if (index == 46) index = 45;
+    float fint = factor - (float)index;
+    const int o = (index - 1) + 46 * ib;
+    extcosno = tb.sw_extice3[o] + fint * (tb.sw_extice3[o + 1] - tb.sw_extice3[o]);
+    ssacosno = tb.sw_ssaice3[o] + fint * (tb.sw_ssaice3[o + 1] - tb.sw_ssaice3[o]);
+    gsno = tb.sw_asyice3[o] + fint * (tb.sw_asyice3[o + 1] - tb.sw_asyice3[o]);
+    float fdelta = tb.sw_fdlice3[o] + fint * (tb.sw_fdlice3[o + 1] - tb.sw_fdlice3[o]);
+    if (fdelta < 0.0f || fdelta > 1.0f) return ARC_ERR_RADIUS;
+    forwsno = fdelta + 0.5f / ssacosno;
+    if (forwsno > gsno) forwsno = gsno;
+  }
+  if (clwp == 0.0f) {
+  } else if (liqflag == 1) {
+    if (radliq < 1.5f || radliq > 60.f) return ARC_ERR_RADIUS;
+    int index = (int)(radliq - 1.5f);
+    if (index == 0) index = 1;
+    if (index == 58) index = 57;
+    float fint = radliq - 1.5f - (float)index;
+    const int o = (index - 1) + 58 * ib;
+    extcoliq = tb.sw_extliq1[o] + fint * (tb.sw_extliq1[o + 1] - tb.sw_extliq1[o]);
+    ssacoliq = tb.sw_ssaliq1[o] + fint * (tb.sw_ssaliq1[o + 1] - tb.sw_ssaliq1[o]);
+    if (fint < 0.f && ssacoliq > 1.f) ssacoliq = tb.sw_ssaliq1[o];
+    gliq = tb.sw_asyliq1[o] + fint * (tb.sw_asyliq1[o + 1] - tb.sw_asyliq1[o]);
+    forwliq = gliq * gliq;
+  }
+  float tauliqorig = clwp * extcoliq;
+  float tauiceorig = ciwp * extcoice;
+  float ssaliq = ssacoliq * (1.f - forwliq) / (1.f - forwliq * ssacoliq);
+  float tauliq = (1.f - forwliq * ssacoliq) * tauliqorig;
+  float ssaice = ssacoice * (1.f - forwice) / (1.f - forwice * ssacoice);
+  float tauice = (1.f - forwice * ssacoice) * tauiceorig;
+  float scatliq = ssaliq * tauliq, scatice = ssaice * tauice, scatsno;
+  if (iceflag < 5) {
+    taormc = tauliqorig + tauiceorig;
+    scatsno = 0.0f;
+    taucmc = tauliq + tauice;
+  } else {
+    float tausnoorig = cswp * extcosno;
+    taormc = tauliqorig + tauiceorig + tausnoorig;
+    float ssasno = ssacosno * (1.f - forwsno) / (1.f - forwsno * ssacosno);
+    float tausno = (1.f - forwsno * ssacosno) * tausnoorig;
+    scatsno = ssasno * tausno;
+    taucmc = tauliq + tauice + tausno;
+  }
+  if (taucmc == 0.f) taucmc = cldmin;
+  if (scatice == 0.f) scatice = cldmin;
+  if (scatsno == 0.f) scatsno = cldmin;
+  if (iceflag < 5) ssacmc = (scatliq + scatice) / taucmc;
+  else ssacmc = (scatliq + scatice + scatsno) / taucmc;
+  if (iceflag == 3 || iceflag == 4) {
+    asmcmc = (1.0f / (scatliq + scatice)) *
+             (scatliq * (gliq - forwliq) / (1.0f - forwliq) + scatice * ((gice - forwice) / (1.0f - forwice)));
+  } else {
+    asmcmc = (1.0f / (scatliq + scatice + scatsno)) *
+             (scatliq * (gliq - forwliq) / (1.0f - forwliq) + scatice * ((gice - forwice) / (1.0f - forwice)) +
+              scatsno * ((gsno - forwsno) / (1.0f - forwsno)));
+  }
+  return 0;
+}
+
+// cldprmc LW:2653-2914 for one (layer, band)
+__device__ inline int lw_cloud_optics(const DevTables &tb, int ib /*0..15*/, int iceflag, int liqflag, float ciwp, float clwp,
+                                      float cswp, float radice, float radliq, float radsno, float &taucmc) {
+  float abscoice = 0.f, abscosno = 0.f, abscoliq = 0.f;
+  if ((ciwp + cswp) == 0.0f) {
+  } else if (iceflag >= 3) {
+    if (radice < 5.0f || radice > 140.0f) return ARC_ERR_RADIUS;
+    float factor = (radice - 2.f) / 3.f;
+    int index = (int)factor;
+    if (index == 46) index = 45;
+    float fint = factor - (float)index;
+    const int o = (index - 1) + 46 * ib;
+    abscoice = tb.lw_absice3[o] + fint * (tb.lw_absice3[o + 1] - (tb.lw_absice3[o]));
+  } else {
+    return ARC_ERR_UNSUPPORTED;
+  }
+  if (cswp > 0.0f && iceflag == 5) {
+    if (radsno < 5.0f || radsno > 140.0f) return ARC_ERR_RADIUS;
+    float factor = (radsno - 2.f) / 3.f;
+    int index = (int)factor;
+    if (index == 46) index = 45;
+    float fint = factor - (float)index;
+    const int o = (index - 1) + 46 * ib;
+    abscosno = tb.lw_absice3[o] + fint * (tb.lw_absice3[o + 1] - (tb.lw_absice3[o]));
+  }
+  if (clwp == 0.0f) {
+  } else if (liqflag == 1) {
+    if (radliq < 2.5f || radliq > 60.f) return ARC_ERR_RADIUS;
+    int index = (int)(radliq - 1.5f);
+    if (index == 0) index = 1;
+    if (index == 58) index = 57;
+    float fint = radliq - 1.5f - (float)index;
+    const int o = (index - 1) + 58 * ib;
+    abscoliq = tb.lw_absliq1[o] + fint * (tb.lw_absliq1[o + 1] - (tb.lw_absliq1[o]));
+  }
+  taucmc = ciwp * abscoice + clwp * abscoliq + cswp * abscosno;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// SW column preparation.  One thread per sunlit column.
+constexpr int PREP_MAXLAY = 160;
+
+__global__ void __launch_bounds__(128) k_sw_prep(SwArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncols) return;
+  const Geo &G = a.geo;
+  const DevTables &tb = a.tb;
+  const SwWs &ws = a.ws;
+  const int tc = ws.cols[c];
+  int i, j; G.ij(tc, i, j);
+  const size_t ij = G.at2(i, j);
+  const int kts = G.kts, nz = G.kte - G.kts + 1, nlay = nz + 1;
+  const size_t cap = ws.cap;
+  const float amdw = 1.607793f, amdo = 0.603461f;
+  const float co2 = 379.e-6f, ch4 = 1774.e-9f, n2o = 319.e-9f, o2 = 0.209488f;
+  (void)n2o;
+  int inflg, iceflg, liqflg;
+  cloud_flags(a.cf, inflg, iceflg, liqflg);
+
+  auto COEF = [&](int f, int l) -> float & { return ws.coef[((size_t)f * nlay + l) * cap + c]; };
+  auto AER = [&](int b, int q, int l) -> float & { return ws.aer[(((size_t)b * 3 + q) * nlay + l) * cap + c]; };
+  auto CLD = [&](int b, int q, int l) -> float & { return ws.cld[(((size_t)b * 4 + q) * nlay + l) * cap + c]; };
+
+  // column scalars
+  const float coszrs = a.xcoszen[ij];
+  {
+    float cossza = coszrs;
+    if (cossza <= 1.e-10f) cossza = 1.e-10f;
+    float asdir, asdif, aldir, aldif;
+    if (a.sf_surface_physics == 8 && a.cf.xland[ij] < 1.5f) {
+      asdir = a.alswvisdir[ij]; asdif = a.alswvisdif[ij]; aldir = a.alswnirdir[ij]; aldif = a.alswnirdif[ij];
+    } else { asdir = asdif = aldir = aldif = a.albedo[ij]; }
+    ws.colf[(size_t)SWF_MU0 * cap + c] = cossza;
+    ws.colf[(size_t)SWF_ALBDIR_NIR * cap + c] = aldir;
+    ws.colf[(size_t)SWF_ALBDIF_NIR * cap + c] = aldif;
+    ws.colf[(size_t)SWF_ALBDIR_UV * cap + c] = asdir;
+    ws.colf[(size_t)SWF_ALBDIF_UV * cap + c] = asdif;
+    // inatm_sw: adjflx = adjes (=1, dyofyr = 0); adjflux(ib) = adjflx * scon/1368.22  (SW:9746-9762)
+    const float solvar = a.solcon / 1.36822e+03f;
+    ws.colf[(size_t)SWF_ADJFLUX * cap + c] = 1.0f * solvar;
+  }
+
+  unsigned char jps[PREP_MAXLAY];
+  float o3top_ref = 0.f, o31d_top = 0.f;   // o3mmr(nz), o31d(nz) for the shifted climatology above the model top
+  float h2o_prev = 0.f;
+  int laytrop = 0;
+  float aersum[NBSW];
+  for (int b = 0; b < NBSW; b++) aersum[b] = 0.f;
+  const float thresh = 1.e-9f;
+  const float stpfac = 296.f / 1013.f;
+  int err = 0;
+
+  for (int l = 0; l < nlay; l++) {
+    const bool model = l < nz;
+    const int k = kts + l;
+    // ---- pressures / temperature of the layer (hPa, K)
+    float plev_b, plev_t, play, tlay;
+    if (model) {
+      plev_b = a.p8w[G.at3(i, k, j)] / 100.f;
+      plev_t = a.p8w[G.at3(i, k + 1, j)] / 100.f;
+      play = a.p3d[G.at3(i, k, j)] / 100.f;
+      tlay = a.cf.t3d[G.at3(i, k, j)];
+    } else {
+      plev_b = a.p8w[G.at3(i, k, j)] / 100.f;     // plev(kte+1)
+      plev_t = 1.0e-5f;                            // plev(kte+2)
+      play = 0.5f * plev_b;
+      tlay = a.t8w[G.at3(i, k, j)] + 0.0f;        // tlev(kte+1) + 0
+    }
+    const float pdel = plev_b - plev_t;
+    // ---- water vapour, ozone (vmr)
+    float h2ovmr;
+    if (model) { h2ovmr = layer_qv(a.cf, G.at3(i, k, j)) * amdw; h2o_prev = h2ovmr; }
+    else h2ovmr = h2o_prev;
+    const float o3mmr = o3_clim(tb, plev_b, plev_t);
+    float o3vmr = o3mmr * amdo;
+    if (a.o33d && a.o3input == 2) {
+      if (model) { o3vmr = a.o33d[G.at3(i, k, j)]; if (l == nz - 1) { o31d_top = o3vmr; o3top_ref = o3mmr; } }
+      else {
+        o3vmr = o31d_top - o3top_ref * amdo + o3mmr * amdo;
+        if (o3vmr <= 0.f) o3vmr = o3mmr * amdo;
+      }
+    }
+    // ---- inatm_sw: column amounts
+    const float coldry = coldry_of(plev_b, plev_t, h2ovmr);
+    const float wk_h2o = coldry * h2ovmr, wk_co2 = coldry * co2, wk_o3 = coldry * o3vmr, wk_ch4 = coldry * ch4,
+                wk_o2 = coldry * o2;
+    // ---- setcoef_sw
+    PTCoef pc;
+    pt_coef(tb.sw_preflog, tb.sw_tref, play, tlay, pc);
+    const float water = wk_h2o / coldry;
+    const float scalefac = play * stpfac / tlay;
+    float forfac, forfrac, selffac, selffrac;
+    int indfor, indself;
+    if (!(pc.plog <= 4.56f)) {
+      laytrop = laytrop + 1;
+      forfac = scalefac / (1.f + water);
+      float factor = (332.0f - tlay) / 36.0f;
+      indfor = min(2, max(1, (int)factor));
+      forfrac = factor - (float)indfor;
+      selffac = water * forfac;
+      factor = (tlay - 188.0f) / 7.2f;
+      indself = min(9, max(1, (int)factor - 7));
+      selffrac = factor - (float)(indself + 7);
+    } else {
+      forfac = scalefac / (1.f + water);
+      float factor = (tlay - 188.0f) / 36.0f;
+      indfor = 3;
+      forfrac = factor - 1.0f;
+      selffac = 0.f; selffrac = 0.f; indself = 0;
+    }
+    float colh2o = 1.e-20f * wk_h2o, colco2 = 1.e-20f * wk_co2, colo3 = 1.e-20f * wk_o3, colch4 = 1.e-20f * wk_ch4,
+          colo2 = 1.e-20f * wk_o2;
+    const float colmol = 1.e-20f * coldry + colh2o;
+    if (colco2 == 0.f) colco2 = 1.e-32f * coldry;
+    if (colch4 == 0.f) colch4 = 1.e-32f * coldry;
+    if (colo2 == 0.f) colo2 = 1.e-32f * coldry;
+    COEF(SWC_FAC00, l) = pc.fac00; COEF(SWC_FAC01, l) = pc.fac01; COEF(SWC_FAC10, l) = pc.fac10; COEF(SWC_FAC11, l) = pc.fac11;
+    COEF(SWC_H2O, l) = colh2o; COEF(SWC_CO2, l) = colco2; COEF(SWC_O3, l) = colo3; COEF(SWC_CH4, l) = colch4;
+    COEF(SWC_O2, l) = colo2; COEF(SWC_MOL, l) = colmol;
+    COEF(SWC_SELFFAC, l) = selffac; COEF(SWC_SELFFRAC, l) = selffrac; COEF(SWC_FORFAC, l) = forfac; COEF(SWC_FORFRAC, l) = forfrac;
+    COEF(SWC_IDX, l) = __int_as_float(pack_idx(pc.jp, pc.jt, pc.jt1, indself, indfor, 0));
+    jps[l] = (unsigned char)pc.jp;
+    if (a.dbg.jp) {
+      const size_t q = (size_t)tc * nlay + l;
+      a.dbg.jp[q] = pc.jp; a.dbg.jt[q] = pc.jt; a.dbg.jt1[q] = pc.jt1; a.dbg.indfor[q] = indfor; a.dbg.indself[q] = indself;
+      a.dbg.fac00[q] = pc.fac00; a.dbg.fac01[q] = pc.fac01; a.dbg.fac10[q] = pc.fac10; a.dbg.fac11[q] = pc.fac11;
+    }
+    // ---- aerosol band optics (SW:10967-11030)
+    float t300 = 0.f, t999 = 0.f, t400 = 0.f, w4 = 0.f, w6 = 0.f, g4 = 0.f, g6 = 0.f, lograt = 0.f;
+    bool chem = false;
+    if (model && a.aer_ra_feedback == 1) {
+      const size_t q = G.at3(i, k, j);
+      t300 = a.tauaer300[q]; t999 = a.tauaer999[q];
+      if (t300 > thresh && t999 > thresh) {
+        chem = true;
+        t400 = a.tauaer400[q]; w4 = a.waer400[q]; w6 = a.waer600[q]; g4 = a.gaer400[q]; g6 = a.gaer600[q];
+        lograt = logf(t300 / t999) / logf(999.f / 300.f);
+      }
+    }
+    for (int b = 0; b < NBSW; b++) {
+      float taua = 0.f, ssaa = 1.f, asma = 0.f;
+      if (model && a.tauaer3d_sw) {
+        const size_t q4 = G.at3(i, k, j) + G.n3() * (size_t)b;
+        taua = a.tauaer3d_sw[q4]; ssaa = a.ssaaer3d_sw[q4]; asma = a.asyaer3d_sw[q4];
+      }
+      if (chem) {
+        const float wavemid = tb.wavemid[b];
+        taua = t400 * powf(0.4f / wavemid, lograt);
+        float slope = (w6 - w4) / .2f;
+        ssaa = slope * (wavemid - .6f) + w6;
+        if (ssaa < 0.4f) ssaa = 0.4f;
+        if (ssaa >= 1.0f) ssaa = 1.0f;
+        slope = (g6 - g4) / .2f;
+        asma = slope * (wavemid - .6f) + g6;
+        if (asma < 0.5f) asma = 0.5f;
+        if (asma >= 1.0f) asma = 1.0f;
+      }
+      AER(b, 0, l) = taua; AER(b, 1, l) = ssaa; AER(b, 2, l) = asma;
+      if (model) aersum[b] = aersum[b] + taua;
+    }
+    // ---- cloud physical properties and band optics (only where some sub-column is cloudy)
+    const bool anycld = (ws.anyc[(size_t)(l >> 5) * cap + c] >> (l & 31)) & 1u;
+    if (anycld) {
+      LayerCloud lc;
+      if (model) layer_cloud(a.cf, G, tb, i, j, k, tlay, tlay, pdel, inflg, iceflg, lc);
+      else { lc.clwp = 0.f; lc.ciwp = 0.f; lc.cswp = 0.f; lc.rel = 10.f; lc.rei = 10.f; lc.res = 10.f; }
+      const float cswp = iceflg == 5 ? lc.cswp : 0.f;        // inatm_sw copies cswp only for iceflag 5 (SW:9852)
+      const float resn = iceflg == 5 ? lc.res : 0.f;
+      const float cwp = lc.ciwp + lc.clwp + cswp;
+      for (int b = 0; b < NBSW; b++) {
+        float tc_ = 0.f, sc = 1.f, ac = 0.f, to = 0.f;
+        if (cwp >= 1.e-20f) {
+          int rc = sw_cloud_optics(tb, b, iceflg, liqflg, lc.ciwp, lc.clwp, cswp, lc.rei, lc.rel, resn, tc_, sc, ac, to);
+          if (rc && !err) err = rc;
+        }
+        CLD(b, 0, l) = tc_; CLD(b, 1, l) = sc; CLD(b, 2, l) = ac; CLD(b, 3, l) = to;
+      }
+    }
+  }
+  // aerosol column checks (SW:11031-11047)
+  if (a.aer_ra_feedback == 1) {
+    for (int b = 0; b < NBSW; b++) {
+      const float slope = aersum[b];
+      if (slope < 0.f) { if (!err) err = ARC_ERR_NEG_AOD; }
+      else if (slope > 6.f) {
+        for (int l = 0; l < nz; l++) AER(b, 0, l) = AER(b, 0, l) * 6.0f / slope;
+      }
+    }
+  }
+  ws.laytrop[c] = laytrop;
+  if (a.dbg.laytrop) a.dbg.laytrop[tc] = laytrop;
+  // layer where each band takes its solar source function (taumol16..29), emulating the reference loops literally
+  for (int b = 0; b < NBSW; b++) {
+    const int layreffr = c_sw[b].layreffr;
+    const int band = b + 16;
+    int last = -1;
+    const bool upper = (band == 16 || band == 17 || band == 27 || band == 28 || band == 29);
+    if (band == 26) {
+      last = laytrop >= 1 ? laytrop - 1 : -1;       // lay == laysolfr == laytrop inside "lay <= laytrop"
+    } else if (upper) {
+      int laysolfr = nlay;                           // 1-based
+      for (int lay = laytrop + 1; lay <= nlay; lay++) {
+        if (lay >= 2 && jps[lay - 2] < layreffr && jps[lay - 1] >= layreffr) laysolfr = lay;
+        if (lay == laysolfr) last = lay - 1;
+      }
+    } else {
+      int laysolfr = laytrop;
+      for (int lay = 1; lay <= laytrop; lay++) {
+        if (lay < nlay && jps[lay - 1] < layreffr && jps[lay] >= layreffr) laysolfr = min(lay + 1, laytrop);
+        if (lay == laysolfr) last = lay - 1;
+      }
+    }
+    ws.laysol[(size_t)b * cap + c] = last;
+  }
+  set_status(a.status, err);
+}
+void launch_sw_prep(const SwArgs &a, cudaStream_t s) {
+  k_sw_prep<<<(a.ncols + 127) / 128, 128, 0, s>>>(a);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// LW column preparation.  One thread per column (all columns; LW has no day/night gate).
+__global__ void __launch_bounds__(128) k_lw_prep(LwArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncols) return;
+  const Geo &G = a.geo;
+  const DevTables &tb = a.tb;
+  const LwWs &ws = a.ws;
+  const int tc = a.col0 + c;
+  int i, j; G.ij(tc, i, j);
+  const size_t ij = G.at2(i, j);
+  const int kts = G.kts, nz = G.kte - G.kts + 1, nlay = ws.nlay;
+  const size_t cap = ws.cap;
+  const float amdw = 1.607793f, amdo = 0.603461f, deltap = 4.f;
+  const float co2 = 379.e-6f, ch4 = 1774.e-9f, n2o = 319.e-9f, o2 = 0.209488f;
+  const float cfc11 = 0.251e-9f, cfc12 = 0.538e-9f, cfc22 = 0.169e-9f, ccl4 = 0.093e-9f;
+  (void)cfc11; (void)cfc12; (void)cfc22; (void)ccl4;
+  const float amd = 28.9660f, amw = 18.0160f;
+  const float thresh = 1.e-9f;
+  const float stpfac = 296.f / 1013.f;
+  int inflg, iceflg, liqflg;
+  cloud_flags(a.cf, inflg, iceflg, liqflg);
+
+  auto COEF = [&](int f, int l) -> float & { return ws.coef[((size_t)f * nlay + l) * cap + c]; };
+
+  // temperature profile interpolated to a pressure level (LW:12220-12243)
+  auto varint = [&](float p) {
+    const int nproflevs = 60;
+    int klev = nproflevs;
+    if (tb.pprof[nproflevs - 1] < p) {
+      for (int LL = 2; LL <= nproflevs; LL++) { if (tb.pprof[LL - 1] < p) { klev = LL - 1; break; } }
+    }
+    float vark, vark1, wght;
+    if (klev != nproflevs) {
+      vark = tb.tprof[klev - 1]; vark1 = tb.tprof[klev];
+      wght = (p - tb.pprof[klev - 1]) / (tb.pprof[klev] - tb.pprof[klev - 1]);
+    } else { vark = tb.tprof[klev - 1]; vark1 = tb.tprof[klev - 1]; wght = 0.0f; }
+    return wght * (vark1 - vark) + vark;
+  };
+
+  // interface pressures / temperatures.  plev(L), L = 1..nlay+1 ; tlev likewise (1-based as in the reference)
+  // model part: plev(k) = p8w/100, tlev(k) = t8w, k = 1..nz+1.  Buffer: plev(L+1) = plev(L) - 4, plev(nlay+1) = 0.
+  // tlev(L) = varint(L) + (tlev(nz) - varint(nz)) for L = nz+1..nlay+1 (note: overwrites tlev(nz+1));
+  // tlay(L-1) = 0.5*(tlev(L) + tlev(L-1))  for the same L (overwrites tlay(nz)).
+  const float tlev_nz = a.t8w[G.at3(i, kts + nz - 1, j)];
+  const float plev_nz = a.p8w[G.at3(i, kts + nz - 1, j)] / 100.f;
+  const float shift = tlev_nz - varint(plev_nz);
+
+  const float tsfc = a.tsk[ij];
+  ws.colf[(size_t)LWF_TBOUND * cap + c] = tsfc;
+  ws.colf[(size_t)LWF_EMISS * cap + c] = a.emiss[ij];
+  ws.colf[(size_t)LWF_TZ0 * cap + c] = a.t8w[G.at3(i, kts, j)];
+
+  float plev_b = a.p8w[G.at3(i, kts, j)] / 100.f;       // plev(1)
+  float tlev_b = a.t8w[G.at3(i, kts, j)];               // tlev(1)
+  const float pz0 = plev_b;
+  float h2o_top = 0.f, o3top_ref = 0.f, o31d_top = 0.f;
+  float amttl = 0.f, wvttl = 0.f;
+  int laytrop = 0;
+  int err = 0;
+  float aersum[NBLW];
+  for (int b = 0; b < NBLW; b++) aersum[b] = 0.f;
+
+  for (int l = 0; l < nlay; l++) {
+    const int L = l + 1;                 // 1-based layer
+    const bool model = L <= nz;
+    const int k = kts + l;
+    float plev_t, tlev_t, play, tlay;
+    if (model) {
+      plev_t = a.p8w[G.at3(i, k + 1, j)] / 100.f;
+      play = a.p3d[G.at3(i, k, j)] / 100.f;
+      tlay = a.cf.t3d[G.at3(i, k, j)];
+      tlev_t = a.t8w[G.at3(i, k + 1, j)];
+      if (L == nz) {                     // top model layer: interface nz+1 and the layer temperature are replaced
+        tlev_t = varint(plev_t) + shift;
+        tlay = 0.5f * (tlev_t + tlev_b);
+      }
+    } else {
+      plev_t = plev_b - deltap;
+      if (L == nlay) plev_t = 0.00f;
+      play = 0.5f * (plev_b + plev_t);
+      tlev_t = varint(plev_t) + shift;
+      tlay = 0.5f * (tlev_t + tlev_b);
+    }
+    const float pdel = plev_b - plev_t;
+    float h2ovmr;
+    if (model) { h2ovmr = layer_qv(a.cf, G.at3(i, k, j)) * amdw; h2o_top = h2ovmr; }
+    else h2ovmr = h2o_top;
+    const float o3mmr = o3_clim(tb, plev_b, plev_t);
+    float o3vmr = o3mmr * amdo;
+    if (a.o33d && a.o3input == 2) {
+      if (model) { o3vmr = a.o33d[G.at3(i, k, j)]; if (L == nz) { o31d_top = o3vmr; o3top_ref = o3mmr; } }
+      else {
+        o3vmr = o31d_top - o3top_ref * amdo + o3mmr * amdo;
+        if (o3vmr <= 0.f) o3vmr = o3mmr * amdo;
+      }
+    }
+    // ---- inatm
+    const float amm = (1.f - h2ovmr) * amd + h2ovmr * amw;
+    const float coldry = (plev_b - plev_t) * 1.e3f * 6.02214199e+23f / (1.e2f * 9.8066f * amm * (1.f + h2ovmr));
+    // summol over imol = 2..7 of the vmr's (co2, o3, n2o, co(=0), ch4, o2) in that order
+    float summol = 0.f;
+    summol = summol + co2; summol = summol + o3vmr; summol = summol + n2o; summol = summol + 0.f; summol = summol + ch4;
+    summol = summol + o2;
+    const float wbroad = coldry * (1.f - summol);
+    const float wk_h2o = coldry * h2ovmr, wk_co2 = coldry * co2, wk_o3 = coldry * o3vmr, wk_n2o = coldry * n2o,
+                wk_co = coldry * 0.f, wk_ch4 = coldry * ch4, wk_o2 = coldry * o2;
+    amttl = amttl + coldry + wk_h2o;
+    wvttl = wvttl + wk_h2o;
+    // ---- setcoef
+    PTCoef pc;
+    pt_coef(tb.lw_preflog, tb.lw_tref, play, tlay, pc);
+    const float water = wk_h2o / coldry;
+    const float scalefac = play * stpfac / tlay;
+    float forfac, forfrac, selffac, selffrac, scaleminor, scaleminorn2, minorfrac;
+    int indfor, indself, indminor;
+    if (!(pc.plog <= 4.56f)) {
+      laytrop = laytrop + 1;
+      forfac = scalefac / (1.f + water);
+      float factor = (332.0f - tlay) / 36.0f;
+      indfor = min(2, max(1, (int)factor));
+      forfrac = factor - (float)indfor;
+      selffac = water * forfac;
+      factor = (tlay - 188.0f) / 7.2f;
+      indself = min(9, max(1, (int)factor - 7));
+      selffrac = factor - (float)(indself + 7);
+    } else {
+      forfac = scalefac / (1.f + water);
+      float factor = (tlay - 188.0f) / 36.0f;
+      indfor = 3;
+      forfrac = factor - 1.0f;
+      selffac = water * forfac;
+      indself = 0; selffrac = 0.f;
+    }
+    scaleminor = play / tlay;
+    scaleminorn2 = (play / tlay) * (wbroad / (coldry + wk_h2o));
+    {
+      float factor = (tlay - 180.8f) / 7.2f;
+      indminor = min(18, max(1, (int)factor));
+      minorfrac = factor - (float)indminor;
+    }
+    float colh2o = 1.e-20f * wk_h2o, colco2 = 1.e-20f * wk_co2, colo3 = 1.e-20f * wk_o3, coln2o = 1.e-20f * wk_n2o,
+          colco = 1.e-20f * wk_co, colch4 = 1.e-20f * wk_ch4, colo2 = 1.e-20f * wk_o2;
+    if (colco2 == 0.f) colco2 = 1.e-32f * coldry;
+    if (colo3 == 0.f) colo3 = 1.e-32f * coldry;
+    if (coln2o == 0.f) coln2o = 1.e-32f * coldry;
+    if (colco == 0.f) colco = 1.e-32f * coldry;
+    if (colch4 == 0.f) colch4 = 1.e-32f * coldry;
+    const float colbrd = 1.e-20f * wbroad;
+    selffac = colh2o * selffac;
+    forfac = colh2o * forfac;
+    COEF(LWC_FAC00, l) = pc.fac00; COEF(LWC_FAC01, l) = pc.fac01; COEF(LWC_FAC10, l) = pc.fac10; COEF(LWC_FAC11, l) = pc.fac11;
+    COEF(LWC_H2O, l) = colh2o; COEF(LWC_CO2, l) = colco2; COEF(LWC_O3, l) = colo3; COEF(LWC_N2O, l) = coln2o;
+    COEF(LWC_CO, l) = colco; COEF(LWC_CH4, l) = colch4; COEF(LWC_O2, l) = colo2; COEF(LWC_BRD, l) = colbrd;
+    COEF(LWC_SELFFAC, l) = selffac; COEF(LWC_SELFFRAC, l) = selffrac; COEF(LWC_FORFAC, l) = forfac; COEF(LWC_FORFRAC, l) = forfrac;
+    COEF(LWC_MINORFRAC, l) = minorfrac; COEF(LWC_SCALEMINOR, l) = scaleminor; COEF(LWC_SCALEMINORN2, l) = scaleminorn2;
+    COEF(LWC_PAVEL, l) = play; COEF(LWC_COLDRY, l) = coldry; COEF(LWC_TAVEL, l) = tlay; COEF(LWC_TZ, l) = tlev_t;
+    COEF(LWC_IDX, l) = __int_as_float(pack_idx(pc.jp, pc.jt, pc.jt1, indself, indfor, indminor));
+    if (a.dbg.jp) {
+      const size_t q = (size_t)tc * nlay + l;
+      a.dbg.jp[q] = pc.jp; a.dbg.jt[q] = pc.jt; a.dbg.jt1[q] = pc.jt1; a.dbg.indfor[q] = indfor; a.dbg.indself[q] = indself;
+      a.dbg.indminor[q] = indminor;
+      a.dbg.fac00[q] = pc.fac00; a.dbg.fac01[q] = pc.fac01; a.dbg.fac10[q] = pc.fac10; a.dbg.fac11[q] = pc.fac11;
+    }
+    // ---- aerosol (LW:12576-12615)
+    bool chem = false;
+    if (model && a.aer_ra_feedback == 1) {
+      const size_t q = G.at3(i, k, j);
+      chem = a.tauaerlw[0][q] > thresh && a.tauaerlw[15][q] > thresh;
+    }
+    for (int b = 0; b < NBLW; b++) {
+      float taua = 0.f;
+      if (chem) taua = a.tauaerlw[b][G.at3(i, k, j)];
+      ws.aer[((size_t)b * nlay + l) * cap + c] = taua;
+      if (model) aersum[b] = aersum[b] + taua;
+    }
+    // ---- clouds
+    const bool anycld = (ws.anyc[(size_t)(l >> 5) * cap + c] >> (l & 31)) & 1u;
+    if (anycld) {
+      LayerCloud lc;
+      if (model) layer_cloud(a.cf, G, tb, i, j, k, a.cf.t3d[G.at3(i, k, j)], tlay, pdel, inflg, iceflg, lc);
+      else { lc.clwp = 0.f; lc.ciwp = 0.f; lc.cswp = 0.f; lc.rel = 10.f; lc.rei = 10.f; lc.res = 10.f; }
+      const float cwp = lc.ciwp + lc.clwp + lc.cswp;
+      for (int b = 0; b < NBLW; b++) {
+        float tcm = 0.f;
+        if (cwp >= 1.e-20f) {
+          int rc = lw_cloud_optics(tb, b, iceflg, liqflg, lc.ciwp, lc.clwp, lc.cswp, lc.rei, lc.rel, lc.res, tcm);
+          if (rc && !err) err = rc;
+        }
+        ws.cld[((size_t)b * nlay + l) * cap + c] = tcm;
+      }
+    }
+    plev_b = plev_t; tlev_b = tlev_t;
+  }
+  if (a.aer_ra_feedback == 1)
+    for (int b = 0; b < NBLW; b++) if (aersum[b] < 0.f && !err) err = ARC_ERR_NEG_AOD;
+  ws.laytrop[c] = laytrop;
+  if (a.dbg.laytrop) a.dbg.laytrop[tc] = laytrop;
+  // precipitable water and the diffusivity angle per band (inatm LW:11397-11399, rtrnmc LW:3170-3183)
+  const float wvsh = (amw * wvttl) / (amd * amttl);
+  const float pwvcm = wvsh * (1.e3f * pz0) / (1.e2f * 9.8066f);
+  for (int b = 0; b < NBLW; b++) {
+    float sd;
+    const int ibnd = b + 1;
+    if (ibnd == 1 || ibnd == 4 || ibnd >= 10) sd = 1.66f;
+    else {
+      sd = tb.a0[b] + tb.a1[b] * expf(tb.a2[b] * pwvcm);
+      if (sd > 1.80f) sd = 1.80f;
+      if (sd < 1.50f) sd = 1.50f;
+    }
+    ws.secdiff[(size_t)b * cap + c] = sd;
+  }
+  set_status(a.status, err);
+}
+void launch_lw_prep(const LwArgs &a, cudaStream_t s) {
+  k_lw_prep<<<(a.ncols + 127) / 128, 128, 0, s>>>(a);
+  count_launch();
+}
+
+}  // namespace arc

@@ -24,7 +24,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libarcrad.so")
+LIB_PATH = os.environ.get("ARC_RAD_LIB") or os.path.join(_HERE, "csrc", "libarcrad.so")
 INLINE_TABLES = os.path.join(_HERE, "data", "rrtmg_inline_tables.bin")
 
 
