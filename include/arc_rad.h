@@ -187,6 +187,14 @@ int  arc_rad_driver_post(const ArcDims *d, int memspace,
                          const float *rthratenlw, const float *rthratensw, float *rthraten,
                          const float *gsw, const float *albedo, float *swdown);
 
+/* Domain statistics of `nfields` 2-D (i,j) fields over the tile: out[f][5] = {sum, sum of squares, count, min, max}
+ * in double precision; `fields` is a host array of pointers in `memspace`, `out` lives in `memspace` too.
+ * Replaces calc_standard_stats' mean/SD/SE inputs (analysis_scripts/NCL_extraction_package/misc_stats_library.ncl:396-461);
+ * partial results of several GPUs combine with one sum- and one max-all-reduce. */
+int  arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const float *const *fields, double *out);
+/* FP32 FMA throughput of the device in TFLOP/s (microbenchmark; roofline denominator of the solver kernels) */
+float arc_rad_measure_fp32_tflops(void);
+
 /* Kernel launch counter (number of this library's CUDA kernels launched since init) */
 long long arc_rad_launch_count(void);
 /* CUDA stream used for all work (cudaStream_t as void*), for event timing by the caller */

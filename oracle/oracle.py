@@ -39,3 +39,22 @@ def oracle() -> RadLib:
         L.arc_oracle_table.restype = C.c_int
         L.arc_oracle_table.argtypes = [C.c_int, C.c_int, C.c_char_p, abi.c_fp, C.c_int]
     return _ORC
+
+
+class _OracleMT(RadLib):
+    """Same interface, but every call is spread over `nthreads` host threads by j-rows (static schedule),
+    like radiation_driver's OpenMP loop over tiles (module_radiation_driver.F:975-978)."""
+
+    def __init__(self, base: RadLib, nthreads: int):
+        self.__dict__.update(base.__dict__)
+        L = base.lib
+        self.nthreads = int(nthreads)
+        self._sw = lambda d, si, so, dbg: L.arc_oracle_sw_omp(d, si, so, self.nthreads)
+        self._lw = lambda d, li, lo, dbg: L.arc_oracle_lw_omp(d, li, lo, self.nthreads)
+
+
+def oracle_mt(nthreads=0) -> RadLib:
+    """Oracle bound to the multi-threaded entry points (nthreads <= 0: all hardware threads)."""
+    base = oracle()
+    n = nthreads if nthreads > 0 else int(base.lib.arc_oracle_max_threads())
+    return _OracleMT(base, n)

@@ -315,7 +315,10 @@ void fill_cloud(CloudFields &cf, int memspace, int &rc, int icloud, int warm_rai
   cf.g = gacc;
   const float **dst3[18] = {&cf.t3d, &cf.cldfra3d, &cf.lradius, &cf.iradius, &cf.qv3d, &cf.qc3d, &cf.qr3d, &cf.qi3d, &cf.qs3d,
                             &cf.qg3d, &cf.qndrop3d, &cf.re_cloud, &cf.re_ice, &cf.re_snow, &cf.f_ice_phy, nullptr, nullptr, nullptr};
-  for (int q = 0; q < 15 && !rc; q++) rc = in_arr(memspace, p3[q], n3, dst3[q]);
+  for (int q = 0; q < 15 && !rc; q++) {
+    if (q == 9) { cf.qg3d = nullptr; continue; }   // graupel is gathered by the reference but never used (SW:10449)
+    rc = in_arr(memspace, p3[q], n3, dst3[q]);
+  }
   const float **dst2[3] = {&cf.xland, &cf.xice, &cf.snow};
   for (int q = 0; q < 3 && !rc; q++) rc = in_arr(memspace, p2[q], n2, dst2[q]);
 }
@@ -476,7 +479,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
     g.err = "arc_rad_sw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG;
   }
   CK(cudaSetDevice(g.device));
-  g.last_ms.clear();
+  for (auto it = g.last_ms.begin(); it != g.last_ms.end();) { if (it->first.compare(0, 3, "sw_") == 0) it = g.last_ms.erase(it); else ++it; }
   g.pool_next = 0; g.backs.clear();
   const int ms = in->memspace;
   SwArgs a{};
@@ -608,7 +611,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
     g.err = "arc_rad_lw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG;
   }
   CK(cudaSetDevice(g.device));
-  g.last_ms.clear();
+  for (auto it = g.last_ms.begin(); it != g.last_ms.end();) { if (it->first.compare(0, 3, "lw_") == 0) it = g.last_ms.erase(it); else ++it; }
   g.pool_next = 0; g.backs.clear();
   const int ms = in->memspace;
   LwArgs a{};
@@ -720,6 +723,100 @@ int arc_rad_driver_post(const ArcDims *d, int memspace, const float *rthratenlw,
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Domain statistics of 2-D diagnostic fields over the tile: [sum, sum of squares, count, min, max] per field, the
+// quantities the offline decomposition needs for means / SD / SE (analysis_scripts/NCL_extraction_package/
+// misc_stats_library.ncl:396-461, RadDecomp_functions.py:119-129).  One block per field, fixed-order tree: reproducible.
+__global__ void __launch_bounds__(1024) k_domain_stats(Geo G, int nfields, const float *const *__restrict__ fields, double *__restrict__ out) {
+  const int f = blockIdx.x;
+  const float *x = fields[f];
+  double s = 0.0, s2 = 0.0; float mn = INFINITY, mx = -INFINITY;
+  for (int tc = threadIdx.x; tc < G.ncol_tile; tc += blockDim.x) {
+    int i, j; G.ij(tc, i, j);
+    const float v = x[G.at2(i, j)];
+    s += (double)v; s2 += (double)v * (double)v; mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+  __shared__ double sh[3][1024];
+  __shared__ float shm[2][1024];
+  sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = s2; shm[0][threadIdx.x] = mn; shm[1][threadIdx.x] = mx;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + off]; sh[1][threadIdx.x] += sh[1][threadIdx.x + off];
+      shm[0][threadIdx.x] = fminf(shm[0][threadIdx.x], shm[0][threadIdx.x + off]);
+      shm[1][threadIdx.x] = fmaxf(shm[1][threadIdx.x], shm[1][threadIdx.x + off]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[5 * f + 0] = sh[0][0]; out[5 * f + 1] = sh[1][0]; out[5 * f + 2] = (double)G.ncol_tile;
+    out[5 * f + 3] = (double)shm[0][0]; out[5 * f + 4] = (double)shm[1][0];
+  }
+}
+
+int arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const float *const *fields, double *out) {
+  if (!g.ready) { g.err = "arc_rad_domain_stats: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !fields || !out || nfields < 1 || nfields > 64) { g.err = "arc_rad_domain_stats: bad argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const float *dev[64];
+  for (int f = 0; f < nfields; f++) {
+    if (!fields[f]) { g.err = "arc_rad_domain_stats: null field"; return ARC_ERR_BAD_ARG; }
+    if ((rc = in_arr(memspace, fields[f], G.n2(), &dev[f]))) return rc;
+  }
+  void *dptrs; if ((rc = stage_slot(sizeof(float *) * 64, &dptrs))) return rc;
+  CK(cudaMemcpyAsync(dptrs, dev, sizeof(float *) * nfields, cudaMemcpyHostToDevice, g.stream));
+  double *dout = out;
+  if (memspace != ARC_MEM_DEVICE) { void *p; if ((rc = stage_slot(sizeof(double) * 5 * 64, &p))) return rc; dout = (double *)p; }
+  k_domain_stats<<<nfields, 1024, 0, g.stream>>>(G, nfields, (const float *const *)dptrs, dout);
+  count_launch();
+  if (memspace != ARC_MEM_DEVICE) CK(cudaMemcpyAsync(out, dout, sizeof(double) * 5 * nfields, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// FP32 FMA throughput of this GPU (TFLOP/s), measured with a dependent-chain-free FMA kernel: the roofline
+// denominator for the FP32-pipe-bound solver kernels (MEASURED_PEAKS.json holds no FP32 figure).
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) a[q] = 1.0f + 1e-3f * (threadIdx.x + q);
+  const float m = 0.999999f, c = 1e-7f;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) a[q] = fmaf(a[q], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; q++) s += a[q];
+  if (s == 12345.678f) out[0] = s;
+}
+float arc_rad_measure_fp32_tflops(void) {
+  if (!g.ready) return -1.f;
+  cudaSetDevice(g.device);
+  float *dout; if (cudaMalloc(&dout, 4) != cudaSuccess) return -1.f;
+  cudaDeviceProp pr; cudaGetDeviceProperties(&pr, g.device);
+  const int blocks = pr.multiProcessorCount * 8, iters = 8192;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 0.f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, g.stream);
+    k_fma_peak<<<blocks, 256, 0, g.stream>>>(dout, iters);
+    cudaEventRecord(e1, g.stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 16.0 * iters * 256.0 * blocks;
+    if (ms > 0.f) best = fmaxf(best, (float)(fl / (ms * 1e-3) / 1e12));
+  }
+  count_launch(5);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dout);
+  return best;
 }
 
 }  // extern "C"
