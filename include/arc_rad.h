@@ -192,6 +192,11 @@ int  arc_rad_driver_post(const ArcDims *d, int memspace,
  * Replaces calc_standard_stats' mean/SD/SE inputs (analysis_scripts/NCL_extraction_package/misc_stats_library.ncl:396-461);
  * partial results of several GPUs combine with one sum- and one max-all-reduce. */
 int  arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const float *const *fields, double *out);
+/* Host-only probe (no GPU needed): parse and g-point-reduce the table files as arc_rad_init does; returns the element count
+ * of the reduced table `name` ("sw16.absa", "lw3.ka_mn2o", "lw_nlayers" ...) and copies it to buf when cap suffices;
+ * name == NULL only validates the files.  Negative return = -ARC_ERR_*.  (sw_kgbNN / cmbgbNN, SW:5022-6065, 11315-12384) */
+int  arc_rad_host_table(const char *inline_tables, const char *sw_data_path, const char *lw_data_path, float cp, float p_top,
+                        int kme, const char *name, float *buf, int cap);
 /* FP32 FMA throughput of the device in TFLOP/s (microbenchmark; roofline denominator of the solver kernels) */
 float arc_rad_measure_fp32_tflops(void);
 

@@ -1,0 +1,309 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on identical synthetic columns and identical synthetic
+k-tables.  Bars (BASELINE.json north_star): jp / jt / jt1 / indfor / indself (+ laytrop, indminor) and the McICA masks
+bit-exact; fluxes within 1e-4 relative or 0.01 W/m2 absolute; heating rates within 1e-4 relative or 0.01 K/day.
+
+One documented exception (DESIGN.md "Parity"): reftra_sw evaluates a removable 0/0 at k*mu0 = 1 through a 10,001-entry
+exp table (SW:2629-2660); within |1-(k*mu0)^2| < 1e-3 the reference's own result is rounding noise (a 1-ulp change of an
+input moves it by O(1)).  The oracle reports that conditioning per column (ArcDebug.sw_cond); columns below the threshold
+are held to a looser bar and counted."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import init, interior, run_pair
+from wrfchem_arc_interactions_b200 import abi, radiation as R, synth
+
+pytestmark = pytest.mark.gpu
+COND_THR = 1.0e-3
+SW2D = ("gsw", "swcf", "swupt", "swuptc", "swuptcln", "swdnt", "swdntc", "swdntcln", "swupb", "swupbc", "swupbcln", "swdnb", "swdnbc",
+        "swdnbcln", "swvisdir", "swvisdif", "swnirdir", "swnirdif", "swddir", "swddni", "swddif", "swuptclnc", "swdntclnc", "swupbclnc", "swdnbclnc")
+SWPROF = ("swupflx", "swupflxc", "swupflxcln", "swdnflx", "swdnflxc", "swdnflxcln")
+
+
+def within(a, b, rel=1e-4, ab=0.01):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    err = np.abs(a - b)
+    return (err <= rel * np.abs(b)) | (err <= ab)
+
+
+def per_column(dom, a):
+    """(nj, [nk,] ni) -> (ncol, [nk])"""
+    a = interior(dom, a)
+    return a.transpose(0, 2, 1).reshape(-1, a.shape[1]) if a.ndim == 3 else a.reshape(-1)
+
+
+def both(which, lib, orc, dom, ktab, **over):
+    init(lib, dom, ktab); init(orc, dom, ktab)
+    ncol = dom["ni"] * dom["nj"]
+    nlay = dom["nk"] + 1 if which == "sw" else lib.lw_nlayers()
+    ng = 112 if which == "sw" else 140
+    dg, tg = abi.alloc_debug(ncol, nlay, ng); do, to = abi.alloc_debug(ncol, nlay, ng)
+    og = run_pair(which, lib, dom, debug=dg, **over)
+    oo = run_pair(which, orc, dom, debug=do, **over)
+    return og, oo, tg, to
+
+
+def check_sw(dom, og, oo, tg, to):
+    sun = to["laytrop"] >= 0
+    assert np.array_equal(tg["laytrop"], to["laytrop"])
+    for k in ("jp", "jt", "jt1", "indfor", "indself", "cldmask"):
+        assert np.array_equal(tg[k][sun], to[k][sun]), "%s not bit-exact" % k
+    for k, tol in (("taug", 2e-5), ("taur", 1e-6), ("sfluxzen", 1e-6), ("taucmc", 1e-6), ("fac00", 2e-3)):
+        a, b = tg[k][sun].astype(np.float64), to[k][sun].astype(np.float64)
+        assert np.all(np.abs(a - b) <= tol * np.abs(b) + 1e-6 * np.abs(b).max()), k
+    good = sun & (to["sw_cond"] >= COND_THR)
+    illc = sun & ~good
+    nbad_ill = np.zeros(sun.size, bool)
+    for k in SW2D + SWPROF:
+        a, b = per_column(dom, og[k]), per_column(dom, oo[k])
+        ok = within(a, b)
+        okc = ok if ok.ndim == 1 else ok.all(axis=1)
+        assert okc[good].all(), "%s: %d well-conditioned columns out of tolerance" % (k, (~okc[good]).sum())
+        assert okc[~sun].all(), k
+        nbad_ill |= ~okc & illc
+        dev = np.abs(a.astype(np.float64) - b) / np.maximum(np.abs(b), 10.0)
+        assert dev.max() < 0.05, "%s: gross deviation %.3g" % (k, dev.max())
+    if illc.sum() >= 50:
+        assert nbad_ill.sum() <= 0.05 * illc.sum(), "ill-conditioned columns out of tolerance: %d of %d" % (nbad_ill.sum(), illc.sum())
+    ok = within(tg["hr"], to["hr"])          # K/day
+    assert ok[good].all(), "heating rate"
+    a, b = per_column(dom, og["rthratensw"]), per_column(dom, oo["rthratensw"])
+    assert within(a * 86400.0, b * 86400.0)[good].all()
+    return dict(sunlit=int(sun.sum()), well_conditioned=int(good.sum()), ill_out_of_tol=int(nbad_ill.sum()))
+
+
+def check_lw(dom, lib, og, oo, tg, to):
+    nz = dom["nk"]
+    assert np.array_equal(tg["laytrop"], to["laytrop"])
+    for k in ("jp", "jt", "jt1", "indfor", "indself", "indminor", "cldmask"):
+        assert np.array_equal(tg[k], to[k]), "%s not bit-exact" % k
+    for k, tol in (("taug", 2e-5), ("taur", 2e-6), ("taucmc", 1e-6)):
+        a, b = tg[k].astype(np.float64), to[k].astype(np.float64)
+        assert np.all(np.abs(a - b) <= tol * np.abs(b) + 1e-6 * np.abs(b).max()), k
+    for k in og:
+        if k == "rthratenlw":
+            continue
+        assert within(og[k], oo[k]).all(), k
+    assert within(tg["hr"][:, :nz], to["hr"][:, :nz]).all()
+    assert within(og["rthratenlw"] * 86400.0, oo["rthratenlw"] * 86400.0).all()
+
+
+def test_sw_c1(lib, orc, ktab):
+    """BASELINE config C1: 1024 columns x 40 levels, 40 % cloudy, 25 % night."""
+    dom = synth.make_domain(32, 32, 40)
+    info = check_sw(dom, *both("sw", lib, orc, dom, ktab))
+    print("SW C1:", info)
+    assert info["well_conditioned"] > 100
+
+
+def test_lw_c1(lib, orc, ktab):
+    dom = synth.make_domain(32, 32, 40)
+    og, oo, tg, to = both("lw", lib, orc, dom, ktab)
+    check_lw(dom, lib, og, oo, tg, to)
+
+
+def test_c4_all_cloudy_with_effective_radii(lib, orc, ktab):
+    """C4-like: every column cloudy, re_cloud / re_ice / re_snow supplied (inflg 5, iceflg 5)."""
+    dom = synth.make_domain(24, 8, 50, seed=5, cloudy_frac=1.0, with_re=True)
+    check_sw(dom, *both("sw", lib, orc, dom, ktab))
+    og, oo, tg, to = both("lw", lib, orc, dom, ktab)
+    check_lw(dom, lib, og, oo, tg, to)
+
+
+def test_c5_hundred_levels(lib, orc, ktab):
+    """High vertical resolution (C5): 100 levels -> SW 101 / LW 113 layers (masks span 4 words)."""
+    dom = synth.make_domain(16, 4, 100, seed=6)
+    check_sw(dom, *both("sw", lib, orc, dom, ktab))
+    og, oo, tg, to = both("lw", lib, orc, dom, ktab)
+    check_lw(dom, lib, og, oo, tg, to)
+
+
+def test_clean_off(lib, orc, ktab):
+    dom = synth.make_domain(16, 4, 40, seed=8)
+    og, oo, tg, to = both("sw", lib, orc, dom, ktab, clean_atm_diag=0)
+    for k in ("swuptcln", "swdntcln", "swupbcln", "swdnbcln", "swupflxcln", "swdnflxcln"):
+        assert not og[k].any()
+    check_sw(dom, og, oo, tg, to)
+    og, oo, tg, to = both("lw", lib, orc, dom, ktab, clean_atm_diag=0)
+    for k in ("lwuptcln", "lwdntcln", "lwupbcln", "lwdnbcln", "lwupflxcln", "lwdnflxcln"):
+        assert not og[k].any()
+    check_lw(dom, lib, og, oo, tg, to)
+
+
+def test_zero_aerosol_clean_equals_full_bitwise(lib, ktab):
+    dom = synth.make_domain(16, 8, 40, seed=9, aerosol=False)
+    init(lib, dom, ktab)
+    sw, lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    for a, b in (("swupt", "swuptcln"), ("swdnb", "swdnbcln"), ("swupflx", "swupflxcln"), ("swdnflx", "swdnflxcln"), ("swuptc", "swuptclnc")):
+        assert np.array_equal(sw[a], sw[b]), (a, b)
+    for a, b in (("lwupt", "lwuptcln"), ("lwdnb", "lwdnbcln"), ("lwupflx", "lwupflxcln"), ("lwdnflx", "lwdnflxcln")):
+        assert np.array_equal(lw[a], lw[b]), (a, b)
+
+
+def test_no_cloud_clear_equals_full_bitwise(lib, ktab):
+    dom = synth.make_domain(16, 8, 40, seed=10, cloudy_frac=0.0)
+    init(lib, dom, ktab)
+    sw, lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    assert np.array_equal(sw["swupt"], sw["swuptc"]) and np.array_equal(sw["swdnflx"], sw["swdnflxc"]) and not sw["swcf"].any()
+    assert np.array_equal(lw["lwupt"], lw["lwuptc"]) and np.array_equal(lw["lwdnflx"], lw["lwdnflxc"]) and not lw["lwcf"].any()
+
+
+def test_night_and_inout_semantics(lib, ktab):
+    dom = synth.make_domain(16, 8, 40, seed=11)
+    init(lib, dom, ktab)
+    outs = R.alloc_outputs(dom, "sw")
+    outs["rthratensw"][:] = 7.0; outs["gsw"][:] = -3.0; outs["swupt"][:] = 9.0; outs["swupflx"][:] = 5.0
+    sw = run_pair("sw", lib, dom, outs=outs)
+    night = dom["xcoszen"] <= 0
+    assert np.all(sw["swupt"][night] == 0) and np.all(sw["swddni"][night] == 0) and np.all(sw["swcf"][night] == 0)
+    assert np.all(sw["gsw"][night] == -3.0) and np.all(sw["rthratensw"].transpose(0, 2, 1)[night] == 7.0)
+    assert np.all(sw["swupflx"].transpose(0, 2, 1)[night] == 5.0)
+    assert np.array_equal(sw["coszr"], dom["xcoszen"])
+    assert np.all(sw["rthratensw"].transpose(0, 2, 1)[~night][:, :40] != 7.0)
+    assert np.all(sw["rthratensw"][:, 40, :] == 7.0)          # kme level is never written
+
+
+def test_halo_and_subtile_untouched(lib, orc, ktab):
+    """Memory bounds != tile bounds: NaN halo cells are never read (results equal the halo-free run bit for bit) nor written."""
+    d0 = synth.make_domain(12, 6, 40, seed=12)
+    dh = synth.make_domain(12, 6, 40, seed=12, halo=2)
+    init(lib, d0, ktab)
+    for which in ("sw", "lw"):
+        o0 = run_pair(which, lib, d0)
+        oh = R.alloc_outputs(dh, which)
+        for k in oh:
+            oh[k][:] = -777.0
+        run_pair(which, lib, dh, outs=oh)
+        night = (dh["xcoszen"] <= 0) if which == "sw" else np.zeros_like(dh["xcoszen"], bool)
+        for k in o0:
+            a = interior(dh, oh[k])
+            assert not np.isnan(a).any(), k
+            m = np.ones(oh[k].shape, bool)
+            h = 2
+            m[h:-h, ..., h:-h] = False
+            assert np.all(oh[k][m] == -777.0), "%s: halo written" % k
+            if k in ("gsw", "rthratensw") or k in SWPROF:
+                continue                               # partially written outputs are covered by the night test
+            assert np.array_equal(a, o0[k]), k
+        # sub-tile: only columns its..ite / jts..jte of a larger memory block
+        dims = dict(d0["dims"]); dims.update(its=3, ite=9, jts=2, jte=5)
+        os_ = R.alloc_outputs(d0, which)
+        for k in os_:
+            os_[k][:] = -777.0
+        flags = R.common_flags(d0)
+        (lib.RRTMG_SWRAD if which == "sw" else lib.RRTMG_LWRAD)(dims, **(R.sw_kwargs if which == "sw" else R.lw_kwargs)(d0, os_, **flags))
+        key = "swdnt" if which == "sw" else "olr"
+        inside = np.zeros(os_[key].shape, bool); inside[1:5, 2:9] = True
+        assert np.all(os_[key][~inside] == -777.0)
+        day = (d0["xcoszen"] > 0) if which == "sw" else np.ones_like(inside)
+        assert np.array_equal(os_[key][inside & day], o0[key][inside & day])
+
+
+def test_chunking_and_determinism(lib, ktab):
+    """Results do not depend on the chunk size of the workspace and are bit-reproducible run to run."""
+    dom = synth.make_domain(40, 20, 40, seed=13)
+    init(lib, dom, ktab)
+    a_sw, a_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    b_sw, b_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    os.environ["ARC_RAD_CHUNK"] = "256"
+    try:
+        c_sw, c_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    finally:
+        del os.environ["ARC_RAD_CHUNK"]
+    for k in a_sw:
+        assert np.array_equal(a_sw[k], b_sw[k]) and np.array_equal(a_sw[k], c_sw[k]), k
+    for k in a_lw:
+        assert np.array_equal(a_lw[k], b_lw[k]) and np.array_equal(a_lw[k], c_lw[k]), k
+
+
+def test_device_memspace_equals_host_memspace(lib, ktab):
+    import torch
+    dom = synth.make_domain(16, 8, 40, seed=14)
+    init(lib, dom, ktab)
+    flags = R.common_flags(dom)
+    dev = torch.device("cuda", 0)
+    ddom = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in dom.items()}
+    for which in ("sw", "lw"):
+        h = run_pair(which, lib, dom)
+        o = R.alloc_outputs(dom, which, like=ddom["xcoszen"])
+        kw = (R.sw_kwargs if which == "sw" else R.lw_kwargs)(ddom, o, **flags)
+        (lib.RRTMG_SWRAD if which == "sw" else lib.RRTMG_LWRAD)(dom["dims"], **kw)
+        for k in h:
+            assert np.array_equal(h[k], o[k].cpu().numpy()), k
+
+
+def test_errors(lib, ktab):
+    dom = synth.make_domain(8, 4, 40, seed=15, all_day=True)
+    init(lib, dom, ktab)
+    bad = dict(dom); bad["tauaer400"] = dom["tauaer400"].copy(); bad["tauaer400"][0, :, 0] = -1.0
+    with pytest.raises(R.RadiationError) as e:
+        run_pair("sw", lib, bad)
+    assert e.value.code == 5 and "Negative total optical depth" in str(e.value)
+    miss = dict(dom); del miss["waer400"]
+    with pytest.raises(R.RadiationError) as e:
+        run_pair("sw", lib, miss)
+    assert e.value.code == 4
+    with pytest.raises(R.RadiationError) as e:
+        run_pair("lw", lib, dom, aer_ra_feedback=0, clean_atm_diag=1)
+    assert e.value.code == 8
+    rbad = synth.make_domain(8, 4, 40, seed=16, cloudy_frac=1.0, with_re=True, all_day=True)
+    rbad["re_ice"] = (rbad["re_ice"] * 100.0).astype(np.float32)         # dge > 140 um -> table bounds (SW:2164)
+    with pytest.raises(R.RadiationError) as e:
+        run_pair("sw", lib, rbad)
+    assert e.value.code == 6
+    # the library recovers after an error
+    run_pair("sw", lib, dom)
+
+
+def test_driver_post_and_domain_stats(lib, ktab):
+    dom = synth.make_domain(20, 10, 40, seed=17)
+    init(lib, dom, ktab)
+    sw, lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    L = lib.lib
+    L.arc_rad_driver_post.restype = C.c_int
+    L.arc_rad_driver_post.argtypes = [C.POINTER(abi.ArcDims), C.c_int] + [abi.c_fp] * 6
+    L.arc_rad_domain_stats.restype = C.c_int
+    L.arc_rad_domain_stats.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_void_p]
+    dims = abi.make_dims(dom["dims"])
+    rth = np.zeros_like(dom["t3d"]); swdown = np.zeros_like(dom["albedo"])
+    lib.check(L.arc_rad_driver_post(C.byref(dims), 0, abi.fptr(lw["rthratenlw"]), abi.fptr(sw["rthratensw"]), abi.fptr(rth),
+                                    abi.fptr(sw["gsw"]), abi.fptr(dom["albedo"]), abi.fptr(swdown)))
+    assert np.array_equal(rth[:, :40], (lw["rthratenlw"] + sw["rthratensw"])[:, :40])     # DRV:1692-1702, 2180-2184
+    assert np.array_equal(swdown, sw["gsw"] / (np.float32(1.0) - dom["albedo"]))          # DRV:2186-2194
+    names = ("swupt", "swuptcln", "swdnb")
+    ptrs = (abi.c_fp * 4)(*[abi.fptr(sw[n]) for n in names], abi.fptr(lw["olr"]))
+    st = np.zeros((4, 5))
+    lib.check(L.arc_rad_domain_stats(C.byref(dims), 0, 4, ptrs, C.c_void_p(st.ctypes.data)))
+    for f, x in enumerate([sw[n] for n in names] + [lw["olr"]]):
+        x = x.astype(np.float64)
+        assert np.isclose(st[f, 0], x.sum(), rtol=1e-12) and np.isclose(st[f, 1], (x * x).sum(), rtol=1e-12)
+        assert st[f, 2] == x.size and st[f, 3] == x.min() and st[f, 4] == x.max()
+
+
+def test_full_size_properties(lib, ktab):
+    """BASELINE config C2 at full size (127,500 columns x 50 levels), checked through size-independent properties:
+    energy bounds, clean == full where the aerosol is zero, clear == full in cloud-free columns, night gate."""
+    dom = synth.make_domain(425, 300, 50)
+    half = dom["tauaer400"].shape[-1] // 2
+    for k in list(dom):
+        if k.startswith("tauaer"):
+            dom[k] = dom[k].copy(); dom[k][:, :, :half] = 0.0            # western half of the domain is aerosol-free
+    init(lib, dom, ktab)
+    sw, lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    day = dom["xcoszen"] > 0
+    assert np.array_equal(sw["swupt"][:, :half], sw["swuptcln"][:, :half]) and np.array_equal(lw["lwdnb"][:, :half], lw["lwdnbcln"][:, :half])
+    assert np.array_equal(sw["swdnflx"][:, :, :half], sw["swdnflxcln"][:, :, :half])
+    assert (sw["swupt"][:, half:] != sw["swuptcln"][:, half:])[day[:, half:]].mean() > 0.99
+    clear = (dom["cldfra3d"] > 0).sum(axis=1) == 0
+    assert np.array_equal(sw["swupt"][clear], sw["swuptc"][clear]) and np.array_equal(lw["lwupt"][clear], lw["lwuptc"][clear])
+    assert np.all(sw["swupt"][~day] == 0)
+    toa = sw["swdnt"][day]
+    assert np.all(toa > 0) and np.all(sw["swupt"][day] < toa) and np.all(sw["swdnb"][day] <= toa * (1 + 1e-6))
+    assert np.all(sw["gsw"][day] > 0) and np.all(np.isfinite(sw["rthratensw"])) and np.all(np.isfinite(lw["rthratenlw"]))
+    # aerosol dims the surface in the clear-sky stream: swdnbc <= clean-clear
+    e = dom["tauaer400"].sum(axis=1) > 0.05
+    assert (sw["swdnbc"][day & e] < sw["swdnbclnc"][day & e]).mean() > 0.999
+    assert np.all(lw["olr"] > 50) and np.all(lw["olr"] < 500) and np.all(lw["glw"] > 20)
+    assert np.all(lw["lwdnt"] == 0)

@@ -2,12 +2,12 @@
 
 Sub-modules:
   radiation  host-side mirror of RRTMG_SWRAD / RRTMG_LWRAD / rrtmg_*init (binds csrc/libarcrad.so)
-  driver     radiation_driver bookkeeping + column sharding over GPUs (torch.distributed)
+  partition  j-slab column partition over GPUs + combination of per-rank domain statistics
   abi        ctypes mirror of include/arc_rad.h
   ktables    synthetic RRTMG_SW_DATA / RRTMG_LW_DATA writer (real record layout)
   synth      seeded synthetic WRF-layout columns
 """
-from . import abi, ktables, synth  # noqa: F401
+from . import abi, ktables, partition, synth  # noqa: F401
 from . import radiation  # noqa: F401
 
-__all__ = ["abi", "ktables", "synth", "radiation"]
+__all__ = ["abi", "ktables", "partition", "synth", "radiation"]

@@ -781,6 +781,27 @@ int arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const floa
   return 0;
 }
 
+// Host-only probe used by the CPU test-suite: parse + reduce the k-distribution files exactly as arc_rad_init does
+// (no GPU needed) and return one reduced table ("sw16.absa", "lw3.ka_mn2o", ...) or, with name == NULL, only validate.
+int arc_rad_host_table(const char *inline_tables, const char *sw_data_path, const char *lw_data_path, float cp, float p_top,
+                       int kme, const char *name, float *buf, int cap) {
+  static HostTables T; static std::string key;
+  if (!inline_tables || !sw_data_path || !lw_data_path) { g.err = "arc_rad_host_table: null argument"; return -ARC_ERR_BAD_ARG; }
+  std::string k = std::string(inline_tables) + "|" + sw_data_path + "|" + lw_data_path;
+  if (k != key) {
+    int rc = build_host_tables(inline_tables, sw_data_path, lw_data_path, cp, p_top, kme, T, g.err);
+    if (rc) { key.clear(); return -rc; }
+    key = k;
+  }
+  if (!name) return 0;
+  if (std::string(name) == "lw_nlayers") return T.lw_nlayers;
+  auto it = T.reduced.find(name);
+  if (it == T.reduced.end()) { g.err = std::string("no such table: ") + name; return -ARC_ERR_BAD_ARG; }
+  const int n = (int)it->second.size();
+  if (buf && cap >= n) memcpy(buf, it->second.data(), (size_t)n * 4);
+  return n;
+}
+
 // FP32 FMA throughput of this GPU (TFLOP/s), measured with a dependent-chain-free FMA kernel: the roofline
 // denominator for the FP32-pipe-bound solver kernels (MEASURED_PEAKS.json holds no FP32 figure).
 __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters) {
