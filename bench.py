@@ -193,7 +193,7 @@ def main():
     # ---- device-resident arm --------------------------------------------------------------------------------
     ddom = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in dom.items()}
     like = ddom["xcoszen"]
-    o_sw, o_lw = R.alloc_outputs(dom, "sw", like=like), R.alloc_outputs(dom, "lw", like=like)
+    o_sw, o_lw = R.alloc_outputs(dom, "sw", like=like, ext=False), R.alloc_outputs(dom, "lw", like=like, ext=False)
     rthraten = torch.zeros_like(ddom["t3d"]); swdown = torch.zeros_like(like)
     nst = len(SW_STATS) + len(LW_STATS)
     stats = torch.zeros(nst, 5, dtype=torch.float64, device=dev)
@@ -263,7 +263,7 @@ def main():
                 a, tt = pin(v); keep.append(tt); hdom[k] = a
             else:
                 hdom[k] = v
-        h_sw, h_lw = R.alloc_outputs(dom, "sw"), R.alloc_outputs(dom, "lw")
+        h_sw, h_lw = R.alloc_outputs(dom, "sw", ext=False), R.alloc_outputs(dom, "lw", ext=False)
         for o in (h_sw, h_lw):
             for k in list(o):
                 a, tt = pin(o[k]); keep.append(tt); o[k] = a

@@ -69,7 +69,7 @@ int upload_vec(const std::vector<float> &v, const float **d) { return upload(v.d
 
 size_t chunk_cap_default() {
   const char *e = getenv("ARC_RAD_CHUNK");
-  long v = e ? atol(e) : 65536;
+  long v = e ? atol(e) : 32768;
   if (v < 256) v = 256;
   return (size_t)((v + 255) / 256 * 256);
 }
@@ -95,7 +95,7 @@ void carve_sw(SwWs &w, char *base, size_t &bytes) {
   w.laytrop = c.take<int>(cap);
   w.laysol = c.take<int>((size_t)NBSW * cap);
   w.colf = c.take<float>((size_t)SWF_N * cap);
-  w.part = c.take<float>((size_t)NGSW * (nl + 1) * NKIND * cap);
+  w.part = c.take<float>((size_t)NGSW * (nl + 1) * w.nk * cap);
   w.dirs = c.take<float>((size_t)NGSW * cap);
   bytes = c.off;
 }
@@ -110,12 +110,22 @@ void carve_lw(LwWs &w, char *base, size_t &bytes) {
   w.laytrop = c.take<int>(cap);
   w.colf = c.take<float>((size_t)LWF_N * cap);
   w.secdiff = c.take<float>((size_t)NBLW * cap);
-  w.part = c.take<float>((size_t)NGLW * (nl + 1) * NKIND * cap);
+  w.part = c.take<float>((size_t)NGLW * (nl + 1) * w.nk * cap);
   bytes = c.off;
 }
 
-int ensure_sw_ws(int nlay, size_t cap) {
-  SwWs w{}; w.cap = (int)cap; w.nlay = nlay; w.W = (nlay + 31) / 32;
+// slots of the flux kinds in use inside the partial buffer
+template <class WS> void set_kinds(WS &w, int variants) {
+  int n = 0;
+  for (int k = 0; k < NKIND; k++) w.kslot[k] = 0;
+  w.kslot[K_FU] = n++; w.kslot[K_FD] = n++; w.kslot[K_CU] = n++; w.kslot[K_CD] = n++;
+  if (variants & ARC_VAR_CLEAN) { w.kslot[K_NU] = n++; w.kslot[K_ND] = n++; }
+  if (variants & ARC_VAR_CLEANCLEAR) { w.kslot[K_XU] = n++; w.kslot[K_XD] = n++; }
+  w.nk = n;
+}
+
+int ensure_sw_ws(int nlay, size_t cap, int variants) {
+  SwWs w{}; w.cap = (int)cap; w.nlay = nlay; w.W = (nlay + 31) / 32; set_kinds(w, variants);
   size_t need; carve_sw(w, nullptr, need);
   if (need > g.sw_bytes) {
     if (g.sw_arena) cudaFree(g.sw_arena);
@@ -127,8 +137,8 @@ int ensure_sw_ws(int nlay, size_t cap) {
   g.sw = w;
   return 0;
 }
-int ensure_lw_ws(int nlay, size_t cap) {
-  LwWs w{}; w.cap = (int)cap; w.nlay = nlay; w.W = (nlay + 31) / 32;
+int ensure_lw_ws(int nlay, size_t cap, int variants) {
+  LwWs w{}; w.cap = (int)cap; w.nlay = nlay; w.W = (nlay + 31) / 32; set_kinds(w, variants);
   size_t need; carve_lw(w, nullptr, need);
   if (need > g.lw_bytes) {
     if (g.lw_arena) cudaFree(g.lw_arena);
@@ -558,7 +568,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   CK(cudaStreamSynchronize(g.stream));
   if (nsun > 0) {
     const size_t cap = std::min(chunk_cap_default(), (size_t)((nsun + 255) / 256 * 256));
-    if ((rc = ensure_sw_ws(nlay, cap))) return rc;
+    if ((rc = ensure_sw_ws(nlay, cap, variants))) return rc;
     for (int c0 = 0; c0 < nsun; c0 += (int)cap) {
       const int nc = std::min((int)cap, nsun - c0);
       a.ws = g.sw;
@@ -655,7 +665,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
 #undef OUT2
 #undef OUTP
   int variants = ARC_VAR_FULL | ARC_VAR_CLEAR;
-  if (in->clean_atm_diag > 0) variants |= ARC_VAR_CLEAN | ARC_VAR_CLEANCLEAR;   // the clean call yields both (LW:11022-11027)
+  if (in->clean_atm_diag > 0) variants |= ARC_VAR_CLEAN | (ext ? ARC_VAR_CLEANCLEAR : 0);   // clean call: LW:11022-11027
   a.variants = variants;
   a.status = g.d_status;
 
@@ -664,7 +674,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
 
   const int ncol = G.ncol_tile;
   const size_t cap = std::min(chunk_cap_default(), (size_t)((ncol + 255) / 256 * 256));
-  if ((rc = ensure_lw_ws(nlay, cap))) return rc;
+  if ((rc = ensure_lw_ws(nlay, cap, variants))) return rc;
   for (int c0 = 0; c0 < ncol; c0 += (int)cap) {
     const int nc = std::min((int)cap, ncol - c0);
     a.ws = g.lw;

@@ -59,7 +59,8 @@ struct SwWs {
   int *laytrop;            // [cap]
   int *laysol;             // [14][cap]            layer (0-based) where sfluxzen is taken, -1 = never
   float *colf;             // [SWF_N][cap]
-  float *part;             // [NGSW][nlay+1][NKIND][cap]
+  float *part;             // [NGSW][nlay+1][nk][cap]   partial fluxes; nk = kinds in use, slot of kind k = kslot[k]
+  int nk; int kslot[NKIND];
   float *dirs;             // [NGSW][cap]          surface direct beam without delta scaling (x incident flux)
 };
 
@@ -103,7 +104,8 @@ struct LwWs {
   int *laytrop;            // [cap]
   float *colf;             // [LWF_N][cap]
   float *secdiff;          // [16][cap]
-  float *part;             // [NGLW][nlay+1][NKIND][cap]
+  float *part;             // [NGLW][nlay+1][nk][cap]
+  int nk; int kslot[NKIND];
 };
 
 struct LwArgs {

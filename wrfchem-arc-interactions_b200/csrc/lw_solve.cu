@@ -50,8 +50,9 @@ __device__ __forceinline__ float lw_major_lower(const float *__restrict__ A, con
   }
 }
 
+constexpr int LW_BLOCK = 512;   // 91 KB of staged tables per block: two 512-thread blocks per SM
 template <int NL>
-__global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
+__global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *s_et = reinterpret_cast<float2 *>(smem_raw);                // 10002 x (exp_tbl, tfn_tbl)
   float *S = reinterpret_cast<float *>(s_et + 10002);                 // slice
@@ -59,9 +60,14 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
   float *s_rat = s_plk + 184;                                         // [6][60] chi_mls ratios by jp
   uint64_t *bar = reinterpret_cast<uint64_t *>(s_rat + 6 * 60);
 
-  const int g = blockIdx.y;
-  const int b = c_lw_ngb[g];
+  // block order: band-major, then column tile, then g-point within the band (see k_sw_solve)
+  const int ntiles = (a.ncols + LW_BLOCK - 1) / LW_BLOCK;
+  int b = 0;
+  while (b < NBLW - 1 && (int)blockIdx.x >= c_lw[b + 1].g0 * ntiles) b++;
   const LwBandDesc &D = c_lw[b];
+  const int rblk = blockIdx.x - D.g0 * ntiles;
+  const int tile = rblk / D.ng;
+  const int g = D.g0 + rblk % D.ng;
   const int band = b + 1;
   const DevTables &tb = a.tb;
   {
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
     s_rat[r * 60 + jp] = __fdiv_rn(chi[num[r]], chi[den[r]]);
   }
   __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = tile * LW_BLOCK + threadIdx.x;
   if (c >= a.ncols) return;
 
   const LwWs &ws = a.ws;
@@ -120,10 +126,16 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
   int iclddn = 0;
   float fracs_bot = 0.f;
   const size_t stf = (size_t)nlay * cap;
-  float *part = ws.part + ((size_t)g * (nlay + 1)) * NKIND * cap + c;
+  const int nk = ws.nk;
+  const bool do_clnc = (a.variants & ARC_VAR_CLEANCLEAR) != 0;
+  float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * cap + c;
+  const size_t oFU = (size_t)ws.kslot[K_FU] * cap, oFD = (size_t)ws.kslot[K_FD] * cap, oCU = (size_t)ws.kslot[K_CU] * cap,
+               oCD = (size_t)ws.kslot[K_CD] * cap, oNU = (size_t)ws.kslot[K_NU] * cap, oND = (size_t)ws.kslot[K_ND] * cap,
+               oXU = (size_t)ws.kslot[K_XU] * cap, oXD = (size_t)ws.kslot[K_XD] * cap;
   // TOA downward radiance is zero
-  part[((size_t)nlay * NKIND + K_FD) * cap] = 0.f; part[((size_t)nlay * NKIND + K_CD) * cap] = 0.f;
-  if (do_clean) { part[((size_t)nlay * NKIND + K_ND) * cap] = 0.f; part[((size_t)nlay * NKIND + K_XD) * cap] = 0.f; }
+  part[(size_t)nlay * nk * cap + oFD] = 0.f; part[(size_t)nlay * nk * cap + oCD] = 0.f;
+  if (do_clean) part[(size_t)nlay * nk * cap + oND] = 0.f;
+  if (do_clnc) part[(size_t)nlay * nk * cap + oXD] = 0.f;
 
   // Planck function at the top interface of the current layer; carried downwards
   auto planck_at = [&](float t) {
@@ -134,9 +146,19 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
     return p0 + frac * (p1 - p0);
   };
 
+  // The fields every band needs are loaded together at the top of the layer iteration (one wait per layer instead of
+  // one per field); band-specific columns are loaded at the top of the band's case.
+  constexpr unsigned COMMON = (1u << LWC_FAC00) | (1u << LWC_FAC01) | (1u << LWC_FAC10) | (1u << LWC_FAC11) | (1u << LWC_SELFFAC) |
+                              (1u << LWC_SELFFRAC) | (1u << LWC_FORFAC) | (1u << LWC_FORFRAC) | (1u << LWC_TAVEL) | (1u << LWC_TZ) | (1u << LWC_IDX);
+  float plev_carry = 0.f;
   for (int lay = nlay - 1; lay >= 0; lay--) {
     const float *p = ws.coef + (size_t)lay * cap + c;
-    auto F = [&](int f) { return p[(size_t)f * stf]; };
+    float fv[LWC_N];
+#pragma unroll
+    for (int f = 0; f < LWC_N; f++) if ((COMMON >> f) & 1u) fv[f] = p[(size_t)f * stf];
+    const float taua = ws.aer[((size_t)b * nlay + lay) * cap + c];
+    const float tz_dn = lay > 0 ? p[(size_t)LWC_TZ * stf - cap] : ws.colf[(size_t)LWF_TZ0 * cap + c];
+    auto F = [&](int f) { return ((COMMON >> f) & 1u) ? fv[f] : p[(size_t)f * stf]; };
     const int pk = __float_as_int(F(LWC_IDX));
     const int jp = IDX_JP(pk), jt = IDX_JT(pk), jt1 = IDX_JT1(pk), indself = IDX_SELF(pk), indfor = IDX_FOR(pk), indminor = IDX_MINOR(pk);
     const float fac00 = F(LWC_FAC00), fac01 = F(LWC_FAC01), fac10 = F(LWC_FAC10), fac11 = F(LWC_FAC11);
@@ -375,8 +397,9 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
 
     // ---- rtrnmc downward step for this layer (LW:3207-3300)
     const float blay = planck_at(F(LWC_TAVEL));
-    const float plev_up = planck_at(F(LWC_TZ));
-    const float plev_dn = planck_at(lay > 0 ? p[(size_t)LWC_TZ * stf - cap] : ws.colf[(size_t)LWF_TZ0 * cap + c]);
+    const float plev_up = lay == nlay - 1 ? planck_at(F(LWC_TZ)) : plev_carry;     // = plev_dn of the layer above
+    const float plev_dn = planck_at(tz_dn);
+    plev_carry = plev_dn;
     const float dplankup = plev_up - blay, dplankdn = plev_dn - blay;
     const float plfrac = fracs;
     const bool icldlyr = (aw[lay >> 5] >> (lay & 31)) & 1u;
@@ -393,7 +416,6 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
     }
     Ef[lay] = efclfrac;
     if (icldlyr) iclddn = 1;
-    const float taua = ws.aer[((size_t)b * nlay + lay) * cap + c];
 #pragma unroll
     for (int v = 0; v < 2; v++) {
       if (v == 1 && !do_clean) break;
@@ -470,8 +492,8 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
       At[v][lay] = atrans; Bg[v][lay] = bbugas;
       if (iclddn == 1) radclrd[v] = radclrd[v] + (bbd - radclrd[v]) * atrans;
       else radclrd[v] = radld[v];
-      part[((size_t)lay * NKIND + (v == 0 ? K_FD : K_ND)) * cap] = radld[v];
-      part[((size_t)lay * NKIND + (v == 0 ? K_CD : K_XD)) * cap] = radclrd[v];
+      part[(size_t)lay * nk * cap + (v == 0 ? oFD : oND)] = radld[v];
+      if (v == 0 || do_clnc) part[(size_t)lay * nk * cap + (v == 0 ? oCD : oXD)] = radclrd[v];
     }
   }
   // ---- surface (LW:3303-3320)
@@ -493,8 +515,8 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
     if (v == 1 && !do_clean) break;
     radlu[v] = rad0 + reflect * radld[v];
     radclru[v] = rad0 + reflect * radclrd[v];
-    part[(size_t)(v == 0 ? K_FU : K_NU) * cap] = radlu[v];
-    part[(size_t)(v == 0 ? K_CU : K_XU) * cap] = radclru[v];
+    part[v == 0 ? oFU : oNU] = radlu[v];
+    if (v == 0 || do_clnc) part[v == 0 ? oCU : oXU] = radclru[v];
   }
   // ---- upward sweep (LW:3322-3356)
   for (int lay = 0; lay < nlay; lay++) {
@@ -514,8 +536,8 @@ __global__ void __launch_bounds__(256) k_lw_solve(LwArgs a) {
       }
       if (iclddn == 1) radclru[v] = radclru[v] + (bbugas - radclru[v]) * atrans;
       else radclru[v] = radlu[v];
-      part[((size_t)(lay + 1) * NKIND + (v == 0 ? K_FU : K_NU)) * cap] = radlu[v];
-      part[((size_t)(lay + 1) * NKIND + (v == 0 ? K_CU : K_XU)) * cap] = radclru[v];
+      part[(size_t)(lay + 1) * nk * cap + (v == 0 ? oFU : oNU)] = radlu[v];
+      if (v == 0 || do_clnc) part[(size_t)(lay + 1) * nk * cap + (v == 0 ? oCU : oXU)] = radclru[v];
     }
   }
 }
@@ -530,48 +552,52 @@ void launch_lw_solve(const LwArgs &a, cudaStream_t s) {
     cudaFuncSetAttribute(k_lw_solve<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, lw_solve_smem());
     attr = true;
   }
-  dim3 grid((a.ncols + 255) / 256, NGLW);
-  if (a.ws.nlay <= 64) k_lw_solve<64><<<grid, 256, lw_solve_smem(), s>>>(a);
-  else if (a.ws.nlay <= 128) k_lw_solve<128><<<grid, 256, lw_solve_smem(), s>>>(a);
-  else k_lw_solve<160><<<grid, 256, lw_solve_smem(), s>>>(a);
+  dim3 grid(NGLW * ((a.ncols + LW_BLOCK - 1) / LW_BLOCK));
+  if (a.ws.nlay <= 64) k_lw_solve<64><<<grid, LW_BLOCK, lw_solve_smem(), s>>>(a);
+  else if (a.ws.nlay <= 128) k_lw_solve<128><<<grid, LW_BLOCK, lw_solve_smem(), s>>>(a);
+  else k_lw_solve<160><<<grid, LW_BLOCK, lw_solve_smem(), s>>>(a);
   count_launch();
 }
 
 // ------------------------------------------------------------------------------------------------------
 // Reduction: per band sum over its g-points in order, x wtdiff x delwave, sum over bands, x fluxfac
-// (LW:3365-3395); heating rates (LW:3397-3408); scatter (LW:12646-12692).  One thread per column.
-__global__ void __launch_bounds__(128) k_lw_reduce(LwArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.ncols) return;
+// (LW:3365-3395); heating rates (LW:3397-3408); scatter (LW:12646-12692).  Block = 32 columns x 8 level-lanes.
+constexpr int RED_CX = 64, RED_LY = 8;
+__global__ void __launch_bounds__(RED_CX * RED_LY) k_lw_reduce(LwArgs a) {
+  __shared__ float s_net[161][RED_CX];
+  const int cx = threadIdx.x, ly = threadIdx.y;
+  const int c = blockIdx.x * RED_CX + cx;
   const Geo &G = a.geo;
   const LwWs &ws = a.ws;
   const int nlay = ws.nlay, nz = G.kte - G.kts + 1;
   const size_t cap = ws.cap;
+  const bool active = c < a.ncols;
   const int tc = a.col0 + c;
-  int i, j; G.ij(tc, i, j);
-  const size_t ij = G.at2(i, j);
+  int i = 0, j = 0; size_t ij = 0;
+  if (active) { G.ij(tc, i, j); ij = G.at2(i, j); }
   const bool do_clean = (a.variants & ARC_VAR_CLEAN) != 0;
   const float wtdiff = 0.5f;
-
-  float fnet_prev = 0.f;
-  for (int lev = 0; lev <= nlay; lev++) {
+  const int nk = ws.nk;
+  const bool do_clnc = (a.variants & ARC_VAR_CLEANCLEAR) != 0;
+  const size_t gstride = (size_t)(nlay + 1) * nk * cap;
+  const size_t oFU = (size_t)ws.kslot[K_FU] * cap, oFD = (size_t)ws.kslot[K_FD] * cap, oCU = (size_t)ws.kslot[K_CU] * cap,
+               oCD = (size_t)ws.kslot[K_CD] * cap, oNU = (size_t)ws.kslot[K_NU] * cap, oND = (size_t)ws.kslot[K_ND] * cap,
+               oXU = (size_t)ws.kslot[K_XU] * cap, oXD = (size_t)ws.kslot[K_XD] * cap;
+  for (int lev = ly; lev <= nlay && active; lev += RED_LY) {
     float tot[NKIND];
 #pragma unroll
     for (int k = 0; k < NKIND; k++) tot[k] = 0.f;
-    int g = 0;
+    const float *p = ws.part + ((size_t)lev * nk) * cap + c;
     for (int b = 0; b < NBLW; b++) {
       float r[NKIND];
 #pragma unroll
       for (int k = 0; k < NKIND; k++) r[k] = 0.f;
       const int ng = c_lw[b].ng;
-      for (int q = 0; q < ng; q++, g++) {
-        const float *p = ws.part + (((size_t)g * (nlay + 1) + lev) * NKIND) * cap + c;
-        r[K_FU] = r[K_FU] + p[(size_t)K_FU * cap]; r[K_FD] = r[K_FD] + p[(size_t)K_FD * cap];
-        r[K_CU] = r[K_CU] + p[(size_t)K_CU * cap]; r[K_CD] = r[K_CD] + p[(size_t)K_CD * cap];
-        if (do_clean) {
-          r[K_NU] = r[K_NU] + p[(size_t)K_NU * cap]; r[K_ND] = r[K_ND] + p[(size_t)K_ND * cap];
-          r[K_XU] = r[K_XU] + p[(size_t)K_XU * cap]; r[K_XD] = r[K_XD] + p[(size_t)K_XD * cap];
-        }
+      for (int q = 0; q < ng; q++, p += gstride) {
+        r[K_FU] = r[K_FU] + p[oFU]; r[K_FD] = r[K_FD] + p[oFD];
+        r[K_CU] = r[K_CU] + p[oCU]; r[K_CD] = r[K_CD] + p[oCD];
+        if (do_clean) { r[K_NU] = r[K_NU] + p[oNU]; r[K_ND] = r[K_ND] + p[oND]; }
+        if (do_clnc) { r[K_XU] = r[K_XU] + p[oXU]; r[K_XD] = r[K_XD] + p[oXD]; }
       }
       const float dw = a.tb.delwave[b];
 #pragma unroll
@@ -579,16 +605,7 @@ __global__ void __launch_bounds__(128) k_lw_reduce(LwArgs a) {
     }
 #pragma unroll
     for (int k = 0; k < NKIND; k++) tot[k] = tot[k] * a.tb.fluxfac;
-    const float fnet = tot[K_FU] - tot[K_FD];
-    if (lev >= 1 && lev <= nz) {
-      const int k = G.kts + lev - 1;
-      const float pz0 = a.p8w[G.at3(i, k, j)] / 100.f, pz1 = a.p8w[G.at3(i, k + 1, j)] / 100.f;
-      const float htr = a.tb.heatfac * (fnet_prev - fnet) / (pz0 - pz1);
-      const float tten = htr / 86400.f;
-      a.rthratenlw[G.at3(i, k, j)] = tten / a.pi3d[G.at3(i, k, j)];
-      if (a.dbg.hr) a.dbg.hr[(size_t)tc * nlay + lev - 1] = htr;
-    }
-    fnet_prev = fnet;
+    s_net[lev][cx] = tot[K_FU] - tot[K_FD];
     if (lev <= nz + 1 && a.lwupflx) {
       const size_t q = G.atp(i, G.kts + lev, j);
       a.lwupflx[q] = tot[K_FU]; a.lwupflxc[q] = tot[K_CU]; a.lwdnflx[q] = tot[K_FD]; a.lwdnflxc[q] = tot[K_CD];
@@ -608,9 +625,18 @@ __global__ void __launch_bounds__(128) k_lw_reduce(LwArgs a) {
       if (a.lwuptclnc) { a.lwuptclnc[ij] = tot[K_XU]; a.lwdntclnc[ij] = tot[K_XD]; }
     }
   }
+  __syncthreads();
+  for (int L = 1 + ly; L <= nz && active; L += RED_LY) {
+    const int k = G.kts + L - 1;
+    const float pz0 = a.p8w[G.at3(i, k, j)] / 100.f, pz1 = a.p8w[G.at3(i, k + 1, j)] / 100.f;
+    const float htr = a.tb.heatfac * (s_net[L - 1][cx] - s_net[L][cx]) / (pz0 - pz1);
+    const float tten = htr / 86400.f;
+    a.rthratenlw[G.at3(i, k, j)] = tten / a.pi3d[G.at3(i, k, j)];
+    if (a.dbg.hr) a.dbg.hr[(size_t)tc * nlay + L - 1] = htr;
+  }
 }
 void launch_lw_reduce(const LwArgs &a, cudaStream_t s) {
-  k_lw_reduce<<<(a.ncols + 127) / 128, 128, 0, s>>>(a);
+  k_lw_reduce<<<(a.ncols + RED_CX - 1) / RED_CX, dim3(RED_CX, RED_LY), 0, s>>>(a);
   count_launch();
 }
 

@@ -154,90 +154,109 @@ __device__ __forceinline__ void sw_taumol(int band, const float *__restrict__ S,
 
 // exp(-x) through the reference's Pade-indexed table (SW:2590-2600, 8445-8460): series below od_lo
 __device__ __forceinline__ float sw_expt(const float *__restrict__ exp_tbl, float x, float bpade) {
-  if (x <= 0.06f) return 1.f - x + 0.5f * x * x;
+  if (x <= 0.06f) return __fadd_rn(__fsub_rn(1.f, x), __fmul_rn(__fmul_rn(0.5f, x), x));
   const float tblind = __fdiv_rn(x, __fadd_rn(bpade, x));
   const int itind = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
   return exp_tbl[itind];
 }
 
-// reftra_sw (kmodts = 2, PIFM) for one layer.  Returns (ref, refd, tra, trad).
-__device__ __forceinline__ float4 sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
+// Unfused IEEE single-precision operations.  reftra_sw and the optical-property mixing that feeds it are evaluated with
+// exactly the reference's operation order and rounding: for nearly conservative layers (1 - w ~ 1e-6, common in the
+// aerosol-free "clean" stream of the Rayleigh-dominated bands) k = sqrt(g1^2 - g2^2) and the numerators of R and T are
+// differences of nearly equal O(1) numbers, so a contracted FMA or an approximate reciprocal would move the layer
+// reflectance by percents relative to the reference.  The adding recurrences (vrtqdr_sw) are well conditioned and keep
+// the fast reciprocal.
+#define M_(a, b) __fmul_rn((a), (b))
+#define A_(a, b) __fadd_rn((a), (b))
+#define S_(a, b) __fsub_rn((a), (b))
+#define D_(a, b) __fdiv_rn((a), (b))
+
+// reftra_sw (kmodts = 2, PIFM) for one layer, SW:2540-2690.  Returns (ref, refd, tra, trad).
+__device__ __noinline__ float4 sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
   const float eps = 1.e-08f, zwcrit = 0.9999995f;
   float4 o;
-  const float zg3 = 3.f * zg;
-  const float zgamma1 = (8.f - zw * (5.f + zg3)) * 0.25f;
-  const float zgamma2 = 3.f * (zw * (1.f - zg)) * 0.25f;
-  const float zgamma3 = (2.f - zg3 * prmuz) * 0.25f;
-  const float zgamma4 = 1.f - zgamma3;
-  const float q = zg * RCP(1.f - zg);
-  const float denom = fmaxf((1.f - (1.f - zw) * (q * q)), 1.0E-30f);
-  const float zwo = zw * RCP(denom);
+  const float zg3 = M_(3.f, zg);
+  const float zgamma1 = M_(S_(8.f, M_(zw, A_(5.f, zg3))), 0.25f);
+  const float zgamma2 = M_(M_(3.f, M_(zw, S_(1.f, zg))), 0.25f);
+  const float zgamma3 = M_(S_(2.f, M_(zg3, prmuz)), 0.25f);
+  const float zgamma4 = S_(1.f, zgamma3);
+  const float q = D_(zg, S_(1.f, zg));
+  const float denom = fmaxf(S_(1.f, M_(S_(1.f, zw), M_(q, q))), 1.0E-30f);
+  const float zwo = D_(zw, denom);
   if (zwo >= zwcrit) {
-    const float za = zgamma1 * prmuz;
-    const float za1 = za - zgamma3;
-    const float zgt = zgamma1 * zto1;
-    const float ze1 = fminf(__fdiv_rn(zto1, prmuz), 500.f);
+    const float za = M_(zgamma1, prmuz);
+    const float za1 = S_(za, zgamma3);
+    const float zgt = M_(zgamma1, zto1);
+    const float ze1 = fminf(D_(zto1, prmuz), 500.f);
     const float ze2 = sw_expt(exp_tbl, ze1, bpade);
-    const float r = RCP(1.f + zgt);
-    o.x = (zgt - za1 * (1.f - ze2)) * r;
-    o.z = 1.f - o.x;
-    o.y = zgt * r;
-    o.w = 1.f - o.y;
+    o.x = D_(S_(zgt, M_(za1, S_(1.f, ze2))), A_(1.f, zgt));
+    o.z = S_(1.f, o.x);
+    o.y = D_(zgt, A_(1.f, zgt));
+    o.w = S_(1.f, o.y);
     if (ze2 == 1.0f) { o.x = 0.f; o.z = 1.f; o.y = 0.f; o.w = 1.f; }
   } else {
-    const float za1 = zgamma1 * zgamma4 + zgamma2 * zgamma3;
-    const float za2 = zgamma1 * zgamma3 + zgamma2 * zgamma4;
-    const float zrk = sqrtf(zgamma1 * zgamma1 - zgamma2 * zgamma2);
-    const float zrp = zrk * prmuz;
-    const float zrp1 = 1.f + zrp, zrm1 = 1.f - zrp, zrk2 = 2.f * zrk;
-    const float zrpp = 1.f - zrp * zrp;
-    const float zrkg = zrk + zgamma1;
-    const float zr1 = zrm1 * (za2 + zrk * zgamma3);
-    const float zr2 = zrp1 * (za2 - zrk * zgamma3);
-    const float zr3 = zrk2 * (zgamma3 - za2 * prmuz);
-    const float zr4 = zrpp * zrkg;
-    const float zr5 = zrpp * (zrk - zgamma1);
-    const float zt1 = zrp1 * (za1 + zrk * zgamma4);
-    const float zt2 = zrm1 * (za1 - zrk * zgamma4);
-    const float zt3 = zrk2 * (zgamma4 + za1 * prmuz);
-    const float zbeta = (zgamma1 - zrk) * RCP(zrkg);
-    const float ze1 = fminf(zrk * zto1, 500.f);
-    const float ze2 = fminf(__fdiv_rn(zto1, prmuz), 500.f);
-    const float zem1 = sw_expt(exp_tbl, ze1, bpade), zep1 = RCP(zem1);
-    const float zem2 = sw_expt(exp_tbl, ze2, bpade), zep2 = RCP(zem2);
-    const float zdenr = zr4 * zep1 + zr5 * zem1;
-    const float zdent = zr4 * zep1 + zr5 * zem1;   // zt4 = zr4, zt5 = zr5
+    const float za1 = A_(M_(zgamma1, zgamma4), M_(zgamma2, zgamma3));
+    const float za2 = A_(M_(zgamma1, zgamma3), M_(zgamma2, zgamma4));
+    const float zrk = __fsqrt_rn(S_(M_(zgamma1, zgamma1), M_(zgamma2, zgamma2)));
+    const float zrp = M_(zrk, prmuz);
+    const float zrp1 = A_(1.f, zrp), zrm1 = S_(1.f, zrp), zrk2 = M_(2.f, zrk);
+    const float zrpp = S_(1.f, M_(zrp, zrp));
+    const float zrkg = A_(zrk, zgamma1);
+    const float zr1 = M_(zrm1, A_(za2, M_(zrk, zgamma3)));
+    const float zr2 = M_(zrp1, S_(za2, M_(zrk, zgamma3)));
+    const float zr3 = M_(zrk2, S_(zgamma3, M_(za2, prmuz)));
+    const float zr4 = M_(zrpp, zrkg);
+    const float zr5 = M_(zrpp, S_(zrk, zgamma1));
+    const float zt1 = M_(zrp1, A_(za1, M_(zrk, zgamma4)));
+    const float zt2 = M_(zrm1, S_(za1, M_(zrk, zgamma4)));
+    const float zt3 = M_(zrk2, A_(zgamma4, M_(za1, prmuz)));
+    const float zbeta = D_(S_(zgamma1, zrk), zrkg);
+    const float ze1 = fminf(M_(zrk, zto1), 500.f);
+    const float ze2 = fminf(D_(zto1, prmuz), 500.f);
+    const float zem1 = sw_expt(exp_tbl, ze1, bpade), zep1 = D_(1.f, zem1);
+    const float zem2 = sw_expt(exp_tbl, ze2, bpade), zep2 = D_(1.f, zem2);
+    const float zdenr = A_(M_(zr4, zep1), M_(zr5, zem1));
+    const float zdent = zdenr;   // zt4 = zr4, zt5 = zr5
     if (zdenr >= -eps && zdenr <= eps) { o.x = eps; o.z = zem2; }
     else {
-      o.x = zw * (zr1 * zep1 - zr2 * zem1 - zr3 * zem2) * RCP(zdenr);
-      o.z = zem2 - zem2 * zw * (zt1 * zep1 - zt2 * zem1 - zt3 * zep2) * RCP(zdent);
+      o.x = D_(M_(zw, S_(S_(M_(zr1, zep1), M_(zr2, zem1)), M_(zr3, zem2))), zdenr);
+      o.z = S_(zem2, D_(M_(M_(zem2, zw), S_(S_(M_(zt1, zep1), M_(zt2, zem1)), M_(zt3, zep2))), zdent));
     }
-    const float zemm = zem1 * zem1;
-    const float zdend = RCP((1.f - zbeta * zemm) * zrkg);
-    o.y = zgamma2 * (1.f - zemm) * zdend;
-    o.w = zrk2 * zem1 * zdend;
+    const float zemm = M_(zem1, zem1);
+    const float zdend = D_(1.f, M_(S_(1.f, M_(zbeta, zemm)), zrkg));
+    o.y = M_(M_(zgamma2, S_(1.f, zemm)), zdend);
+    o.w = M_(M_(zrk2, zem1), zdend);
   }
   return o;
 }
 
 // ------------------------------------------------------------------------------------------------------
+#ifndef SW_MINBLOCKS
+#define SW_MINBLOCKS 3
+#endif
 template <int NL>
-__global__ void __launch_bounds__(256) k_sw_solve(SwArgs a) {
+__global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *s_exp = reinterpret_cast<float *>(smem_raw);                 // 10004 floats
   float *S = s_exp + 10004;                                           // slice
   uint64_t *bar = reinterpret_cast<uint64_t *>(S + SLICE_MAX);
 
-  const int g = blockIdx.y;
-  const int b = c_sw_ngb[g];
+  // Block order: band-major, then column tile, then g-point within the band.  Blocks resident at the same time run the
+  // same band (one code path in the instruction cache) and the g-points of a band share the tile's workspace lines in L2.
+  const int ntiles = (a.ncols + 255) >> 8;
+  int b = 0;
+  while (b < NBSW - 1 && (int)blockIdx.x >= c_sw[b + 1].g0 * ntiles) b++;
   const SwBandDesc &D = c_sw[b];
+  const int rblk = blockIdx.x - D.g0 * ntiles;
+  const int tile = rblk / D.ng;
+  const int g = D.g0 + rblk % D.ng;
   const int band = b + 16;
   {
     StageReq req[2] = {{s_exp, a.tb.sw_exp, 10004 * 4},
                        {S, a.tb.sw_tab + D.slice_base + (size_t)D.slice_floats * (g - D.g0), (uint32_t)D.slice_floats * 4}};
     stage_tables(bar, req, 2);
   }
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = tile * 256 + threadIdx.x;
   if (c >= a.ncols) return;
 
   const SwWs &ws = a.ws;
@@ -270,19 +289,29 @@ __global__ void __launch_bounds__(256) k_sw_solve(SwArgs a) {
   float sfluxzen = 0.f;
   float tdir_nodel = 1.f;     // product of the un-delta-scaled direct transmittances of the FULL stream
 
+  // Software pipeline: the workspace words of layer lay+1 are requested while layer lay is being computed, so the
+  // ~1 us DRAM/L2 latency of these (coalesced, read-once) loads hides behind one full layer of arithmetic.
   const float *coef = ws.coef + c;
+  const size_t stf = (size_t)nlay * cap;
+  auto load_layer = [&](int lay, SwLay &L, int &pk, float &ta, float &om, float &as) {
+    const float *p = coef + (size_t)lay * cap;
+    L.fac00 = p[SWC_FAC00 * stf]; L.fac01 = p[SWC_FAC01 * stf]; L.fac10 = p[SWC_FAC10 * stf]; L.fac11 = p[SWC_FAC11 * stf];
+    L.h2o = p[SWC_H2O * stf]; L.co2 = p[SWC_CO2 * stf]; L.o3 = p[SWC_O3 * stf]; L.ch4 = p[SWC_CH4 * stf]; L.o2 = p[SWC_O2 * stf];
+    L.mol = p[SWC_MOL * stf];
+    L.selffac = p[SWC_SELFFAC * stf]; L.selffrac = p[SWC_SELFFRAC * stf]; L.forfac = p[SWC_FORFAC * stf]; L.forfrac = p[SWC_FORFRAC * stf];
+    pk = __float_as_int(p[SWC_IDX * stf]);
+    ta = ws.aer[(((size_t)b * 3 + 0) * nlay + lay) * cap + c];
+    om = ws.aer[(((size_t)b * 3 + 1) * nlay + lay) * cap + c];
+    as = ws.aer[(((size_t)b * 3 + 2) * nlay + lay) * cap + c];
+  };
+  SwLay Lnx; int pk_nx; float ta_nx, om_nx, as_nx;
+  load_layer(0, Lnx, pk_nx, ta_nx, om_nx, as_nx);
   for (int lay = 0; lay < nlay; lay++) {
-    SwLay L;
-    {
-      const size_t st = (size_t)nlay * cap;
-      const float *p = coef + (size_t)lay * cap;
-      L.fac00 = p[SWC_FAC00 * st]; L.fac01 = p[SWC_FAC01 * st]; L.fac10 = p[SWC_FAC10 * st]; L.fac11 = p[SWC_FAC11 * st];
-      L.h2o = p[SWC_H2O * st]; L.co2 = p[SWC_CO2 * st]; L.o3 = p[SWC_O3 * st]; L.ch4 = p[SWC_CH4 * st]; L.o2 = p[SWC_O2 * st];
-      L.mol = p[SWC_MOL * st];
-      L.selffac = p[SWC_SELFFAC * st]; L.selffrac = p[SWC_SELFFRAC * st]; L.forfac = p[SWC_FORFAC * st]; L.forfrac = p[SWC_FORFRAC * st];
-      const int pk = __float_as_int(p[SWC_IDX * st]);
-      L.jp = IDX_JP(pk); L.jt = IDX_JT(pk); L.jt1 = IDX_JT1(pk); L.indself = IDX_SELF(pk); L.indfor = IDX_FOR(pk);
-    }
+    SwLay L = Lnx;
+    const int pk = pk_nx;
+    const float taua = ta_nx, omga = om_nx, asya = as_nx;
+    if (lay + 1 < nlay) load_layer(lay + 1, Lnx, pk_nx, ta_nx, om_nx, as_nx);
+    L.jp = IDX_JP(pk); L.jt = IDX_JT(pk); L.jt1 = IDX_JT1(pk); L.indself = IDX_SELF(pk); L.indfor = IDX_FOR(pk);
     const bool lower = lay < laytrop;
     float taug, taur, sfl = 0.f;
     sw_taumol(band, S, D, L, lower, oneminus, taug, taur, sfl);
@@ -291,9 +320,6 @@ __global__ void __launch_bounds__(256) k_sw_solve(SwArgs a) {
       const size_t q = ((size_t)ws.cols[c] * nlay + lay) * NGSW + g;
       a.dbg.taug[q] = taug; a.dbg.taur[q] = taur;
     }
-    const float taua = ws.aer[(((size_t)b * 3 + 0) * nlay + lay) * cap + c];
-    const float omga = ws.aer[(((size_t)b * 3 + 1) * nlay + lay) * cap + c];
-    const float asya = ws.aer[(((size_t)b * 3 + 2) * nlay + lay) * cap + c];
     const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
     float taucmc = 0.f, ssacmc = 1.f, asmcmc = 0.f, taormc = 0.f;
     if (cloudy) {
@@ -311,29 +337,29 @@ __global__ void __launch_bounds__(256) k_sw_solve(SwArgs a) {
     for (int v = 0; v < 2; v++) {
       if (v == 1 && !noaer) break;
       const float ta = v == 0 ? taua : 0.f;
-      float ztauc = taur + taug + ta;
-      float zomcc = taur * 1.0f + ta * omga;
-      float zgcc = asya * omga * ta * RCP(zomcc);
-      zomcc = zomcc * RCP(ztauc);
+      float ztauc = A_(A_(taur, taug), ta);
+      float zomcc = A_(M_(taur, 1.0f), M_(ta, omga));
+      float zgcc = D_(M_(M_(asya, omga), ta), zomcc);
+      zomcc = D_(zomcc, ztauc);
       if (v == 0) {
         // direct beam without delta scaling (diagnostic surface direct flux of the FULL stream)
-        const float tauorig = cloudy ? ztauc + taormc : ztauc;
-        tdir_nodel = tdir_nodel * sw_expt(s_exp, __fdiv_rn(tauorig, prmu0), bpade);
+        const float tauorig = cloudy ? A_(ztauc, taormc) : ztauc;
+        tdir_nodel = tdir_nodel * sw_expt(s_exp, D_(tauorig, prmu0), bpade);
       }
-      const float zf = zgcc * zgcc;
-      const float zwf = zomcc * zf;
-      ztauc = (1.0f - zwf) * ztauc;
-      zomcc = (zomcc - zwf) * RCP(fmaxf(1.0f - zwf, 1.0E-30f));
-      zgcc = (zgcc - zf) * RCP(fmaxf(1.0f - zf, 1.0E-30f));
+      const float zf = M_(zgcc, zgcc);
+      const float zwf = M_(zomcc, zf);
+      ztauc = M_(S_(1.0f, zwf), ztauc);
+      zomcc = D_(S_(zomcc, zwf), fmaxf(S_(1.0f, zwf), 1.0E-30f));
+      zgcc = D_(S_(zgcc, zf), fmaxf(S_(1.0f, zf), 1.0E-30f));
       pclr[v] = sw_reftra(s_exp, bpade, zgcc, prmu0, ztauc, zomcc);
-      eclr[v] = sw_expt(s_exp, __fdiv_rn(ztauc, prmu0), bpade);
+      eclr[v] = sw_expt(s_exp, D_(ztauc, prmu0), bpade);
       if (cloudy) {
-        const float ztauo = ztauc + taucmc;
-        float zomco = ztauc * zomcc + taucmc * ssacmc;
-        const float zgco = (taucmc * ssacmc * asmcmc + ztauc * zomcc * zgcc) * RCP(zomco);
-        zomco = zomco * RCP(ztauo);
+        const float ztauo = A_(ztauc, taucmc);
+        float zomco = A_(M_(ztauc, zomcc), M_(taucmc, ssacmc));
+        const float zgco = D_(A_(M_(M_(taucmc, ssacmc), asmcmc), M_(M_(ztauc, zomcc), zgcc)), zomco);
+        zomco = D_(zomco, ztauo);
         pcld[v] = sw_reftra(s_exp, bpade, zgco, prmu0, ztauo, zomco);
-        ecld[v] = sw_expt(s_exp, __fdiv_rn(ztauo, prmu0), bpade);
+        ecld[v] = sw_expt(s_exp, D_(ztauo, prmu0), bpade);
       }
     }
     Pa[lay] = pclr[0]; Ea[lay] = eclr[0];
@@ -352,9 +378,11 @@ __global__ void __launch_bounds__(256) k_sw_solve(SwArgs a) {
       else if (s == 1) { P = cloudy ? pcld[0] : pclr[0]; e = cloudy ? ecld[0] : eclr[0]; }
       else if (s == 2) { P = cloudy ? pcld[1] : pclr[1]; e = cloudy ? ecld[1] : eclr[1]; }
       else { P = pclr[1]; e = eclr[1]; }
-      const float zreflect = RCP(1.f - rupd[s] * P.y);
-      const float nrup = P.x + (P.w * ((P.z - e) * rupd[s] + e * rup[s])) * zreflect;
-      const float nrupd = P.y + P.w * P.w * rupd[s] * zreflect;
+      // explicit operation order: every stream gets the identical instruction sequence, so streams with identical
+      // inputs (zero aerosol: clean == full; no cloud: clear == full) stay bit-identical like in the reference
+      const float zreflect = RCP(fmaf(-rupd[s], P.y, 1.f));
+      const float nrup = fmaf(__fmul_rn(P.w, fmaf(e, rup[s], __fmul_rn(__fsub_rn(P.z, e), rupd[s]))), zreflect, P.x);
+      const float nrupd = fmaf(__fmul_rn(__fmul_rn(P.w, P.w), rupd[s]), zreflect, P.y);
       rup[s] = nrup; rupd[s] = nrupd;
       Ru[s][lay] = make_float2(nrup, nrupd);
     }
@@ -366,44 +394,61 @@ __global__ void __launch_bounds__(256) k_sw_solve(SwArgs a) {
   float tdbt[4], tdn[4], rdnd[4];
 #pragma unroll
   for (int s = 0; s < 4; s++) { tdbt[s] = 1.f; tdn[s] = 1.f; rdnd[s] = 0.f; }
-  float *part = ws.part + ((size_t)g * (nlay + 1)) * NKIND * cap + c;
+  const int nk = ws.nk;
+  float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * cap + c;
+  // pass-2 operands of one interface + the layer below it, fetched one iteration ahead (see pass 1)
+  struct Lev2 { float2 ru[4]; float4 pa, pn, pf, pc; float ea, en, ef, ec; };
+  auto load_level = [&](int lev, Lev2 &V) {
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      if (s == 2 && !do_clean) continue;
+      if (s == 3 && !do_clnc) continue;
+      V.ru[s] = lev > 0 ? Ru[s][lev - 1] : make_float2(albp, albd);
+    }
+    if (lev == 0) return;
+    const int lay = lev - 1;
+    const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
+    V.pa = Pa[lay]; V.ea = Ea[lay];
+    V.pn = V.pa; V.en = V.ea;
+    if (noaer) { V.pn = Pn[lay]; V.en = En[lay]; }
+    V.pf = V.pa; V.pc = V.pn; V.ef = V.ea; V.ec = V.en;
+    if (cloudy) { V.pf = Pca[lay]; V.ef = Eca[lay]; if (do_clean) { V.pc = Pcn[lay]; V.ec = Ecn[lay]; } }
+  };
+  Lev2 Vnx;
+  load_level(nlay, Vnx);
   for (int lev = nlay; lev >= 0; lev--) {
+    const Lev2 V = Vnx;
+    if (lev > 0) load_level(lev - 1, Vnx);
     // flux at interface lev
 #pragma unroll
     for (int s = 0; s < 4; s++) {
       if (s == 2 && !do_clean) continue;
       if (s == 3 && !do_clnc) continue;
-      float ru, rud;
-      if (lev > 0) { const float2 r = Ru[s][lev - 1]; ru = r.x; rud = r.y; } else { ru = albp; rud = albd; }
-      const float zreflect = RCP(1.f - rdnd[s] * rud);
-      const float fu = (tdbt[s] * ru + (tdn[s] - tdbt[s]) * rud) * zreflect;
-      const float fd = tdbt[s] + (tdn[s] - tdbt[s] + tdbt[s] * ru * rdnd[s]) * zreflect;
+      const float ru = V.ru[s].x, rud = V.ru[s].y;
+      const float zreflect = RCP(fmaf(-rdnd[s], rud, 1.f));
+      const float dif = __fsub_rn(tdn[s], tdbt[s]);
+      const float fu = __fmul_rn(fmaf(tdbt[s], ru, __fmul_rn(dif, rud)), zreflect);
+      const float fd = fmaf(fmaf(__fmul_rn(tdbt[s], ru), rdnd[s], dif), zreflect, tdbt[s]);
       const int ku = s == 0 ? K_CU : s == 1 ? K_FU : s == 2 ? K_NU : K_XU;
-      part[((size_t)lev * NKIND + ku) * cap] = zincflx * fu;
-      part[((size_t)lev * NKIND + ku + 1) * cap] = zincflx * fd;
+      part[((size_t)lev * nk + ws.kslot[ku]) * cap] = __fmul_rn(zincflx, fu);
+      part[((size_t)lev * nk + ws.kslot[ku + 1]) * cap] = __fmul_rn(zincflx, fd);
     }
     if (lev == 0) break;
-    const int lay = lev - 1;
-    const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
-    float4 pa = Pa[lay]; float ea = Ea[lay];
-    float4 pn = pa; float en = ea;
-    if (noaer) { pn = Pn[lay]; en = En[lay]; }
-    float4 pf = pa, pc = pn; float ef = ea, ec = en;
-    if (cloudy) { pf = Pca[lay]; ef = Eca[lay]; if (do_clean) { pc = Pcn[lay]; ec = Ecn[lay]; } }
 #pragma unroll
     for (int s = 0; s < 4; s++) {
       if (s == 2 && !do_clean) continue;
       if (s == 3 && !do_clnc) continue;
-      const float4 P = s == 0 ? pa : s == 1 ? pf : s == 2 ? pc : pn;
-      const float e = s == 0 ? ea : s == 1 ? ef : s == 2 ? ec : en;
-      const float zreflect = RCP(1.f - P.y * rdnd[s]);
-      const float ntdn = tdbt[s] * P.z + (P.w * ((tdn[s] - tdbt[s]) + tdbt[s] * P.x * rdnd[s])) * zreflect;
-      const float nrdnd = P.y + P.w * P.w * rdnd[s] * zreflect;
+      const float4 P = s == 0 ? V.pa : s == 1 ? V.pf : s == 2 ? V.pc : V.pn;
+      const float e = s == 0 ? V.ea : s == 1 ? V.ef : s == 2 ? V.ec : V.en;
+      const float zreflect = RCP(fmaf(-P.y, rdnd[s], 1.f));
+      const float ntdn = fmaf(__fmul_rn(P.w, fmaf(__fmul_rn(tdbt[s], P.x), rdnd[s], __fsub_rn(tdn[s], tdbt[s]))), zreflect,
+                              __fmul_rn(tdbt[s], P.z));
+      const float nrdnd = fmaf(__fmul_rn(__fmul_rn(P.w, P.w), rdnd[s]), zreflect, P.y);
       tdn[s] = ntdn; rdnd[s] = nrdnd;
-      tdbt[s] = e * tdbt[s];
+      tdbt[s] = __fmul_rn(e, tdbt[s]);
     }
   }
-  ws.dirs[(size_t)g * cap + c] = zincflx * tdir_nodel;
+  ws.dirs[(size_t)g * cap + c] = __fmul_rn(zincflx, tdir_nodel);
 }
 
 static int sw_solve_smem() { return (10004 + SLICE_MAX) * 4 + 16; }
@@ -416,7 +461,7 @@ void launch_sw_solve(const SwArgs &a, cudaStream_t s) {
     cudaFuncSetAttribute(k_sw_solve<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, sw_solve_smem());
     attr = true;
   }
-  dim3 grid((a.ncols + 255) / 256, NGSW);
+  dim3 grid(NGSW * ((a.ncols + 255) / 256));
   if (a.ws.nlay <= 64) k_sw_solve<64><<<grid, 256, sw_solve_smem(), s>>>(a);
   else if (a.ws.nlay <= 128) k_sw_solve<128><<<grid, 256, sw_solve_smem(), s>>>(a);
   else k_sw_solve<160><<<grid, 256, sw_solve_smem(), s>>>(a);
@@ -425,60 +470,55 @@ void launch_sw_solve(const SwArgs &a, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------------
 // Reduction over g-points (in index order = the reference's accumulation order SW:8617-8650), fluxes -> heating
-// rates (SW:9391-9434) and scatter to the WRF arrays (SW:11125-11172).  One thread per column; all partial-buffer
-// reads are coalesced over columns.
-__global__ void __launch_bounds__(128) k_sw_reduce(SwArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.ncols) return;
+// rates (SW:9391-9434) and scatter to the WRF arrays (SW:11125-11172).  Block = 32 columns x 8 level-lanes; a thread sums
+// the 112 partials of its (column, level) sequentially, net fluxes meet in shared memory for the heating rates.  All
+// partial-buffer reads are 128-byte coalesced over columns.
+constexpr int RED_CX = 64, RED_LY = 8;
+__global__ void __launch_bounds__(RED_CX * RED_LY) k_sw_reduce(SwArgs a) {
+  __shared__ float s_net[161][RED_CX];
+  const int cx = threadIdx.x, ly = threadIdx.y;
+  const int c = blockIdx.x * RED_CX + cx;
   const Geo &G = a.geo;
   const SwWs &ws = a.ws;
   const int nlay = ws.nlay, nz = nlay - 1;
   const size_t cap = ws.cap;
-  const int tc = ws.cols[c];
-  int i, j; G.ij(tc, i, j);
-  const size_t ij = G.at2(i, j);
+  const bool active = c < a.ncols;
   const bool do_clean = (a.variants & ARC_VAR_CLEAN) != 0;
   const bool do_clnc = (a.variants & ARC_VAR_CLEANCLEAR) != 0;
-  const float coszrs = a.xcoszen[ij];
-
-  float net_prev = 0.f;
-  for (int lev = 0; lev <= nlay; lev++) {
+  int tc = 0, i = 0, j = 0; size_t ij = 0;
+  if (active) { tc = ws.cols[c]; G.ij(tc, i, j); ij = G.at2(i, j); }
+  for (int lev = ly; lev <= nlay && active; lev += RED_LY) {
     float f[NKIND];
 #pragma unroll
     for (int k = 0; k < NKIND; k++) f[k] = 0.f;
     float uvfd = 0.f, nifd = 0.f;
-    for (int g = 0; g < NGSW; g++) {
-      const float *p = ws.part + (((size_t)g * (nlay + 1) + lev) * NKIND) * cap + c;
-      f[K_FU] = f[K_FU] + p[(size_t)K_FU * cap];
-      const float fd = p[(size_t)K_FD * cap];
+    const int nk = ws.nk;
+    const float *p = ws.part + ((size_t)lev * nk) * cap + c;
+    const size_t gstride = (size_t)(nlay + 1) * nk * cap;
+    const size_t oFU = (size_t)ws.kslot[K_FU] * cap, oFD = (size_t)ws.kslot[K_FD] * cap, oCU = (size_t)ws.kslot[K_CU] * cap,
+                 oCD = (size_t)ws.kslot[K_CD] * cap, oNU = (size_t)ws.kslot[K_NU] * cap, oND = (size_t)ws.kslot[K_ND] * cap,
+                 oXU = (size_t)ws.kslot[K_XU] * cap, oXD = (size_t)ws.kslot[K_XD] * cap;
+    for (int g = 0; g < NGSW; g++, p += gstride) {
+      f[K_FU] = f[K_FU] + p[oFU];
+      const float fd = p[oFD];
       f[K_FD] = f[K_FD] + fd;
-      f[K_CU] = f[K_CU] + p[(size_t)K_CU * cap];
-      f[K_CD] = f[K_CD] + p[(size_t)K_CD * cap];
-      if (do_clean) { f[K_NU] = f[K_NU] + p[(size_t)K_NU * cap]; f[K_ND] = f[K_ND] + p[(size_t)K_ND * cap]; }
-      if (do_clnc) { f[K_XU] = f[K_XU] + p[(size_t)K_XU * cap]; f[K_XD] = f[K_XD] + p[(size_t)K_XD * cap]; }
+      f[K_CU] = f[K_CU] + p[oCU];
+      f[K_CD] = f[K_CD] + p[oCD];
+      if (do_clean) { f[K_NU] = f[K_NU] + p[oNU]; f[K_ND] = f[K_ND] + p[oND]; }
+      if (do_clnc) { f[K_XU] = f[K_XU] + p[oXU]; f[K_XD] = f[K_XD] + p[oXD]; }
       if (lev == 0) {
         const int b = c_sw_ngb[g];
         if (b >= 9 && b <= 12) uvfd = uvfd + fd; else nifd = nifd + fd;
       }
     }
-    // heating rate of the layer below this interface
-    const float net = f[K_FD] - f[K_FU];
-    if (lev >= 1 && lev <= nz) {
-      const int k = G.kts + lev - 1;
-      const float pdp = a.p8w[G.at3(i, k, j)] / 100.f - a.p8w[G.at3(i, k + 1, j)] / 100.f;
-      const float zdpgcp = a.tb.heatfac / pdp;
-      const float swhr = (net - net_prev) * zdpgcp;
-      const float tten = swhr / 86400.f;
-      a.rthratensw[G.at3(i, k, j)] = tten / a.pi3d[G.at3(i, k, j)];
-      if (a.dbg.hr) a.dbg.hr[(size_t)tc * nlay + lev - 1] = swhr;
-    }
-    net_prev = net;
-    if (lev <= nz + 1 && a.swupflx) {
+    s_net[lev][cx] = f[K_FD] - f[K_FU];
+    if (a.swupflx) {        // lev <= nz + 1 always
       const size_t q = G.atp(i, G.kts + lev, j);
       a.swupflx[q] = f[K_FU]; a.swupflxc[q] = f[K_CU]; a.swupflxcln[q] = f[K_NU];
       a.swdnflx[q] = f[K_FD]; a.swdnflxc[q] = f[K_CD]; a.swdnflxcln[q] = f[K_ND];
     }
     if (lev == 0) {
+      const float coszrs = a.xcoszen[ij];
       a.gsw[ij] = f[K_FD] - f[K_FU];
       if (a.swupt) {
         a.swupb[ij] = f[K_FU]; a.swupbc[ij] = f[K_CU]; a.swupbcln[ij] = f[K_NU];
@@ -510,10 +550,21 @@ __global__ void __launch_bounds__(128) k_sw_reduce(SwArgs a) {
       if (a.swuptclnc) { a.swuptclnc[ij] = f[K_XU]; a.swdntclnc[ij] = f[K_XD]; }
     }
   }
-  if (a.dbg.hr) a.dbg.hr[(size_t)tc * nlay + nlay - 1] = 0.f;
+  __syncthreads();
+  // heating rate of layer L (1-based) between interfaces L-1 and L; the extra top layer is forced to 0 and not output
+  for (int L = 1 + ly; L <= nz && active; L += RED_LY) {
+    const int k = G.kts + L - 1;
+    const float pdp = a.p8w[G.at3(i, k, j)] / 100.f - a.p8w[G.at3(i, k + 1, j)] / 100.f;
+    const float zdpgcp = a.tb.heatfac / pdp;
+    const float swhr = (s_net[L][cx] - s_net[L - 1][cx]) * zdpgcp;
+    const float tten = swhr / 86400.f;
+    a.rthratensw[G.at3(i, k, j)] = tten / a.pi3d[G.at3(i, k, j)];
+    if (a.dbg.hr) a.dbg.hr[(size_t)tc * nlay + L - 1] = swhr;
+  }
+  if (active && ly == 0 && a.dbg.hr) a.dbg.hr[(size_t)tc * nlay + nlay - 1] = 0.f;
 }
 void launch_sw_reduce(const SwArgs &a, cudaStream_t s) {
-  k_sw_reduce<<<(a.ncols + 127) / 128, 128, 0, s>>>(a);
+  k_sw_reduce<<<(a.ncols + RED_CX - 1) / RED_CX, dim3(RED_CX, RED_LY), 0, s>>>(a);
   count_launch();
 }
 

@@ -201,12 +201,12 @@ def common_flags(dom, clean_atm_diag=1, aer_ra_feedback=1):
                 f_qv=1, f_qc=1, f_qr=1, f_qi=1, f_qs=1, f_qg=1, r=float(dom["r"]), g=float(dom["g"]))
 
 
-def alloc_outputs(dom, which, xp=None, like=None):
-    """Allocate output arrays (numpy, or torch on like.device) for 'sw' or 'lw'."""
+def alloc_outputs(dom, which, xp=None, like=None, ext=True):
+    """Allocate output arrays (numpy, or torch on like.device) for 'sw' or 'lw'; ext adds the 4th (clean+clear) stream."""
     nj, ni = dom["xcoszen"].shape[-2:] if like is None else like.shape[-2:]
     nkm = dom["t3d"].shape[-2]
     names3 = abi.SW_OUT_3D if which == "sw" else abi.LW_OUT_3D
-    names2 = (abi.SW_OUT_2D + abi.SW_OUT_EXT) if which == "sw" else (abi.LW_OUT_2D + abi.LW_OUT_EXT)
+    names2 = (abi.SW_OUT_2D + (abi.SW_OUT_EXT if ext else ())) if which == "sw" else (abi.LW_OUT_2D + (abi.LW_OUT_EXT if ext else ()))
     namesp = abi.SW_OUT_PROF if which == "sw" else abi.LW_OUT_PROF
     out = {}
     if like is not None:
