@@ -261,6 +261,18 @@ def test_errors(lib, ktab):
     run_pair("sw", lib, dom)
 
 
+def test_branch_free_division_is_ieee(lib, ktab):
+    """The kernels' division (reciprocal + Newton + two residual corrections, no range-check branch) rounds like IEEE
+    division over the operand ranges the path uses."""
+    dom = synth.make_domain(4, 2, 40, seed=1)
+    init(lib, dom, ktab)
+    lib.lib.arc_rad_selftest_div.restype = C.c_int
+    lib.lib.arc_rad_selftest_div.argtypes = [C.c_int, C.c_uint]
+    n = 1 << 24
+    bad = lib.lib.arc_rad_selftest_div(n, 12345)
+    assert bad == 0, "%d of %d quotients differ from IEEE" % (bad, n)
+
+
 def test_driver_post_and_domain_stats(lib, ktab):
     dom = synth.make_domain(20, 10, 40, seed=17)
     init(lib, dom, ktab)

@@ -812,6 +812,35 @@ int arc_rad_host_table(const char *inline_tables, const char *sw_data_path, cons
   return n;
 }
 
+// Self-test of the branch-free division used by the solver kernels against the compiler's IEEE division, over n
+// pseudo-random operand pairs with magnitudes 1e-30 .. 1e+10 (and exact zeros as numerators).  Returns mismatches.
+__global__ void k_selftest_div(int n, unsigned seed, int *bad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  unsigned x = seed ^ (t * 2654435761u);
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; };
+  const float ea = -30.f + 40.f * (rnd() >> 8) * (1.0f / 16777216.0f), eb = -30.f + 40.f * (rnd() >> 8) * (1.0f / 16777216.0f);
+  float a = exp10f(ea) * (1.f + (rnd() >> 9) * (1.0f / 8388608.0f)), b = exp10f(eb) * (1.f + (rnd() >> 9) * (1.0f / 8388608.0f));
+  if ((rnd() & 63u) == 0u) a = 0.f;
+  if (rnd() & 1u) a = -a;
+  const float q0 = __fdiv_rn(a, b), q1 = div_rn(a, b);
+  const bool normal = q0 == 0.f || (fabsf(q0) > 1e-37f && fabsf(q0) < 1e37f);
+  if (normal && !(q0 == q1)) atomicAdd(bad, 1);     // value comparison: -0/b gives +0 here, -0 in IEEE
+}
+int arc_rad_selftest_div(int n, unsigned seed) {
+  if (!g.ready) return -1;
+  cudaSetDevice(g.device);
+  int *d; if (cudaMalloc(&d, 4) != cudaSuccess) return -1;
+  cudaMemsetAsync(d, 0, 4, g.stream);
+  k_selftest_div<<<(n + 255) / 256, 256, 0, g.stream>>>(n, seed, d);
+  count_launch();
+  int h = -1;
+  cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, g.stream);
+  cudaStreamSynchronize(g.stream);
+  cudaFree(d);
+  return h;
+}
+
 // FP32 FMA throughput of this GPU (TFLOP/s), measured with a dependent-chain-free FMA kernel: the roofline
 // denominator for the FP32-pipe-bound solver kernels (MEASURED_PEAKS.json holds no FP32 figure).
 __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters) {

@@ -22,7 +22,7 @@ struct LwEta { float speccomb, specparm, f; int j; };
 __device__ __forceinline__ LwEta lw_eta(float cola, float ratio, float colb, float mult, float oneminus) {
   LwEta e;
   e.speccomb = mul_add_rn(ratio, colb, cola);
-  e.specparm = __fdiv_rn(cola, e.speccomb);
+  e.specparm = div_rn(cola, e.speccomb);
   if (e.specparm >= oneminus) e.specparm = oneminus;
   const float specmult = __fmul_rn(mult, e.specparm);
   e.j = 1 + (int)specmult;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
     const int r = t / 59, jp = t % 59;          // jp 0-based
     const float *chi = tb.chi_mls + 7 * jp;
     const int num[6] = {0, 0, 0, 0, 3, 2}, den[6] = {1, 2, 3, 5, 1, 1};
-    s_rat[r * 60 + jp] = __fdiv_rn(chi[num[r]], chi[den[r]]);
+    s_rat[r * 60 + jp] = div_rn(chi[num[r]], chi[den[r]]);
   }
   __syncthreads();
   const int c = tile * LW_BLOCK + threadIdx.x;
@@ -99,16 +99,16 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
   // band constants (reference ratios at fixed pressure levels)
   float rp_a = 0.f, rp_b = 0.f, rm_a = 0.f, rm_b = 0.f, rm_a3 = 0.f;
   switch (band) {
-    case 3: rp_a = __fdiv_rn(CHI(1, 9), CHI(2, 9)); rp_b = __fdiv_rn(CHI(1, 13), CHI(2, 13));
-            rm_a = __fdiv_rn(CHI(1, 3), CHI(2, 3)); rm_b = __fdiv_rn(CHI(1, 13), CHI(2, 13)); break;
-    case 4: rp_a = __fdiv_rn(CHI(1, 11), CHI(2, 11)); rp_b = __fdiv_rn(CHI(3, 13), CHI(2, 13)); break;
-    case 5: rp_a = __fdiv_rn(CHI(1, 5), CHI(2, 5)); rp_b = __fdiv_rn(CHI(3, 43), CHI(2, 43)); rm_a = __fdiv_rn(CHI(1, 7), CHI(2, 7)); break;
-    case 7: rp_a = __fdiv_rn(CHI(1, 3), CHI(3, 3)); rm_a = __fdiv_rn(CHI(1, 3), CHI(3, 3)); break;
-    case 9: rp_a = __fdiv_rn(CHI(1, 9), CHI(6, 9)); rm_a = __fdiv_rn(CHI(1, 3), CHI(6, 3)); break;
-    case 12: rp_a = __fdiv_rn(CHI(1, 10), CHI(2, 10)); break;
-    case 13: rp_a = __fdiv_rn(CHI(1, 5), CHI(4, 5)); rm_a = __fdiv_rn(CHI(1, 1), CHI(4, 1)); rm_a3 = __fdiv_rn(CHI(1, 3), CHI(4, 3)); break;
-    case 15: rp_a = __fdiv_rn(CHI(4, 1), CHI(2, 1)); rm_a = __fdiv_rn(CHI(4, 1), CHI(2, 1)); break;
-    case 16: rp_a = __fdiv_rn(CHI(1, 6), CHI(6, 6)); break;
+    case 3: rp_a = div_rn(CHI(1, 9), CHI(2, 9)); rp_b = div_rn(CHI(1, 13), CHI(2, 13));
+            rm_a = div_rn(CHI(1, 3), CHI(2, 3)); rm_b = div_rn(CHI(1, 13), CHI(2, 13)); break;
+    case 4: rp_a = div_rn(CHI(1, 11), CHI(2, 11)); rp_b = div_rn(CHI(3, 13), CHI(2, 13)); break;
+    case 5: rp_a = div_rn(CHI(1, 5), CHI(2, 5)); rp_b = div_rn(CHI(3, 43), CHI(2, 43)); rm_a = div_rn(CHI(1, 7), CHI(2, 7)); break;
+    case 7: rp_a = div_rn(CHI(1, 3), CHI(3, 3)); rm_a = div_rn(CHI(1, 3), CHI(3, 3)); break;
+    case 9: rp_a = div_rn(CHI(1, 9), CHI(6, 9)); rm_a = div_rn(CHI(1, 3), CHI(6, 3)); break;
+    case 12: rp_a = div_rn(CHI(1, 10), CHI(2, 10)); break;
+    case 13: rp_a = div_rn(CHI(1, 5), CHI(4, 5)); rm_a = div_rn(CHI(1, 1), CHI(4, 1)); rm_a3 = div_rn(CHI(1, 3), CHI(4, 3)); break;
+    case 15: rp_a = div_rn(CHI(4, 1), CHI(2, 1)); rm_a = div_rn(CHI(4, 1), CHI(2, 1)); break;
+    case 16: rp_a = div_rn(CHI(1, 6), CHI(6, 6)); break;
     default: break;
   }
 
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
           atrans = odepth - 0.5f * odepth * odepth;
           const float odepth_rec = 0.166667f * odepth;
           gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
-          const float tblind = __fdiv_rn(odtot, __fadd_rn(bpade, odtot));
+          const float tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
           const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
           const float2 et = s_et[ittot];
           const float tfactot = et.y;
@@ -450,17 +450,17 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
           bbugas = plfrac * (blay + dplankup * odepth_rec);
           bbutot = plfrac * (blay + tfactot * dplankup);
         } else {
-          float tblind = __fdiv_rn(odepth, __fadd_rn(bpade, odepth));
+          float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
           const int itgas = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
           // tau_tbl(itgas) recomputed with the table generator's arithmetic (LW:7944-7950)
           if (itgas >= 10000) odepth = 1.e10f;
-          else { const float tfn = __fdiv_rn((float)itgas, 10000.0f); odepth = __fdiv_rn(__fmul_rn(bpade, tfn), __fsub_rn(1.0f, tfn)); }
+          else { const float tfn = div_rn((float)itgas, 10000.0f); odepth = div_rn(__fmul_rn(bpade, tfn), __fsub_rn(1.0f, tfn)); }
           const float2 eg = s_et[itgas];
           atrans = 1.f - eg.x;
           const float tfacgas = eg.y;
           gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
           odtot = odepth + odcld;
-          tblind = __fdiv_rn(odtot, __fadd_rn(bpade, odtot));
+          tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
           const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
           const float2 et = s_et[ittot];
           const float tfactot = et.y;
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
           bbd = plfrac * (blay + dplankdn * odepth);
           bbugas = plfrac * (blay + dplankup * odepth);
         } else {
-          const float tblind = __fdiv_rn(odepth, __fadd_rn(bpade, odepth));
+          const float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
           const int itr = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
           const float2 et = s_et[itr];
           atrans = 1.f - et.x;

@@ -44,7 +44,7 @@ __device__ __forceinline__ SwBin sw_binary(const SwLay &L, float cola, float col
                                            float oneminus) {
   SwBin b;
   b.speccomb = __fadd_rn(cola, colb_scaled);
-  float specparm = __fdiv_rn(cola, b.speccomb);
+  float specparm = div_rn(cola, b.speccomb);
   if (specparm >= oneminus) specparm = oneminus;
   const float specmult = __fmul_rn(mult, specparm);
   b.js = 1 + (int)specmult;
@@ -154,10 +154,12 @@ __device__ __forceinline__ void sw_taumol(int band, const float *__restrict__ S,
 
 // exp(-x) through the reference's Pade-indexed table (SW:2590-2600, 8445-8460): series below od_lo
 __device__ __forceinline__ float sw_expt(const float *__restrict__ exp_tbl, float x, float bpade) {
-  if (x <= 0.06f) return __fadd_rn(__fsub_rn(1.f, x), __fmul_rn(__fmul_rn(0.5f, x), x));
-  const float tblind = __fdiv_rn(x, __fadd_rn(bpade, x));
+  // both branches are evaluated and selected (the table index of a small x is valid): no divergence, more ILP
+  const float ser = __fadd_rn(__fsub_rn(1.f, x), __fmul_rn(__fmul_rn(0.5f, x), x));
+  const float tblind = div_rn(x, __fadd_rn(bpade, x));
   const int itind = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-  return exp_tbl[itind];
+  const float tab = exp_tbl[itind];
+  return x <= 0.06f ? ser : tab;
 }
 
 // Unfused IEEE single-precision operations.  reftra_sw and the optical-property mixing that feeds it are evaluated with
@@ -169,7 +171,7 @@ __device__ __forceinline__ float sw_expt(const float *__restrict__ exp_tbl, floa
 #define M_(a, b) __fmul_rn((a), (b))
 #define A_(a, b) __fadd_rn((a), (b))
 #define S_(a, b) __fsub_rn((a), (b))
-#define D_(a, b) __fdiv_rn((a), (b))
+#define D_(a, b) div_rn((a), (b))
 
 // reftra_sw (kmodts = 2, PIFM) for one layer, SW:2540-2690.  Returns (ref, refd, tra, trad).
 __device__ __noinline__ float4 sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
@@ -289,28 +291,22 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
   float sfluxzen = 0.f;
   float tdir_nodel = 1.f;     // product of the un-delta-scaled direct transmittances of the FULL stream
 
-  // Software pipeline: the workspace words of layer lay+1 are requested while layer lay is being computed, so the
-  // ~1 us DRAM/L2 latency of these (coalesced, read-once) loads hides behind one full layer of arithmetic.
+  // all workspace words of a layer are requested together at the top of the iteration (one wait per layer)
   const float *coef = ws.coef + c;
-  const size_t stf = (size_t)nlay * cap;
+  const unsigned stf = (unsigned)nlay * (unsigned)cap, ucap = (unsigned)cap;      // 32-bit offsets: SWC_N*nlay*cap < 2^31
   auto load_layer = [&](int lay, SwLay &L, int &pk, float &ta, float &om, float &as) {
-    const float *p = coef + (size_t)lay * cap;
+    const float *p = coef + (unsigned)lay * ucap;
     L.fac00 = p[SWC_FAC00 * stf]; L.fac01 = p[SWC_FAC01 * stf]; L.fac10 = p[SWC_FAC10 * stf]; L.fac11 = p[SWC_FAC11 * stf];
     L.h2o = p[SWC_H2O * stf]; L.co2 = p[SWC_CO2 * stf]; L.o3 = p[SWC_O3 * stf]; L.ch4 = p[SWC_CH4 * stf]; L.o2 = p[SWC_O2 * stf];
     L.mol = p[SWC_MOL * stf];
     L.selffac = p[SWC_SELFFAC * stf]; L.selffrac = p[SWC_SELFFRAC * stf]; L.forfac = p[SWC_FORFAC * stf]; L.forfrac = p[SWC_FORFRAC * stf];
     pk = __float_as_int(p[SWC_IDX * stf]);
-    ta = ws.aer[(((size_t)b * 3 + 0) * nlay + lay) * cap + c];
-    om = ws.aer[(((size_t)b * 3 + 1) * nlay + lay) * cap + c];
-    as = ws.aer[(((size_t)b * 3 + 2) * nlay + lay) * cap + c];
+    const float *pa = ws.aer + c + (unsigned)(b * 3) * stf + (unsigned)lay * ucap;
+    ta = pa[0]; om = pa[stf]; as = pa[2u * stf];
   };
-  SwLay Lnx; int pk_nx; float ta_nx, om_nx, as_nx;
-  load_layer(0, Lnx, pk_nx, ta_nx, om_nx, as_nx);
   for (int lay = 0; lay < nlay; lay++) {
-    SwLay L = Lnx;
-    const int pk = pk_nx;
-    const float taua = ta_nx, omga = om_nx, asya = as_nx;
-    if (lay + 1 < nlay) load_layer(lay + 1, Lnx, pk_nx, ta_nx, om_nx, as_nx);
+    SwLay L; int pk; float taua, omga, asya;
+    load_layer(lay, L, pk, taua, omga, asya);
     L.jp = IDX_JP(pk); L.jt = IDX_JT(pk); L.jt1 = IDX_JT1(pk); L.indself = IDX_SELF(pk); L.indfor = IDX_FOR(pk);
     const bool lower = lay < laytrop;
     float taug, taur, sfl = 0.f;
@@ -323,10 +319,8 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
     const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
     float taucmc = 0.f, ssacmc = 1.f, asmcmc = 0.f, taormc = 0.f;
     if (cloudy) {
-      taucmc = ws.cld[(((size_t)b * 4 + 0) * nlay + lay) * cap + c];
-      ssacmc = ws.cld[(((size_t)b * 4 + 1) * nlay + lay) * cap + c];
-      asmcmc = ws.cld[(((size_t)b * 4 + 2) * nlay + lay) * cap + c];
-      taormc = ws.cld[(((size_t)b * 4 + 3) * nlay + lay) * cap + c];
+      const float *pc = ws.cld + c + (unsigned)(b * 4) * stf + (unsigned)lay * ucap;
+      taucmc = pc[0]; ssacmc = pc[stf]; asmcmc = pc[2u * stf]; taormc = pc[3u * stf];
     }
     if (a.dbg.taucmc) a.dbg.taucmc[((size_t)ws.cols[c] * nlay + lay) * NGSW + g] = taucmc;
 
@@ -396,7 +390,7 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
   for (int s = 0; s < 4; s++) { tdbt[s] = 1.f; tdn[s] = 1.f; rdnd[s] = 0.f; }
   const int nk = ws.nk;
   float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * cap + c;
-  // pass-2 operands of one interface + the layer below it, fetched one iteration ahead (see pass 1)
+  // pass-2 operands of one interface + the layer below it, requested together
   struct Lev2 { float2 ru[4]; float4 pa, pn, pf, pc; float ea, en, ef, ec; };
   auto load_level = [&](int lev, Lev2 &V) {
 #pragma unroll
@@ -414,11 +408,9 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
     V.pf = V.pa; V.pc = V.pn; V.ef = V.ea; V.ec = V.en;
     if (cloudy) { V.pf = Pca[lay]; V.ef = Eca[lay]; if (do_clean) { V.pc = Pcn[lay]; V.ec = Ecn[lay]; } }
   };
-  Lev2 Vnx;
-  load_level(nlay, Vnx);
   for (int lev = nlay; lev >= 0; lev--) {
-    const Lev2 V = Vnx;
-    if (lev > 0) load_level(lev - 1, Vnx);
+    Lev2 V;
+    load_level(lev, V);
     // flux at interface lev
 #pragma unroll
     for (int s = 0; s < 4; s++) {
