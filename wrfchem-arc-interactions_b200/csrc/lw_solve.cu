@@ -51,42 +51,17 @@ __device__ __forceinline__ float lw_major_lower(const float *__restrict__ A, con
 }
 
 constexpr int LW_BLOCK = 512;   // 91 KB of staged tables per block: two 512-thread blocks per SM
-template <int NL>
-__global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *s_et = reinterpret_cast<float2 *>(smem_raw);                // 10002 x (exp_tbl, tfn_tbl)
-  float *S = reinterpret_cast<float *>(s_et + 10002);                 // slice
-  float *s_plk = S + SLICE_MAX;                                       // totplnk(1:181, band), padded to 184
-  float *s_rat = s_plk + 184;                                         // [6][60] chi_mls ratios by jp
-  uint64_t *bar = reinterpret_cast<uint64_t *>(s_rat + 6 * 60);
+struct LwSmem { const float2 *et; const float *S, *plk, *rat, *chi; };
 
-  // block order: band-major, then column tile, then g-point within the band (see k_sw_solve)
-  const int ntiles = (a.ncols + LW_BLOCK - 1) / LW_BLOCK;
-  int b = 0;
-  while (b < NBLW - 1 && (int)blockIdx.x >= c_lw[b + 1].g0 * ntiles) b++;
-  const LwBandDesc &D = c_lw[b];
-  const int rblk = blockIdx.x - D.g0 * ntiles;
-  const int tile = rblk / D.ng;
-  const int g = D.g0 + rblk % D.ng;
-  const int band = b + 1;
+// One (column, g-point) of band BAND: taumol + both rtrnmc calls.  BAND is a template parameter so that each band's
+// instantiation only contains (and requests up front) the workspace loads and the table arithmetic of that band.
+template <int NL, int BAND>
+__device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm, const LwBandDesc &D, int g, int c) {
+  const float2 *s_et = sm.et;
+  const float *S = sm.S, *s_plk = sm.plk, *s_rat = sm.rat, *s_chi = sm.chi;
   const DevTables &tb = a.tb;
-  {
-    StageReq req[3] = {{s_et, tb.lw_exptfn, 10002 * 8},
-                       {S, tb.lw_tab + D.slice_base + (size_t)D.slice_floats * (g - D.g0), (uint32_t)D.slice_floats * 4},
-                       {s_plk, tb.totplnk + 184 * b, 184 * 4}};
-    stage_tables(bar, req, 3);
-  }
-  // chi_mls(7,59) ratios: 0 h2o/co2, 1 h2o/o3, 2 h2o/n2o, 3 h2o/ch4, 4 n2o/co2, 5 o3/co2   (setcoef LW:3700-3760)
-  for (int t = threadIdx.x; t < 6 * 59; t += blockDim.x) {
-    const int r = t / 59, jp = t % 59;          // jp 0-based
-    const float *chi = tb.chi_mls + 7 * jp;
-    const int num[6] = {0, 0, 0, 0, 3, 2}, den[6] = {1, 2, 3, 5, 1, 1};
-    s_rat[r * 60 + jp] = div_rn(chi[num[r]], chi[den[r]]);
-  }
-  __syncthreads();
-  const int c = tile * LW_BLOCK + threadIdx.x;
-  if (c >= a.ncols) return;
-
+  constexpr int band = BAND;
+  constexpr int b = BAND - 1;
   const LwWs &ws = a.ws;
   const int nlay = ws.nlay;
   const size_t cap = ws.cap;
@@ -94,7 +69,7 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
   const bool do_clean = (a.variants & ARC_VAR_CLEAN) != 0;
   const int laytrop = ws.laytrop[c];
   const float secdiff = ws.secdiff[(size_t)b * cap + c];
-  auto CHI = [&](int imol, int jp) { return tb.chi_mls[(imol - 1) + 7 * (jp - 1)]; };   // 1-based like the reference
+  auto CHI = [&](int imol, int jp) { return s_chi[(imol - 1) + 7 * (jp - 1)]; };   // 1-based like the reference
 
   // band constants (reference ratios at fixed pressure levels)
   float rp_a = 0.f, rp_b = 0.f, rm_a = 0.f, rm_b = 0.f, rm_a3 = 0.f;
@@ -146,19 +121,29 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
     return p0 + frac * (p1 - p0);
   };
 
-  // The fields every band needs are loaded together at the top of the layer iteration (one wait per layer instead of
-  // one per field); band-specific columns are loaded at the top of the band's case.
+  // Every workspace field this band reads is requested at the top of the layer iteration (one wait per layer instead of
+  // one per field); BAND is a compile-time constant, so the other loads do not exist in this instantiation.
   constexpr unsigned COMMON = (1u << LWC_FAC00) | (1u << LWC_FAC01) | (1u << LWC_FAC10) | (1u << LWC_FAC11) | (1u << LWC_SELFFAC) |
-                              (1u << LWC_SELFFRAC) | (1u << LWC_FORFAC) | (1u << LWC_FORFRAC) | (1u << LWC_TAVEL) | (1u << LWC_TZ) | (1u << LWC_IDX);
-  float plev_carry = 0.f;
+                              (1u << LWC_SELFFRAC) | (1u << LWC_FORFAC) | (1u << LWC_FORFRAC) | (1u << LWC_TAVEL) | (1u << LWC_IDX);
+  constexpr unsigned H2O = 1u << LWC_H2O, CO2 = 1u << LWC_CO2, O3 = 1u << LWC_O3, N2O = 1u << LWC_N2O, CO = 1u << LWC_CO, CH4 = 1u << LWC_CH4,
+                     O2 = 1u << LWC_O2, BRD = 1u << LWC_BRD, MF = 1u << LWC_MINORFRAC, SM = 1u << LWC_SCALEMINOR, SN2 = 1u << LWC_SCALEMINORN2,
+                     PAV = 1u << LWC_PAVEL, DRY = 1u << LWC_COLDRY;
+  constexpr unsigned per_band[16] = {H2O | BRD | SN2 | MF | PAV, H2O | PAV, H2O | CO2 | N2O | MF | DRY, H2O | CO2 | O3, H2O | CO2 | O3 | MF | DRY,
+                                     H2O | CO2 | MF | DRY, H2O | O3 | CO2 | MF | DRY, H2O | O3 | CO2 | N2O | MF | DRY, H2O | CH4 | N2O | MF | DRY,
+                                     H2O, H2O | O2 | SM | MF, H2O | CO2, H2O | N2O | CO2 | CO | O3 | MF | DRY, CO2, N2O | CO2 | BRD | SM | MF, H2O | CH4};
+  constexpr unsigned need = COMMON | per_band[BAND - 1];
+  const unsigned ucap = (unsigned)cap, ustf = (unsigned)nlay * (unsigned)cap;     // 32-bit offsets: LWC_N*nlay*cap < 2^31
+  const float *coefc = ws.coef + c, *aerc = ws.aer + c + (unsigned)b * ustf;
+  float tz_up = coefc[(unsigned)LWC_TZ * ustf + (unsigned)(nlay - 1) * ucap];      // temperature of the interface above the layer
+  float plev_up = planck_at(tz_up);
   for (int lay = nlay - 1; lay >= 0; lay--) {
-    const float *p = ws.coef + (size_t)lay * cap + c;
+    const float *p = coefc + (unsigned)lay * ucap;
     float fv[LWC_N];
 #pragma unroll
-    for (int f = 0; f < LWC_N; f++) if ((COMMON >> f) & 1u) fv[f] = p[(size_t)f * stf];
-    const float taua = ws.aer[((size_t)b * nlay + lay) * cap + c];
-    const float tz_dn = lay > 0 ? p[(size_t)LWC_TZ * stf - cap] : ws.colf[(size_t)LWF_TZ0 * cap + c];
-    auto F = [&](int f) { return ((COMMON >> f) & 1u) ? fv[f] : p[(size_t)f * stf]; };
+    for (int f = 0; f < LWC_N; f++) fv[f] = ((need >> f) & 1u) ? p[(unsigned)f * ustf] : 0.f;
+    const float taua = aerc[(unsigned)lay * ucap];
+    const float tz_dn = lay > 0 ? p[(unsigned)LWC_TZ * ustf - ucap] : ws.colf[(size_t)LWF_TZ0 * cap + c];
+    auto F = [&](int f) { return fv[f]; };
     const int pk = __float_as_int(F(LWC_IDX));
     const int jp = IDX_JP(pk), jt = IDX_JT(pk), jt1 = IDX_JT1(pk), indself = IDX_SELF(pk), indfor = IDX_FOR(pk), indminor = IDX_MINOR(pk);
     const float fac00 = F(LWC_FAC00), fac01 = F(LWC_FAC01), fac10 = F(LWC_FAC10), fac11 = F(LWC_FAC11);
@@ -397,9 +382,7 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
 
     // ---- rtrnmc downward step for this layer (LW:3207-3300)
     const float blay = planck_at(F(LWC_TAVEL));
-    const float plev_up = lay == nlay - 1 ? planck_at(F(LWC_TZ)) : plev_carry;     // = plev_dn of the layer above
     const float plev_dn = planck_at(tz_dn);
-    plev_carry = plev_dn;
     const float dplankup = plev_up - blay, dplankdn = plev_dn - blay;
     const float plfrac = fracs;
     const bool icldlyr = (aw[lay >> 5] >> (lay & 31)) & 1u;
@@ -407,7 +390,7 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
     float odcld = 0.f, efclfrac = 0.f;
     const float cldfmc = cloudy ? 1.f : 0.f;
     if (cloudy) {
-      const float taucmc = ws.cld[((size_t)b * nlay + lay) * cap + c];
+      const float taucmc = ws.cld[(size_t)((unsigned)b * ustf + (unsigned)lay * ucap) + c];
       if (a.dbg.taucmc) a.dbg.taucmc[((size_t)(a.col0 + c) * nlay + lay) * NGLW + g] = taucmc;
       odcld = secdiff * taucmc;
       const float transcld = expf(-odcld);
@@ -495,6 +478,7 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
       part[(size_t)lay * nk * cap + (v == 0 ? oFD : oND)] = radld[v];
       if (v == 0 || do_clnc) part[(size_t)lay * nk * cap + (v == 0 ? oCD : oXD)] = radclrd[v];
     }
+    plev_up = plev_dn;
   }
   // ---- surface (LW:3303-3320)
   const float emis = ws.colf[(size_t)LWF_EMISS * cap + c];
@@ -518,19 +502,34 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
     part[v == 0 ? oFU : oNU] = radlu[v];
     if (v == 0 || do_clnc) part[v == 0 ? oCU : oXU] = radclru[v];
   }
-  // ---- upward sweep (LW:3322-3356)
-  for (int lay = 0; lay < nlay; lay++) {
-    const bool icldlyr = (aw[lay >> 5] >> (lay & 31)) & 1u;
-    const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
-    const float cldfmc = cloudy ? 1.f : 0.f;
-    const float efclfrac = Ef[lay];
+  // ---- upward sweep (LW:3322-3356); the stored layer quantities are fetched one layer ahead of their use
+  struct Up { float at[2], bg[2], ao[2], bt[2], ef; };
+  auto load_up = [&](int lay, Up &u) {
+    const bool icl = (aw[lay >> 5] >> (lay & 31)) & 1u;
+    u.ef = Ef[lay];
 #pragma unroll
     for (int v = 0; v < 2; v++) {
       if (v == 1 && !do_clean) break;
-      const float atrans = At[v][lay], bbugas = Bg[v][lay];
+      u.at[v] = At[v][lay]; u.bg[v] = Bg[v][lay];
+      if (icl) { u.ao[v] = Ao[v][lay]; u.bt[v] = Bt[v][lay]; }
+    }
+  };
+  Up unx;
+  load_up(0, unx);
+  for (int lay = 0; lay < nlay; lay++) {
+    const Up u = unx;
+    if (lay + 1 < nlay) load_up(lay + 1, unx);
+    const bool icldlyr = (aw[lay >> 5] >> (lay & 31)) & 1u;
+    const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
+    const float cldfmc = cloudy ? 1.f : 0.f;
+    const float efclfrac = u.ef;
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+      if (v == 1 && !do_clean) break;
+      const float atrans = u.at[v], bbugas = u.bg[v];
       if (icldlyr) {
         const float gassrc = bbugas * atrans;
-        radlu[v] = radlu[v] - radlu[v] * (atrans + efclfrac * (1.f - atrans)) + gassrc + cldfmc * (Bt[v][lay] * Ao[v][lay] - gassrc);
+        radlu[v] = radlu[v] - radlu[v] * (atrans + efclfrac * (1.f - atrans)) + gassrc + cldfmc * (u.bt[v] * u.ao[v] - gassrc);
       } else {
         radlu[v] = radlu[v] + (bbugas - radlu[v]) * atrans;
       }
@@ -542,7 +541,64 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
   }
 }
 
-static int lw_solve_smem() { return 10002 * 8 + (SLICE_MAX + 184 + 6 * 60) * 4 + 16; }
+template <int NL>
+__global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *s_et = reinterpret_cast<float2 *>(smem_raw);                // 10002 x (exp_tbl, tfn_tbl)
+  float *S = reinterpret_cast<float *>(s_et + 10002);                 // slice
+  float *s_plk = S + SLICE_MAX;                                       // totplnk(1:181, band), padded to 184
+  float *s_rat = s_plk + 184;                                         // [6][60] chi_mls ratios by jp
+  float *s_chi = s_rat + 6 * 60;                                      // chi_mls(7,59)
+  uint64_t *bar = reinterpret_cast<uint64_t *>(s_chi + 416);
+
+  // block order: band-major, then column tile, then g-point within the band (see k_sw_solve)
+  const int ntiles = (a.ncols + LW_BLOCK - 1) / LW_BLOCK;
+  int b = 0;
+  while (b < NBLW - 1 && (int)blockIdx.x >= c_lw[b + 1].g0 * ntiles) b++;
+  const LwBandDesc &D = c_lw[b];
+  const int rblk = blockIdx.x - D.g0 * ntiles;
+  const int tile = rblk / D.ng;
+  const int g = D.g0 + rblk % D.ng;
+  const DevTables &tb = a.tb;
+  {
+    StageReq req[3] = {{s_et, tb.lw_exptfn, 10002 * 8},
+                       {S, tb.lw_tab + D.slice_base + (size_t)D.slice_floats * (g - D.g0), (uint32_t)D.slice_floats * 4},
+                       {s_plk, tb.totplnk + 184 * b, 184 * 4}};
+    stage_tables(bar, req, 3);
+  }
+  // chi_mls(7,59) ratios: 0 h2o/co2, 1 h2o/o3, 2 h2o/n2o, 3 h2o/ch4, 4 n2o/co2, 5 o3/co2   (setcoef LW:3700-3760)
+  for (int t = threadIdx.x; t < 6 * 59; t += blockDim.x) {
+    const int r = t / 59, jp = t % 59;          // jp 0-based
+    const float *chi = tb.chi_mls + 7 * jp;
+    const int num[6] = {0, 0, 0, 0, 3, 2}, den[6] = {1, 2, 3, 5, 1, 1};
+    s_rat[r * 60 + jp] = div_rn(chi[num[r]], chi[den[r]]);
+  }
+  for (int t = threadIdx.x; t < 7 * 59; t += blockDim.x) s_chi[t] = tb.chi_mls[t];
+  __syncthreads();
+  const int c = tile * LW_BLOCK + threadIdx.x;
+  if (c >= a.ncols) return;
+  const LwSmem sm{s_et, S, s_plk, s_rat, s_chi};
+  switch (b) {
+    case 0: lw_solve_band<NL, 1>(a, sm, D, g, c); break;
+    case 1: lw_solve_band<NL, 2>(a, sm, D, g, c); break;
+    case 2: lw_solve_band<NL, 3>(a, sm, D, g, c); break;
+    case 3: lw_solve_band<NL, 4>(a, sm, D, g, c); break;
+    case 4: lw_solve_band<NL, 5>(a, sm, D, g, c); break;
+    case 5: lw_solve_band<NL, 6>(a, sm, D, g, c); break;
+    case 6: lw_solve_band<NL, 7>(a, sm, D, g, c); break;
+    case 7: lw_solve_band<NL, 8>(a, sm, D, g, c); break;
+    case 8: lw_solve_band<NL, 9>(a, sm, D, g, c); break;
+    case 9: lw_solve_band<NL, 10>(a, sm, D, g, c); break;
+    case 10: lw_solve_band<NL, 11>(a, sm, D, g, c); break;
+    case 11: lw_solve_band<NL, 12>(a, sm, D, g, c); break;
+    case 12: lw_solve_band<NL, 13>(a, sm, D, g, c); break;
+    case 13: lw_solve_band<NL, 14>(a, sm, D, g, c); break;
+    case 14: lw_solve_band<NL, 15>(a, sm, D, g, c); break;
+    default: lw_solve_band<NL, 16>(a, sm, D, g, c); break;
+  }
+}
+
+static int lw_solve_smem() { return 10002 * 8 + (SLICE_MAX + 184 + 6 * 60 + 416) * 4 + 16; }
 
 void launch_lw_solve(const LwArgs &a, cudaStream_t s) {
   static bool attr = false;
