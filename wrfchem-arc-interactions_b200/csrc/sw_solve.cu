@@ -408,7 +408,6 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
     V.pf = V.pa; V.pc = V.pn; V.ef = V.ea; V.ec = V.en;
     if (cloudy) { V.pf = Pca[lay]; V.ef = Eca[lay]; if (do_clean) { V.pc = Pcn[lay]; V.ec = Ecn[lay]; } }
   };
-#pragma unroll 2
   for (int lev = nlay; lev >= 0; lev--) {
     Lev2 V;
     load_level(lev, V);
