@@ -211,11 +211,11 @@ def test_chunking_and_determinism(lib, ktab):
     init(lib, dom, ktab)
     a_sw, a_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
     b_sw, b_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
-    os.environ["ARC_RAD_CHUNK"] = "256"
+    os.environ["ARC_RAD_CHUNK"] = "256"; os.environ["ARC_RAD_OUTER"] = "512"
     try:
         c_sw, c_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
     finally:
-        del os.environ["ARC_RAD_CHUNK"]
+        del os.environ["ARC_RAD_CHUNK"]; del os.environ["ARC_RAD_OUTER"]
     for k in a_sw:
         assert np.array_equal(a_sw[k], b_sw[k]) and np.array_equal(a_sw[k], c_sw[k]), k
     for k in a_lw:

@@ -67,11 +67,20 @@ int upload(const T *h, size_t n, const T **d) {
 }
 int upload_vec(const std::vector<float> &v, const float **d) { return upload(v.data(), v.size(), d); }
 
+// Two chunk levels: the per-column / per-layer workspace is sized for an outer chunk (ARC_RAD_OUTER, default 262144
+// columns: the column-parallel McICA and prep kernels need that many threads to fill the GPU) and the much larger partial
+// flux buffer (~0.2 MB per column) for an inner chunk (ARC_RAD_CHUNK, default 32768 columns).
 size_t chunk_cap_default() {
   const char *e = getenv("ARC_RAD_CHUNK");
   long v = e ? atol(e) : 32768;
   if (v < 256) v = 256;
   return (size_t)((v + 255) / 256 * 256);
+}
+size_t outer_cap_default() {
+  const char *e = getenv("ARC_RAD_OUTER");
+  long v = e ? atol(e) : 262144;
+  if (v < 256) v = 256;
+  return std::max(chunk_cap_default(), (size_t)((v + 255) / 256 * 256));
 }
 
 struct Carver {
@@ -86,7 +95,7 @@ struct Carver {
 
 void carve_sw(SwWs &w, char *base, size_t &bytes) {
   Carver c{base};
-  const size_t cap = w.cap, nl = w.nlay;
+  const size_t cap = w.cap, pcap = w.pcap, nl = w.nlay;
   w.coef = c.take<float>((size_t)SWC_N * nl * cap);
   w.aer = c.take<float>((size_t)NBSW * 3 * nl * cap);
   w.cld = c.take<float>((size_t)NBSW * 4 * nl * cap);
@@ -95,13 +104,13 @@ void carve_sw(SwWs &w, char *base, size_t &bytes) {
   w.laytrop = c.take<int>(cap);
   w.laysol = c.take<int>((size_t)NBSW * cap);
   w.colf = c.take<float>((size_t)SWF_N * cap);
-  w.part = c.take<float>((size_t)NGSW * (nl + 1) * w.nk * cap);
-  w.dirs = c.take<float>((size_t)NGSW * cap);
+  w.part = c.take<float>((size_t)NGSW * (nl + 1) * w.nk * pcap);
+  w.dirs = c.take<float>((size_t)NGSW * pcap);
   bytes = c.off;
 }
 void carve_lw(LwWs &w, char *base, size_t &bytes) {
   Carver c{base};
-  const size_t cap = w.cap, nl = w.nlay;
+  const size_t cap = w.cap, pcap = w.pcap, nl = w.nlay;
   w.coef = c.take<float>((size_t)LWC_N * nl * cap);
   w.aer = c.take<float>((size_t)NBLW * nl * cap);
   w.cld = c.take<float>((size_t)NBLW * nl * cap);
@@ -110,7 +119,7 @@ void carve_lw(LwWs &w, char *base, size_t &bytes) {
   w.laytrop = c.take<int>(cap);
   w.colf = c.take<float>((size_t)LWF_N * cap);
   w.secdiff = c.take<float>((size_t)NBLW * cap);
-  w.part = c.take<float>((size_t)NGLW * (nl + 1) * w.nk * cap);
+  w.part = c.take<float>((size_t)NGLW * (nl + 1) * w.nk * pcap);
   bytes = c.off;
 }
 
@@ -124,8 +133,8 @@ template <class WS> void set_kinds(WS &w, int variants) {
   w.nk = n;
 }
 
-int ensure_sw_ws(int nlay, size_t cap, int variants) {
-  SwWs w{}; w.cap = (int)cap; w.nlay = nlay; w.W = (nlay + 31) / 32; set_kinds(w, variants);
+int ensure_sw_ws(int nlay, size_t cap, size_t pcap, int variants) {
+  SwWs w{}; w.cap = (int)cap; w.pcap = (int)pcap; w.nlay = nlay; w.W = (nlay + 31) / 32; set_kinds(w, variants);
   size_t need; carve_sw(w, nullptr, need);
   if (need > g.sw_bytes) {
     if (g.sw_arena) cudaFree(g.sw_arena);
@@ -137,8 +146,8 @@ int ensure_sw_ws(int nlay, size_t cap, int variants) {
   g.sw = w;
   return 0;
 }
-int ensure_lw_ws(int nlay, size_t cap, int variants) {
-  LwWs w{}; w.cap = (int)cap; w.nlay = nlay; w.W = (nlay + 31) / 32; set_kinds(w, variants);
+int ensure_lw_ws(int nlay, size_t cap, size_t pcap, int variants) {
+  LwWs w{}; w.cap = (int)cap; w.pcap = (int)pcap; w.nlay = nlay; w.W = (nlay + 31) / 32; set_kinds(w, variants);
   size_t need; carve_lw(w, nullptr, need);
   if (need > g.lw_bytes) {
     if (g.lw_arena) cudaFree(g.lw_arena);
@@ -567,24 +576,32 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   CK(cudaMemcpyAsync(&nsun, g.d_count, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   if (nsun > 0) {
-    const size_t cap = std::min(chunk_cap_default(), (size_t)((nsun + 255) / 256 * 256));
-    if ((rc = ensure_sw_ws(nlay, cap, variants))) return rc;
-    for (int c0 = 0; c0 < nsun; c0 += (int)cap) {
-      const int nc = std::min((int)cap, nsun - c0);
+    const size_t cap = std::min(outer_cap_default(), (size_t)((nsun + 255) / 256 * 256));
+    const size_t pcap = std::min(chunk_cap_default(), cap);
+    if ((rc = ensure_sw_ws(nlay, cap, pcap, variants))) return rc;
+    for (int o0 = 0; o0 < nsun; o0 += (int)cap) {
+      const int no = std::min((int)cap, nsun - o0);
       a.ws = g.sw;
-      a.ws.cols = g.d_cols + c0;
-      a.ncols = nc;
+      a.ws.cols = g.d_cols + o0;
+      a.ncols = no;
       McicaArgs m{};
-      m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGSW; m.permuteseed = 1; m.ncols = nc; m.W = a.ws.W; m.icloud = in->icloud;
+      m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGSW; m.permuteseed = 1; m.ncols = no; m.W = a.ws.W; m.icloud = in->icloud;
       m.cap = (int)cap; m.col0 = 0; m.lw_buffer = 0; m.cols = a.ws.cols; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
       m.mask = a.ws.mask; m.anyc = a.ws.anyc;
       { Timed t("sw_mcica"); launch_mcica(m, g.stream); }
       { Timed t("sw_prep"); launch_sw_prep(a, g.stream); }
-      { Timed t("sw_solve"); launch_sw_solve(a, g.stream); }
-      { Timed t("sw_reduce"); launch_sw_reduce(a, g.stream); }
       if (a.dbg.cldmask) {
-        k_unpack_mask<<<(nc + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, a.ws.cols, 0, nc, (int)cap, a.ws.W, nlay, NGSW, a.dbg.cldmask);
+        k_unpack_mask<<<(no + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, a.ws.cols, 0, no, (int)cap, a.ws.W, nlay, NGSW, a.dbg.cldmask);
         count_launch();
+      }
+      // inner chunks: column-indexed workspace pointers advance by c0, the partial buffers restart at 0
+      for (int c0 = 0; c0 < no; c0 += (int)pcap) {
+        SwArgs b = a;
+        b.ncols = std::min((int)pcap, no - c0);
+        b.ws.cols += c0; b.ws.coef += c0; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0;
+        b.ws.laytrop += c0; b.ws.laysol += c0; b.ws.colf += c0;
+        { Timed t("sw_solve"); launch_sw_solve(b, g.stream); }
+        { Timed t("sw_reduce"); launch_sw_reduce(b, g.stream); }
       }
     }
   }
@@ -673,25 +690,33 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   if ((rc = setup_debug(dbg, (size_t)G.ncol_tile, nlay, NGLW, a.dbg, dbglist))) return rc;
 
   const int ncol = G.ncol_tile;
-  const size_t cap = std::min(chunk_cap_default(), (size_t)((ncol + 255) / 256 * 256));
-  if ((rc = ensure_lw_ws(nlay, cap, variants))) return rc;
-  for (int c0 = 0; c0 < ncol; c0 += (int)cap) {
-    const int nc = std::min((int)cap, ncol - c0);
+  const size_t cap = std::min(outer_cap_default(), (size_t)((ncol + 255) / 256 * 256));
+  const size_t pcap = std::min(chunk_cap_default(), cap);
+  if ((rc = ensure_lw_ws(nlay, cap, pcap, variants))) return rc;
+  for (int o0 = 0; o0 < ncol; o0 += (int)cap) {
+    const int no = std::min((int)cap, ncol - o0);
     a.ws = g.lw;
     a.ws.cols = nullptr;
-    a.col0 = c0;
-    a.ncols = nc;
+    a.col0 = o0;
+    a.ncols = no;
     McicaArgs m{};
-    m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGLW; m.permuteseed = 150; m.ncols = nc; m.W = a.ws.W; m.icloud = in->icloud;
-    m.cap = (int)cap; m.col0 = c0; m.lw_buffer = 1; m.cols = nullptr; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
+    m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGLW; m.permuteseed = 150; m.ncols = no; m.W = a.ws.W; m.icloud = in->icloud;
+    m.cap = (int)cap; m.col0 = o0; m.lw_buffer = 1; m.cols = nullptr; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
     m.mask = a.ws.mask; m.anyc = a.ws.anyc;
     { Timed t("lw_mcica"); launch_mcica(m, g.stream); }
     { Timed t("lw_prep"); launch_lw_prep(a, g.stream); }
-    { Timed t("lw_solve"); launch_lw_solve(a, g.stream); }
-    { Timed t("lw_reduce"); launch_lw_reduce(a, g.stream); }
     if (a.dbg.cldmask) {
-      k_unpack_mask<<<(nc + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, nullptr, c0, nc, (int)cap, a.ws.W, nlay, NGLW, a.dbg.cldmask);
+      k_unpack_mask<<<(no + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, nullptr, o0, no, (int)cap, a.ws.W, nlay, NGLW, a.dbg.cldmask);
       count_launch();
+    }
+    for (int c0 = 0; c0 < no; c0 += (int)pcap) {
+      LwArgs b = a;
+      b.ncols = std::min((int)pcap, no - c0);
+      b.col0 = o0 + c0;
+      b.ws.coef += c0; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0; b.ws.laytrop += c0; b.ws.colf += c0;
+      b.ws.secdiff += c0;
+      { Timed t("lw_solve"); launch_lw_solve(b, g.stream); }
+      { Timed t("lw_reduce"); launch_lw_reduce(b, g.stream); }
     }
   }
   return finish_call(dbglist);

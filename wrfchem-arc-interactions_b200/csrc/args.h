@@ -47,7 +47,8 @@ enum { SWC_FAC00 = 0, SWC_FAC01, SWC_FAC10, SWC_FAC11, SWC_H2O, SWC_CO2, SWC_O3,
 enum { SWF_MU0 = 0, SWF_ALBDIR_NIR, SWF_ALBDIF_NIR, SWF_ALBDIR_UV, SWF_ALBDIF_UV, SWF_ADJFLUX, SWF_N };
 
 struct SwWs {
-  int cap;                 // column stride (chunk capacity)
+  int cap;                 // column stride of the per-column / per-layer workspace (outer chunk capacity)
+  int pcap;                // column stride of the partial-flux buffers (inner chunk capacity)
   int nlay;                // kte-kts+2
   int W;                   // mask words per (g, column)
   int *cols;               // [cap] tile column id of each chunk column
@@ -94,7 +95,7 @@ enum { LWC_FAC00 = 0, LWC_FAC01, LWC_FAC10, LWC_FAC11, LWC_H2O, LWC_CO2, LWC_O3,
 enum { LWF_TZ0 = 0, LWF_TBOUND, LWF_EMISS, LWF_N };
 
 struct LwWs {
-  int cap, nlay, W;
+  int cap, pcap, nlay, W;
   int *cols;               // nullable (identity)
   float *coef;             // [LWC_N][nlay][cap]
   float *aer;              // [16][nlay][cap]

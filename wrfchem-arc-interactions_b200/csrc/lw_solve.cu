@@ -103,14 +103,15 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
   const size_t stf = (size_t)nlay * cap;
   const int nk = ws.nk;
   const bool do_clnc = (a.variants & ARC_VAR_CLEANCLEAR) != 0;
-  float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * cap + c;
-  const size_t oFU = (size_t)ws.kslot[K_FU] * cap, oFD = (size_t)ws.kslot[K_FD] * cap, oCU = (size_t)ws.kslot[K_CU] * cap,
-               oCD = (size_t)ws.kslot[K_CD] * cap, oNU = (size_t)ws.kslot[K_NU] * cap, oND = (size_t)ws.kslot[K_ND] * cap,
-               oXU = (size_t)ws.kslot[K_XU] * cap, oXD = (size_t)ws.kslot[K_XD] * cap;
+  const size_t pcap = ws.pcap;
+  float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * pcap + c;
+  const size_t oFU = (size_t)ws.kslot[K_FU] * pcap, oFD = (size_t)ws.kslot[K_FD] * pcap, oCU = (size_t)ws.kslot[K_CU] * pcap,
+               oCD = (size_t)ws.kslot[K_CD] * pcap, oNU = (size_t)ws.kslot[K_NU] * pcap, oND = (size_t)ws.kslot[K_ND] * pcap,
+               oXU = (size_t)ws.kslot[K_XU] * pcap, oXD = (size_t)ws.kslot[K_XD] * pcap;
   // TOA downward radiance is zero
-  part[(size_t)nlay * nk * cap + oFD] = 0.f; part[(size_t)nlay * nk * cap + oCD] = 0.f;
-  if (do_clean) part[(size_t)nlay * nk * cap + oND] = 0.f;
-  if (do_clnc) part[(size_t)nlay * nk * cap + oXD] = 0.f;
+  part[(size_t)nlay * nk * pcap + oFD] = 0.f; part[(size_t)nlay * nk * pcap + oCD] = 0.f;
+  if (do_clean) part[(size_t)nlay * nk * pcap + oND] = 0.f;
+  if (do_clnc) part[(size_t)nlay * nk * pcap + oXD] = 0.f;
 
   // Planck function at the top interface of the current layer; carried downwards
   auto planck_at = [&](float t) {
@@ -475,8 +476,8 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
       At[v][lay] = atrans; Bg[v][lay] = bbugas;
       if (iclddn == 1) radclrd[v] = radclrd[v] + (bbd - radclrd[v]) * atrans;
       else radclrd[v] = radld[v];
-      part[(size_t)lay * nk * cap + (v == 0 ? oFD : oND)] = radld[v];
-      if (v == 0 || do_clnc) part[(size_t)lay * nk * cap + (v == 0 ? oCD : oXD)] = radclrd[v];
+      part[(size_t)lay * nk * pcap + (v == 0 ? oFD : oND)] = radld[v];
+      if (v == 0 || do_clnc) part[(size_t)lay * nk * pcap + (v == 0 ? oCD : oXD)] = radclrd[v];
     }
     plev_up = plev_dn;
   }
@@ -535,8 +536,8 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
       }
       if (iclddn == 1) radclru[v] = radclru[v] + (bbugas - radclru[v]) * atrans;
       else radclru[v] = radlu[v];
-      part[(size_t)(lay + 1) * nk * cap + (v == 0 ? oFU : oNU)] = radlu[v];
-      if (v == 0 || do_clnc) part[(size_t)(lay + 1) * nk * cap + (v == 0 ? oCU : oXU)] = radclru[v];
+      part[(size_t)(lay + 1) * nk * pcap + (v == 0 ? oFU : oNU)] = radlu[v];
+      if (v == 0 || do_clnc) part[(size_t)(lay + 1) * nk * pcap + (v == 0 ? oCU : oXU)] = radclru[v];
     }
   }
 }
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(RED_CX * RED_LY) k_lw_reduce(LwArgs a) {
   const Geo &G = a.geo;
   const LwWs &ws = a.ws;
   const int nlay = ws.nlay, nz = G.kte - G.kts + 1;
-  const size_t cap = ws.cap;
+  const size_t cap = ws.pcap;      // the reduce only touches the partial buffer
   const bool active = c < a.ncols;
   const int tc = a.col0 + c;
   int i = 0, j = 0; size_t ij = 0;

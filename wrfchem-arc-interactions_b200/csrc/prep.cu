@@ -10,6 +10,8 @@
 //   mcica_subcol_sw/generate_stochastic_clouds_sw/kissvec SW:1392-1932 (LW twins LW:2089-2618),
 //   RRTMG_LWRAD LW:11877-12629, inatm LW:11067-11403, setcoef LW:3444-3809, cldprmc LW:2653-2914,
 //   taumol_sw's laysolfr selection SW:3293-4538.
+#include <vector>
+
 #include "adapter.cuh"
 #include "../../include/arc_rad.h"
 
@@ -119,24 +121,28 @@ void launch_sw_night(const SwArgs &a, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------------
 // McICA masks: generate_stochastic_clouds(_sw) with icld = 2 (maximum-random), irng = 0 (kissvec).
-// One thread per column runs the serial KISS chain (sub-column major, layer minor: SW:1745-1750) and applies
-// the maximum-random overlap rescale (SW:1762-1772) on the fly -- the rescale of layer l only needs the final
-// value of layer l-1 of the same sub-column, which precedes it in the chain.
-constexpr int MCICA_MAXLAY = 160;
+//
+// The reference draws one serial KISS chain per column (sub-column major, layer minor: SW:1745-1750), 112*nlay or
+// 140*nlay steps.  Here every (column, sub-column) thread JUMPS to its own position in that chain and then draws its nlay
+// numbers, which is exact because each of the four KISS sub-generators has a closed-form k-step map:
+//   s1  LCG x -> 69069 x + 1327217885 (mod 2^32):        x_k = A_k x + C_k (mod 2^32)
+//   s2  xorshift (13, -17, 5), linear over GF(2):        x_k = M_k x, M_k stored as the 32 images of the unit vectors
+//   s3  multiply-with-carry x -> 18000 (x & 65535) + (x >> 16): with m = 18000*2^16 - 1, 18000*2^16 = 1 (mod m) gives
+//       x_{n+1} = 18000 x_n (mod m) as integers in [0, m), so x_k = x_0 * 18000^k mod m    (seeds are < 1e9 < m)
+//   s4  the same with 30903.
+// The per-sub-column constants (A, C, M[32], J3, J4) are built on the host for k = permuteseed + g*nlay.
+// The maximum-random rescale (SW:1762-1772) only couples layers of the same sub-column, so it is applied on the fly.
+struct KissJump { uint32_t A, C, J3, J4, M[32]; };
+static KissJump *g_jump[2] = {nullptr, nullptr};
+static int g_jump_key[2][3] = {{0, 0, 0}, {0, 0, 0}};
 
-__global__ void __launch_bounds__(128) k_mcica(McicaArgs a) {
+__global__ void __launch_bounds__(256) k_mcica(McicaArgs a, const KissJump *__restrict__ jump) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
   if (c >= a.ncols) return;
   const int tc = a.cols ? a.cols[c] : a.col0 + c;
   int i, j; a.geo.ij(tc, i, j);
   const int kts = a.geo.kts;
-  float omc[MCICA_MAXLAY];      // 1 - cldf(l)
-  for (int l = 0; l < a.nlay; l++) {
-    float cf = 0.f;
-    if (l < a.nz && a.icloud != 0 && a.cldfra3d) cf = a.cldfra3d[a.geo.at3(i, kts + l, j)];
-    if (cf < 1.0e-20f) cf = 0.f;
-    omc[l] = 1.0f - cf;
-  }
   Kiss K;
   {
     float pm[4];
@@ -144,35 +150,72 @@ __global__ void __launch_bounds__(128) k_mcica(McicaArgs a) {
       float play = a.p3d[a.geo.at3(i, kts + l, j)] / 100.f;       // p1d = p3d/100 ; play = p1d
       pm[l] = play * 1.e2f;                                        // pmid = play*1.e2
     }
-    K.s1 = (uint32_t)(int32_t)((pm[0] - (float)(int)pm[0]) * 1000000000.f);
-    K.s2 = (uint32_t)(int32_t)((pm[1] - (float)(int)pm[1]) * 1000000000.f);
-    K.s3 = (uint32_t)(int32_t)((pm[2] - (float)(int)pm[2]) * 1000000000.f);
-    K.s4 = (uint32_t)(int32_t)((pm[3] - (float)(int)pm[3]) * 1000000000.f);
+    const uint32_t s1 = (uint32_t)(int32_t)((pm[0] - (float)(int)pm[0]) * 1000000000.f);
+    const uint32_t s2 = (uint32_t)(int32_t)((pm[1] - (float)(int)pm[1]) * 1000000000.f);
+    const uint32_t s3 = (uint32_t)(int32_t)((pm[2] - (float)(int)pm[2]) * 1000000000.f);
+    const uint32_t s4 = (uint32_t)(int32_t)((pm[3] - (float)(int)pm[3]) * 1000000000.f);
+    const KissJump &J = jump[g];
+    K.s1 = J.A * s1 + J.C;
+    uint32_t x = 0u;
+#pragma unroll
+    for (int b = 0; b < 32; b++) x ^= ((s2 >> b) & 1u) ? J.M[b] : 0u;
+    K.s2 = x;
+    K.s3 = (uint32_t)(((unsigned long long)s3 * J.J3) % 1179647999ull);     // 18000 * 65536 - 1
+    K.s4 = (uint32_t)(((unsigned long long)s4 * J.J4) % 2025259007ull);     // 30903 * 65536 - 1
   }
-  for (int q = 0; q < a.permuteseed; q++) (void)K.next();
-  uint32_t any[MCICA_MAXLAY / 32];
-  for (int w = 0; w < a.W; w++) any[w] = 0u;
-  for (int g = 0; g < a.ngpt; g++) {
-    float prev = 0.f;
-    uint32_t word = 0u;
-    for (int l = 0; l < a.nlay; l++) {
-      float x = K.next();
-      if (l > 0) {
-        if (prev > omc[l - 1]) x = prev; else x = x * omc[l - 1];
-      }
-      prev = x;
-      if (x >= omc[l]) word |= 1u << (l & 31);
-      if ((l & 31) == 31 || l == a.nlay - 1) {
-        a.mask[((size_t)g * a.W + (l >> 5)) * a.cap + c] = word;
-        any[l >> 5] |= word;
-        word = 0u;
-      }
+  float prev = 0.f, omc_prev = 1.f;
+  uint32_t word = 0u;
+  for (int l = 0; l < a.nlay; l++) {
+    float cf = 0.f;
+    if (l < a.nz && a.icloud != 0 && a.cldfra3d) cf = a.cldfra3d[a.geo.at3(i, kts + l, j)];
+    if (cf < 1.0e-20f) cf = 0.f;
+    const float omc = 1.0f - cf;
+    float x = K.next();
+    if (l > 0) {
+      if (prev > omc_prev) x = prev; else x = x * omc_prev;
+    }
+    prev = x; omc_prev = omc;
+    if (x >= omc) word |= 1u << (l & 31);
+    if ((l & 31) == 31 || l == a.nlay - 1) {
+      a.mask[((size_t)g * a.W + (l >> 5)) * a.cap + c] = word;
+      if (word) atomicOr(&a.anyc[(size_t)(l >> 5) * a.cap + c], word);
+      word = 0u;
     }
   }
-  for (int w = 0; w < a.W; w++) a.anyc[(size_t)w * a.cap + c] = any[w];
 }
+
+static void build_jump_table(int which, int nlay, int ngpt, int permuteseed) {
+  if (g_jump[which] && g_jump_key[which][0] == nlay && g_jump_key[which][1] == ngpt && g_jump_key[which][2] == permuteseed) return;
+  std::vector<KissJump> T(ngpt);
+  const unsigned long long m3 = 1179647999ull, m4 = 2025259007ull;
+  // transform after k steps, advanced incrementally: start with k = permuteseed, then + nlay per sub-column
+  uint32_t A = 1u, C = 0u, M[32];
+  unsigned long long J3 = 1ull, J4 = 1ull;
+  for (int b = 0; b < 32; b++) M[b] = 1u << b;
+  auto advance = [&](int steps) {
+    for (int q = 0; q < steps; q++) {
+      A = 69069u * A; C = 69069u * C + 1327217885u;
+      for (int b = 0; b < 32; b++) { uint32_t x = M[b]; x ^= x << 13; x ^= x >> 17; x ^= x << 5; M[b] = x; }
+      J3 = (J3 * 18000ull) % m3; J4 = (J4 * 30903ull) % m4;
+    }
+  };
+  advance(permuteseed);
+  for (int gq = 0; gq < ngpt; gq++) {
+    T[gq].A = A; T[gq].C = C; T[gq].J3 = (uint32_t)J3; T[gq].J4 = (uint32_t)J4;
+    for (int b = 0; b < 32; b++) T[gq].M[b] = M[b];
+    advance(nlay);
+  }
+  if (!g_jump[which]) cudaMalloc(&g_jump[which], sizeof(KissJump) * 160);
+  cudaMemcpy(g_jump[which], T.data(), sizeof(KissJump) * ngpt, cudaMemcpyHostToDevice);
+  g_jump_key[which][0] = nlay; g_jump_key[which][1] = ngpt; g_jump_key[which][2] = permuteseed;
+}
+
 void launch_mcica(const McicaArgs &a, cudaStream_t s) {
-  k_mcica<<<(a.ncols + 127) / 128, 128, 0, s>>>(a);
+  const int which = a.lw_buffer ? 1 : 0;
+  build_jump_table(which, a.nlay, a.ngpt, a.permuteseed);
+  cudaMemsetAsync(a.anyc, 0, sizeof(uint32_t) * (size_t)a.W * a.cap, s);
+  dim3 grid((a.ncols + 255) / 256, a.ngpt);
+  k_mcica<<<grid, 256, 0, s>>>(a, g_jump[which]);
   count_launch();
 }
 

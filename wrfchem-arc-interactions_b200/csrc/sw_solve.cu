@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
 #pragma unroll
   for (int s = 0; s < 4; s++) { tdbt[s] = 1.f; tdn[s] = 1.f; rdnd[s] = 0.f; }
   const int nk = ws.nk;
-  float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * cap + c;
+  const size_t pcap = ws.pcap;
+  float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * pcap + c;
   // pass-2 operands of one interface + the layer below it, requested together
   struct Lev2 { float2 ru[4]; float4 pa, pn, pf, pc; float ea, en, ef, ec; };
   auto load_level = [&](int lev, Lev2 &V) {
@@ -422,8 +423,8 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
       const float fu = __fmul_rn(fmaf(tdbt[s], ru, __fmul_rn(dif, rud)), zreflect);
       const float fd = fmaf(fmaf(__fmul_rn(tdbt[s], ru), rdnd[s], dif), zreflect, tdbt[s]);
       const int ku = s == 0 ? K_CU : s == 1 ? K_FU : s == 2 ? K_NU : K_XU;
-      part[((size_t)lev * nk + ws.kslot[ku]) * cap] = __fmul_rn(zincflx, fu);
-      part[((size_t)lev * nk + ws.kslot[ku + 1]) * cap] = __fmul_rn(zincflx, fd);
+      part[((size_t)lev * nk + ws.kslot[ku]) * pcap] = __fmul_rn(zincflx, fu);
+      part[((size_t)lev * nk + ws.kslot[ku + 1]) * pcap] = __fmul_rn(zincflx, fd);
     }
     if (lev == 0) break;
 #pragma unroll
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
       tdbt[s] = __fmul_rn(e, tdbt[s]);
     }
   }
-  ws.dirs[(size_t)g * cap + c] = __fmul_rn(zincflx, tdir_nodel);
+  ws.dirs[(size_t)g * pcap + c] = __fmul_rn(zincflx, tdir_nodel);
 }
 
 static int sw_solve_smem() { return (10004 + SLICE_MAX) * 4 + 16; }
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(RED_CX * RED_LY) k_sw_reduce(SwArgs a) {
   const Geo &G = a.geo;
   const SwWs &ws = a.ws;
   const int nlay = ws.nlay, nz = nlay - 1;
-  const size_t cap = ws.cap;
+  const size_t cap = ws.pcap;      // the reduce only touches the partial buffers
   const bool active = c < a.ncols;
   const bool do_clean = (a.variants & ARC_VAR_CLEAN) != 0;
   const bool do_clnc = (a.variants & ARC_VAR_CLEANCLEAR) != 0;
