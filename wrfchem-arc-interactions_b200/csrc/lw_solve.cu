@@ -619,8 +619,8 @@ void launch_lw_solve(const LwArgs &a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------------
 // Reduction: per band sum over its g-points in order, x wtdiff x delwave, sum over bands, x fluxfac
 // (LW:3365-3395); heating rates (LW:3397-3408); scatter (LW:12646-12692).  Block = 32 columns x 8 level-lanes.
-constexpr int RED_CX = 64, RED_LY = 8;
-__global__ void __launch_bounds__(RED_CX * RED_LY) k_lw_reduce(LwArgs a) {
+constexpr int RED_CX = 64, RED_LY = 4;
+__global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_lw_reduce(LwArgs a) {
   __shared__ float s_net[161][RED_CX];
   const int cx = threadIdx.x, ly = threadIdx.y;
   const int c = blockIdx.x * RED_CX + cx;
@@ -637,9 +637,9 @@ __global__ void __launch_bounds__(RED_CX * RED_LY) k_lw_reduce(LwArgs a) {
   const int nk = ws.nk;
   const bool do_clnc = (a.variants & ARC_VAR_CLEANCLEAR) != 0;
   const size_t gstride = (size_t)(nlay + 1) * nk * cap;
-  const size_t oFU = (size_t)ws.kslot[K_FU] * cap, oFD = (size_t)ws.kslot[K_FD] * cap, oCU = (size_t)ws.kslot[K_CU] * cap,
-               oCD = (size_t)ws.kslot[K_CD] * cap, oNU = (size_t)ws.kslot[K_NU] * cap, oND = (size_t)ws.kslot[K_ND] * cap,
-               oXU = (size_t)ws.kslot[K_XU] * cap, oXD = (size_t)ws.kslot[K_XD] * cap;
+  const unsigned ucap = (unsigned)cap;       // 32-bit kind offsets: nk * pcap < 2^31
+  const unsigned oFU = ws.kslot[K_FU] * ucap, oFD = ws.kslot[K_FD] * ucap, oCU = ws.kslot[K_CU] * ucap, oCD = ws.kslot[K_CD] * ucap,
+                 oNU = ws.kslot[K_NU] * ucap, oND = ws.kslot[K_ND] * ucap, oXU = ws.kslot[K_XU] * ucap, oXD = ws.kslot[K_XD] * ucap;
   for (int lev = ly; lev <= nlay && active; lev += RED_LY) {
     float tot[NKIND];
 #pragma unroll
@@ -650,6 +650,7 @@ __global__ void __launch_bounds__(RED_CX * RED_LY) k_lw_reduce(LwArgs a) {
 #pragma unroll
       for (int k = 0; k < NKIND; k++) r[k] = 0.f;
       const int ng = c_lw[b].ng;
+#pragma unroll 4
       for (int q = 0; q < ng; q++, p += gstride) {
         r[K_FU] = r[K_FU] + p[oFU]; r[K_FD] = r[K_FD] + p[oFD];
         r[K_CU] = r[K_CU] + p[oCU]; r[K_CD] = r[K_CD] + p[oCD];

@@ -466,8 +466,8 @@ void launch_sw_solve(const SwArgs &a, cudaStream_t s) {
 // rates (SW:9391-9434) and scatter to the WRF arrays (SW:11125-11172).  Block = 32 columns x 8 level-lanes; a thread sums
 // the 112 partials of its (column, level) sequentially, net fluxes meet in shared memory for the heating rates.  All
 // partial-buffer reads are 128-byte coalesced over columns.
-constexpr int RED_CX = 64, RED_LY = 8;
-__global__ void __launch_bounds__(RED_CX * RED_LY) k_sw_reduce(SwArgs a) {
+constexpr int RED_CX = 64, RED_LY = 4;
+__global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_sw_reduce(SwArgs a) {
   __shared__ float s_net[161][RED_CX];
   const int cx = threadIdx.x, ly = threadIdx.y;
   const int c = blockIdx.x * RED_CX + cx;
@@ -488,9 +488,10 @@ __global__ void __launch_bounds__(RED_CX * RED_LY) k_sw_reduce(SwArgs a) {
     const int nk = ws.nk;
     const float *p = ws.part + ((size_t)lev * nk) * cap + c;
     const size_t gstride = (size_t)(nlay + 1) * nk * cap;
-    const size_t oFU = (size_t)ws.kslot[K_FU] * cap, oFD = (size_t)ws.kslot[K_FD] * cap, oCU = (size_t)ws.kslot[K_CU] * cap,
-                 oCD = (size_t)ws.kslot[K_CD] * cap, oNU = (size_t)ws.kslot[K_NU] * cap, oND = (size_t)ws.kslot[K_ND] * cap,
-                 oXU = (size_t)ws.kslot[K_XU] * cap, oXD = (size_t)ws.kslot[K_XD] * cap;
+    const unsigned ucap = (unsigned)cap;       // 32-bit kind offsets: nk * pcap < 2^31
+    const unsigned oFU = ws.kslot[K_FU] * ucap, oFD = ws.kslot[K_FD] * ucap, oCU = ws.kslot[K_CU] * ucap, oCD = ws.kslot[K_CD] * ucap,
+                   oNU = ws.kslot[K_NU] * ucap, oND = ws.kslot[K_ND] * ucap, oXU = ws.kslot[K_XU] * ucap, oXD = ws.kslot[K_XD] * ucap;
+#pragma unroll 4
     for (int g = 0; g < NGSW; g++, p += gstride) {
       f[K_FU] = f[K_FU] + p[oFU];
       const float fd = p[oFD];
