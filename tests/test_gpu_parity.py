@@ -222,6 +222,33 @@ def test_chunking_and_determinism(lib, ktab):
         assert np.array_equal(a_lw[k], b_lw[k]) and np.array_equal(a_lw[k], c_lw[k]), k
 
 
+@pytest.mark.parametrize("halo", [0, 2])
+def test_pipelined_host_path_is_bit_identical(lib, ktab, halo):
+    """Host arrays go through j-slab pipelining (upload / compute / download overlapped); results, including every cell the
+    call must leave untouched (night columns, halo, levels above kte), equal the unpipelined path bit for bit."""
+    dom = synth.make_domain(24, 12, 40, seed=19, halo=halo)
+    init(lib, dom, ktab)
+
+    def run(slab_cols):
+        os.environ["ARC_RAD_SLAB_COLUMNS"] = str(slab_cols)
+        try:
+            outs = {}
+            for which in ("sw", "lw"):
+                o = R.alloc_outputs(dom, which)
+                for k in o:
+                    o[k][:] = -555.0
+                outs[which] = run_pair(which, lib, dom, outs=o)
+            return outs
+        finally:
+            del os.environ["ARC_RAD_SLAB_COLUMNS"]
+    ref, pip, pip2 = run(0), run(24 * 5), run(24)          # off, 5-row slabs (3 slabs, ragged last), 1-row slabs
+    for which in ("sw", "lw"):
+        for k in ref[which]:
+            assert np.array_equal(ref[which][k], pip[which][k], equal_nan=True), (which, k)
+            assert np.array_equal(ref[which][k], pip2[which][k], equal_nan=True), (which, k)
+    assert (ref["sw"]["swupt"] == -555.0).any() == (halo > 0)
+
+
 def test_device_memspace_equals_host_memspace(lib, ktab):
     import torch
     dom = synth.make_domain(16, 8, 40, seed=14)

@@ -40,9 +40,14 @@ struct Ctx {
   std::vector<Slot> pool; size_t pool_next = 0;
   struct Back { void *host; void *dev; size_t bytes; };
   std::vector<Back> backs;
+  // pipelined host path: copy streams, events and two staging sets
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  std::vector<Slot> slab[2];
   // timing
   std::vector<EvPair> evs; size_t ev_next = 0;
   std::map<std::string, float> last_ms;
+  bool keep_ms = false;        // pipelined path: accumulate kernel times over the slabs of one call
   std::string err;
 };
 Ctx g;
@@ -342,6 +347,171 @@ void fill_cloud(CloudFields &cf, int memspace, int &rc, int icloud, int warm_rai
   for (int q = 0; q < 3 && !rc; q++) rc = in_arr(memspace, p2[q], n2, dst2[q]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined host path.  With host arrays the tile is cut into j-slabs (in (i,k,j) order a row range of every field is one
+// contiguous block): while slab s computes, slab s+1 is uploaded on a second stream and the outputs of slab s-1 are
+// downloaded on a third, through two staging sets.  Each slab runs the ordinary device-memory entry point on staged
+// copies whose memory bounds are the slab's rows.  Output arrays are INOUT in the reference (night columns, halo cells and
+// levels above kte keep the caller's values): an output is uploaded first only if the call can leave some of its
+// staged cells unwritten; otherwise exactly the written sub-block comes back through a strided copy.
+enum FieldKind { F3 = 0, F2 = 1, FP = 2 };
+struct FieldRef { size_t off; int kind; bool partial; };     // partial: some tile cells may stay unwritten (SW night)
+#define FIN(T, f, k) {offsetof(T, f), k, false}
+static const FieldRef SW_INS[] = {
+    FIN(ArcSwIn, t3d, F3), FIN(ArcSwIn, t8w, F3), FIN(ArcSwIn, p3d, F3), FIN(ArcSwIn, p8w, F3), FIN(ArcSwIn, pi3d, F3),
+    FIN(ArcSwIn, cldfra3d, F3), FIN(ArcSwIn, lradius, F3), FIN(ArcSwIn, iradius, F3), FIN(ArcSwIn, qv3d, F3), FIN(ArcSwIn, qc3d, F3),
+    FIN(ArcSwIn, qr3d, F3), FIN(ArcSwIn, qi3d, F3), FIN(ArcSwIn, qs3d, F3), FIN(ArcSwIn, qndrop3d, F3), FIN(ArcSwIn, o33d, F3),
+    FIN(ArcSwIn, re_cloud, F3), FIN(ArcSwIn, re_ice, F3), FIN(ArcSwIn, re_snow, F3), FIN(ArcSwIn, f_ice_phy, F3),
+    FIN(ArcSwIn, tauaer300, F3), FIN(ArcSwIn, tauaer400, F3), FIN(ArcSwIn, tauaer600, F3), FIN(ArcSwIn, tauaer999, F3),
+    FIN(ArcSwIn, gaer400, F3), FIN(ArcSwIn, gaer600, F3), FIN(ArcSwIn, waer400, F3), FIN(ArcSwIn, waer600, F3),
+    FIN(ArcSwIn, xcoszen, F2), FIN(ArcSwIn, albedo, F2), FIN(ArcSwIn, tsk, F2), FIN(ArcSwIn, xland, F2), FIN(ArcSwIn, xice, F2),
+    FIN(ArcSwIn, snow, F2), FIN(ArcSwIn, alswvisdir, F2), FIN(ArcSwIn, alswvisdif, F2), FIN(ArcSwIn, alswnirdir, F2), FIN(ArcSwIn, alswnirdif, F2)};
+// inputs the kernels never read: staged as aliases of a neighbour so the "missing field" checks still see them
+static const size_t SW_ALIAS[][2] = {{offsetof(ArcSwIn, gaer300), offsetof(ArcSwIn, gaer400)}, {offsetof(ArcSwIn, gaer999), offsetof(ArcSwIn, gaer400)},
+                                     {offsetof(ArcSwIn, waer300), offsetof(ArcSwIn, waer400)}, {offsetof(ArcSwIn, waer999), offsetof(ArcSwIn, waer400)}};
+#define FOUT(T, f, k, part) {offsetof(T, f), k, part}
+static const FieldRef SW_OUTS[] = {
+    FOUT(ArcSwOut, rthratensw, F3, true), FOUT(ArcSwOut, gsw, F2, true), FOUT(ArcSwOut, swcf, F2, false), FOUT(ArcSwOut, coszr, F2, false),
+    FOUT(ArcSwOut, swupt, F2, false), FOUT(ArcSwOut, swuptc, F2, false), FOUT(ArcSwOut, swuptcln, F2, false), FOUT(ArcSwOut, swdnt, F2, false),
+    FOUT(ArcSwOut, swdntc, F2, false), FOUT(ArcSwOut, swdntcln, F2, false), FOUT(ArcSwOut, swupb, F2, false), FOUT(ArcSwOut, swupbc, F2, false),
+    FOUT(ArcSwOut, swupbcln, F2, false), FOUT(ArcSwOut, swdnb, F2, false), FOUT(ArcSwOut, swdnbc, F2, false), FOUT(ArcSwOut, swdnbcln, F2, false),
+    FOUT(ArcSwOut, swvisdir, F2, false), FOUT(ArcSwOut, swvisdif, F2, false), FOUT(ArcSwOut, swnirdir, F2, false), FOUT(ArcSwOut, swnirdif, F2, false),
+    FOUT(ArcSwOut, swddir, F2, false), FOUT(ArcSwOut, swddni, F2, false), FOUT(ArcSwOut, swddif, F2, false),
+    FOUT(ArcSwOut, swupflx, FP, true), FOUT(ArcSwOut, swupflxc, FP, true), FOUT(ArcSwOut, swupflxcln, FP, true),
+    FOUT(ArcSwOut, swdnflx, FP, true), FOUT(ArcSwOut, swdnflxc, FP, true), FOUT(ArcSwOut, swdnflxcln, FP, true),
+    FOUT(ArcSwOut, swuptclnc, F2, false), FOUT(ArcSwOut, swdntclnc, F2, false), FOUT(ArcSwOut, swupbclnc, F2, false), FOUT(ArcSwOut, swdnbclnc, F2, false)};
+static const FieldRef LW_INS[] = {
+    FIN(ArcLwIn, p8w, F3), FIN(ArcLwIn, p3d, F3), FIN(ArcLwIn, pi3d, F3), FIN(ArcLwIn, t3d, F3), FIN(ArcLwIn, t8w, F3),
+    FIN(ArcLwIn, cldfra3d, F3), FIN(ArcLwIn, lradius, F3), FIN(ArcLwIn, iradius, F3), FIN(ArcLwIn, qv3d, F3), FIN(ArcLwIn, qc3d, F3),
+    FIN(ArcLwIn, qr3d, F3), FIN(ArcLwIn, qi3d, F3), FIN(ArcLwIn, qs3d, F3), FIN(ArcLwIn, qndrop3d, F3), FIN(ArcLwIn, o33d, F3),
+    FIN(ArcLwIn, re_cloud, F3), FIN(ArcLwIn, re_ice, F3), FIN(ArcLwIn, re_snow, F3), FIN(ArcLwIn, f_ice_phy, F3),
+    FIN(ArcLwIn, tauaerlw[0], F3), FIN(ArcLwIn, tauaerlw[1], F3), FIN(ArcLwIn, tauaerlw[2], F3), FIN(ArcLwIn, tauaerlw[3], F3),
+    FIN(ArcLwIn, tauaerlw[4], F3), FIN(ArcLwIn, tauaerlw[5], F3), FIN(ArcLwIn, tauaerlw[6], F3), FIN(ArcLwIn, tauaerlw[7], F3),
+    FIN(ArcLwIn, tauaerlw[8], F3), FIN(ArcLwIn, tauaerlw[9], F3), FIN(ArcLwIn, tauaerlw[10], F3), FIN(ArcLwIn, tauaerlw[11], F3),
+    FIN(ArcLwIn, tauaerlw[12], F3), FIN(ArcLwIn, tauaerlw[13], F3), FIN(ArcLwIn, tauaerlw[14], F3), FIN(ArcLwIn, tauaerlw[15], F3),
+    FIN(ArcLwIn, emiss, F2), FIN(ArcLwIn, tsk, F2), FIN(ArcLwIn, xland, F2), FIN(ArcLwIn, xice, F2), FIN(ArcLwIn, snow, F2)};
+static const FieldRef LW_OUTS[] = {
+    FOUT(ArcLwOut, rthratenlw, F3, false), FOUT(ArcLwOut, glw, F2, false), FOUT(ArcLwOut, olr, F2, false), FOUT(ArcLwOut, lwcf, F2, false),
+    FOUT(ArcLwOut, lwupt, F2, false), FOUT(ArcLwOut, lwuptc, F2, false), FOUT(ArcLwOut, lwuptcln, F2, false), FOUT(ArcLwOut, lwdnt, F2, false),
+    FOUT(ArcLwOut, lwdntc, F2, false), FOUT(ArcLwOut, lwdntcln, F2, false), FOUT(ArcLwOut, lwupb, F2, false), FOUT(ArcLwOut, lwupbc, F2, false),
+    FOUT(ArcLwOut, lwupbcln, F2, false), FOUT(ArcLwOut, lwdnb, F2, false), FOUT(ArcLwOut, lwdnbc, F2, false), FOUT(ArcLwOut, lwdnbcln, F2, false),
+    FOUT(ArcLwOut, lwupflx, FP, false), FOUT(ArcLwOut, lwupflxc, FP, false), FOUT(ArcLwOut, lwupflxcln, FP, false),
+    FOUT(ArcLwOut, lwdnflx, FP, false), FOUT(ArcLwOut, lwdnflxc, FP, false), FOUT(ArcLwOut, lwdnflxcln, FP, false),
+    FOUT(ArcLwOut, lwuptclnc, F2, false), FOUT(ArcLwOut, lwdntclnc, F2, false), FOUT(ArcLwOut, lwupbclnc, F2, false), FOUT(ArcLwOut, lwdnbclnc, F2, false)};
+
+template <class T> static inline const float *&fld(T &st, size_t off) { return *reinterpret_cast<const float **>(reinterpret_cast<char *>(&st) + off); }
+template <class T> static inline float *&fldw(T &st, size_t off) { return *reinterpret_cast<float **>(reinterpret_cast<char *>(&st) + off); }
+
+static int slab_slot(int set, size_t idx, size_t bytes, void **d) {
+  if (g.slab[set].size() <= idx) g.slab[set].resize(idx + 1);
+  Ctx::Slot &s = g.slab[set][idx];
+  if (s.bytes < bytes) {
+    if (s.d) cudaFree(s.d);
+    s.d = nullptr; s.bytes = 0;
+    CK(cudaMalloc(&s.d, bytes));
+    s.bytes = bytes;
+  }
+  *d = s.d;
+  return 0;
+}
+
+static int slab_rows_default(int nrows, int ni) {
+  const char *e = getenv("ARC_RAD_SLAB_COLUMNS");
+  long cols = e ? atol(e) : 16384;
+  if (cols <= 0) return nrows;                  // 0: pipelining off
+  long r = std::max(1L, cols / std::max(ni, 1));
+  return (int)std::min<long>(r, nrows);
+}
+
+// IN / OUT = the C structs; `call` runs the device-memory entry point.  Returns -1 when the call is not eligible.
+template <class IN, class OUT, class CALL>
+static int run_pipelined(const ArcDims &d, const IN &in, OUT &out, const FieldRef *ins, int nins, const FieldRef *outs, int nouts,
+                         const size_t (*alias)[2], int nalias, CALL call) {
+  const int nrows = d.jte - d.jts + 1;
+  const int ni = d.ime - d.ims + 1, nk = d.kme - d.kms + 1;
+  const int rows_per = slab_rows_default(nrows, d.ite - d.its + 1);
+  if (rows_per >= nrows) return -1;
+  const int nslab = (nrows + rows_per - 1) / rows_per;
+  const bool ihalo = d.its != d.ims || d.ite != d.ime;
+  const int nz = d.kte - d.kts + 1;
+  const size_t row3 = (size_t)ni * nk, row2 = (size_t)ni, rowp = (size_t)ni * (nk + 2);
+  auto rowsz = [&](int kind) { return kind == F3 ? row3 : kind == F2 ? row2 : rowp; };
+  CK(cudaSetDevice(g.device));
+
+  auto upload = [&](int s) -> int {
+    const int set = s & 1;
+    const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1), nr = j1 - j0 + 1;
+    CK(cudaStreamWaitEvent(g.h2d, g.ev_out[set], 0));          // the previous user of this set has been downloaded
+    size_t idx = 0;
+    for (int f = 0; f < nins; f++, idx++) {
+      const float *h = fld(const_cast<IN &>(in), ins[f].off);
+      if (!h) continue;
+      const size_t rs = rowsz(ins[f].kind);
+      void *dv; int rc = slab_slot(set, idx, (size_t)rows_per * rs * 4, &dv); if (rc) return rc;
+      CK(cudaMemcpyAsync(dv, h + (size_t)(j0 - d.jms) * rs, (size_t)nr * rs * 4, cudaMemcpyHostToDevice, g.h2d));
+    }
+    for (int f = 0; f < nouts; f++, idx++) {
+      float *h = fldw(out, outs[f].off);
+      if (!h) continue;
+      const size_t rs = rowsz(outs[f].kind);
+      void *dv; int rc = slab_slot(set, idx, (size_t)rows_per * rs * 4, &dv); if (rc) return rc;
+      if (ihalo || outs[f].partial)
+        CK(cudaMemcpyAsync(dv, h + (size_t)(j0 - d.jms) * rs, (size_t)nr * rs * 4, cudaMemcpyHostToDevice, g.h2d));
+    }
+    CK(cudaEventRecord(g.ev_in[set], g.h2d));
+    return 0;
+  };
+  auto download = [&](int s) -> int {
+    const int set = s & 1;
+    const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1), nr = j1 - j0 + 1;
+    size_t idx = nins;
+    for (int f = 0; f < nouts; f++, idx++) {
+      float *h = fldw(out, outs[f].off);
+      if (!h) continue;
+      const size_t rs = rowsz(outs[f].kind);
+      const float *dv = (const float *)g.slab[set][idx].d;
+      float *hd = h + (size_t)(j0 - d.jms) * rs;
+      if (ihalo || outs[f].partial || outs[f].kind == F2) {
+        CK(cudaMemcpyAsync(hd, dv, (size_t)nr * rs * 4, cudaMemcpyDeviceToHost, g.d2h));
+      } else {
+        // exactly the written levels of every row: kts..kte (3-D tendency) or kts..kte+2 (flux profile)
+        const size_t lev0 = (size_t)(d.kts - d.kms) * ni, nlev = (size_t)(outs[f].kind == F3 ? nz : nz + 2) * ni;
+        CK(cudaMemcpy2DAsync(hd + lev0, rs * 4, dv + lev0, rs * 4, nlev * 4, nr, cudaMemcpyDeviceToHost, g.d2h));
+      }
+    }
+    CK(cudaEventRecord(g.ev_out[set], g.d2h));
+    return 0;
+  };
+
+  int rc = upload(0);
+  if (rc) return rc;
+  int status = 0;
+  for (int s = 0; s < nslab; s++) {
+    const int set = s & 1;
+    if (s + 1 < nslab && (rc = upload(s + 1))) return rc;
+    const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1);
+    ArcDims ds = d;
+    ds.jms = j0; ds.jme = j1; ds.jts = j0; ds.jte = j1;
+    IN din = in; OUT dout = out;
+    din.memspace = ARC_MEM_DEVICE;
+    size_t idx = 0;
+    for (int f = 0; f < nins; f++, idx++) if (fld(din, ins[f].off)) fld(din, ins[f].off) = (const float *)g.slab[set][idx].d;
+    for (int f = 0; f < nouts; f++, idx++) if (fldw(dout, outs[f].off)) fldw(dout, outs[f].off) = (float *)g.slab[set][idx].d;
+    for (int q = 0; q < nalias; q++) if (fld(din, alias[q][0])) fld(din, alias[q][0]) = fld(din, alias[q][1]);
+    CK(cudaStreamWaitEvent(g.stream, g.ev_in[set], 0));
+    g.keep_ms = s > 0;
+    rc = call(ds, din, dout);                  // synchronises g.stream before returning
+    g.keep_ms = false;
+    if (rc && !status) status = rc;
+    if ((rc = download(s))) return rc;
+    if (status) break;
+  }
+  CK(cudaStreamSynchronize(g.d2h));
+  CK(cudaStreamSynchronize(g.h2d));
+  return status;
+}
+
 }  // namespace
 
 extern "C" {
@@ -366,6 +536,16 @@ void arc_rad_finalize(void) {
   g.sw_arena = g.lw_arena = nullptr; g.sw_bytes = g.lw_bytes = 0;
   for (auto &s : g.pool) if (s.d) cudaFree(s.d);
   g.pool.clear();
+  for (int q = 0; q < 2; q++) {
+    for (auto &s : g.slab[q]) if (s.d) cudaFree(s.d);
+    g.slab[q].clear();
+    if (g.ev_in[q]) cudaEventDestroy(g.ev_in[q]);
+    if (g.ev_out[q]) cudaEventDestroy(g.ev_out[q]);
+    g.ev_in[q] = g.ev_out[q] = nullptr;
+  }
+  if (g.h2d) cudaStreamDestroy(g.h2d);
+  if (g.d2h) cudaStreamDestroy(g.d2h);
+  g.h2d = g.d2h = nullptr;
   if (g.d_cols) cudaFree(g.d_cols);
   g.d_cols = nullptr; g.cols_cap = 0;
   if (g.d_status) cudaFree(g.d_status);
@@ -395,6 +575,9 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
   if (cfg->device >= 0) { CK(cudaSetDevice(cfg->device)); g.device = cfg->device; }
   else CK(cudaGetDevice(&g.device));
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g.h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g.d2h, cudaStreamNonBlocking));
+  for (int q = 0; q < 2; q++) { CK(cudaEventCreateWithFlags(&g.ev_in[q], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.ev_out[q], cudaEventDisableTiming)); }
   CK(cudaMalloc(&g.d_status, sizeof(int)));
   CK(cudaMalloc(&g.d_count, sizeof(int)));
 
@@ -467,6 +650,12 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   if (!d || !in || !out) { g.err = "arc_rad_sw: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
   if (rc) return rc;
+  if (in->memspace == ARC_MEM_HOST && !dbg && !in->tauaer3d_sw) {
+    rc = run_pipelined(*d, *in, *out, SW_INS, (int)(sizeof(SW_INS) / sizeof(FieldRef)), SW_OUTS, (int)(sizeof(SW_OUTS) / sizeof(FieldRef)),
+                       SW_ALIAS, 4, [](const ArcDims &ds, const ArcSwIn &di, ArcSwOut &dout) { return arc_rad_sw_debug(&ds, &di, &dout, nullptr); });
+    if (rc != -1) return rc;
+    rc = 0;
+  }
   // argument checks of the reference (SW:10288-10305, chemics_init.F:406-408)
   if (in->aer_ra_feedback == 1 &&
       !(in->tauaer300 && in->tauaer400 && in->tauaer600 && in->tauaer999 && in->gaer300 && in->gaer400 && in->gaer600 &&
@@ -498,7 +687,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
     g.err = "arc_rad_sw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG;
   }
   CK(cudaSetDevice(g.device));
-  for (auto it = g.last_ms.begin(); it != g.last_ms.end();) { if (it->first.compare(0, 3, "sw_") == 0) it = g.last_ms.erase(it); else ++it; }
+  if (!g.keep_ms) for (auto it = g.last_ms.begin(); it != g.last_ms.end();) { if (it->first.compare(0, 3, "sw_") == 0) it = g.last_ms.erase(it); else ++it; }
   g.pool_next = 0; g.backs.clear();
   const int ms = in->memspace;
   SwArgs a{};
@@ -616,6 +805,12 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   if (!d || !in || !out) { g.err = "arc_rad_lw: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
   if (rc) return rc;
+  if (in->memspace == ARC_MEM_HOST && !dbg) {
+    rc = run_pipelined(*d, *in, *out, LW_INS, (int)(sizeof(LW_INS) / sizeof(FieldRef)), LW_OUTS, (int)(sizeof(LW_OUTS) / sizeof(FieldRef)),
+                       nullptr, 0, [](const ArcDims &ds, const ArcLwIn &di, ArcLwOut &dout) { return arc_rad_lw_debug(&ds, &di, &dout, nullptr); });
+    if (rc != -1) return rc;
+    rc = 0;
+  }
   if (in->aer_ra_feedback == 1)
     for (int b = 0; b < 16; b++)
       if (!in->tauaerlw[b]) { g.err = "Warning: missing fields required for aerosol radiation"; return ARC_ERR_MISSING_FIELD; }
@@ -638,7 +833,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
     g.err = "arc_rad_lw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG;
   }
   CK(cudaSetDevice(g.device));
-  for (auto it = g.last_ms.begin(); it != g.last_ms.end();) { if (it->first.compare(0, 3, "lw_") == 0) it = g.last_ms.erase(it); else ++it; }
+  if (!g.keep_ms) for (auto it = g.last_ms.begin(); it != g.last_ms.end();) { if (it->first.compare(0, 3, "lw_") == 0) it = g.last_ms.erase(it); else ++it; }
   g.pool_next = 0; g.backs.clear();
   const int ms = in->memspace;
   LwArgs a{};
