@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU arm: target seconds per step")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--clean", type=int, default=1, help="clean_atm_diag (1: full+clear+clean, 0: full+clear only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -187,7 +188,7 @@ def main():
     L.arc_rad_driver_post.restype = C.c_int
     L.arc_rad_driver_post.argtypes = [C.POINTER(abi.ArcDims), C.c_int] + [abi.c_fp] * 6
     nlay_lw = lib.lw_nlayers()
-    flags = R.common_flags(dom)
+    flags = R.common_flags(dom, clean_atm_diag=args.clean)
     dims = abi.make_dims(dom["dims"])
 
     # ---- device-resident arm --------------------------------------------------------------------------------
@@ -324,7 +325,7 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %dx%d columns x %d levels per GPU (SW %d / LW %d layers), 4-wavelength aerosol optics in, 40%% cloudy, 25%% night columns, clean_atm_diag=1, all six flux profiles out" % (args.workload, ni, nj, nk, nk + 1, nlay_lw),
+        "config": {"workload": "%s: %dx%d columns x %d levels per GPU (SW %d / LW %d layers), 4-wavelength aerosol optics in, 40%% cloudy, 25%% night columns, clean_atm_diag=%d, all six flux profiles out" % (args.workload, ni, nj, nk, nk + 1, nlay_lw, args.clean),
                    "l2": "inputs (%.0f MB) and workspaces exceed the 126 MB L2" % (sum(v.nbytes for v in dom.values() if isinstance(v, np.ndarray)) / 1e6),
                    "columns_per_gpu": ncol, "sunlit_columns": nsun, "partition": "j-slabs, one tile per rank; NCCL all-reduce of 24x5 domain statistics per step" if world > 1 else "single tile"},
         "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
