@@ -202,6 +202,48 @@ int  arc_rad_selftest_div(int n, unsigned seed);
 /* FP32 FMA throughput of the device in TFLOP/s (microbenchmark; roofline denominator of the solver kernels) */
 float arc_rad_measure_fp32_tflops(void);
 
+/* --------------------------------------------------------------------------------------------
+ * Aerosol optical properties: optical_averaging -> optical_prep_sectional / optical_prep_modal -> mieaer of WRF-Chem
+ * v3.9.1 chem/module_optical_averaging.F.  That module is NOT part of the reference repository (only its outputs are
+ * consumed: module_radiation_driver.F:113-124, Registry/registry.chem:1332-1390), so this stage restates the published
+ * algorithm and is self-consistent only.  Output arrays are exactly the inputs of arc_rad_sw /
+ * arc_rad_lw: tauaer300..999, gaer*, waer*, tauaerlw1..16 (+ extaerlw1..16 in 1/km).                               */
+#define ARC_AER_MAXBIN   8
+#define ARC_AER_MAXSPEC 24
+#define ARC_AER_SECTIONAL 1   /* MOSAIC 4 or 8 size sections (aer_op_opt volume_approx)              */
+#define ARC_AER_MODAL     2   /* MADE/SORGAM: 3 log-normal modes mapped onto 8 sections              */
+/* species classes (density, refractive index): */
+enum { ARC_CLS_SO4 = 0, ARC_CLS_NO3, ARC_CLS_CL, ARC_CLS_NH4, ARC_CLS_NA, ARC_CLS_OIN, ARC_CLS_OC, ARC_CLS_BC, ARC_CLS_WATER, ARC_CLS_N };
+
+typedef struct ArcAerIn {
+  int memspace;
+  int mode;                                  /* ARC_AER_SECTIONAL / ARC_AER_MODAL */
+  int nbin;                                  /* sections (4 or 8) or modes (3) */
+  int nspec[ARC_AER_MAXBIN];                 /* species per section / mode */
+  int cls[ARC_AER_MAXBIN][ARC_AER_MAXSPEC];  /* class of each species */
+  const float *mass[ARC_AER_MAXBIN][ARC_AER_MAXSPEC];   /* chem(i,k,j,l): ug/kg-dryair */
+  const float *num[ARC_AER_MAXBIN];          /* #/kg-dryair */
+  float sigmag[ARC_AER_MAXBIN];              /* modal: geometric standard deviation of each mode (1.7, 2.0, 2.5) */
+  const float *alt, *dz8w;                   /* inverse density m3/kg, layer thickness m (i,k,j) */
+} ArcAerIn;
+
+typedef struct ArcAerOut {
+  float *tauaer[4], *gaer[4], *waer[4];      /* 300, 400, 600, 999 nm */
+  float *tauaerlw[16];
+  float *extaerlw[16];                       /* optional, 1/km */
+} ArcAerOut;
+
+/* refr / refi: [ARC_CLS_N][20] species refractive indices n + i k at the 4 SW wavelengths then the 16 LW band centres
+ * (module_data_rrtmgaeropt.F in WRF-Chem); NULL selects the built-in representative values. Builds the Chebyshev-Mie tables. */
+int  arc_aer_init(const float *refr, const float *refi);
+/* copies the built-in refractive indices ([ARC_CLS_N][20] each); host only, no GPU needed */
+void arc_aer_default_refindex(float *refr, float *refi);
+int  arc_aer_optics(const ArcDims *d, const ArcAerIn *in, ArcAerOut *out);
+/* test taps (host): Chebyshev-interpolated Q_ext, Q_sca, g of one sphere through the same tables (CPU evaluation of the
+ * uploaded coefficients) and direct Mie theory for comparison */
+int  arc_aer_table_eval(int wl, float radius_cm, float refr, float refi, float *qext, float *qsca, float *g);
+int  arc_aer_mie_direct(int wl, float radius_cm, float refr, float refi, float *qext, float *qsca, float *g);
+
 /* Kernel launch counter (number of this library's CUDA kernels launched since init) */
 long long arc_rad_launch_count(void);
 /* CUDA stream used for all work (cudaStream_t as void*), for event timing by the caller */

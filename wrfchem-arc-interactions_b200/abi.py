@@ -93,6 +93,21 @@ class ArcDebug(C.Structure):
                 [(n, c_fp) for n in DBG_F2])
 
 
+ARC_AER_MAXBIN, ARC_AER_MAXSPEC = 8, 24
+ARC_AER_SECTIONAL, ARC_AER_MODAL = 1, 2
+AER_CLASSES = ("so4", "no3", "cl", "nh4", "na", "oin", "oc", "bc", "water")
+
+
+class ArcAerIn(C.Structure):
+    _fields_ = [("memspace", C.c_int), ("mode", C.c_int), ("nbin", C.c_int), ("nspec", C.c_int * ARC_AER_MAXBIN),
+                ("cls", (C.c_int * ARC_AER_MAXSPEC) * ARC_AER_MAXBIN), ("mass", (c_fp * ARC_AER_MAXSPEC) * ARC_AER_MAXBIN),
+                ("num", c_fp * ARC_AER_MAXBIN), ("sigmag", C.c_float * ARC_AER_MAXBIN), ("alt", c_fp), ("dz8w", c_fp)]
+
+
+class ArcAerOut(C.Structure):
+    _fields_ = [("tauaer", c_fp * 4), ("gaer", c_fp * 4), ("waer", c_fp * 4), ("tauaerlw", c_fp * 16), ("extaerlw", c_fp * 16)]
+
+
 def fptr(a):
     """float* of a numpy float32 C-contiguous array, an int (device address) or None."""
     if a is None:

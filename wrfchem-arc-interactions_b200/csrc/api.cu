@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/arc_rad.h"
+#include "aer.h"
 #include "args.h"
 
 using namespace arc;
@@ -553,6 +554,7 @@ void arc_rad_finalize(void) {
   g.d_status = g.d_count = nullptr;
   for (auto &e : g.evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   g.evs.clear();
+  aer_finalize();
   if (g.stream) cudaStreamDestroy(g.stream);
   g.stream = nullptr;
   g.ready = false;
@@ -1059,6 +1061,117 @@ int arc_rad_selftest_div(int n, unsigned seed) {
   cudaStreamSynchronize(g.stream);
   cudaFree(d);
   return h;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+void arc_aer_default_refindex(float *refr, float *refi) {
+  float a[AER_NCLASS][AER_NWL], b[AER_NCLASS][AER_NWL];
+  default_refindex(a, b);
+  if (refr) memcpy(refr, a, sizeof(a));
+  if (refi) memcpy(refi, b, sizeof(b));
+}
+
+int arc_aer_init(const float *refr, const float *refi) {
+  if (!g.ready) { g.err = "arc_aer_init: call arc_rad_init first"; return ARC_ERR_NOT_INIT; }
+  CK(cudaSetDevice(g.device));
+  return aer_init(refr, refi, g.err);
+}
+
+int arc_aer_optics(const ArcDims *d, const ArcAerIn *in, ArcAerOut *out) {
+  if (!g.ready) { g.err = "arc_aer_optics: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !in || !out) { g.err = "arc_aer_optics: null argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if (in->mode != ARC_AER_SECTIONAL && in->mode != ARC_AER_MODAL) { g.err = "arc_aer_optics: unknown mode"; return ARC_ERR_BAD_ARG; }
+  if (in->nbin < 1 || in->nbin > ARC_AER_MAXBIN || !in->alt || !in->dz8w) { g.err = "arc_aer_optics: bad nbin / missing alt, dz8w"; return ARC_ERR_BAD_ARG; }
+  CK(cudaSetDevice(g.device));
+  if (!aer_ready() && (rc = aer_init(nullptr, nullptr, g.err))) return rc;
+  g.pool_next = 0; g.backs.clear();
+  const int ms = in->memspace;
+  AerArgs a{};
+  a.geo = make_geo(*d);
+  const Geo &G = a.geo;
+  const size_t n3 = G.n3();
+  const int nz = d->kte - d->kts + 1;
+  a.npts = G.ncol_tile * nz;
+  a.nsec = in->mode == ARC_AER_SECTIONAL ? in->nbin : 8;
+  AerSpecList sl{};
+  sl.mode = in->mode; sl.nbin = in->nbin;
+  for (int b = 0; b < in->nbin; b++) {
+    if (in->nspec[b] < 1 || in->nspec[b] > ARC_AER_MAXSPEC || !in->num[b]) { g.err = "arc_aer_optics: bad species list"; return ARC_ERR_BAD_ARG; }
+    sl.nspec[b] = in->nspec[b];
+    sl.sigmag[b] = in->sigmag[b];
+    if (in->mode == ARC_AER_MODAL && !(in->sigmag[b] > 1.0f)) { g.err = "arc_aer_optics: sigmag must be > 1 for modal input"; return ARC_ERR_BAD_ARG; }
+    if ((rc = in_arr(ms, in->num[b], n3, &sl.num[b]))) return rc;
+    for (int m = 0; m < in->nspec[b]; m++) {
+      if (in->cls[b][m] < 0 || in->cls[b][m] >= ARC_CLS_N || !in->mass[b][m]) { g.err = "arc_aer_optics: bad species class / null mass array"; return ARC_ERR_BAD_ARG; }
+      sl.cls[b][m] = in->cls[b][m];
+      if ((rc = in_arr(ms, in->mass[b][m], n3, &sl.mass[b][m]))) return rc;
+    }
+  }
+  if ((rc = in_arr(ms, in->alt, n3, &a.alt))) return rc;
+  if ((rc = in_arr(ms, in->dz8w, n3, &a.dz8w))) return rc;
+  for (int w = 0; w < 4; w++) {
+    if (!out->tauaer[w] || !out->gaer[w] || !out->waer[w]) { g.err = "arc_aer_optics: SW output array missing"; return ARC_ERR_BAD_ARG; }
+    if ((rc = out_arr(ms, out->tauaer[w], n3, &a.tauaer[w]))) return rc;
+    if ((rc = out_arr(ms, out->gaer[w], n3, &a.gaer[w]))) return rc;
+    if ((rc = out_arr(ms, out->waer[w], n3, &a.waer[w]))) return rc;
+  }
+  for (int w = 0; w < 16; w++) {
+    if (!out->tauaerlw[w]) { g.err = "arc_aer_optics: LW output array missing"; return ARC_ERR_BAD_ARG; }
+    if ((rc = out_arr(ms, out->tauaerlw[w], n3, &a.tauaerlw[w]))) return rc;
+    if ((rc = out_arr(ms, out->extaerlw[w], n3, &a.extaerlw[w]))) return rc;
+  }
+  {
+    Timed t("aer_optics");
+    if ((rc = aer_run(a, sl, g.stream, g.err))) return rc;
+  }
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  g.last_ms.erase("aer_optics");
+  collect_times();
+  return 0;
+}
+
+// CPU evaluation of the uploaded Chebyshev tables for one sphere (same interpolation as k_aer_mie) -- test tap
+int arc_aer_table_eval(int wl, float radius_cm, float refr, float refi, float *qext, float *qsca, float *gg) {
+  if (!aer_ready()) { g.err = "arc_aer_table_eval: tables not built"; return ARC_ERR_NOT_INIT; }
+  const AerTables &T = aer_tables();
+  if (wl < 0 || wl >= AER_NWL) return ARC_ERR_BAD_ARG;
+  double r = std::min(std::max((double)radius_cm, T.rmin), T.rmax);
+  double tr = (refr - T.refr_lo[wl]) / (T.refr_hi[wl] - T.refr_lo[wl]) * (AER_NREFR - 1);
+  tr = std::min(std::max(tr, 0.0), (double)(AER_NREFR - 1));
+  int ir = std::min((int)tr, AER_NREFR - 2); double t = tr - ir;
+  double ti = (std::log(std::max((double)refi, 1e-30)) - std::log((double)T.refi_lo[wl])) / (std::log((double)T.refi_hi[wl]) - std::log((double)T.refi_lo[wl])) * (AER_NREFI - 1);
+  ti = std::min(std::max(ti, 0.0), (double)(AER_NREFI - 1));
+  int ii = std::min((int)ti, AER_NREFI - 2); double u = ti - ii;
+  const double xrmin = std::log(T.rmin), xrmax = std::log(T.rmax);
+  const double x = (2.0 * std::log(r) - xrmax - xrmin) / (xrmax - xrmin);
+  double out[AER_NQ];
+  for (int q = 0; q < AER_NQ; q++) {
+    auto C = [&](int a_, int b_, int j) { return (double)T.coef[((((size_t)wl * AER_NQ + q) * AER_NREFR + a_) * AER_NREFI + b_) * AER_NCOEF_PAD + j]; };
+    double tjm1 = 1.0, tj = x, acc = 0.0;
+    for (int j = 0; j < AER_NCOEF; j++) {
+      double v;
+      if (j == 0) v = 0.5; else if (j == 1) v = x; else { v = 2.0 * x * tj - tjm1; tjm1 = tj; tj = v; }
+      const double c = (1 - t) * (1 - u) * C(ir, ii, j) + t * (1 - u) * C(ir + 1, ii, j) + (1 - t) * u * C(ir, ii + 1, j) + t * u * C(ir + 1, ii + 1, j);
+      acc += c * v;
+    }
+    out[q] = std::exp(acc);
+  }
+  *qext = (float)out[0]; *qsca = (float)std::min(out[1], out[0]); *gg = (float)out[2];
+  return 0;
+}
+int arc_aer_mie_direct(int wl, float radius_cm, float refr, float refi, float *qext, float *qsca, float *gg) {
+  if (wl < 0 || wl >= AER_NWL) return ARC_ERR_BAD_ARG;
+  const double sw_um[4] = {0.30, 0.40, 0.60, 0.999};
+  const double lw_nu[16] = {180., 425., 565., 665., 760., 900., 1030., 1130., 1285., 1435., 1640., 1940., 2165., 2315., 2490., 2925.};
+  const double lam = wl < 4 ? sw_um[wl] * 1e-4 : 1.0 / lw_nu[wl - 4];
+  double qe, qs, ga;
+  mie_efficiencies(2.0 * M_PI * radius_cm / lam, refr, refi, qe, qs, ga);
+  *qext = (float)qe; *qsca = (float)qs; *gg = (float)ga;
+  return 0;
 }
 
 // FP32 FMA throughput of this GPU (TFLOP/s), measured with a dependent-chain-free FMA kernel: the roofline

@@ -151,6 +151,62 @@ class RadLib:
         self.check(self._lw(C.byref(d), C.byref(li), C.byref(lo), C.byref(debug) if debug is not None else None))
 
 
+    # optical_averaging (WRF-Chem chem/module_optical_averaging.F; restated)
+    def optical_averaging(self, dims, mode, bins, alt, dz8w, outs, sigmag=None):
+        """bins: list (one per size section, or per mode) of dicts {species_name: array, ..., "num": array}; a species name
+        starts with its class (so4, no3, cl, nh4, na, oin, oc, bc, water), e.g. "oc_orgaro1j".  outs: dict with
+        tauaer300..999, gaer*, waer*, tauaerlw1..16 (+ optional extaerlw1..16)."""
+        d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        ai, ao = abi.ArcAerIn(), abi.ArcAerOut()
+        arrays = [alt, dz8w] + [v for b in bins for v in b.values()]
+        dev = [_is_device(v) for v in arrays]
+        if any(dev) and not all(dev):
+            raise ValueError("mix of host and device arrays")
+        ai.memspace = abi.ARC_MEM_DEVICE if dev[0] else abi.ARC_MEM_HOST
+        ai.mode = abi.ARC_AER_SECTIONAL if mode == "sectional" else abi.ARC_AER_MODAL
+        ai.nbin = len(bins)
+        for b, spec in enumerate(bins):
+            names = [k for k in spec if k != "num"]
+            ai.nspec[b] = len(names)
+            ai.num[b] = _ptr(spec["num"])
+            ai.sigmag[b] = float(sigmag[b]) if sigmag is not None else 0.0
+            for m, name in enumerate(names):
+                ai.cls[b][m] = abi.AER_CLASSES.index(name.split("_")[0])
+                ai.mass[b][m] = _ptr(spec[name])
+        ai.alt, ai.dz8w = _ptr(alt), _ptr(dz8w)
+        for w, wl in enumerate((300, 400, 600, 999)):
+            ao.tauaer[w] = _ptr(outs["tauaer%d" % wl]); ao.gaer[w] = _ptr(outs["gaer%d" % wl]); ao.waer[w] = _ptr(outs["waer%d" % wl])
+        for w in range(16):
+            ao.tauaerlw[w] = _ptr(outs["tauaerlw%d" % (w + 1)])
+            ao.extaerlw[w] = _ptr(outs.get("extaerlw%d" % (w + 1)))
+        fn = getattr(self.lib, ("arc_aer_optics" if self.prefix == "arc_rad_" else "arc_oracle_aer_optics"))
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(abi.ArcDims), C.POINTER(abi.ArcAerIn), C.POINTER(abi.ArcAerOut)]
+        rc = fn(C.byref(d), C.byref(ai), C.byref(ao))
+        if rc != 0:
+            err = getattr(self.lib, "arc_rad_last_error" if self.prefix == "arc_rad_" else "arc_oracle_aer_last_error")
+            err.restype = C.c_char_p
+            raise RadiationError(rc, (err() or b"").decode(errors="replace"))
+
+
+def alloc_aer_outputs(dom, like=None, ext=False):
+    nj, nkm, ni = dom["t3d"].shape
+    if like is not None:
+        import torch
+        z = lambda: torch.zeros(nj, nkm, ni, dtype=torch.float32, device=like.device)
+    else:
+        z = lambda: np.zeros((nj, nkm, ni), np.float32)
+    o = {}
+    for wl in (300, 400, 600, 999):
+        for p in ("tauaer", "gaer", "waer"):
+            o["%s%d" % (p, wl)] = z()
+    for b in range(16):
+        o["tauaerlw%d" % (b + 1)] = z()
+        if ext:
+            o["extaerlw%d" % (b + 1)] = z()
+    return o
+
+
 _LIB = None
 
 

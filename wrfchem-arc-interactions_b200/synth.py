@@ -142,6 +142,70 @@ def make_domain(ni, nj, nk, seed=SEED, p_top=5000.0, cloudy_frac=0.4, night_frac
     return d
 
 
+MOSAIC_SPECIES = ("so4", "no3", "cl", "nh4", "na", "oin", "oc", "bc", "water")
+MODAL_SPECIES = {  # MADE/SORGAM names per mode (registry.chem:3820): i = Aitken, j = accumulation, c = coarse
+    "i": ("so4_so4ai", "nh4_nh4ai", "no3_no3ai", "na_naai", "cl_clai", "oc_orgaro1i", "oc_orgalk1i", "oc_orgpai", "bc_eci", "oin_p25i", "water_h2oai"),
+    "j": ("so4_so4aj", "nh4_nh4aj", "no3_no3aj", "na_naaj", "cl_claj", "oc_orgaro1j", "oc_orgalk1j", "oc_orgpaj", "bc_ecj", "oin_p25j", "water_h2oaj"),
+    "c": ("oin_antha", "na_seas", "oin_soila"),
+}
+MODAL_SIGMAG = (1.7, 2.0, 2.5)
+
+
+def make_aerosol(dom, nbin=8, modal=False, seed=SEED + 7):
+    """Synthetic aerosol mass / number fields in WRF layout for the optics stage.  Returns (bins, alt, sigmag):
+    sectional: `nbin` dicts {species: ug/kg array, "num": #/kg}; modal: three dicts (Aitken, accumulation, coarse)."""
+    rng = np.random.default_rng(seed)
+    nj, nkm, ni = dom["t3d"].shape
+    f32 = np.float32
+    rho = np.where(dom["rho3d"] > 0, dom["rho3d"], 1.0).astype(np.float64)
+    alt = (1.0 / rho).astype(f32)
+    alt[~np.isfinite(alt)] = 1.0
+    z = np.cumsum(np.nan_to_num(dom["dz8w"].astype(np.float64)), axis=1) / 1000.0           # km
+    total = 12.0 * np.exp(-z / 2.0) * np.exp(rng.normal(0.0, 0.5, (nj, 1, ni)))            # ug/kg dry aerosol, all sizes
+    dens = dict(so4=1.8, no3=1.8, cl=2.2, nh4=1.8, na=2.2, oin=2.6, oc=1.0, bc=1.7, water=1.0)
+    comp = dict(so4=0.30, no3=0.10, cl=0.02, nh4=0.12, na=0.03, oin=0.18, oc=0.20, bc=0.05)
+    bins = []
+    if not modal:
+        lo, hi = 3.90625e-6, 1.0e-3
+        edges = lo * (hi / lo) ** (np.arange(nbin + 1) / nbin)
+        dc = np.sqrt(edges[:-1] * edges[1:])                                                # cm
+        wmass = np.exp(-0.5 * (np.log(dc / 3.0e-5) / np.log(2.2)) ** 2) + 0.25 * np.exp(-0.5 * (np.log(dc / 3.0e-4) / np.log(1.8)) ** 2)
+        wmass /= wmass.sum()
+        for b in range(nbin):
+            spec = {}
+            vol = 0.0
+            for sp, fr in comp.items():
+                tilt = 1.0 + (0.6 if sp in ("oin", "na", "cl") else -0.3) * (b - nbin / 2) / nbin
+                m = total * wmass[b] * fr * tilt * rng.uniform(0.8, 1.2, (nj, nkm, ni))
+                spec[sp] = m.astype(f32)
+                vol = vol + m * 1e-6 / dens[sp]                                             # dry volume, cm3 per kg-air
+            water = 0.6 * sum(spec[s_].astype(np.float64) for s_ in ("so4", "no3", "nh4", "na", "cl")) * rng.uniform(0.2, 1.5, (nj, 1, ni))
+            spec["water"] = water.astype(f32)
+            dmean = dc[b] * rng.uniform(0.85, 1.15, (nj, nkm, ni))
+            spec["num"] = (vol / (np.pi / 6.0 * dmean ** 3)).astype(f32)                    # #/kg-air
+            bins.append(spec)
+        return bins, alt, None
+    shares = {"i": 0.05, "j": 0.70, "c": 0.25}
+    dgs = {"i": 3.0e-6, "j": 1.5e-5, "c": 1.0e-4}                                           # number median diameters, cm
+    for mi, md in enumerate(("i", "j", "c")):
+        spec = {}
+        vol = 0.0
+        names = MODAL_SPECIES[md]
+        for nm in names:
+            cls = nm.split("_")[0]
+            if cls == "water":
+                m = 0.5 * total * shares[md] * rng.uniform(0.2, 1.0, (nj, 1, ni))
+            else:
+                m = total * shares[md] * comp.get(cls, 0.1) / max(1, sum(1 for q in names if q.split("_")[0] == cls)) * rng.uniform(0.8, 1.2, (nj, nkm, ni))
+                vol = vol + m * 1e-6 / dens[cls]
+            spec[nm] = m.astype(f32)
+        ls = np.log(MODAL_SIGMAG[mi])
+        dg = dgs[md] * rng.uniform(0.8, 1.25, (nj, nkm, ni))
+        spec["num"] = (vol / (np.pi / 6.0 * dg ** 3 * np.exp(4.5 * ls * ls))).astype(f32)
+        bins.append(spec)
+    return bins, alt, MODAL_SIGMAG
+
+
 CONFIGS = {
     # name: (ni, nj, nk, kwargs)   -- BASELINE.md section 3
     "C1": (32, 32, 40, dict()),
