@@ -3,7 +3,7 @@
 // Upstream algorithm: WRF-Chem v3.9.1 chem/module_optical_averaging.F.  That file is NOT in the reference repository
 // (SURVEY.md section 0.4); only its outputs are consumed there (module_radiation_driver.F:113-124, registry.chem:1332-1390).
 // This is a restatement of the published algorithm and is "self-consistent only": parity is pinned against our own CPU
-// restatement (oracle/aer.cpp) and against direct Mie theory, not against the Fortran.
+// restatement (the test oracle) and against direct Mie theory, not against the Fortran.
 //
 //   k_aer_prep   one thread per (column, level): per size section, species volumes (mass / density), volume-averaged
 //                complex refractive index weights, wet radius and number; modal input is first mapped onto the
