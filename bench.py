@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--clean", type=int, default=1, help="clean_atm_diag (1: full+clear+clean, 0: full+clear only)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-aer", action="store_true", help="skip the separately reported aerosol-optics stage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -298,6 +299,26 @@ def main():
                "h2d_bytes_per_step": int(in_sw + in_lw + inout_b), "d2h_bytes_per_step": int(out_b),
                "steps": n_e2e, "note": "host pinned WRF-layout arrays through RRTMG_LWRAD + RRTMG_SWRAD (+ statistics); the library pipelines j-slabs: upload / compute / download overlap on three streams"}
 
+    # ---- aerosol optical-property stage (MOSAIC 8-bin sectional), reported separately ------------------
+    aer = None
+    if not args.no_aer and rank == 0:
+        bins, alt, _ = synth.make_aerosol(dom, nbin=8)
+        dbins = [{k: torch.from_numpy(v).to(dev) for k, v in b.items()} for b in bins]
+        dalt = torch.from_numpy(alt).to(dev)
+        ao = R.alloc_aer_outputs(dom, like=like)
+        for _ in range(2):
+            lib.optical_averaging(dims, "sectional", dbins, dalt, ddom["dz8w"], ao)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter(); n_a = 3; kms_a = 0.0
+        for _ in range(n_a):
+            lib.optical_averaging(dims, "sectional", dbins, dalt, ddom["dz8w"], ao)
+            kms_a += float(L.arc_rad_last_kernel_ms(b"aer_optics"))
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / n_a
+        aer = {"columns_per_s": ncol / dt, "ms": dt * 1e3, "kernel_ms": kms_a / n_a, "config": "MOSAIC 8-bin sectional, 9 species classes, 4 SW + 16 LW wavelengths, %d levels" % nk,
+               "column_aod400_median": float(ao["tauaer400"].sum(dim=1).median()), "parity": "self-consistent only (module_optical_averaging.F is not in the reference repository)"}
+        del dbins, ao
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -330,7 +351,7 @@ def main():
                    "columns_per_gpu": ncol, "sunlit_columns": nsun, "partition": "j-slabs, one tile per rank; NCCL all-reduce of 24x5 domain statistics per step" if world > 1 else "single tile"},
         "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "aer_optics": aer,
     }
     print(json.dumps(out))
     if dist is not None:
