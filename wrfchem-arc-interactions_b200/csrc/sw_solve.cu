@@ -234,7 +234,7 @@ __device__ __noinline__ float4 sw_reftra(const float *__restrict__ exp_tbl, floa
 
 // ------------------------------------------------------------------------------------------------------
 #ifndef SW_MINBLOCKS
-#define SW_MINBLOCKS 3
+#define SW_MINBLOCKS 4
 #endif
 template <int NL>
 __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
