@@ -187,6 +187,16 @@ int  arc_rad_driver_post(const ArcDims *d, int memspace,
                          const float *rthratenlw, const float *rthratensw, float *rthraten,
                          const float *gsw, const float *albedo, float *swdown);
 
+/* Solar geometry of radiation_driver (module_radiation_driver.F:2595-2666, called at DRV:954-973):
+ *   radconst:    declination and solar constant 1370*eccfac(julian)        (host scalar arithmetic, FP32 like the reference)
+ *   calc_coszen: cos(zenith) and hour angle with the equation of time, at the time the caller passes (xtime + radt/2)   */
+void arc_rad_radconst(float xtime, float julian, float degrad, float dpd, float *declin, float *solcon);
+int  arc_rad_calc_coszen(const ArcDims *d, int memspace, float julian, float xtime, float gmt, float declin, float degrad,
+                         const float *xlon, const float *xlat, float *coszen, float *hrang);
+/* time accumulation AC{SW,LW}{UP,DN}{T,B}[C] += flux*DTaccum for `nfields` 2-D field pairs (DRV:2308-2377; the reference
+ * does not accumulate the *CLN fields) */
+int  arc_rad_accumulate(const ArcDims *d, int memspace, float dtaccum, int nfields, const float *const *flux, float *const *acc);
+
 /* Domain statistics of `nfields` 2-D (i,j) fields over the tile: out[f][5] = {sum, sum of squares, count, min, max}
  * in double precision; `fields` is a host array of pointers in `memspace`, `out` lives in `memspace` too.
  * Replaces calc_standard_stats' mean/SD/SE inputs (analysis_scripts/NCL_extraction_package/misc_stats_library.ncl:396-461);

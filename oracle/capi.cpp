@@ -1,4 +1,5 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.hpp).  C entry points for ctypes.
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,6 +65,35 @@ int arc_oracle_lw_omp(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, int nt
   return run_tiles(d, nthreads, [&](const ArcDims &t, std::string &e) { return orc::oracle_lwrad(t, *in, *out, nullptr, e); });
 }
 int arc_oracle_max_threads(void) { int n = (int)std::thread::hardware_concurrency(); return n > 0 ? n : 1; }
+
+// radconst + calc_coszen, module_radiation_driver.F:2595-2666 (scalar restatement)
+void arc_oracle_radconst(float xtime, float julian, float degrad, float dpd, float *declin, float *solcon) {
+  (void)xtime;
+  float obecl = 23.5f * degrad, sinob = sinf(obecl), sxlong;
+  if (julian >= 80.f) sxlong = dpd * (julian - 80.f); else sxlong = dpd * (julian + 285.f);
+  sxlong = sxlong * degrad;
+  float arg = sinob * sinf(sxlong);
+  *declin = asinf(arg);
+  float djul = julian * 360.f / 365.f, rjul = djul * degrad;
+  float eccfac = 1.000110f + 0.034221f * cosf(rjul) + 0.001280f * sinf(rjul) + 0.000719f * cosf(2 * rjul) + 0.000077f * sinf(2 * rjul);
+  *solcon = 1370.f * eccfac;
+}
+int arc_oracle_calc_coszen(const ArcDims *d, float julian, float xtime, float gmt, float declin, float degrad, const float *xlon,
+                           const float *xlat, float *coszen, float *hrang) {
+  const int ni = d->ime - d->ims + 1;
+  float da = 6.2831853071795862f * (julian - 1) / 365.f;
+  float eot = (0.000075f + 0.001868f * cosf(da) - 0.032077f * sinf(da) - 0.014615f * cosf(2 * da) - 0.04089f * sinf(2 * da)) * (229.18f);
+  float xt24 = fmodf(xtime, 1440.f) + eot;
+  for (int j = d->jts; j <= d->jte; j++)
+    for (int i = d->its; i <= d->ite; i++) {
+      size_t q = (size_t)(i - d->ims) + (size_t)ni * (size_t)(j - d->jms);
+      float tloctm = gmt + xt24 / 60.f + xlon[q] / 15.f;
+      hrang[q] = 15.f * (tloctm - 12.f) * degrad;
+      float xxlat = xlat[q] * degrad;
+      coszen[q] = sinf(xxlat) * sinf(declin) + cosf(xxlat) * cosf(declin) * cosf(hrang[q]);
+    }
+  return 0;
+}
 
 // Reduced-table taps so tests can compare the product's init against this restatement.
 // kind: 0 = SW, 1 = LW; name: "absa","absb","selfref","forref","sfluxref"/"fracrefa","fracrefb", ...

@@ -325,6 +325,37 @@ def test_driver_post_and_domain_stats(lib, ktab):
         assert st[f, 2] == x.size and st[f, 3] == x.min() and st[f, 4] == x.max()
 
 
+def test_coszen_and_accumulation(lib, orc, ktab):
+    """calc_coszen (DRV:2640-2666) against the oracle, and AC* += flux*DT (DRV:2308-2377)."""
+    dom = synth.make_domain(36, 9, 40, seed=23)
+    init(lib, dom, ktab)
+    L, O = lib.lib, orc.lib
+    L.arc_rad_calc_coszen.restype = C.c_int
+    L.arc_rad_calc_coszen.argtypes = [C.POINTER(abi.ArcDims), C.c_int] + [C.c_float] * 5 + [abi.c_fp] * 4
+    O.arc_oracle_calc_coszen.restype = C.c_int
+    O.arc_oracle_calc_coszen.argtypes = [C.POINTER(abi.ArcDims)] + [C.c_float] * 5 + [abi.c_fp] * 4
+    dims = abi.make_dims(dom["dims"])
+    rng = np.random.default_rng(3)
+    lon = rng.uniform(-180, 180, dom["xcoszen"].shape).astype(np.float32); lat = rng.uniform(-89, 89, lon.shape).astype(np.float32)
+    degrad = float(np.float32(3.1415926 / 180.0))
+    for julian, xtime, gmt, declin in ((80.0, 735.0, 0.0, 0.0), (172.3, 4000.5, 6.0, 0.409), (355.0, 90.0, 18.0, -0.408)):
+        a, ah, b, bh = (np.full_like(lon, -9.0) for _ in range(4))
+        lib.check(L.arc_rad_calc_coszen(C.byref(dims), 0, julian, xtime, gmt, declin, degrad, abi.fptr(lon), abi.fptr(lat), abi.fptr(a), abi.fptr(ah)))
+        O.arc_oracle_calc_coszen(C.byref(dims), julian, xtime, gmt, declin, degrad, abi.fptr(lon), abi.fptr(lat), abi.fptr(b), abi.fptr(bh))
+        assert np.allclose(ah, bh, rtol=0, atol=2e-6) and np.allclose(a, b, rtol=0, atol=2e-6)
+        assert a.min() >= -1.0 - 1e-6 and a.max() <= 1.0 + 1e-6
+    L.arc_rad_accumulate.restype = C.c_int
+    L.arc_rad_accumulate.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_float, C.c_int, C.POINTER(abi.c_fp), C.POINTER(abi.c_fp)]
+    sw = run_pair("sw", lib, dom)
+    names = ("swupt", "swuptc", "swdnt", "swdntc", "swupb", "swupbc", "swdnb", "swdnbc")
+    acc = [rng.uniform(0, 1e6, sw["swupt"].shape).astype(np.float32) for _ in names]
+    ref = [x + sw[n] * np.float32(18.0) for x, n in zip(acc, names)]
+    fl = (abi.c_fp * 8)(*[abi.fptr(sw[n]) for n in names]); ac = (abi.c_fp * 8)(*[abi.fptr(x) for x in acc])
+    lib.check(L.arc_rad_accumulate(C.byref(dims), 0, 18.0, 8, fl, ac))
+    for x, r in zip(acc, ref):
+        assert np.array_equal(x, r)
+
+
 def test_full_size_properties(lib, ktab):
     """BASELINE config C2 at full size (127,500 columns x 50 levels), checked through size-independent properties:
     energy bounds, clean == full where the aerosol is zero, clear == full in cloud-free columns, night gate."""

@@ -958,6 +958,97 @@ int arc_rad_driver_post(const ArcDims *d, int memspace, const float *rthratenlw,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// radconst / calc_coszen (module_radiation_driver.F:2595-2666) and the flux accumulation (DRV:2308-2377)
+void arc_rad_radconst(float xtime, float julian, float degrad, float dpd, float *declin, float *solcon) {
+  (void)xtime;
+  const float obecl = 23.5f * degrad;
+  const float sinob = sinf(obecl);
+  float sxlong;
+  if (julian >= 80.f) sxlong = dpd * (julian - 80.f); else sxlong = dpd * (julian + 285.f);
+  sxlong = sxlong * degrad;
+  const float arg = sinob * sinf(sxlong);
+  if (declin) *declin = asinf(arg);
+  const float djul = julian * 360.f / 365.f;
+  const float rjul = djul * degrad;
+  const float eccfac = 1.000110f + 0.034221f * cosf(rjul) + 0.001280f * sinf(rjul) + 0.000719f * cosf(2 * rjul) + 0.000077f * sinf(2 * rjul);
+  if (solcon) *solcon = 1370.f * eccfac;
+}
+
+__global__ void k_calc_coszen(Geo G, float xt24, float gmt, float declin, float degrad, const float *__restrict__ xlon,
+                              const float *__restrict__ xlat, float *__restrict__ coszen, float *__restrict__ hrang) {
+  const int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tc >= G.ncol_tile) return;
+  int i, j; G.ij(tc, i, j);
+  const size_t q = G.at2(i, j);
+  const float tloctm = gmt + xt24 / 60.f + xlon[q] / 15.f;
+  const float hr = 15.f * (tloctm - 12.f) * degrad;
+  const float xxlat = xlat[q] * degrad;
+  if (hrang) hrang[q] = hr;
+  coszen[q] = sinf(xxlat) * sinf(declin) + cosf(xxlat) * cosf(declin) * cosf(hr);
+}
+
+int arc_rad_calc_coszen(const ArcDims *d, int memspace, float julian, float xtime, float gmt, float declin, float degrad,
+                        const float *xlon, const float *xlat, float *coszen, float *hrang) {
+  if (!g.ready) { g.err = "arc_rad_calc_coszen: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !xlon || !xlat || !coszen) { g.err = "arc_rad_calc_coszen: null argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  // equation of time (jararias 2013), scalar part evaluated on the host in FP32 like the reference
+  const float da = 6.2831853071795862f * (julian - 1) / 365.f;
+  const float eot = (0.000075f + 0.001868f * cosf(da) - 0.032077f * sinf(da) - 0.014615f * cosf(2 * da) - 0.04089f * sinf(2 * da)) * (229.18f);
+  const float xt24 = fmodf(xtime, 1440.f) + eot;
+  const float *lo, *la; float *cz, *hr;
+  if ((rc = in_arr(memspace, xlon, G.n2(), &lo))) return rc;
+  if ((rc = in_arr(memspace, xlat, G.n2(), &la))) return rc;
+  if ((rc = out_arr(memspace, coszen, G.n2(), &cz))) return rc;
+  if ((rc = out_arr(memspace, hrang, G.n2(), &hr))) return rc;
+  k_calc_coszen<<<(G.ncol_tile + 255) / 256, 256, 0, g.stream>>>(G, xt24, gmt, declin, degrad, lo, la, cz, hr);
+  count_launch();
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void k_accumulate(Geo G, float dt, int nf, const float *const *__restrict__ flux, float *const *__restrict__ acc) {
+  const int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tc >= G.ncol_tile) return;
+  int i, j; G.ij(tc, i, j);
+  const size_t q = G.at2(i, j);
+  for (int f = 0; f < nf; f++) acc[f][q] = __fadd_rn(acc[f][q], __fmul_rn(flux[f][q], dt));   // unfused like the reference
+}
+
+int arc_rad_accumulate(const ArcDims *d, int memspace, float dtaccum, int nfields, const float *const *flux, float *const *acc) {
+  if (!g.ready) { g.err = "arc_rad_accumulate: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !flux || !acc || nfields < 1 || nfields > 32) { g.err = "arc_rad_accumulate: bad argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const float *df[32]; float *da[32];
+  for (int f = 0; f < nfields; f++) {
+    if (!flux[f] || !acc[f]) { g.err = "arc_rad_accumulate: null field"; return ARC_ERR_BAD_ARG; }
+    if ((rc = in_arr(memspace, flux[f], G.n2(), &df[f]))) return rc;
+    if ((rc = out_arr(memspace, acc[f], G.n2(), &da[f]))) return rc;
+  }
+  void *pf, *pa;
+  if ((rc = stage_slot(sizeof(float *) * 32, &pf))) return rc;
+  if ((rc = stage_slot(sizeof(float *) * 32, &pa))) return rc;
+  CK(cudaMemcpyAsync(pf, df, sizeof(float *) * nfields, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(pa, da, sizeof(float *) * nfields, cudaMemcpyHostToDevice, g.stream));
+  k_accumulate<<<(G.ncol_tile + 255) / 256, 256, 0, g.stream>>>(G, dtaccum, nfields, (const float *const *)pf, (float *const *)pa);
+  count_launch();
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Domain statistics of 2-D diagnostic fields over the tile: [sum, sum of squares, count, min, max] per field, the
 // quantities the offline decomposition needs for means / SD / SE (analysis_scripts/NCL_extraction_package/
 // misc_stats_library.ncl:396-461, RadDecomp_functions.py:119-129).  One block per field, fixed-order tree: reproducible.
