@@ -172,6 +172,9 @@ typedef struct ArcDebug {
 int  arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_data_path);
 int  arc_rad_sw(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out);
 int  arc_rad_lw(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out);
+/* One radiation step: RRTMG_LWRAD then RRTMG_SWRAD on the same tile (the order of radiation_driver, DRV:1526-2009).  With
+ * host arrays both adapters run inside one j-slab pipeline (shared inputs uploaded once); results equal the two calls. */
+int  arc_rad_lwsw(const ArcDims *d, const ArcLwIn *lwin, ArcLwOut *lwout, const ArcSwIn *swin, ArcSwOut *swout);
 /* same as above with intermediate taps (tests only) */
 int  arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebug *dbg);
 int  arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebug *dbg);

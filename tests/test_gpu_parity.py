@@ -249,6 +249,32 @@ def test_pipelined_host_path_is_bit_identical(lib, ktab, halo):
     assert (ref["sw"]["swupt"] == -555.0).any() == (halo > 0)
 
 
+def test_combined_lwsw_step_equals_separate_calls(lib, ktab):
+    """arc_rad_lwsw (LW then SW in one slab pipeline, shared inputs uploaded once) == the two separate calls, bit for bit."""
+    dom = synth.make_domain(24, 12, 40, seed=20, halo=1)
+    init(lib, dom, ktab)
+    flags = R.common_flags(dom)
+    ref_sw, ref_lw = R.alloc_outputs(dom, "sw"), R.alloc_outputs(dom, "lw")
+    for o in (ref_sw, ref_lw):
+        for k in o:
+            o[k][:] = -555.0
+    run_pair("sw", lib, dom, outs=ref_sw); run_pair("lw", lib, dom, outs=ref_lw)
+    for slab in (0, 24 * 5):
+        os.environ["ARC_RAD_SLAB_COLUMNS"] = str(slab)
+        try:
+            o_sw, o_lw = R.alloc_outputs(dom, "sw"), R.alloc_outputs(dom, "lw")
+            for o in (o_sw, o_lw):
+                for k in o:
+                    o[k][:] = -555.0
+            lib.RRTMG_LWSW(dom["dims"], R.lw_kwargs(dom, o_lw, **flags), R.sw_kwargs(dom, o_sw, **flags))
+        finally:
+            del os.environ["ARC_RAD_SLAB_COLUMNS"]
+        for k in ref_sw:
+            assert np.array_equal(ref_sw[k], o_sw[k], equal_nan=True), (slab, k)
+        for k in ref_lw:
+            assert np.array_equal(ref_lw[k], o_lw[k], equal_nan=True), (slab, k)
+
+
 def test_device_memspace_equals_host_memspace(lib, ktab):
     import torch
     dom = synth.make_domain(16, 8, 40, seed=14)

@@ -425,10 +425,21 @@ static int slab_rows_default(int nrows, int ni) {
   return (int)std::min<long>(r, nrows);
 }
 
-// IN / OUT = the C structs; `call` runs the device-memory entry point.  Returns -1 when the call is not eligible.
-template <class IN, class OUT, class CALL>
-static int run_pipelined(const ArcDims &d, const IN &in, OUT &out, const FieldRef *ins, int nins, const FieldRef *outs, int nouts,
-                         const size_t (*alias)[2], int nalias, CALL call) {
+// One "part" of a pipelined call = one reference entry point (RRTMG_LWRAD or RRTMG_SWRAD) with its argument structs.
+// A call may have several parts (arc_rad_lwsw: LW then SW on the same slab); host arrays that several parts share
+// (t3d, p3d, qv3d, ... are passed to both adapters by radiation_driver) are uploaded once per slab.
+struct PipePart {
+  const void *in; size_t in_size;            // host-memspace argument struct (first member: int memspace)
+  void *out; size_t out_size;
+  const FieldRef *ins; int nins;
+  const FieldRef *outs; int nouts;
+  const size_t (*alias)[2]; int nalias;
+  int (*call)(const ArcDims *, const void *, void *);
+};
+static inline const float *&fldv(void *st, size_t off) { return *reinterpret_cast<const float **>(reinterpret_cast<char *>(st) + off); }
+
+// Returns -1 when the call is not eligible (too few rows for more than one slab).
+static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
   const int nrows = d.jte - d.jts + 1;
   const int ni = d.ime - d.ims + 1, nk = d.kme - d.kms + 1;
   const int rows_per = slab_rows_default(nrows, d.ite - d.its + 1);
@@ -439,26 +450,49 @@ static int run_pipelined(const ArcDims &d, const IN &in, OUT &out, const FieldRe
   const size_t row3 = (size_t)ni * nk, row2 = (size_t)ni, rowp = (size_t)ni * (nk + 2);
   auto rowsz = [&](int kind) { return kind == F3 ? row3 : kind == F2 ? row2 : rowp; };
   CK(cudaSetDevice(g.device));
+  // staging slot of every field; inputs whose host pointer was already seen (in an earlier part) share that slot
+  struct Slotmap { std::vector<int> in_slot, out_slot; };
+  std::vector<Slotmap> maps(nparts);
+  std::vector<const float *> seen; std::vector<int> seen_slot; std::vector<bool> upload_in;
+  int nslots = 0;
+  for (int p = 0; p < nparts; p++) {
+    maps[p].in_slot.assign(parts[p].nins, -1); maps[p].out_slot.assign(parts[p].nouts, -1);
+    for (int f = 0; f < parts[p].nins; f++) {
+      const float *h = fldv(const_cast<void *>(parts[p].in), parts[p].ins[f].off);
+      if (!h) continue;
+      int found = -1;
+      for (size_t q = 0; q < seen.size(); q++) if (seen[q] == h) { found = seen_slot[q]; break; }
+      if (found < 0) { found = nslots++; seen.push_back(h); seen_slot.push_back(found); }
+      maps[p].in_slot[f] = found;
+    }
+    for (int f = 0; f < parts[p].nouts; f++)
+      if (fldv(parts[p].out, parts[p].outs[f].off)) maps[p].out_slot[f] = nslots++;
+  }
 
   auto upload = [&](int s) -> int {
     const int set = s & 1;
     const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1), nr = j1 - j0 + 1;
     CK(cudaStreamWaitEvent(g.h2d, g.ev_out[set], 0));          // the previous user of this set has been downloaded
-    size_t idx = 0;
-    for (int f = 0; f < nins; f++, idx++) {
-      const float *h = fld(const_cast<IN &>(in), ins[f].off);
-      if (!h) continue;
-      const size_t rs = rowsz(ins[f].kind);
-      void *dv; int rc = slab_slot(set, idx, (size_t)rows_per * rs * 4, &dv); if (rc) return rc;
-      CK(cudaMemcpyAsync(dv, h + (size_t)(j0 - d.jms) * rs, (size_t)nr * rs * 4, cudaMemcpyHostToDevice, g.h2d));
-    }
-    for (int f = 0; f < nouts; f++, idx++) {
-      float *h = fldw(out, outs[f].off);
-      if (!h) continue;
-      const size_t rs = rowsz(outs[f].kind);
-      void *dv; int rc = slab_slot(set, idx, (size_t)rows_per * rs * 4, &dv); if (rc) return rc;
-      if (ihalo || outs[f].partial)
+    std::vector<bool> done(nslots, false);
+    for (int p = 0; p < nparts; p++) {
+      for (int f = 0; f < parts[p].nins; f++) {
+        const int slot = maps[p].in_slot[f];
+        if (slot < 0 || done[slot]) continue;
+        done[slot] = true;
+        const float *h = fldv(const_cast<void *>(parts[p].in), parts[p].ins[f].off);
+        const size_t rs = rowsz(parts[p].ins[f].kind);
+        void *dv; int rc = slab_slot(set, slot, (size_t)rows_per * rs * 4, &dv); if (rc) return rc;
         CK(cudaMemcpyAsync(dv, h + (size_t)(j0 - d.jms) * rs, (size_t)nr * rs * 4, cudaMemcpyHostToDevice, g.h2d));
+      }
+      for (int f = 0; f < parts[p].nouts; f++) {
+        const int slot = maps[p].out_slot[f];
+        if (slot < 0) continue;
+        float *h = const_cast<float *>(fldv(parts[p].out, parts[p].outs[f].off));
+        const size_t rs = rowsz(parts[p].outs[f].kind);
+        void *dv; int rc = slab_slot(set, slot, (size_t)rows_per * rs * 4, &dv); if (rc) return rc;
+        if (ihalo || parts[p].outs[f].partial)
+          CK(cudaMemcpyAsync(dv, h + (size_t)(j0 - d.jms) * rs, (size_t)nr * rs * 4, cudaMemcpyHostToDevice, g.h2d));
+      }
     }
     CK(cudaEventRecord(g.ev_in[set], g.h2d));
     return 0;
@@ -466,21 +500,23 @@ static int run_pipelined(const ArcDims &d, const IN &in, OUT &out, const FieldRe
   auto download = [&](int s) -> int {
     const int set = s & 1;
     const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1), nr = j1 - j0 + 1;
-    size_t idx = nins;
-    for (int f = 0; f < nouts; f++, idx++) {
-      float *h = fldw(out, outs[f].off);
-      if (!h) continue;
-      const size_t rs = rowsz(outs[f].kind);
-      const float *dv = (const float *)g.slab[set][idx].d;
-      float *hd = h + (size_t)(j0 - d.jms) * rs;
-      if (ihalo || outs[f].partial || outs[f].kind == F2) {
-        CK(cudaMemcpyAsync(hd, dv, (size_t)nr * rs * 4, cudaMemcpyDeviceToHost, g.d2h));
-      } else {
-        // exactly the written levels of every row: kts..kte (3-D tendency) or kts..kte+2 (flux profile)
-        const size_t lev0 = (size_t)(d.kts - d.kms) * ni, nlev = (size_t)(outs[f].kind == F3 ? nz : nz + 2) * ni;
-        CK(cudaMemcpy2DAsync(hd + lev0, rs * 4, dv + lev0, rs * 4, nlev * 4, nr, cudaMemcpyDeviceToHost, g.d2h));
+    for (int p = 0; p < nparts; p++)
+      for (int f = 0; f < parts[p].nouts; f++) {
+        const int slot = maps[p].out_slot[f];
+        if (slot < 0) continue;
+        float *h = const_cast<float *>(fldv(parts[p].out, parts[p].outs[f].off));
+        const FieldRef &fr = parts[p].outs[f];
+        const size_t rs = rowsz(fr.kind);
+        const float *dv = (const float *)g.slab[set][slot].d;
+        float *hd = h + (size_t)(j0 - d.jms) * rs;
+        if (ihalo || fr.partial || fr.kind == F2) {
+          CK(cudaMemcpyAsync(hd, dv, (size_t)nr * rs * 4, cudaMemcpyDeviceToHost, g.d2h));
+        } else {
+          // exactly the written levels of every row: kts..kte (3-D tendency) or kts..kte+2 (flux profile)
+          const size_t lev0 = (size_t)(d.kts - d.kms) * ni, nlev = (size_t)(fr.kind == F3 ? nz : nz + 2) * ni;
+          CK(cudaMemcpy2DAsync(hd + lev0, rs * 4, dv + lev0, rs * 4, nlev * 4, nr, cudaMemcpyDeviceToHost, g.d2h));
+        }
       }
-    }
     CK(cudaEventRecord(g.ev_out[set], g.d2h));
     return 0;
   };
@@ -488,29 +524,46 @@ static int run_pipelined(const ArcDims &d, const IN &in, OUT &out, const FieldRe
   int rc = upload(0);
   if (rc) return rc;
   int status = 0;
+  std::vector<std::vector<char>> din(nparts), dout(nparts);
   for (int s = 0; s < nslab; s++) {
     const int set = s & 1;
     if (s + 1 < nslab && (rc = upload(s + 1))) return rc;
     const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1);
     ArcDims ds = d;
     ds.jms = j0; ds.jme = j1; ds.jts = j0; ds.jte = j1;
-    IN din = in; OUT dout = out;
-    din.memspace = ARC_MEM_DEVICE;
-    size_t idx = 0;
-    for (int f = 0; f < nins; f++, idx++) if (fld(din, ins[f].off)) fld(din, ins[f].off) = (const float *)g.slab[set][idx].d;
-    for (int f = 0; f < nouts; f++, idx++) if (fldw(dout, outs[f].off)) fldw(dout, outs[f].off) = (float *)g.slab[set][idx].d;
-    for (int q = 0; q < nalias; q++) if (fld(din, alias[q][0])) fld(din, alias[q][0]) = fld(din, alias[q][1]);
     CK(cudaStreamWaitEvent(g.stream, g.ev_in[set], 0));
-    g.keep_ms = s > 0;
-    rc = call(ds, din, dout);                  // synchronises g.stream before returning
-    g.keep_ms = false;
-    if (rc && !status) status = rc;
+    for (int p = 0; p < nparts && !status; p++) {
+      din[p].assign((const char *)parts[p].in, (const char *)parts[p].in + parts[p].in_size);
+      dout[p].assign((const char *)parts[p].out, (const char *)parts[p].out + parts[p].out_size);
+      *reinterpret_cast<int *>(din[p].data()) = ARC_MEM_DEVICE;
+      for (int f = 0; f < parts[p].nins; f++)
+        if (maps[p].in_slot[f] >= 0) fldv(din[p].data(), parts[p].ins[f].off) = (const float *)g.slab[set][maps[p].in_slot[f]].d;
+      for (int f = 0; f < parts[p].nouts; f++)
+        if (maps[p].out_slot[f] >= 0) fldv(dout[p].data(), parts[p].outs[f].off) = (const float *)g.slab[set][maps[p].out_slot[f]].d;
+      for (int q = 0; q < parts[p].nalias; q++)
+        if (fldv(din[p].data(), parts[p].alias[q][0])) fldv(din[p].data(), parts[p].alias[q][0]) = fldv(din[p].data(), parts[p].alias[q][1]);
+      g.keep_ms = s > 0;
+      rc = parts[p].call(&ds, din[p].data(), dout[p].data());     // synchronises g.stream before returning
+      g.keep_ms = false;
+      if (rc && !status) status = rc;
+    }
     if ((rc = download(s))) return rc;
     if (status) break;
   }
   CK(cudaStreamSynchronize(g.d2h));
   CK(cudaStreamSynchronize(g.h2d));
   return status;
+}
+
+static int call_sw(const ArcDims *d, const void *in, void *out) { return arc_rad_sw_debug(d, (const ArcSwIn *)in, (ArcSwOut *)out, nullptr); }
+static int call_lw(const ArcDims *d, const void *in, void *out) { return arc_rad_lw_debug(d, (const ArcLwIn *)in, (ArcLwOut *)out, nullptr); }
+static PipePart sw_part(const ArcSwIn *in, ArcSwOut *out) {
+  return PipePart{in, sizeof(ArcSwIn), out, sizeof(ArcSwOut), SW_INS, (int)(sizeof(SW_INS) / sizeof(FieldRef)), SW_OUTS,
+                  (int)(sizeof(SW_OUTS) / sizeof(FieldRef)), SW_ALIAS, 4, call_sw};
+}
+static PipePart lw_part(const ArcLwIn *in, ArcLwOut *out) {
+  return PipePart{in, sizeof(ArcLwIn), out, sizeof(ArcLwOut), LW_INS, (int)(sizeof(LW_INS) / sizeof(FieldRef)), LW_OUTS,
+                  (int)(sizeof(LW_OUTS) / sizeof(FieldRef)), nullptr, 0, call_lw};
 }
 
 }  // namespace
@@ -653,8 +706,8 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   int rc = check_dims(*d);
   if (rc) return rc;
   if (in->memspace == ARC_MEM_HOST && !dbg && !in->tauaer3d_sw) {
-    rc = run_pipelined(*d, *in, *out, SW_INS, (int)(sizeof(SW_INS) / sizeof(FieldRef)), SW_OUTS, (int)(sizeof(SW_OUTS) / sizeof(FieldRef)),
-                       SW_ALIAS, 4, [](const ArcDims &ds, const ArcSwIn &di, ArcSwOut &dout) { return arc_rad_sw_debug(&ds, &di, &dout, nullptr); });
+    const PipePart part = sw_part(in, out);
+    rc = run_pipelined(*d, &part, 1);
     if (rc != -1) return rc;
     rc = 0;
   }
@@ -808,8 +861,8 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   int rc = check_dims(*d);
   if (rc) return rc;
   if (in->memspace == ARC_MEM_HOST && !dbg) {
-    rc = run_pipelined(*d, *in, *out, LW_INS, (int)(sizeof(LW_INS) / sizeof(FieldRef)), LW_OUTS, (int)(sizeof(LW_OUTS) / sizeof(FieldRef)),
-                       nullptr, 0, [](const ArcDims &ds, const ArcLwIn &di, ArcLwOut &dout) { return arc_rad_lw_debug(&ds, &di, &dout, nullptr); });
+    const PipePart part = lw_part(in, out);
+    rc = run_pipelined(*d, &part, 1);
     if (rc != -1) return rc;
     rc = 0;
   }
@@ -920,6 +973,23 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
 }
 
 int arc_rad_lw(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out) { return arc_rad_lw_debug(d, in, out, nullptr); }
+
+// One radiation step = RRTMG_LWRAD then RRTMG_SWRAD on the same tile (the order radiation_driver uses, DRV:1526-2009).
+// With host arrays both run inside ONE slab pipeline: the arrays the two adapters share are uploaded once and the
+// pipeline fills and drains once; otherwise this is simply the two calls.
+int arc_rad_lwsw(const ArcDims *d, const ArcLwIn *lwin, ArcLwOut *lwout, const ArcSwIn *swin, ArcSwOut *swout) {
+  if (!g.ready) { g.err = "arc_rad_lwsw: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !lwin || !lwout || !swin || !swout) { g.err = "arc_rad_lwsw: null argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if (lwin->memspace == ARC_MEM_HOST && swin->memspace == ARC_MEM_HOST && !swin->tauaer3d_sw) {
+    const PipePart parts[2] = {lw_part(lwin, lwout), sw_part(swin, swout)};
+    rc = run_pipelined(*d, parts, 2);
+    if (rc != -1) return rc;
+  }
+  if ((rc = arc_rad_lw(d, lwin, lwout))) return rc;
+  return arc_rad_sw(d, swin, swout);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // radiation_driver bookkeeping around the two calls (module_radiation_driver.F:1692-1702, 2180-2194)

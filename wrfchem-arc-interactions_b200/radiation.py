@@ -97,6 +97,10 @@ class RadLib:
     def RRTMG_SWRAD(self, dims, debug=None, **kw):
         """kw: Fortran dummy names -> arrays / scalars.  F_Qx flags: True/False or omitted (= not PRESENT)."""
         d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        si, so = self._build_sw(kw)
+        self.check(self._sw(C.byref(d), C.byref(si), C.byref(so), C.byref(debug) if debug is not None else None))
+
+    def _build_sw(self, kw):
         si, so = abi.ArcSwIn(), abi.ArcSwOut()
         used = set()
         dev = [_is_device(v) for v in kw.values() if v is not None and (hasattr(v, "data_ptr") or isinstance(v, np.ndarray))]
@@ -119,10 +123,25 @@ class RadLib:
                     "p3d", "p8w", "pi3d", "qv3d", "tsk", "xland", "xice", "snow"):
             if kw.get(req) is None:
                 raise TypeError("RRTMG_SWRAD: required argument %s missing" % req)
-        self.check(self._sw(C.byref(d), C.byref(si), C.byref(so), C.byref(debug) if debug is not None else None))
+        return si, so
 
     def RRTMG_LWRAD(self, dims, debug=None, **kw):
         d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        li, lo = self._build_lw(kw)
+        self.check(self._lw(C.byref(d), C.byref(li), C.byref(lo), C.byref(debug) if debug is not None else None))
+
+    def RRTMG_LWSW(self, dims, lw_kw, sw_kw):
+        """One radiation step, RRTMG_LWRAD then RRTMG_SWRAD (the order of radiation_driver), through arc_rad_lwsw: with host
+        arrays both adapters share one upload / compute / download pipeline."""
+        d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        li, lo = self._build_lw(lw_kw)
+        si, so = self._build_sw(sw_kw)
+        fn = self.lib.arc_rad_lwsw
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(abi.ArcDims), C.POINTER(abi.ArcLwIn), C.POINTER(abi.ArcLwOut), C.POINTER(abi.ArcSwIn), C.POINTER(abi.ArcSwOut)]
+        self.check(fn(C.byref(d), C.byref(li), C.byref(lo), C.byref(si), C.byref(so)))
+
+    def _build_lw(self, kw):
         li, lo = abi.ArcLwIn(), abi.ArcLwOut()
         used = set()
         dev = [_is_device(v) for v in kw.values() if v is not None and (hasattr(v, "data_ptr") or isinstance(v, np.ndarray))]
@@ -148,7 +167,7 @@ class RadLib:
                     "xland", "xice", "snow"):
             if kw.get(req) is None:
                 raise TypeError("RRTMG_LWRAD: required argument %s missing" % req)
-        self.check(self._lw(C.byref(d), C.byref(li), C.byref(lo), C.byref(debug) if debug is not None else None))
+        return li, lo
 
 
     # optical_averaging (WRF-Chem chem/module_optical_averaging.F; restated)
