@@ -419,7 +419,7 @@ static int slab_slot(int set, size_t idx, size_t bytes, void **d) {
 
 static int slab_rows_default(int nrows, int ni) {
   const char *e = getenv("ARC_RAD_SLAB_COLUMNS");
-  long cols = e ? atol(e) : 16384;
+  long cols = e ? atol(e) : 32768;
   if (cols <= 0) return nrows;                  // 0: pipelining off
   long r = std::max(1L, cols / std::max(ni, 1));
   return (int)std::min<long>(r, nrows);
