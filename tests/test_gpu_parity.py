@@ -120,6 +120,70 @@ def test_c5_hundred_levels(lib, orc, ktab):
     check_lw(dom, lib, og, oo, tg, to)
 
 
+OPTION_SETS = [
+    dict(name="o3input2", flags=dict(o3input=2), extra="o33d"),
+    dict(name="ssib_albedo", flags=dict(sf_surface_physics=8), extra="alsw"),
+    dict(name="progn_qndrop", flags=dict(progn=1, f_qndrop=1), extra="qndrop"),
+    dict(name="cammgmp_radii", flags=dict(is_cammgmp_used=1), extra="radii"),
+    dict(name="no_ice_species_cold_rain", flags=dict(f_qi=0, f_qs=0, f_qg=0, warm_rain=0), extra=None),
+    dict(name="warm_rain", flags=dict(f_qi=0, f_qs=0, f_qg=0, warm_rain=1), extra=None),
+    dict(name="icloud0", flags=dict(icloud=0), extra=None),
+    dict(name="reqc_only", flags=dict(has_reqc=1), extra="re_cloud"),
+    dict(name="reqc_reqi_no_reqs", flags=dict(has_reqc=1, has_reqi=1), extra="re_cloud_ice"),
+    dict(name="no_aerosol_feedback", flags=dict(aer_ra_feedback=0, clean_atm_diag=0), extra=None),
+]
+
+
+@pytest.mark.parametrize("opt", OPTION_SETS, ids=[o["name"] for o in OPTION_SETS])
+def test_adapter_option_matrix(lib, orc, ktab, opt):
+    """Branches of the WRF<->RRTMG adapters (SW:10351-10906, LW:11897-12452): ozone from o33d with the shifted climatology
+    above the model top, SSiB albedos, prognostic droplet number, CAM-MG radii, missing ice species, warm rain, icloud = 0,
+    partial re_* sets.  Same bars as C1."""
+    dom = synth.make_domain(20, 6, 40, seed=50, cloudy_frac=0.8)
+    rng = np.random.default_rng(51)
+    shp3, shp2 = dom["t3d"].shape, dom["xcoszen"].shape
+    ex = opt["extra"]
+    if ex == "o33d":
+        dom["o33d"] = (rng.uniform(2e-8, 8e-6, shp3)).astype(np.float32)
+    if ex == "alsw":
+        for k in ("alswvisdir", "alswvisdif", "alswnirdir", "alswnirdif"):
+            dom[k] = rng.uniform(0.05, 0.5, shp2).astype(np.float32)
+    if ex == "qndrop":
+        dom["qndrop3d"] = rng.uniform(1e6, 5e8, shp3).astype(np.float32)
+    if ex == "radii":
+        dom["lradius"] = rng.uniform(4.0, 20.0, shp3).astype(np.float32); dom["iradius"] = rng.uniform(10.0, 120.0, shp3).astype(np.float32)
+    if ex in ("re_cloud", "re_cloud_ice"):
+        dom["re_cloud"] = np.where(dom["qc3d"] > 0, rng.uniform(2e-6, 20e-6, shp3), 0.0).astype(np.float32)
+        dom["re_ice"] = np.where(dom["qi3d"] > 0, rng.uniform(3e-6, 80e-6, shp3), 0.0).astype(np.float32)
+        dom["re_snow"] = np.zeros(shp3, np.float32)
+    init(lib, dom, ktab); init(orc, dom, ktab)
+    flags = R.common_flags(dom)
+    flags.update(dict(has_reqc=0, has_reqi=0, has_reqs=0))
+    flags.update(opt["flags"])
+    extra_sw = {k: dom[k] for k in ("o33d", "alswvisdir", "alswvisdif", "alswnirdir", "alswnirdif", "qndrop3d", "lradius", "iradius") if k in dom}
+    extra_lw = {k: dom[k] for k in ("o33d", "qndrop3d", "lradius", "iradius") if k in dom}
+    for which, extra in (("sw", extra_sw), ("lw", extra_lw)):
+        ncol = dom["ni"] * dom["nj"]
+        nlay = dom["nk"] + 1 if which == "sw" else lib.lw_nlayers()
+        dg, tg = abi.alloc_debug(ncol, nlay, 112 if which == "sw" else 140); do, to = abi.alloc_debug(ncol, nlay, 112 if which == "sw" else 140)
+        og, oo = R.alloc_outputs(dom, which), R.alloc_outputs(dom, which)
+        fl = dict(flags)
+        if which == "lw":
+            fl.pop("sf_surface_physics", None)
+        kwf = R.sw_kwargs if which == "sw" else R.lw_kwargs
+        fn_g = lib.RRTMG_SWRAD if which == "sw" else lib.RRTMG_LWRAD
+        fn_o = orc.RRTMG_SWRAD if which == "sw" else orc.RRTMG_LWRAD
+        kg = kwf(dom, og, **fl); kg.update(extra); ko = kwf(dom, oo, **fl); ko.update(extra)
+        if not flags.get("has_reqc"):
+            for k in ("re_cloud", "re_ice", "re_snow"):
+                kg.pop(k, None); ko.pop(k, None)
+        fn_g(dom["dims"], debug=dg, **kg); fn_o(dom["dims"], debug=do, **ko)
+        if which == "sw":
+            check_sw(dom, og, oo, tg, to)
+        else:
+            check_lw(dom, lib, og, oo, tg, to)
+
+
 def test_clean_off(lib, orc, ktab):
     dom = synth.make_domain(16, 4, 40, seed=8)
     og, oo, tg, to = both("sw", lib, orc, dom, ktab, clean_atm_diag=0)
