@@ -210,6 +210,8 @@ int  arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const flo
  * name == NULL only validates the files.  Negative return = -ARC_ERR_*.  (sw_kgbNN / cmbgbNN, SW:5022-6065, 11315-12384) */
 int  arc_rad_host_table(const char *inline_tables, const char *sw_data_path, const char *lw_data_path, float cp, float p_top,
                         int kme, const char *name, float *buf, int cap);
+/* Self-test (GPU): setcoef's jp | jt << 8 | jt1 << 12 for n host (p hPa, T K) pairs (SW:2854-2887), same device code as the prep kernels */
+int  arc_rad_selftest_pt(const float *p, const float *t, int n, int *packed);
 /* Self-test (GPU): mismatches of the kernels' branch-free division against IEEE division over n random operand pairs */
 int  arc_rad_selftest_div(int n, unsigned seed);
 /* FP32 FMA throughput of the device in TFLOP/s (microbenchmark; roofline denominator of the solver kernels) */

@@ -66,6 +66,24 @@ int arc_oracle_lw_omp(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, int nt
 }
 int arc_oracle_max_threads(void) { int n = (int)std::thread::hardware_concurrency(); return n > 0 ? n : 1; }
 
+// jp | jt << 8 | jt1 << 12 of setcoef_sw (SW:2854-2887) for n (p hPa, T K) pairs, with glibc logf like the oracle's setcoef
+int arc_oracle_pt(const float *p, const float *t, int n, int *packed) {
+  const orc::Tables &T = orc::tables();
+  if (!T.ready) return ARC_ERR_NOT_INIT;
+  const orc::FArr &preflog = T.in.get("sw_preflog"), &tref = T.in.get("sw_tref");
+  for (int q = 0; q < n; q++) {
+    float plog = logf(p[q]);
+    int jp = (int)(36.f - 5 * (plog + 0.04f));
+    if (jp < 1) jp = 1; else if (jp > 58) jp = 58;
+    int jt = (int)(3.f + (t[q] - tref(jp)) / 15.f);
+    if (jt < 1) jt = 1; else if (jt > 4) jt = 4;
+    int jt1 = (int)(3.f + (t[q] - tref(jp + 1)) / 15.f);
+    if (jt1 < 1) jt1 = 1; else if (jt1 > 4) jt1 = 4;
+    packed[q] = jp | (jt << 8) | (jt1 << 12);
+  }
+  return 0;
+}
+
 // radconst + calc_coszen, module_radiation_driver.F:2595-2666 (scalar restatement)
 void arc_oracle_radconst(float xtime, float julian, float degrad, float dpd, float *declin, float *solcon) {
   (void)xtime;

@@ -378,6 +378,34 @@ def test_errors(lib, ktab):
     run_pair("sw", lib, dom)
 
 
+def test_pressure_index_sweep(lib, orc, ktab):
+    """jp = int(36 - 5(ln p + 0.04)) and jt, jt1 on the device equal the oracle's (glibc logf) for every 11th float between 1e-3
+    and 1100 hPa and for every float within 256 ulps of each of the 58 jp boundaries ('hard parts')."""
+    dom = synth.make_domain(4, 2, 40, seed=1)
+    init(lib, dom, ktab); init(orc, dom, ktab)
+    L, O = lib.lib, orc.lib
+    for fn in (L.arc_rad_selftest_pt, O.arc_oracle_pt):
+        fn.restype = C.c_int
+        fn.argtypes = [abi.c_fp, abi.c_fp, C.c_int, abi.c_ip]
+    lo, hi = np.float32(1e-3).view(np.uint32), np.float32(1100.0).view(np.uint32)
+    bits = [np.arange(lo, hi, 11, dtype=np.uint32)]
+    for jb in range(1, 59):                                  # boundary: 36 - 5 (ln p + 0.04) = jb
+        pb = np.float32(np.exp((36.0 - jb) / 5.0 - 0.04)).view(np.uint32)
+        bits.append(np.arange(pb - 256, pb + 257, dtype=np.uint32))
+    p = np.concatenate(bits).view(np.float32)
+    rng = np.random.default_rng(9)
+    t = rng.uniform(160.0, 330.0, p.size).astype(np.float32)
+    a, b = np.zeros(p.size, np.int32), np.zeros(p.size, np.int32)
+    step = 1 << 22
+    for s0 in range(0, p.size, step):
+        n = min(step, p.size - s0)
+        pp, tt = np.ascontiguousarray(p[s0:s0 + n]), np.ascontiguousarray(t[s0:s0 + n])
+        lib.check(L.arc_rad_selftest_pt(abi.fptr(pp), abi.fptr(tt), n, a[s0:s0 + n].ctypes.data_as(abi.c_ip)))
+        assert O.arc_oracle_pt(abi.fptr(pp), abi.fptr(tt), n, b[s0:s0 + n].ctypes.data_as(abi.c_ip)) == 0
+    assert p.size > 15_000_000
+    assert np.array_equal(a, b), "%d index triples differ" % int((a != b).sum())
+
+
 def test_branch_free_division_is_ieee(lib, ktab):
     """The kernels' division (reciprocal + Newton + two residual corrections, no range-check branch) rounds like IEEE
     division over the operand ranges the path uses."""

@@ -1195,6 +1195,23 @@ int arc_rad_host_table(const char *inline_tables, const char *sw_data_path, cons
   return n;
 }
 
+// Self-test (GPU): jp | jt << 8 | jt1 << 12 of setcoef for n host (p [hPa], T [K]) pairs, through the prep kernels' own code
+int arc_rad_selftest_pt(const float *p, const float *t, int n, int *packed) {
+  if (!g.ready) { g.err = "arc_rad_selftest_pt: not initialised"; return ARC_ERR_NOT_INIT; }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  const float *dp, *dt; void *dout;
+  int rc;
+  if ((rc = in_arr(ARC_MEM_HOST, p, n, &dp))) return rc;
+  if ((rc = in_arr(ARC_MEM_HOST, t, n, &dt))) return rc;
+  if ((rc = stage_slot((size_t)n * 4, &dout))) return rc;
+  launch_selftest_pt(g.D, dp, dt, n, (int *)dout, g.stream);
+  CK(cudaMemcpyAsync(packed, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // Self-test of the branch-free division used by the solver kernels against the compiler's IEEE division, over n
 // pseudo-random operand pairs with magnitudes 1e-30 .. 1e+10 (and exact zeros as numerators).  Returns mismatches.
 __global__ void k_selftest_div(int n, unsigned seed, int *bad) {

@@ -149,6 +149,7 @@ void launch_lw_prep(const LwArgs &a, cudaStream_t s);
 void launch_lw_solve(const LwArgs &a, cudaStream_t s);
 void launch_lw_reduce(const LwArgs &a, cudaStream_t s);
 void upload_band_descs(const HostTables &T);
+void launch_selftest_pt(const DevTables &tb, const float *p, const float *t, int n, int *packed, cudaStream_t s);
 void count_launch(int n = 1);
 long long launch_count();
 

@@ -350,6 +350,20 @@ __device__ inline int lw_cloud_optics(const DevTables &tb, int ib /*0..15*/, int
   return 0;
 }
 
+// Self-test tap: the pressure / temperature indices of setcoef for arbitrary (p, T) pairs, through the same pt_coef code
+// the prep kernels use (jp | jt << 8 | jt1 << 12).
+__global__ void k_selftest_pt(DevTables tb, const float *__restrict__ p, const float *__restrict__ t, int n, int *__restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  PTCoef c;
+  pt_coef(tb.sw_preflog, tb.sw_tref, p[q], t[q], c);
+  out[q] = c.jp | (c.jt << 8) | (c.jt1 << 12);
+}
+void launch_selftest_pt(const DevTables &tb, const float *p, const float *t, int n, int *packed, cudaStream_t s) {
+  k_selftest_pt<<<(n + 255) / 256, 256, 0, s>>>(tb, p, t, n, packed);
+  count_launch();
+}
+
 // ------------------------------------------------------------------------------------------------------
 // SW column preparation.  One thread per sunlit column.
 constexpr int PREP_MAXLAY = 160;
