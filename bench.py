@@ -332,7 +332,11 @@ def main():
     ls = nk + 1
     sw_bytes = nsun * 4.0 * (112 * ls * (15 + 3) + 112 * (ls + 1) * 6)
     roofline = {"kernel": "k_sw_solve", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+                "frac": ach / fp32_peak if fp32_peak > 0 else None,
+                # DRAM bytes of k_sw_solve per step: ncu --set full (profiles/r1_summary.md) measured 30.29 GB read+write for a
+                # 24,566-sunlit-column launch = 1.233 MB per sunlit column (layer solutions kept for the second sweep + per-g fluxes)
+                "traffic": 1.233e6 * nsun, "traffic_unit": "bytes per step (all k_sw_solve launches)",
+                "issue_slot_utilisation_ncu": 0.68,
                 "ms_per_step": sw_solve_ms,
                 "peak_source": "FP32 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP32 figure; nominal 74.5)",
                 "algorithmic_flops_per_column": fsw, "hbm_view": {"algorithmic_GB_per_step": sw_bytes / 1e9,
