@@ -165,35 +165,40 @@ __global__ void __launch_bounds__(256) k_aer_mie(AerArgs a, AerDev d) {
     const float u = ti - (float)ii;
     const float w00 = (1.f - t) * (1.f - u), w10 = t * (1.f - u), w01 = (1.f - t) * u, w11 = t * u;
     const float x = (2.f * logf(r) - xrmax - xrmin) / (xrmax - xrmin);
-    // series sum_j c_j T_j(x) with the bilinearly interpolated coefficients, c_0 halved (chebev)
-    float acc[AER_NQ] = {0.f, 0.f, 0.f};
+    // series sum_j c_j T_j(x), c_0 halved (chebev), evaluated at the four refractive-index corners (12 accumulators), then
+    // blended bilinearly.  The coefficient rows are zero-padded from 50 to 52, so the padding needs no special case.
+    float a4[AER_NQ][4];
+#pragma unroll
+    for (int qn = 0; qn < AER_NQ; qn++) { a4[qn][0] = 0.f; a4[qn][1] = 0.f; a4[qn][2] = 0.f; a4[qn][3] = 0.f; }
+    const float *cell = tab + (ir * AER_NREFI + ii) * AER_NCOEF_PAD;
     float tjm1 = 1.f, tj = x;          // T_0, T_1
+    const float x2 = 2.f * x;
 #pragma unroll 1
     for (int j4 = 0; j4 < AER_NCOEF_PAD; j4 += 4) {
-      float T[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int jj = j4 + e;
-        float v;
-        if (jj == 0) v = 0.5f;
-        else if (jj == 1) v = x;
-        else { v = 2.f * x * tj - tjm1; tjm1 = tj; tj = v; }
-        T[e] = jj < AER_NCOEF ? v : 0.f;
+      float T0, T1, T2, T3;
+      if (j4 == 0) {
+        T0 = 0.5f; T1 = x;
+        T2 = fmaf(x2, tj, -tjm1); T3 = fmaf(x2, T2, -tj);
+      } else {
+        T0 = fmaf(x2, tj, -tjm1); T1 = fmaf(x2, T0, -tj); T2 = fmaf(x2, T1, -T0); T3 = fmaf(x2, T2, -T1);
       }
+      tjm1 = T2; tj = T3;
 #pragma unroll
       for (int qn = 0; qn < AER_NQ; qn++) {
-        const float *base = tab + ((qn * AER_NREFR + ir) * AER_NREFI + ii) * AER_NCOEF_PAD + j4;
+        const float *base = cell + qn * (AER_NREFR * AER_NREFI * AER_NCOEF_PAD) + j4;
         const float4 c00 = *reinterpret_cast<const float4 *>(base);
         const float4 c01 = *reinterpret_cast<const float4 *>(base + AER_NCOEF_PAD);
         const float4 c10 = *reinterpret_cast<const float4 *>(base + AER_NREFI * AER_NCOEF_PAD);
         const float4 c11 = *reinterpret_cast<const float4 *>(base + (AER_NREFI + 1) * AER_NCOEF_PAD);
-        const float cx = w00 * c00.x + w01 * c01.x + w10 * c10.x + w11 * c11.x;
-        const float cy = w00 * c00.y + w01 * c01.y + w10 * c10.y + w11 * c11.y;
-        const float cz = w00 * c00.z + w01 * c01.z + w10 * c10.z + w11 * c11.z;
-        const float cw = w00 * c00.w + w01 * c01.w + w10 * c10.w + w11 * c11.w;
-        acc[qn] += cx * T[0] + cy * T[1] + cz * T[2] + cw * T[3];
+        a4[qn][0] = fmaf(c00.w, T3, fmaf(c00.z, T2, fmaf(c00.y, T1, fmaf(c00.x, T0, a4[qn][0]))));
+        a4[qn][1] = fmaf(c01.w, T3, fmaf(c01.z, T2, fmaf(c01.y, T1, fmaf(c01.x, T0, a4[qn][1]))));
+        a4[qn][2] = fmaf(c10.w, T3, fmaf(c10.z, T2, fmaf(c10.y, T1, fmaf(c10.x, T0, a4[qn][2]))));
+        a4[qn][3] = fmaf(c11.w, T3, fmaf(c11.z, T2, fmaf(c11.y, T1, fmaf(c11.x, T0, a4[qn][3]))));
       }
     }
+    float acc[AER_NQ];
+#pragma unroll
+    for (int qn = 0; qn < AER_NQ; qn++) acc[qn] = w00 * a4[qn][0] + w01 * a4[qn][1] + w10 * a4[qn][2] + w11 * a4[qn][3];
     const float pext = expf(acc[0]);
     const float pscat = fminf(expf(acc[1]), pext);
     const float pasm = expf(acc[2]);
