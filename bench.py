@@ -172,7 +172,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")           # keep NCCL's version banner off stdout: one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]                      # NCCL prints its version banner to stdout at these levels: one JSON line only
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
