@@ -239,7 +239,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
-        for n in ("sw_mcica", "sw_prep", "sw_solve", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_reduce"):
+        for n in ("sw_mcica", "sw_prep", "sw_solve", "sw_sweep", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_sweep", "lw_reduce"):
             kms[n] = kms.get(n, 0.0) + float(L.arc_rad_last_kernel_ms(n.encode()))
     e1.record(stream)
     barrier()

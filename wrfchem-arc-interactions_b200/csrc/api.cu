@@ -125,7 +125,12 @@ void carve_lw(LwWs &w, char *base, size_t &bytes) {
   w.laytrop = c.take<int>(cap);
   w.colf = c.take<float>((size_t)LWF_N * cap);
   w.secdiff = c.take<float>((size_t)NBLW * cap);
-  w.part = c.take<float>((size_t)NGLW * (nl + 1) * w.nk * pcap);
+  const size_t nv = (w.kslot[K_NU] != 0) ? 2 : 1;          // streams: full (+ clear) [, clean (+ clean-clear)]
+  w.scrU = c.take<float2>(nv * NGLW * (nl + 1) * pcap);
+  w.scrC = c.take<float2>(nv * NGLW * (nl + 1) * pcap);
+  w.scrD = c.take<float2>(nv * NGLW * (nl + 1) * pcap);
+  w.scrS = c.take<float2>(nv * NGLW * pcap);
+  w.bpart = c.take<float>((size_t)NBLW * (nl + 1) * w.nk * pcap);
   bytes = c.off;
 }
 
@@ -966,6 +971,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       b.ws.coef += c0; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0; b.ws.laytrop += c0; b.ws.colf += c0;
       b.ws.secdiff += c0;
       { Timed t("lw_solve"); launch_lw_solve(b, g.stream); }
+      { Timed t("lw_sweep"); launch_lw_sweep(b, g.stream); }
       { Timed t("lw_reduce"); launch_lw_reduce(b, g.stream); }
     }
   }

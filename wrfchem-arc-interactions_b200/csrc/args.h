@@ -105,7 +105,14 @@ struct LwWs {
   int *laytrop;            // [cap]
   float *colf;             // [LWF_N][cap]
   float *secdiff;          // [16][cap]
-  float *part;             // [NGLW][nlay+1][nk][cap]
+  // Level-indexed records handed from k_lw_solve (taumol + downward sweep) to k_lw_sweep (upward sweep + band sum):
+  // [stream v][NGLW][nlay+1][pcap] float2, v = 0 full (+ clear), 1 clean (+ clean-clear).  level = layer + 1 for the layer
+  // quantities, = the layer's lower interface for scrD.
+  float2 *scrU;            // (atrans, bbugas)
+  float2 *scrC;            // (X, Y) of radlu' = radlu - radlu X + Y; written only where the column has cloud in the layer
+  float2 *scrD;            // downward radiances at the level: (all-sky, clear-sky)
+  float2 *scrS;            // [v][NGLW][pcap] upward radiances leaving the surface: (all-sky, clear-sky)
+  float *bpart;            // [16][nlay+1][nk][pcap]  per-band sums of the radiances; nk = kinds in use, slot of kind k = kslot[k]
   int nk; int kslot[NKIND];
 };
 
@@ -147,6 +154,7 @@ void launch_sw_solve(const SwArgs &a, cudaStream_t s);
 void launch_sw_reduce(const SwArgs &a, cudaStream_t s);
 void launch_lw_prep(const LwArgs &a, cudaStream_t s);
 void launch_lw_solve(const LwArgs &a, cudaStream_t s);
+void launch_lw_sweep(const LwArgs &a, cudaStream_t s);
 void launch_lw_reduce(const LwArgs &a, cudaStream_t s);
 void upload_band_descs(const HostTables &T);
 void launch_selftest_pt(const DevTables &tb, const float *p, const float *t, int n, int *packed, cudaStream_t s);

@@ -10,8 +10,10 @@ namespace arc {
 
 static __constant__ LwBandDesc c_lw[16];
 static __constant__ int c_lw_ngb[NGLW];    // band index 0..15 of each LW g-point
+static int h_lw_ng[16];                    // host copy: g-points per band (block shape of k_lw_sweep)
 void upload_band_descs_lw(const HostTables &T) {
   cudaMemcpyToSymbol(c_lw, T.lw, sizeof(LwBandDesc) * 16);
+  for (int b = 0; b < 16; b++) h_lw_ng[b] = T.lw[b].ng;
   int ngb[NGLW];
   for (int i = 0; i < NGLW; i++) ngb[i] = T.lw_ngb[i] - 1;
   cudaMemcpyToSymbol(c_lw_ngb, ngb, sizeof(int) * NGLW);
@@ -94,24 +96,18 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
     aw[w] = w < ws.W ? ws.anyc[(size_t)w * cap + c] : 0u;
   }
 
-  // per-layer results of the downward sweep needed by the upward sweep; v = 0 full (taug + taua), 1 clean (taug)
-  float At[2][NL], Bg[2][NL], Ao[2][NL], Bt[2][NL], Ef[NL];
-
+  // Per-layer results of the downward sweep that the upward sweep (k_lw_sweep) needs go to level-indexed scratch
+  // records (layout in args.h): level = layer + 1 for the layer quantities, level = the layer's lower interface for the
+  // downward fluxes.  v = 0 full (taug + taua), 1 clean (taug).
   float radld[2] = {0.f, 0.f}, radclrd[2] = {0.f, 0.f};
   int iclddn = 0;
   float fracs_bot = 0.f;
-  const size_t stf = (size_t)nlay * cap;
-  const int nk = ws.nk;
-  const bool do_clnc = (a.variants & ARC_VAR_CLEANCLEAR) != 0;
   const size_t pcap = ws.pcap;
-  float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * pcap + c;
-  const size_t oFU = (size_t)ws.kslot[K_FU] * pcap, oFD = (size_t)ws.kslot[K_FD] * pcap, oCU = (size_t)ws.kslot[K_CU] * pcap,
-               oCD = (size_t)ws.kslot[K_CD] * pcap, oNU = (size_t)ws.kslot[K_NU] * pcap, oND = (size_t)ws.kslot[K_ND] * pcap,
-               oXU = (size_t)ws.kslot[K_XU] * pcap, oXD = (size_t)ws.kslot[K_XD] * pcap;
-  // TOA downward radiance is zero
-  part[(size_t)nlay * nk * pcap + oFD] = 0.f; part[(size_t)nlay * nk * pcap + oCD] = 0.f;
-  if (do_clean) part[(size_t)nlay * nk * pcap + oND] = 0.f;
-  if (do_clnc) part[(size_t)nlay * nk * pcap + oXD] = 0.f;
+  const size_t lvs = (size_t)g * (nlay + 1) * pcap + c;      // record of level 0, stream 0
+  const size_t vs = (size_t)NGLW * (nlay + 1) * pcap;        // stream stride
+  float2 *scrU = ws.scrU + lvs, *scrC = ws.scrC + lvs, *scrD = ws.scrD + lvs;
+  scrD[(size_t)nlay * pcap] = make_float2(0.f, 0.f);         // TOA downward radiance is zero
+  if (do_clean) scrD[vs + (size_t)nlay * pcap] = make_float2(0.f, 0.f);
 
   // Planck function at the top interface of the current layer; carried downwards
   auto planck_at = [&](float t) {
@@ -398,7 +394,6 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
       const float abscld = 1.f - transcld;
       efclfrac = abscld * cldfmc;
     }
-    Ef[lay] = efclfrac;
     if (icldlyr) iclddn = 1;
 #pragma unroll
     for (int v = 0; v < 2; v++) {
@@ -455,7 +450,9 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
           bbutot = plfrac * (blay + tfactot * dplankup);
         }
         radld[v] = radld[v] - radld[v] * (atrans + efclfrac * (1.f - atrans)) + gassrc + cldfmc * (bbdtot * atot - gassrc);
-        Ao[v][lay] = atot; Bt[v][lay] = bbutot;
+        // the same step for the upward radiance is radlu - radlu * X + Y (LW:3334-3338): hand over X and Y
+        const float gassrcu = bbugas * atrans;
+        scrC[v * vs + (size_t)(lay + 1) * pcap] = make_float2(atrans + efclfrac * (1.f - atrans), gassrcu + cldfmc * (bbutot * atot - gassrcu));
       } else {
         if (odepth <= 0.06f) {
           atrans = odepth - 0.5f * odepth * odepth;
@@ -473,11 +470,10 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
         }
         radld[v] = radld[v] + (bbd - radld[v]) * atrans;
       }
-      At[v][lay] = atrans; Bg[v][lay] = bbugas;
       if (iclddn == 1) radclrd[v] = radclrd[v] + (bbd - radclrd[v]) * atrans;
       else radclrd[v] = radld[v];
-      part[(size_t)lay * nk * pcap + (v == 0 ? oFD : oND)] = radld[v];
-      if (v == 0 || do_clnc) part[(size_t)lay * nk * pcap + (v == 0 ? oCD : oXD)] = radclrd[v];
+      scrU[v * vs + (size_t)(lay + 1) * pcap] = make_float2(atrans, bbugas);
+      scrD[v * vs + (size_t)lay * pcap] = make_float2(radld[v], radclrd[v]);
     }
     plev_up = plev_dn;
   }
@@ -494,52 +490,9 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
   }
   const float rad0 = fracs_bot * plankbnd;
   const float reflect = 1.f - emis;
-  float radlu[2], radclru[2];
-#pragma unroll
-  for (int v = 0; v < 2; v++) {
-    if (v == 1 && !do_clean) break;
-    radlu[v] = rad0 + reflect * radld[v];
-    radclru[v] = rad0 + reflect * radclrd[v];
-    part[v == 0 ? oFU : oNU] = radlu[v];
-    if (v == 0 || do_clnc) part[v == 0 ? oCU : oXU] = radclru[v];
-  }
-  // ---- upward sweep (LW:3322-3356); the stored layer quantities are fetched one layer ahead of their use
-  struct Up { float at[2], bg[2], ao[2], bt[2], ef; };
-  auto load_up = [&](int lay, Up &u) {
-    const bool icl = (aw[lay >> 5] >> (lay & 31)) & 1u;
-    u.ef = Ef[lay];
-#pragma unroll
-    for (int v = 0; v < 2; v++) {
-      if (v == 1 && !do_clean) break;
-      u.at[v] = At[v][lay]; u.bg[v] = Bg[v][lay];
-      if (icl) { u.ao[v] = Ao[v][lay]; u.bt[v] = Bt[v][lay]; }
-    }
-  };
-  Up unx;
-  load_up(0, unx);
-  for (int lay = 0; lay < nlay; lay++) {
-    const Up u = unx;
-    if (lay + 1 < nlay) load_up(lay + 1, unx);
-    const bool icldlyr = (aw[lay >> 5] >> (lay & 31)) & 1u;
-    const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
-    const float cldfmc = cloudy ? 1.f : 0.f;
-    const float efclfrac = u.ef;
-#pragma unroll
-    for (int v = 0; v < 2; v++) {
-      if (v == 1 && !do_clean) break;
-      const float atrans = u.at[v], bbugas = u.bg[v];
-      if (icldlyr) {
-        const float gassrc = bbugas * atrans;
-        radlu[v] = radlu[v] - radlu[v] * (atrans + efclfrac * (1.f - atrans)) + gassrc + cldfmc * (u.bt[v] * u.ao[v] - gassrc);
-      } else {
-        radlu[v] = radlu[v] + (bbugas - radlu[v]) * atrans;
-      }
-      if (iclddn == 1) radclru[v] = radclru[v] + (bbugas - radclru[v]) * atrans;
-      else radclru[v] = radlu[v];
-      part[(size_t)(lay + 1) * nk * pcap + (v == 0 ? oFU : oNU)] = radlu[v];
-      if (v == 0 || do_clnc) part[(size_t)(lay + 1) * nk * pcap + (v == 0 ? oCU : oXU)] = radclru[v];
-    }
-  }
+  // upward radiances leaving the surface; the upward sweep itself runs in k_lw_sweep
+  ws.scrS[(size_t)g * pcap + c] = make_float2(rad0 + reflect * radld[0], rad0 + reflect * radclrd[0]);
+  if (do_clean) ws.scrS[(size_t)(NGLW + g) * pcap + c] = make_float2(rad0 + reflect * radld[1], rad0 + reflect * radclrd[1]);
 }
 
 template <int NL>
@@ -617,6 +570,95 @@ void launch_lw_solve(const LwArgs &a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Upward sweep of rtrnmc (LW:3322-3356) + ordered sum over the g-points of a band (LW:3365-3395).
+// One thread per (column, band, stream): the NG upward radiances of the band's g-points are its register state; per
+// level it requests the 2 NG records of that level together (they were written by k_lw_solve; the addresses do not depend
+// on the recurrence, so the memory system sees 2 NG independent loads per thread), advances the NG two-term recurrences
+// and adds the NG up / down radiances in g order.  It writes ONE band partial [band][level][kind][c] per kind instead of
+// NG per-g partials.  No shared memory, no barriers, no atomics; lanes = neighbouring columns, so every access is a
+// full line.  HBM-bound: 16 B per (column, g, level, stream).
+template <int NG>
+__global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int b) {
+  const LwWs &ws = a.ws;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= a.ncols) return;
+  const int v = blockIdx.y;                    // 0 full (+ clear), 1 clean (+ clean-clear)
+  const int g0 = c_lw[b].g0;
+  const int nlay = ws.nlay, nk = ws.nk;
+  const size_t pcap = ws.pcap, cap = ws.cap;
+  const size_t lstride = (size_t)(nlay + 1) * pcap;            // g-point stride of the records
+  const size_t base = ((size_t)v * NGLW + g0) * lstride + c;
+  const float2 *scrU = ws.scrU + base, *scrC = ws.scrC + base, *scrD = ws.scrD + base;
+
+  bool iclddn = false;                         // the flag the downward sweep leaves behind (LW:3218): any cloud in the column
+  for (int w = 0; w < ws.W; w++) iclddn = iclddn || ws.anyc[(size_t)w * cap + c] != 0u;
+
+  float rl[NG], rc[NG];
+  float *bpart = ws.bpart + (size_t)b * (nlay + 1) * nk * pcap + c;
+  const int kU = ws.kslot[v == 0 ? K_FU : K_NU], kD = ws.kslot[v == 0 ? K_FD : K_ND];
+  const int kCU = ws.kslot[v == 0 ? K_CU : K_XU], kCD = ws.kslot[v == 0 ? K_CD : K_XD];
+  const bool clr = v == 0 || (a.variants & ARC_VAR_CLEANCLEAR) != 0;
+  {
+    float2 d[NG];
+    float sU = 0.f, sCU = 0.f, sD = 0.f, sCD = 0.f;
+#pragma unroll
+    for (int i = 0; i < NG; i++) {
+      const float2 s0 = ws.scrS[((size_t)v * NGLW + g0 + i) * pcap + c];
+      rl[i] = s0.x; rc[i] = s0.y;
+      d[i] = __ldcs(scrD + i * lstride);
+    }
+#pragma unroll
+    for (int i = 0; i < NG; i++) { sU = sU + rl[i]; sCU = sCU + rc[i]; sD = sD + d[i].x; sCD = sCD + d[i].y; }
+    __stcs(bpart + (size_t)kU * pcap, sU); __stcs(bpart + (size_t)kD * pcap, sD);
+    if (clr) { __stcs(bpart + (size_t)kCU * pcap, sCU); __stcs(bpart + (size_t)kCD * pcap, sCD); }
+  }
+  uint32_t aw = 0u;
+  for (int lev = 1; lev <= nlay; lev++) {
+    const int lay = lev - 1;
+    if ((lay & 31) == 0) aw = ws.anyc[(size_t)(lay >> 5) * cap + c];
+    const bool icldlyr = (aw >> (lay & 31)) & 1u;
+    float2 u[NG], d[NG];
+    const size_t lo = (size_t)lev * pcap;
+#pragma unroll
+    for (int i = 0; i < NG; i++) { u[i] = __ldcs(scrU + i * lstride + lo); d[i] = __ldcs(scrD + i * lstride + lo); }
+    float sU = 0.f, sCU = 0.f, sD = 0.f, sCD = 0.f;
+    if (icldlyr) {
+#pragma unroll
+      for (int i = 0; i < NG; i++) {
+        const float2 xy = __ldcs(scrC + i * lstride + lo);
+        rl[i] = rl[i] - rl[i] * xy.x + xy.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NG; i++) rl[i] = rl[i] + (u[i].y - rl[i]) * u[i].x;
+    }
+#pragma unroll
+    for (int i = 0; i < NG; i++) {
+      if (iclddn) rc[i] = rc[i] + (u[i].y - rc[i]) * u[i].x;
+      else rc[i] = rl[i];
+      sU = sU + rl[i]; sCU = sCU + rc[i]; sD = sD + d[i].x; sCD = sCD + d[i].y;
+    }
+    float *bp = bpart + (size_t)lev * nk * pcap;
+    __stcs(bp + (size_t)kU * pcap, sU); __stcs(bp + (size_t)kD * pcap, sD);
+    if (clr) { __stcs(bp + (size_t)kCU * pcap, sCU); __stcs(bp + (size_t)kCD * pcap, sCD); }
+  }
+}
+
+void launch_lw_sweep(const LwArgs &a, cudaStream_t s) {
+  const dim3 grid((a.ncols + 127) / 128, (a.variants & ARC_VAR_CLEAN) ? 2 : 1);
+  for (int b = 0; b < NBLW; b++) {
+    switch (h_lw_ng[b]) {
+#define SWEEP_CASE(N) case N: k_lw_sweep<N><<<grid, 128, 0, s>>>(a, b); break;
+      SWEEP_CASE(1) SWEEP_CASE(2) SWEEP_CASE(3) SWEEP_CASE(4) SWEEP_CASE(5) SWEEP_CASE(6) SWEEP_CASE(7) SWEEP_CASE(8)
+      SWEEP_CASE(9) SWEEP_CASE(10) SWEEP_CASE(11) SWEEP_CASE(12) SWEEP_CASE(13) SWEEP_CASE(14) SWEEP_CASE(15) SWEEP_CASE(16)
+#undef SWEEP_CASE
+      default: break;
+    }
+  }
+  count_launch(NBLW);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Reduction: per band sum over its g-points in order, x wtdiff x delwave, sum over bands, x fluxfac
 // (LW:3365-3395); heating rates (LW:3397-3408); scatter (LW:12646-12692).  Block = 32 columns x 8 level-lanes.
 constexpr int RED_CX = 64, RED_LY = 4;
@@ -644,19 +686,15 @@ __global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_lw_reduce(LwArgs a) {
     float tot[NKIND];
 #pragma unroll
     for (int k = 0; k < NKIND; k++) tot[k] = 0.f;
-    const float *p = ws.part + ((size_t)lev * nk) * cap + c;
-    for (int b = 0; b < NBLW; b++) {
+    const float *p = ws.bpart + ((size_t)lev * nk) * cap + c;      // band sums from k_lw_sweep
+#pragma unroll 4
+    for (int b = 0; b < NBLW; b++, p += gstride) {
       float r[NKIND];
 #pragma unroll
       for (int k = 0; k < NKIND; k++) r[k] = 0.f;
-      const int ng = c_lw[b].ng;
-#pragma unroll 4
-      for (int q = 0; q < ng; q++, p += gstride) {
-        r[K_FU] = r[K_FU] + p[oFU]; r[K_FD] = r[K_FD] + p[oFD];
-        r[K_CU] = r[K_CU] + p[oCU]; r[K_CD] = r[K_CD] + p[oCD];
-        if (do_clean) { r[K_NU] = r[K_NU] + p[oNU]; r[K_ND] = r[K_ND] + p[oND]; }
-        if (do_clnc) { r[K_XU] = r[K_XU] + p[oXU]; r[K_XD] = r[K_XD] + p[oXD]; }
-      }
+      r[K_FU] = p[oFU]; r[K_FD] = p[oFD]; r[K_CU] = p[oCU]; r[K_CD] = p[oCD];
+      if (do_clean) { r[K_NU] = p[oNU]; r[K_ND] = p[oND]; }
+      if (do_clnc) { r[K_XU] = p[oXU]; r[K_XD] = p[oXD]; }
       const float dw = a.tb.delwave[b];
 #pragma unroll
       for (int k = 0; k < NKIND; k++) tot[k] = tot[k] + (r[k] * wtdiff) * dw;
