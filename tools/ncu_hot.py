@@ -3,6 +3,9 @@
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]; data = rows[2:]
+for _i, _r in enumerate(data):
+    if _r and _r[0] == 'Kernel Name': data = data[:_i]; break
+data = [r for r in data if len(r) == len(hdr)]
 ix = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
 reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]

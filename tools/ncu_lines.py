@@ -9,6 +9,9 @@ csvf, obj, kern = sys.argv[1:4]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 rows = list(csv.reader(open(csvf)))
 hdr = rows[1]; data = rows[2:]
+for _i, _r in enumerate(data):
+    if _r and _r[0] == 'Kernel Name': data = data[:_i]; break
+data = [r for r in data if len(r) == len(hdr)]
 ix = {h: i for i, h in enumerate(hdr)}
 import tempfile, os, glob
 if obj.endswith(".cubin"):

@@ -110,7 +110,12 @@ void carve_sw(SwWs &w, char *base, size_t &bytes) {
   w.laytrop = c.take<int>(cap);
   w.laysol = c.take<int>((size_t)NBSW * cap);
   w.colf = c.take<float>((size_t)SWF_N * cap);
-  w.part = c.take<float>((size_t)NGSW * (nl + 1) * w.nk * pcap);
+  const size_t ns = w.nk / 2;                              // streams = pairs of flux kinds
+  w.recP = c.take<float4>(ns * NGSW * (nl + 1) * pcap);
+  w.recE = c.take<float>(ns * NGSW * (nl + 1) * pcap);
+  w.recR = c.take<float2>(ns * NGSW * (nl + 1) * pcap);
+  w.zinc = c.take<float>((size_t)NGSW * pcap);
+  w.bpart = c.take<float>((size_t)sw_sweep_groups() * (nl + 1) * w.nk * pcap);
   w.dirs = c.take<float>((size_t)NGSW * pcap);
   bytes = c.off;
 }
@@ -130,7 +135,7 @@ void carve_lw(LwWs &w, char *base, size_t &bytes) {
   w.scrC = c.take<float2>(nv * NGLW * (nl + 1) * pcap);
   w.scrD = c.take<float2>(nv * NGLW * (nl + 1) * pcap);
   w.scrS = c.take<float2>(nv * NGLW * pcap);
-  w.bpart = c.take<float>((size_t)NBLW * (nl + 1) * w.nk * pcap);
+  w.bpart = c.take<float>((size_t)lw_sweep_groups() * (nl + 1) * w.nk * pcap);
   bytes = c.off;
 }
 
@@ -804,6 +809,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   if (ext && (variants & ARC_VAR_CLEAN)) variants |= ARC_VAR_CLEANCLEAR;
   if (!ext) variants &= ~ARC_VAR_CLEANCLEAR;
   a.variants = variants;
+  a.ngroups = sw_sweep_groups();
   a.status = g.d_status;
 
   std::vector<std::pair<void *, std::pair<void *, size_t>>> dbglist;
@@ -850,6 +856,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
         b.ws.cols += c0; b.ws.coef += c0; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0;
         b.ws.laytrop += c0; b.ws.laysol += c0; b.ws.colf += c0;
         { Timed t("sw_solve"); launch_sw_solve(b, g.stream); }
+        { Timed t("sw_sweep"); launch_sw_sweep(b, g.stream); }
         { Timed t("sw_reduce"); launch_sw_reduce(b, g.stream); }
       }
     }
@@ -939,6 +946,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   int variants = ARC_VAR_FULL | ARC_VAR_CLEAR;
   if (in->clean_atm_diag > 0) variants |= ARC_VAR_CLEAN | (ext ? ARC_VAR_CLEANCLEAR : 0);   // clean call: LW:11022-11027
   a.variants = variants;
+  a.ngroups = lw_sweep_groups();
   a.status = g.d_status;
 
   std::vector<std::pair<void *, std::pair<void *, size_t>>> dbglist;

@@ -37,6 +37,23 @@ struct CloudFields {
   const float *re_cloud, *re_ice, *re_snow, *f_ice_phy, *xland, *xice, *snow;
 };
 
+// Sweep groups (k_sw_sweep / k_lw_sweep): consecutive g-points of one band handled by one thread per column
+constexpr int SWEEP_MAXGRP = 32;
+struct SweepGroups { int n; int band[SWEEP_MAXGRP], g0[SWEEP_MAXGRP], ng[SWEEP_MAXGRP]; };
+inline SweepGroups make_sweep_groups(const int *ng, const int *g0, int nbands, int gmax) {
+  SweepGroups G{};
+  for (int b = 0; b < nbands; b++) {
+    const int parts = (ng[b] + gmax - 1) / gmax;
+    int done = 0;
+    for (int q = 0; q < parts; q++) {
+      const int n = (ng[b] - done + (parts - q) - 1) / (parts - q);
+      G.band[G.n] = b; G.g0[G.n] = g0[b] + done; G.ng[G.n] = n; G.n++;
+      done += n;
+    }
+  }
+  return G;
+}
+
 // flux "kinds" in the partial buffer: full up/down, clear up/down, clean up/down, clean-clear up/down
 enum { K_FU = 0, K_FD, K_CU, K_CD, K_NU, K_ND, K_XU, K_XD, NKIND };
 
@@ -60,7 +77,13 @@ struct SwWs {
   int *laytrop;            // [cap]
   int *laysol;             // [14][cap]            layer (0-based) where sfluxzen is taken, -1 = never
   float *colf;             // [SWF_N][cap]
-  float *part;             // [NGSW][nlay+1][nk][cap]   partial fluxes; nk = kinds in use, slot of kind k = kslot[k]
+  // Level records handed from k_sw_solve (taumol, reftra, bottom-up sweep) to k_sw_sweep (top-down sweep + band sum):
+  // [stream slot][NGSW][nlay+1][pcap]; stream slots in the order clear, full [, clean][, clean-clear]
+  float4 *recP;            // (ref, refd, tra, trad) of the layer below the level (level 0 unused)
+  float *recE;             // direct-beam transmittance of that layer
+  float2 *recR;            // (rup, rupd) at the level; level 0 = surface albedos
+  float *zinc;             // [NGSW][pcap]        incident flux of the g-point (adjflux x sfluxzen x mu0)
+  float *bpart;            // [sweep group][nlay+1][nk][pcap]  per-group sums of the fluxes; nk = kinds in use, slot of kind k = kslot[k]
   int nk; int kslot[NKIND];
   float *dirs;             // [NGSW][cap]          surface direct beam without delta scaling (x incident flux)
 };
@@ -71,6 +94,7 @@ struct SwArgs {
   CloudFields cf;
   SwWs ws;
   int ncols;                // columns in this chunk
+  int ngroups;              // sweep groups (sw_sweep_groups())
   int variants;             // ARC_VAR_* mask
   int o3input, aer_ra_feedback, sf_surface_physics;
   float solcon;
@@ -112,7 +136,7 @@ struct LwWs {
   float2 *scrC;            // (X, Y) of radlu' = radlu - radlu X + Y; written only where the column has cloud in the layer
   float2 *scrD;            // downward radiances at the level: (all-sky, clear-sky)
   float2 *scrS;            // [v][NGLW][pcap] upward radiances leaving the surface: (all-sky, clear-sky)
-  float *bpart;            // [16][nlay+1][nk][pcap]  per-band sums of the radiances; nk = kinds in use, slot of kind k = kslot[k]
+  float *bpart;            // [sweep group][nlay+1][nk][pcap]  per-group sums of the radiances; nk = kinds in use, slot of kind k = kslot[k]
   int nk; int kslot[NKIND];
 };
 
@@ -123,6 +147,7 @@ struct LwArgs {
   LwWs ws;
   int col0;                 // first tile column of this chunk
   int ncols;
+  int ngroups;              // sweep groups (lw_sweep_groups())
   int variants;
   int o3input, aer_ra_feedback;
   const float *t8w, *p3d, *p8w, *pi3d, *o33d, *tsk, *emiss;
@@ -151,6 +176,9 @@ void launch_sw_night(const SwArgs &a, cudaStream_t s);
 void launch_mcica(const McicaArgs &a, cudaStream_t s);
 void launch_sw_prep(const SwArgs &a, cudaStream_t s);
 void launch_sw_solve(const SwArgs &a, cudaStream_t s);
+void launch_sw_sweep(const SwArgs &a, cudaStream_t s);
+int sw_sweep_groups();
+int lw_sweep_groups();
 void launch_sw_reduce(const SwArgs &a, cudaStream_t s);
 void launch_lw_prep(const LwArgs &a, cudaStream_t s);
 void launch_lw_solve(const LwArgs &a, cudaStream_t s);

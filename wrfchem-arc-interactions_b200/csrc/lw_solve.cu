@@ -10,10 +10,14 @@ namespace arc {
 
 static __constant__ LwBandDesc c_lw[16];
 static __constant__ int c_lw_ngb[NGLW];    // band index 0..15 of each LW g-point
-static int h_lw_ng[16];                    // host copy: g-points per band (block shape of k_lw_sweep)
+static SweepGroups h_lw_grp;               // sweep groups, see sw_solve.cu
+static __constant__ int c_lw_grp_band[SWEEP_MAXGRP];
 void upload_band_descs_lw(const HostTables &T) {
   cudaMemcpyToSymbol(c_lw, T.lw, sizeof(LwBandDesc) * 16);
-  for (int b = 0; b < 16; b++) h_lw_ng[b] = T.lw[b].ng;
+  int ngs[16], g0s[16];
+  for (int b = 0; b < 16; b++) { ngs[b] = T.lw[b].ng; g0s[b] = T.lw[b].g0; }
+  h_lw_grp = make_sweep_groups(ngs, g0s, 16, 16);
+  cudaMemcpyToSymbol(c_lw_grp_band, h_lw_grp.band, sizeof(int) * SWEEP_MAXGRP);
   int ngb[NGLW];
   for (int i = 0; i < NGLW; i++) ngb[i] = T.lw_ngb[i] - 1;
   cudaMemcpyToSymbol(c_lw_ngb, ngb, sizeof(int) * NGLW);
@@ -578,23 +582,22 @@ void launch_lw_solve(const LwArgs &a, cudaStream_t s) {
 // NG per-g partials.  No shared memory, no barriers, no atomics; lanes = neighbouring columns, so every access is a
 // full line.  HBM-bound: 16 B per (column, g, level, stream).
 template <int NG>
-__global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int b) {
+__global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int grp, int g0) {
   const LwWs &ws = a.ws;
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= a.ncols) return;
   const int v = blockIdx.y;                    // 0 full (+ clear), 1 clean (+ clean-clear)
-  const int g0 = c_lw[b].g0;
   const int nlay = ws.nlay, nk = ws.nk;
   const size_t pcap = ws.pcap, cap = ws.cap;
   const size_t lstride = (size_t)(nlay + 1) * pcap;            // g-point stride of the records
   const size_t base = ((size_t)v * NGLW + g0) * lstride + c;
-  const float2 *scrU = ws.scrU + base, *scrC = ws.scrC + base, *scrD = ws.scrD + base;
+  const float2 *__restrict__ scrU = ws.scrU + base, *__restrict__ scrC = ws.scrC + base, *__restrict__ scrD = ws.scrD + base;
 
   bool iclddn = false;                         // the flag the downward sweep leaves behind (LW:3218): any cloud in the column
   for (int w = 0; w < ws.W; w++) iclddn = iclddn || ws.anyc[(size_t)w * cap + c] != 0u;
 
   float rl[NG], rc[NG];
-  float *bpart = ws.bpart + (size_t)b * (nlay + 1) * nk * pcap + c;
+  float *__restrict__ bpart = ws.bpart + (size_t)grp * (nlay + 1) * nk * pcap + c;
   const int kU = ws.kslot[v == 0 ? K_FU : K_NU], kD = ws.kslot[v == 0 ? K_FD : K_ND];
   const int kCU = ws.kslot[v == 0 ? K_CU : K_XU], kCD = ws.kslot[v == 0 ? K_CD : K_XD];
   const bool clr = v == 0 || (a.variants & ARC_VAR_CLEANCLEAR) != 0;
@@ -644,18 +647,20 @@ __global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int b) {
   }
 }
 
+int lw_sweep_groups() { return h_lw_grp.n; }
 void launch_lw_sweep(const LwArgs &a, cudaStream_t s) {
   const dim3 grid((a.ncols + 127) / 128, (a.variants & ARC_VAR_CLEAN) ? 2 : 1);
-  for (int b = 0; b < NBLW; b++) {
-    switch (h_lw_ng[b]) {
-#define SWEEP_CASE(N) case N: k_lw_sweep<N><<<grid, 128, 0, s>>>(a, b); break;
+  for (int q = 0; q < h_lw_grp.n; q++) {
+    const int g0 = h_lw_grp.g0[q];
+    switch (h_lw_grp.ng[q]) {
+#define SWEEP_CASE(N) case N: k_lw_sweep<N><<<grid, 128, 0, s>>>(a, q, g0); break;
       SWEEP_CASE(1) SWEEP_CASE(2) SWEEP_CASE(3) SWEEP_CASE(4) SWEEP_CASE(5) SWEEP_CASE(6) SWEEP_CASE(7) SWEEP_CASE(8)
       SWEEP_CASE(9) SWEEP_CASE(10) SWEEP_CASE(11) SWEEP_CASE(12) SWEEP_CASE(13) SWEEP_CASE(14) SWEEP_CASE(15) SWEEP_CASE(16)
 #undef SWEEP_CASE
       default: break;
     }
   }
-  count_launch(NBLW);
+  count_launch(h_lw_grp.n);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -687,17 +692,20 @@ __global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_lw_reduce(LwArgs a) {
 #pragma unroll
     for (int k = 0; k < NKIND; k++) tot[k] = 0.f;
     const float *p = ws.bpart + ((size_t)lev * nk) * cap + c;      // band sums from k_lw_sweep
+    float r[NKIND];
+#pragma unroll
+    for (int k = 0; k < NKIND; k++) r[k] = 0.f;
 #pragma unroll 4
-    for (int b = 0; b < NBLW; b++, p += gstride) {
-      float r[NKIND];
+    for (int q = 0; q < a.ngroups; q++, p += gstride) {       // sweep groups in g order; a band's groups are consecutive
+      r[K_FU] = r[K_FU] + p[oFU]; r[K_FD] = r[K_FD] + p[oFD]; r[K_CU] = r[K_CU] + p[oCU]; r[K_CD] = r[K_CD] + p[oCD];
+      if (do_clean) { r[K_NU] = r[K_NU] + p[oNU]; r[K_ND] = r[K_ND] + p[oND]; }
+      if (do_clnc) { r[K_XU] = r[K_XU] + p[oXU]; r[K_XD] = r[K_XD] + p[oXD]; }
+      const int b = c_lw_grp_band[q];
+      if (q + 1 == a.ngroups || c_lw_grp_band[q + 1] != b) {
+        const float dw = a.tb.delwave[b];
 #pragma unroll
-      for (int k = 0; k < NKIND; k++) r[k] = 0.f;
-      r[K_FU] = p[oFU]; r[K_FD] = p[oFD]; r[K_CU] = p[oCU]; r[K_CD] = p[oCD];
-      if (do_clean) { r[K_NU] = p[oNU]; r[K_ND] = p[oND]; }
-      if (do_clnc) { r[K_XU] = p[oXU]; r[K_XD] = p[oXD]; }
-      const float dw = a.tb.delwave[b];
-#pragma unroll
-      for (int k = 0; k < NKIND; k++) tot[k] = tot[k] + (r[k] * wtdiff) * dw;
+        for (int k = 0; k < NKIND; k++) { tot[k] = tot[k] + (r[k] * wtdiff) * dw; r[k] = 0.f; }
+      }
     }
 #pragma unroll
     for (int k = 0; k < NKIND; k++) tot[k] = tot[k] * a.tb.fluxfac;

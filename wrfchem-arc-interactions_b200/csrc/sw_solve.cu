@@ -26,8 +26,16 @@ namespace arc {
 
 static __constant__ SwBandDesc c_sw[14];
 static __constant__ int c_sw_ngb[NGSW];    // band index 0..13 of each SW g-point
+// Sweep groups: the g-points of a band are swept by one thread per column in groups of at most SWEEP_GMAX consecutive
+// g-points (register state); bands with more g-points are cut into two equal groups.
+static SweepGroups h_sw_grp;
+static __constant__ int c_sw_grp_band[SWEEP_MAXGRP];
 void upload_band_descs_sw(const HostTables &T) {
   cudaMemcpyToSymbol(c_sw, T.sw, sizeof(SwBandDesc) * 14);
+  int ngs[14], g0s[14];
+  for (int b = 0; b < 14; b++) { ngs[b] = T.sw[b].ng; g0s[b] = T.sw[b].g0; }
+  h_sw_grp = make_sweep_groups(ngs, g0s, 14, 8);
+  cudaMemcpyToSymbol(c_sw_grp_band, h_sw_grp.band, sizeof(int) * SWEEP_MAXGRP);
   int ngb[NGSW];
   for (int i = 0; i < NGSW; i++) ngb[i] = T.sw_ngb[i] - 1;
   cudaMemcpyToSymbol(c_sw_ngb, ngb, sizeof(int) * NGSW);
@@ -280,14 +288,20 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
 #pragma unroll
   for (int w = 0; w < NL / 32; w++) mw[w] = w < ws.W ? ws.mask[((size_t)g * ws.W + w) * cap + c] : 0u;
 
-  // per-layer two-stream solutions and the upward reflectances at every interface (thread-private, coalesced local memory)
-  float4 Pa[NL], Pn[NL], Pca[NL], Pcn[NL];
-  float Ea[NL], En[NL], Eca[NL], Ecn[NL];
-  float2 Ru[4][NL];          // (rup, rupd) at interface lay+1 for streams clear, full, clean, cleanclear
-
+  // Level records handed to k_sw_sweep (layout in args.h): for every stream the two-stream solution (P, e) of the layer
+  // below the level and the upward reflectances (rup, rupd) at the level.  Stream order: clear, full, clean, clean-clear.
+  const size_t pcap = ws.pcap;
+  const size_t sstride = (size_t)NGSW * (nlay + 1) * pcap;            // stream stride of the records
+  const size_t rec0 = (size_t)g * (nlay + 1) * pcap + c;              // level 0 of stream 0
+  const int slot[4] = {0, 1, 2, do_clean ? 3 : 2};                     // compact stream slots
   float rup[4], rupd[4];
 #pragma unroll
-  for (int s = 0; s < 4; s++) { rup[s] = albp; rupd[s] = albd; }
+  for (int s = 0; s < 4; s++) {
+    rup[s] = albp; rupd[s] = albd;
+    if (s == 2 && !do_clean) continue;
+    if (s == 3 && !do_clnc) continue;
+    ws.recR[slot[s] * sstride + rec0] = make_float2(albp, albd);
+  }
   float sfluxzen = 0.f;
   float tdir_nodel = 1.f;     // product of the un-delta-scaled direct transmittances of the FULL stream
 
@@ -356,12 +370,6 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
         ecld[v] = sw_expt(s_exp, D_(ztauo, prmu0), bpade);
       }
     }
-    Pa[lay] = pclr[0]; Ea[lay] = eclr[0];
-    if (noaer) { Pn[lay] = pclr[1]; En[lay] = eclr[1]; }
-    if (cloudy) {
-      Pca[lay] = pcld[0]; Eca[lay] = ecld[0];
-      if (do_clean) { Pcn[lay] = pcld[1]; Ecn[lay] = ecld[1]; }
-    }
     // ---- upward reflectances at the top of this layer (vrtqdr_sw bottom-up sweep)
 #pragma unroll
     for (int s = 0; s < 4; s++) {
@@ -378,69 +386,15 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
       const float nrup = fmaf(__fmul_rn(P.w, fmaf(e, rup[s], __fmul_rn(__fsub_rn(P.z, e), rupd[s]))), zreflect, P.x);
       const float nrupd = fmaf(__fmul_rn(__fmul_rn(P.w, P.w), rupd[s]), zreflect, P.y);
       rup[s] = nrup; rupd[s] = nrupd;
-      Ru[s][lay] = make_float2(nrup, nrupd);
+      const size_t q = slot[s] * sstride + rec0 + (size_t)(lay + 1) * pcap;
+      ws.recP[q] = P; ws.recE[q] = e; ws.recR[q] = make_float2(nrup, nrupd);
     }
   }
   if (a.dbg.sfluxzen) a.dbg.sfluxzen[(size_t)ws.cols[c] * NGSW + g] = sfluxzen;
 
-  // ---- top-down sweep: transmittances and fluxes at every interface
+  // incident flux of this g-point and the un-delta-scaled direct beam at the surface; the top-down sweep runs in k_sw_sweep
   const float zincflx = ws.colf[(size_t)SWF_ADJFLUX * cap + c] * sfluxzen * prmu0;
-  float tdbt[4], tdn[4], rdnd[4];
-#pragma unroll
-  for (int s = 0; s < 4; s++) { tdbt[s] = 1.f; tdn[s] = 1.f; rdnd[s] = 0.f; }
-  const int nk = ws.nk;
-  const size_t pcap = ws.pcap;
-  float *part = ws.part + ((size_t)g * (nlay + 1)) * nk * pcap + c;
-  // pass-2 operands of one interface + the layer below it, requested together
-  struct Lev2 { float2 ru[4]; float4 pa, pn, pf, pc; float ea, en, ef, ec; };
-  auto load_level = [&](int lev, Lev2 &V) {
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      if (s == 2 && !do_clean) continue;
-      if (s == 3 && !do_clnc) continue;
-      V.ru[s] = lev > 0 ? Ru[s][lev - 1] : make_float2(albp, albd);
-    }
-    if (lev == 0) return;
-    const int lay = lev - 1;
-    const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
-    V.pa = Pa[lay]; V.ea = Ea[lay];
-    V.pn = V.pa; V.en = V.ea;
-    if (noaer) { V.pn = Pn[lay]; V.en = En[lay]; }
-    V.pf = V.pa; V.pc = V.pn; V.ef = V.ea; V.ec = V.en;
-    if (cloudy) { V.pf = Pca[lay]; V.ef = Eca[lay]; if (do_clean) { V.pc = Pcn[lay]; V.ec = Ecn[lay]; } }
-  };
-  for (int lev = nlay; lev >= 0; lev--) {
-    Lev2 V;
-    load_level(lev, V);
-    // flux at interface lev
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      if (s == 2 && !do_clean) continue;
-      if (s == 3 && !do_clnc) continue;
-      const float ru = V.ru[s].x, rud = V.ru[s].y;
-      const float zreflect = RCP(fmaf(-rdnd[s], rud, 1.f));
-      const float dif = __fsub_rn(tdn[s], tdbt[s]);
-      const float fu = __fmul_rn(fmaf(tdbt[s], ru, __fmul_rn(dif, rud)), zreflect);
-      const float fd = fmaf(fmaf(__fmul_rn(tdbt[s], ru), rdnd[s], dif), zreflect, tdbt[s]);
-      const int ku = s == 0 ? K_CU : s == 1 ? K_FU : s == 2 ? K_NU : K_XU;
-      part[((size_t)lev * nk + ws.kslot[ku]) * pcap] = __fmul_rn(zincflx, fu);
-      part[((size_t)lev * nk + ws.kslot[ku + 1]) * pcap] = __fmul_rn(zincflx, fd);
-    }
-    if (lev == 0) break;
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      if (s == 2 && !do_clean) continue;
-      if (s == 3 && !do_clnc) continue;
-      const float4 P = s == 0 ? V.pa : s == 1 ? V.pf : s == 2 ? V.pc : V.pn;
-      const float e = s == 0 ? V.ea : s == 1 ? V.ef : s == 2 ? V.ec : V.en;
-      const float zreflect = RCP(fmaf(-P.y, rdnd[s], 1.f));
-      const float ntdn = fmaf(__fmul_rn(P.w, fmaf(__fmul_rn(tdbt[s], P.x), rdnd[s], __fsub_rn(tdn[s], tdbt[s]))), zreflect,
-                              __fmul_rn(tdbt[s], P.z));
-      const float nrdnd = fmaf(__fmul_rn(__fmul_rn(P.w, P.w), rdnd[s]), zreflect, P.y);
-      tdn[s] = ntdn; rdnd[s] = nrdnd;
-      tdbt[s] = __fmul_rn(e, tdbt[s]);
-    }
-  }
+  ws.zinc[(size_t)g * pcap + c] = zincflx;
   ws.dirs[(size_t)g * pcap + c] = __fmul_rn(zincflx, tdir_nodel);
 }
 
@@ -459,6 +413,88 @@ void launch_sw_solve(const SwArgs &a, cudaStream_t s) {
   else if (a.ws.nlay <= 128) k_sw_solve<128><<<grid, 256, sw_solve_smem(), s>>>(a);
   else k_sw_solve<160><<<grid, 256, sw_solve_smem(), s>>>(a);
   count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Top-down sweep of vrtqdr_sw (SW:8007-8045) + ordered sum over the g-points of a band (SW:8617-8650).
+// One thread per (column, band, stream): the (tdbt, tdn, rdnd) of the band's NG g-points are its register state; per level
+// it requests the 3 NG records of that level together (written by k_sw_solve; the addresses do not depend on the
+// recurrence), forms the NG up / down fluxes, adds them in g order and writes ONE band partial [band][level][kind][c] per
+// kind.  No shared memory, no barriers, no atomics; lanes = neighbouring columns.  HBM-bound: 28 B per (column, g, level,
+// stream).
+template <int NG>
+__global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0) {
+  const SwWs &ws = a.ws;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= a.ncols) return;
+  const int si = blockIdx.y;                   // compact stream slot
+  const bool do_clean = (a.variants & ARC_VAR_CLEAN) != 0;
+  const int s = si < 2 ? si : (si == 2 && do_clean ? 2 : 3);      // 0 clear, 1 full, 2 clean, 3 clean-clear
+  const int nlay = ws.nlay, nk = ws.nk;
+  const size_t pcap = ws.pcap;
+  const size_t lstride = (size_t)(nlay + 1) * pcap;
+  const size_t base = ((size_t)si * NGSW + g0) * lstride + c;
+  const float4 *__restrict__ recP = ws.recP + base;
+  const float2 *__restrict__ recR = ws.recR + base;
+  const float *__restrict__ recE = ws.recE + base;
+  const int ku = ws.kslot[s == 0 ? K_CU : s == 1 ? K_FU : s == 2 ? K_NU : K_XU];
+  const int kd = ws.kslot[s == 0 ? K_CD : s == 1 ? K_FD : s == 2 ? K_ND : K_XD];
+  float *__restrict__ bpart = ws.bpart + (size_t)grp * (nlay + 1) * nk * pcap + c;
+
+  float zinc[NG], tdbt[NG], tdn[NG], rdnd[NG];
+#pragma unroll
+  for (int i = 0; i < NG; i++) { zinc[i] = ws.zinc[(size_t)(g0 + i) * pcap + c]; tdbt[i] = 1.f; tdn[i] = 1.f; rdnd[i] = 0.f; }
+  for (int lev = nlay; lev >= 0; lev--) {
+    const size_t lo = (size_t)lev * pcap;
+    float2 R[NG]; float4 P[NG]; float e[NG];
+#pragma unroll
+    for (int i = 0; i < NG; i++) {
+      R[i] = __ldcs(recR + i * lstride + lo);
+      if (lev > 0) { P[i] = __ldcs(recP + i * lstride + lo); e[i] = __ldcs(recE + i * lstride + lo); }
+    }
+    float su = 0.f, sd = 0.f;
+#pragma unroll
+    for (int i = 0; i < NG; i++) {
+      // flux at interface lev (SW:8036-8045); same operation order as the bottom-up sweep of k_sw_solve, so streams
+      // with identical inputs stay bit-identical
+      const float ru = R[i].x, rud = R[i].y;
+      const float zreflect = RCP(fmaf(-rdnd[i], rud, 1.f));
+      const float dif = __fsub_rn(tdn[i], tdbt[i]);
+      const float fu = __fmul_rn(fmaf(tdbt[i], ru, __fmul_rn(dif, rud)), zreflect);
+      const float fd = fmaf(fmaf(__fmul_rn(tdbt[i], ru), rdnd[i], dif), zreflect, tdbt[i]);
+      su = su + __fmul_rn(zinc[i], fu);
+      sd = sd + __fmul_rn(zinc[i], fd);
+    }
+    __stcs(bpart + ((size_t)lev * nk + ku) * pcap, su);
+    __stcs(bpart + ((size_t)lev * nk + kd) * pcap, sd);
+    if (lev == 0) break;
+#pragma unroll
+    for (int i = 0; i < NG; i++) {
+      // transmittances through the layer below the interface (SW:8007-8034)
+      const float zr = RCP(fmaf(-P[i].y, rdnd[i], 1.f));
+      const float ntdn = fmaf(__fmul_rn(P[i].w, fmaf(__fmul_rn(tdbt[i], P[i].x), rdnd[i], __fsub_rn(tdn[i], tdbt[i]))), zr,
+                              __fmul_rn(tdbt[i], P[i].z));
+      const float nrdnd = fmaf(__fmul_rn(__fmul_rn(P[i].w, P[i].w), rdnd[i]), zr, P[i].y);
+      tdn[i] = ntdn; rdnd[i] = nrdnd;
+      tdbt[i] = __fmul_rn(e[i], tdbt[i]);
+    }
+  }
+}
+
+int sw_sweep_groups() { return h_sw_grp.n; }
+void launch_sw_sweep(const SwArgs &a, cudaStream_t s) {
+  const int nstream = 2 + ((a.variants & ARC_VAR_CLEAN) ? 1 : 0) + ((a.variants & ARC_VAR_CLEANCLEAR) ? 1 : 0);
+  const dim3 grid((a.ncols + 127) / 128, nstream);
+  for (int q = 0; q < h_sw_grp.n; q++) {
+    const int g0 = h_sw_grp.g0[q];
+    switch (h_sw_grp.ng[q]) {
+#define SWEEP_CASE(N) case N: k_sw_sweep<N><<<grid, 128, 0, s>>>(a, q, g0); break;
+      SWEEP_CASE(1) SWEEP_CASE(2) SWEEP_CASE(3) SWEEP_CASE(4) SWEEP_CASE(5) SWEEP_CASE(6) SWEEP_CASE(7) SWEEP_CASE(8)
+#undef SWEEP_CASE
+      default: break;
+    }
+  }
+  count_launch(h_sw_grp.n);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -486,13 +522,13 @@ __global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_sw_reduce(SwArgs a) {
     for (int k = 0; k < NKIND; k++) f[k] = 0.f;
     float uvfd = 0.f, nifd = 0.f;
     const int nk = ws.nk;
-    const float *p = ws.part + ((size_t)lev * nk) * cap + c;
+    const float *p = ws.bpart + ((size_t)lev * nk) * cap + c;     // band sums from k_sw_sweep
     const size_t gstride = (size_t)(nlay + 1) * nk * cap;
     const unsigned ucap = (unsigned)cap;       // 32-bit kind offsets: nk * pcap < 2^31
     const unsigned oFU = ws.kslot[K_FU] * ucap, oFD = ws.kslot[K_FD] * ucap, oCU = ws.kslot[K_CU] * ucap, oCD = ws.kslot[K_CD] * ucap,
                    oNU = ws.kslot[K_NU] * ucap, oND = ws.kslot[K_ND] * ucap, oXU = ws.kslot[K_XU] * ucap, oXD = ws.kslot[K_XD] * ucap;
-#pragma unroll 4
-    for (int g = 0; g < NGSW; g++, p += gstride) {
+    for (int q = 0; q < a.ngroups; q++, p += gstride) {
+      const int b = c_sw_grp_band[q];
       f[K_FU] = f[K_FU] + p[oFU];
       const float fd = p[oFD];
       f[K_FD] = f[K_FD] + fd;
@@ -500,10 +536,7 @@ __global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_sw_reduce(SwArgs a) {
       f[K_CD] = f[K_CD] + p[oCD];
       if (do_clean) { f[K_NU] = f[K_NU] + p[oNU]; f[K_ND] = f[K_ND] + p[oND]; }
       if (do_clnc) { f[K_XU] = f[K_XU] + p[oXU]; f[K_XD] = f[K_XD] + p[oXD]; }
-      if (lev == 0) {
-        const int b = c_sw_ngb[g];
-        if (b >= 9 && b <= 12) uvfd = uvfd + fd; else nifd = nifd + fd;
-      }
+      if (lev == 0) { if (b >= 9 && b <= 12) uvfd = uvfd + fd; else nifd = nifd + fd; }
     }
     s_net[lev][cx] = f[K_FD] - f[K_FU];
     if (a.swupflx) {        // lev <= nz + 1 always
