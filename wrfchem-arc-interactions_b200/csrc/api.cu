@@ -28,6 +28,11 @@ struct Ctx {
   bool ready = false;
   int device = 0;
   cudaStream_t stream = nullptr;
+  // second compute stream: the memory-bound sweep + reduce of inner chunk k run here while the compute-bound solver of
+  // chunk k+1 runs on `stream` (double-buffered level records); ARC_RAD_OVERLAP=0 puts everything on `stream`
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_solved = nullptr, ev_swept[2] = {nullptr, nullptr};
+  bool overlap = true;
   HostTables H;
   DevTables D;
   std::vector<void *> table_allocs;
@@ -111,12 +116,13 @@ void carve_sw(SwWs &w, char *base, size_t &bytes) {
   w.laysol = c.take<int>((size_t)NBSW * cap);
   w.colf = c.take<float>((size_t)SWF_N * cap);
   const size_t ns = w.nk / 2;                              // streams = pairs of flux kinds
-  w.recP = c.take<float4>(ns * NGSW * (nl + 1) * pcap);
-  w.recE = c.take<float>(ns * NGSW * (nl + 1) * pcap);
-  w.recR = c.take<float2>(ns * NGSW * (nl + 1) * pcap);
-  w.zinc = c.take<float>((size_t)NGSW * pcap);
+  w.rec_n = ns * NGSW * (nl + 1) * pcap;                  // two buffers of level records (solver k+1 overlaps sweep k)
+  w.recP = c.take<float4>(2 * w.rec_n);
+  w.recE = c.take<float>(2 * w.rec_n);
+  w.recR = c.take<float2>(2 * w.rec_n);
+  w.zinc = c.take<float>((size_t)2 * NGSW * pcap);
   w.bpart = c.take<float>((size_t)sw_sweep_groups() * (nl + 1) * w.nk * pcap);
-  w.dirs = c.take<float>((size_t)NGSW * pcap);
+  w.dirs = c.take<float>((size_t)2 * NGSW * pcap);
   bytes = c.off;
 }
 void carve_lw(LwWs &w, char *base, size_t &bytes) {
@@ -131,10 +137,11 @@ void carve_lw(LwWs &w, char *base, size_t &bytes) {
   w.colf = c.take<float>((size_t)LWF_N * cap);
   w.secdiff = c.take<float>((size_t)NBLW * cap);
   const size_t nv = (w.kslot[K_NU] != 0) ? 2 : 1;          // streams: full (+ clear) [, clean (+ clean-clear)]
-  w.scrU = c.take<float2>(nv * NGLW * (nl + 1) * pcap);
-  w.scrC = c.take<float2>(nv * NGLW * (nl + 1) * pcap);
-  w.scrD = c.take<float2>(nv * NGLW * (nl + 1) * pcap);
-  w.scrS = c.take<float2>(nv * NGLW * pcap);
+  w.rec_n = nv * NGLW * (nl + 1) * pcap;                  // two buffers of level records (solver k+1 overlaps sweep k)
+  w.scrU = c.take<float2>(2 * w.rec_n);
+  w.scrC = c.take<float2>(2 * w.rec_n);
+  w.scrD = c.take<float2>(2 * w.rec_n);
+  w.scrS = c.take<float2>(2 * nv * NGLW * pcap);
   w.bpart = c.take<float>((size_t)lw_sweep_groups() * (nl + 1) * w.nk * pcap);
   bytes = c.off;
 }
@@ -223,7 +230,8 @@ int copy_back() {
 // ---- timing ----------------------------------------------------------------------------------------------
 struct Timed {
   EvPair *e;
-  explicit Timed(const char *name) {
+  cudaStream_t st;
+  explicit Timed(const char *name, cudaStream_t s = nullptr) : st(s ? s : g.stream) {
     if (g.ev_next >= g.evs.size()) {
       EvPair p; p.name = name;
       cudaEventCreate(&p.a); cudaEventCreate(&p.b);
@@ -231,9 +239,9 @@ struct Timed {
     }
     e = &g.evs[g.ev_next++];
     e->name = name;
-    cudaEventRecord(e->a, g.stream);
+    cudaEventRecord(e->a, st);
   }
-  ~Timed() { cudaEventRecord(e->b, g.stream); }
+  ~Timed() { cudaEventRecord(e->b, st); }
 };
 void collect_times() {
   for (size_t i = 0; i < g.ev_next; i++) {
@@ -619,7 +627,11 @@ void arc_rad_finalize(void) {
   g.evs.clear();
   aer_finalize();
   if (g.stream) cudaStreamDestroy(g.stream);
-  g.stream = nullptr;
+  if (g.stream2) cudaStreamDestroy(g.stream2);
+  g.stream = g.stream2 = nullptr;
+  if (g.ev_solved) cudaEventDestroy(g.ev_solved);
+  for (int q = 0; q < 2; q++) if (g.ev_swept[q]) cudaEventDestroy(g.ev_swept[q]);
+  g.ev_solved = g.ev_swept[0] = g.ev_swept[1] = nullptr;
   g.ready = false;
 }
 
@@ -640,6 +652,16 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
   if (cfg->device >= 0) { CK(cudaSetDevice(cfg->device)); g.device = cfg->device; }
   else CK(cudaGetDevice(&g.device));
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // hi = numerically lowest = greatest priority
+    const char *e = getenv("ARC_RAD_OVERLAP");
+    g.overlap = !(e && atoi(e) == 0);
+    const char *pr = getenv("ARC_RAD_SWEEP_PRIO");
+    CK(cudaStreamCreateWithPriority(&g.stream2, cudaStreamNonBlocking, (pr && atoi(pr) == 0) ? lo : hi));
+    CK(cudaEventCreateWithFlags(&g.ev_solved, cudaEventDisableTiming));
+    for (int q = 0; q < 2; q++) CK(cudaEventCreateWithFlags(&g.ev_swept[q], cudaEventDisableTiming));
+  }
   CK(cudaStreamCreateWithFlags(&g.h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&g.d2h, cudaStreamNonBlocking));
   for (int q = 0; q < 2; q++) { CK(cudaEventCreateWithFlags(&g.ev_in[q], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.ev_out[q], cudaEventDisableTiming)); }
@@ -850,15 +872,24 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
         count_launch();
       }
       // inner chunks: column-indexed workspace pointers advance by c0, the partial buffers restart at 0
-      for (int c0 = 0; c0 < no; c0 += (int)pcap) {
+      cudaStream_t s2 = g.overlap ? g.stream2 : g.stream;
+      int kc = 0;
+      for (int c0 = 0; c0 < no; c0 += (int)pcap, kc++) {
         SwArgs b = a;
         b.ncols = std::min((int)pcap, no - c0);
         b.ws.cols += c0; b.ws.coef += c0; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0;
         b.ws.laytrop += c0; b.ws.laysol += c0; b.ws.colf += c0;
+        const int buf = kc & 1;
+        b.ws.recP += buf * a.ws.rec_n; b.ws.recE += buf * a.ws.rec_n; b.ws.recR += buf * a.ws.rec_n;
+        b.ws.zinc += (size_t)buf * NGSW * pcap; b.ws.dirs += (size_t)buf * NGSW * pcap;
+        if (g.overlap && kc >= 2) CK(cudaStreamWaitEvent(g.stream, g.ev_swept[buf], 0));      // records of chunk k-2 consumed
         { Timed t("sw_solve"); launch_sw_solve(b, g.stream); }
-        { Timed t("sw_sweep"); launch_sw_sweep(b, g.stream); }
-        { Timed t("sw_reduce"); launch_sw_reduce(b, g.stream); }
+        if (g.overlap) { CK(cudaEventRecord(g.ev_solved, g.stream)); CK(cudaStreamWaitEvent(s2, g.ev_solved, 0)); }
+        { Timed t("sw_sweep", s2); launch_sw_sweep(b, s2); }
+        { Timed t("sw_reduce", s2); launch_sw_reduce(b, s2); }
+        if (g.overlap) CK(cudaEventRecord(g.ev_swept[buf], s2));
       }
+      if (g.overlap) { CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0)); }
     }
   }
   return finish_call(dbglist);
@@ -972,16 +1003,25 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       k_unpack_mask<<<(no + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, nullptr, o0, no, (int)cap, a.ws.W, nlay, NGLW, a.dbg.cldmask);
       count_launch();
     }
-    for (int c0 = 0; c0 < no; c0 += (int)pcap) {
+    cudaStream_t s2 = g.overlap ? g.stream2 : g.stream;
+    int kc = 0;
+    for (int c0 = 0; c0 < no; c0 += (int)pcap, kc++) {
       LwArgs b = a;
       b.ncols = std::min((int)pcap, no - c0);
       b.col0 = o0 + c0;
       b.ws.coef += c0; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0; b.ws.laytrop += c0; b.ws.colf += c0;
       b.ws.secdiff += c0;
+      const int buf = kc & 1;
+      b.ws.scrU += buf * a.ws.rec_n; b.ws.scrC += buf * a.ws.rec_n; b.ws.scrD += buf * a.ws.rec_n;
+      b.ws.scrS += (size_t)buf * (a.ws.rec_n / (nlay + 1));
+      if (g.overlap && kc >= 2) CK(cudaStreamWaitEvent(g.stream, g.ev_swept[buf], 0));      // records of chunk k-2 consumed
       { Timed t("lw_solve"); launch_lw_solve(b, g.stream); }
-      { Timed t("lw_sweep"); launch_lw_sweep(b, g.stream); }
-      { Timed t("lw_reduce"); launch_lw_reduce(b, g.stream); }
+      if (g.overlap) { CK(cudaEventRecord(g.ev_solved, g.stream)); CK(cudaStreamWaitEvent(s2, g.ev_solved, 0)); }
+      { Timed t("lw_sweep", s2); launch_lw_sweep(b, s2); }
+      { Timed t("lw_reduce", s2); launch_lw_reduce(b, s2); }
+      if (g.overlap) CK(cudaEventRecord(g.ev_swept[buf], s2));
     }
+    if (g.overlap) { CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0)); }
   }
   return finish_call(dbglist);
 }

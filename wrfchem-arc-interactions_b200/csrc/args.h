@@ -79,6 +79,7 @@ struct SwWs {
   float *colf;             // [SWF_N][cap]
   // Level records handed from k_sw_solve (taumol, reftra, bottom-up sweep) to k_sw_sweep (top-down sweep + band sum):
   // [stream slot][NGSW][nlay+1][pcap]; stream slots in the order clear, full [, clean][, clean-clear]
+  size_t rec_n;            // elements per buffer of the level records (host-side: two buffers are carved)
   float4 *recP;            // (ref, refd, tra, trad) of the layer below the level (level 0 unused)
   float *recE;             // direct-beam transmittance of that layer
   float2 *recR;            // (rup, rupd) at the level; level 0 = surface albedos
@@ -132,6 +133,7 @@ struct LwWs {
   // Level-indexed records handed from k_lw_solve (taumol + downward sweep) to k_lw_sweep (upward sweep + band sum):
   // [stream v][NGLW][nlay+1][pcap] float2, v = 0 full (+ clear), 1 clean (+ clean-clear).  level = layer + 1 for the layer
   // quantities, = the layer's lower interface for scrD.
+  size_t rec_n;            // elements per buffer of the level records (host-side: two buffers are carved)
   float2 *scrU;            // (atrans, bbugas)
   float2 *scrC;            // (X, Y) of radlu' = radlu - radlu X + Y; written only where the column has cloud in the layer
   float2 *scrD;            // downward radiances at the level: (all-sky, clear-sky)
