@@ -44,6 +44,16 @@ def flops_per_column(nk, nlay_lw):
     return 112.0 * ls * (30 + 3 * 240), 140.0 * nlay_lw * (60 + 2 * 55)
 
 
+def sw_solve_flops_per_column(nk):
+    """Share of the SW figure that k_sw_solve executes: taumol 30 + per variant layer prep 40 + reftra 120 +
+    combine/direct 25 + the bottom-up half of the adding method 22 = 207; the top-down half (23) and the accumulation over
+    g (10) run in k_sw_sweep."""
+    return 112.0 * (nk + 1) * (30 + 3 * 207)
+
+
+KERNEL_CLASSES = ("sw_mcica", "sw_prep", "sw_solve", "sw_sweep", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_sweep", "lw_reduce")
+
+
 class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -239,7 +249,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
-        for n in ("sw_mcica", "sw_prep", "sw_solve", "sw_sweep", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_sweep", "lw_reduce"):
+        for n in KERNEL_CLASSES:
             kms[n] = kms.get(n, 0.0) + float(L.arc_rad_last_kernel_ms(n.encode()))
     e1.record(stream)
     barrier()
@@ -247,6 +257,17 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     launches = int(L.arc_rad_launch_count()) - launches0
     clocks = sampler.stop()
+    # per-kernel durations with every kernel alone on the GPU (sweep overlap off), outside the timed region: the timed
+    # region's per-class times include the slow-down from the other stream's kernels running beside them
+    kms_alone = {}
+    L.arc_rad_set_overlap.restype = C.c_int
+    prev = L.arc_rad_set_overlap(0)
+    n_alone = 2
+    for _ in range(n_alone):
+        step_device()
+        for n in KERNEL_CLASSES:
+            kms_alone[n] = kms_alone.get(n, 0.0) + float(L.arc_rad_last_kernel_ms(n.encode())) / n_alone
+    L.arc_rad_set_overlap(prev)
     t = torch.tensor([max(dev_ms, 0.0), wall_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,23 +348,41 @@ def main():
         return
 
     fsw, flw = flops_per_column(nk, nlay_lw)
+    f_solve = sw_solve_flops_per_column(nk)
     sw_solve_ms = kms["sw_solve"] / args.steps
-    ach = fsw * nsun / (sw_solve_ms * 1e-3) / 1e12 if sw_solve_ms > 0 else 0.0
-    # bytes the dominant kernel must move per launch set: workspace reads (coef 15 + aerosol 3 words per layer, masks)
-    # and the partial flux profile written once: 112 * (Ls+1) * 6 floats per column
+    ach = f_solve * nsun / (sw_solve_ms * 1e-3) / 1e12 if sw_solve_ms > 0 else 0.0
+    alone_ms = kms_alone.get("sw_solve", 0.0)
     ls = nk + 1
-    sw_bytes = nsun * 4.0 * (112 * ls * (15 + 3) + 112 * (ls + 1) * 6)
+    nstream = 2 + (1 if args.clean else 0)
+    # HBM-bound sweep kernels: algorithmic bytes = the level records read once + the group partials written once
+    # (DESIGN.md 3.2): SW 28 B per (sunlit column, g, level, stream), LW 16 B per (column, g, level, stream)
+    sw_sweep_bytes = nsun * 112.0 * (ls + 1) * 28.0 * nstream
+    lw_sweep_bytes = ncol * 140.0 * (nlay_lw + 1) * 16.0 * (2 if args.clean else 1)
+    def gbps(bytes_, ms):
+        return bytes_ / 1e9 / (ms * 1e-3) if ms > 0 else None
     roofline = {"kernel": "k_sw_solve", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak if fp32_peak > 0 else None,
-                # DRAM bytes of k_sw_solve per step: ncu --set full (profiles/r1_summary.md) measured 30.29 GB read+write for a
-                # 24,566-sunlit-column launch = 1.233 MB per sunlit column (layer solutions kept for the second sweep + per-g fluxes)
-                "traffic": 1.233e6 * nsun, "traffic_unit": "bytes per step (all k_sw_solve launches)",
-                "issue_slot_utilisation_ncu": 0.68,
+                # DRAM bytes of k_sw_solve: ncu --set full (profiles/r1_summary.md) measured 17.66 GB read+write for a
+                # 24,566-sunlit-column launch = 0.719 MB per sunlit column (the level records written for k_sw_sweep)
+                "traffic": 0.719e6 * nsun, "traffic_unit": "bytes per step (all k_sw_solve launches)",
+                "issue_slot_utilisation_ncu": 0.80,
                 "ms_per_step": sw_solve_ms,
+                "ms_per_step_alone": alone_ms,
+                "frac_alone": (f_solve * nsun / (alone_ms * 1e-3) / 1e12 / fp32_peak) if alone_ms > 0 and fp32_peak > 0 else None,
+                "note": "ms_per_step is measured in the timed region, where the sweep kernels of the previous chunk run beside the solver on a second stream; *_alone is the same kernel with the overlap off (outside the timed region)",
                 "peak_source": "FP32 FMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP32 figure; nominal 74.5)",
-                "algorithmic_flops_per_column": fsw, "hbm_view": {"algorithmic_GB_per_step": sw_bytes / 1e9,
-                                                                  "GBps": sw_bytes / 1e9 / (sw_solve_ms * 1e-3) if sw_solve_ms > 0 else None,
-                                                                  "peak_GBps": 6545.6}}
+                "algorithmic_flops_per_column": f_solve,
+                "other_kernels": {
+                    "k_sw_sweep": {"bound": "hbm", "unit": "GB/s", "peak": 6545.6, "algorithmic_GB_per_step": sw_sweep_bytes / 1e9,
+                                   "achieved": gbps(sw_sweep_bytes, kms["sw_sweep"] / args.steps),
+                                   "achieved_alone": gbps(sw_sweep_bytes, kms_alone.get("sw_sweep", 0.0))},
+                    "k_lw_sweep": {"bound": "hbm", "unit": "GB/s", "peak": 6545.6, "algorithmic_GB_per_step": lw_sweep_bytes / 1e9,
+                                   "achieved": gbps(lw_sweep_bytes, kms["lw_sweep"] / args.steps),
+                                   "achieved_alone": gbps(lw_sweep_bytes, kms_alone.get("lw_sweep", 0.0))},
+                    "k_lw_solve": {"bound": "fp32", "unit": "TFLOP/s", "peak": fp32_peak,
+                                   "algorithmic_flops_per_column": 140.0 * nlay_lw * (60 + 2 * 42),
+                                   "achieved": 140.0 * nlay_lw * (60 + 2 * 42) * ncol / (kms["lw_solve"] / args.steps * 1e-3) / 1e12 if kms["lw_solve"] > 0 else None,
+                                   "achieved_alone": 140.0 * nlay_lw * (60 + 2 * 42) * ncol / (kms_alone["lw_solve"] * 1e-3) / 1e12 if kms_alone.get("lw_solve", 0) > 0 else None}}}
     cpu_baseline = None
     if not args.no_cpu_baseline:
         a2 = argparse.Namespace(**vars(args)); a2.steps, a2.warmup, a2.ref_seconds = 1, 0, args.cpu_baseline_seconds
@@ -357,6 +396,7 @@ def main():
                    "columns_per_gpu": ncol, "sunlit_columns": nsun, "partition": "j-slabs, one tile per rank; NCCL all-reduce of 24x5 domain statistics per step" if world > 1 else "single tile"},
         "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
+        "kernel_ms_per_step_alone": kms_alone,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "aer_optics": aer,
     }
     print(json.dumps(out))

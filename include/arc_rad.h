@@ -263,9 +263,15 @@ int  arc_aer_mie_direct(int wl, float radius_cm, float refr, float refi, float *
 long long arc_rad_launch_count(void);
 /* CUDA stream used for all work (cudaStream_t as void*), for event timing by the caller */
 void *arc_rad_stream(void);
-/* time (ms, CUDA events on the library stream) spent in the named kernel class during the last call:
- * "sw_solver", "sw_taumol", "lw_rtrnmc", ...; returns <0 if unknown */
+/* time (ms, CUDA events on the launching stream) spent in the named kernel class during the last call:
+ * "sw_mcica", "sw_prep", "sw_solve", "sw_sweep", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_sweep", "lw_reduce",
+ * "aer_optics"; returns <0 if unknown.  With the sweep overlap on, a class's time includes the slow-down from the kernels
+ * of the other stream running beside it. */
 float arc_rad_last_kernel_ms(const char *name);
+/* Sweep overlap (default on, or $ARC_RAD_OVERLAP=0): the memory-bound sweep + reduce kernels of inner chunk k run on a second,
+ * higher-priority stream while the compute-bound solver of chunk k+1 runs on the main stream.  Results are bit-identical
+ * either way; off is for per-kernel timing.  Returns the previous setting. */
+int arc_rad_set_overlap(int on);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,7 @@ want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
-W("## ncu --set full (one launch of each solver, tile 256x128x50 = 32768 columns; report: gpurun_out/%s, not tracked)\n" % os.path.basename(rep))
+W("## ncu --set full (one launch of each hot kernel, tile 256x128x50 = 32768 columns; report: gpurun_out/%s, not tracked)\n" % os.path.basename(rep))
 for r in rr[2:]:
     W("### `%s`\n" % r[h.index("Kernel Name")])
     W("| metric | value | unit |\n|---|---|---|")
@@ -49,7 +49,7 @@ for r in rr[2:]:
             W("| %s | %s | %s |" % (w, r[h.index(w)], u[h.index(w)]))
     W()
 det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
-keep = [l for l in det.splitlines() if any(s in l for s in ("k_sw_solve", "k_lw_solve", "Stall", "stalled", "Issue Slots Busy", "No Eligible", "Warp Cycles Per Issued", "Achieved Occupancy", "L2 Hit Rate", "DRAM Throughput"))]
+keep = [l for l in det.splitlines() if any(s in l for s in ("k_sw_solve", "k_lw_solve", "k_sw_sweep", "k_lw_sweep", "k_sw_reduce", "k_lw_reduce", "Stall", "stalled", "Issue Slots Busy", "No Eligible", "Warp Cycles Per Issued", "Achieved Occupancy", "L2 Hit Rate", "DRAM Throughput"))]
 W("## ncu details excerpts\n\n```\n" + "\n".join(keep) + "\n```")
 out.close()
 import shutil

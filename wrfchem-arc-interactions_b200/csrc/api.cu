@@ -592,6 +592,7 @@ const char *arc_rad_last_error(void) { return g.err.c_str(); }
 int arc_rad_lw_nlayers(void) { return g.ready ? g.H.lw_nlayers : 0; }
 long long arc_rad_launch_count(void) { return launch_count(); }
 void *arc_rad_stream(void) { return (void *)g.stream; }
+int arc_rad_set_overlap(int on) { const int prev = g.overlap ? 1 : 0; g.overlap = on != 0; return prev; }
 float arc_rad_last_kernel_ms(const char *name) {
   auto it = g.last_ms.find(name ? name : "");
   return it == g.last_ms.end() ? -1.f : it->second;

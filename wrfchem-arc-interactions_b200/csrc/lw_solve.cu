@@ -56,7 +56,10 @@ __device__ __forceinline__ float lw_major_lower(const float *__restrict__ A, con
   }
 }
 
-constexpr int LW_BLOCK = 512;   // 91 KB of staged tables per block: two 512-thread blocks per SM
+#ifndef LW_BLOCK_SZ
+#define LW_BLOCK_SZ 512
+#endif
+constexpr int LW_BLOCK = LW_BLOCK_SZ;   // 91 KB of staged tables per block: two blocks per SM
 struct LwSmem { const float2 *et; const float *S, *plk, *rat, *chi; };
 
 // One (column, g-point) of band BAND: taumol + both rtrnmc calls.  BAND is a template parameter so that each band's

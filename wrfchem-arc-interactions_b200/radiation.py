@@ -237,6 +237,8 @@ def lib() -> RadLib:
         L = _LIB.lib
         L.arc_rad_launch_count.restype = C.c_longlong
         L.arc_rad_stream.restype = C.c_void_p
+        L.arc_rad_set_overlap.restype = C.c_int
+        L.arc_rad_set_overlap.argtypes = [C.c_int]
         L.arc_rad_last_kernel_ms.restype = C.c_float
         L.arc_rad_last_kernel_ms.argtypes = [C.c_char_p]
         L.arc_rad_finalize.restype = None
