@@ -1,5 +1,6 @@
-// Longwave spectral solver: taumol (taugb1..16) + rtrnmc for the full and the clean (aerosol-free) call in one
-// pass, one thread per (column, g-point); plus the band/g reduction, heating rates and scatter.
+// Longwave spectral solver: k_lw_solve = taumol (taugb1..16) + downward sweep of rtrnmc for the full and the clean
+// (aerosol-free) call, k_lw_sweep = upward sweep + ordered sum over the g-points of a band, k_lw_reduce = band sum,
+// heating rates and scatter.
 //
 // Reference (module_ra_rrtmg_lw.F v3.9.1): taumol 4712-7828, rtrnmc 2974-3410, rrtmg_lw 10984-11044
 // (taut = taug + taua; clean rtrnmc(taug) then rtrnmc(taut)), RRTMG_LWRAD output scatter 12646-12692.

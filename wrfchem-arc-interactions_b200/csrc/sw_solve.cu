@@ -1,5 +1,6 @@
-// Shortwave spectral solver: taumol_sw + spcvmc_sw (reftra_sw, vrtqdr_sw) for all call variants in one pass,
-// one thread per (column, g-point); plus the g-point reduction / heating-rate / scatter kernel.
+// Shortwave spectral solver: k_sw_solve = taumol_sw + layer optics + reftra_sw + bottom-up half of vrtqdr_sw for all call
+// variants, k_sw_sweep = top-down half + fluxes + ordered sum over the g-points of a band,
+// k_sw_reduce = band sum / heating rates / scatter.
 //
 // Reference (module_ra_rrtmg_sw.F v3.9.1): taumol_sw 3081-4540, reftra_sw 2422-2701, vrtqdr_sw 7922-8046,
 // spcvmc_sw 8083-8658, rrtmg_sw 9376-9478 (full+clear call, then the clean call with ztauacln = 0),
