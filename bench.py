@@ -216,8 +216,7 @@ def main():
     P = lambda t: abi.fptr(int(t.data_ptr()))
 
     def step_device():
-        lib.RRTMG_LWRAD(dims, **kw_lw)
-        lib.RRTMG_SWRAD(dims, **kw_sw)
+        lib.RRTMG_LWSW(dims, kw_lw, kw_sw)        # arc_rad_lwsw: LW then SW as one continuous multi-stream pipeline
         lib.check(L.arc_rad_driver_post(C.byref(dims), abi.ARC_MEM_DEVICE, P(o_lw["rthratenlw"]), P(o_sw["rthratensw"]), P(rthraten),
                                         P(o_sw["gsw"]), P(ddom["albedo"]), P(swdown)))
         lib.check(L.arc_rad_domain_stats(C.byref(dims), abi.ARC_MEM_DEVICE, nst, fptrs, C.c_void_p(int(stats.data_ptr()))))

@@ -339,6 +339,38 @@ def test_combined_lwsw_step_equals_separate_calls(lib, ktab):
             assert np.array_equal(ref_lw[k], o_lw[k], equal_nan=True), (slab, k)
 
 
+def test_chained_device_step_equals_separate_calls(lib, ktab):
+    """arc_rad_lwsw with device arrays runs LW and SW as one continuous multi-stream pipeline (SW column kernels beside the LW
+    ones, the last LW sweep beside the first SW solver): bit-identical to the two separate calls, repeatedly, with several inner
+    chunks, and also with the sweep overlap off."""
+    import torch
+    dom = synth.make_domain(48, 24, 40, seed=33)
+    init(lib, dom, ktab)
+    flags = R.common_flags(dom)
+    dev = torch.device("cuda", 0)
+    ddom = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in dom.items()}
+    like = ddom["xcoszen"]
+    os.environ["ARC_RAD_CHUNK"] = "256"          # 1152 columns -> 5 inner chunks (LW), 4 (SW)
+    try:
+        r_sw, r_lw = R.alloc_outputs(dom, "sw", like=like), R.alloc_outputs(dom, "lw", like=like)
+        lib.RRTMG_LWRAD(dom["dims"], **R.lw_kwargs(ddom, r_lw, **flags))
+        lib.RRTMG_SWRAD(dom["dims"], **R.sw_kwargs(ddom, r_sw, **flags))
+        for overlap in (1, 1, 0, 1):
+            prev = lib.lib.arc_rad_set_overlap(overlap)
+            try:
+                o_sw, o_lw = R.alloc_outputs(dom, "sw", like=like), R.alloc_outputs(dom, "lw", like=like)
+                # (outputs start from zero like the reference run: night columns and levels above kte keep the caller's values)
+                lib.RRTMG_LWSW(dom["dims"], R.lw_kwargs(ddom, o_lw, **flags), R.sw_kwargs(ddom, o_sw, **flags))
+            finally:
+                lib.lib.arc_rad_set_overlap(prev)
+            for k in r_sw:
+                assert np.array_equal(r_sw[k].cpu().numpy(), o_sw[k].cpu().numpy(), equal_nan=True), (overlap, k)
+            for k in r_lw:
+                assert torch.equal(r_lw[k], o_lw[k]), (overlap, k)
+    finally:
+        del os.environ["ARC_RAD_CHUNK"]
+
+
 def test_device_memspace_equals_host_memspace(lib, ktab):
     import torch
     dom = synth.make_domain(16, 8, 40, seed=14)

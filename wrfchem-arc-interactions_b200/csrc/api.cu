@@ -33,6 +33,11 @@ struct Ctx {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_solved = nullptr, ev_swept[2] = {nullptr, nullptr};
   bool overlap = true;
+  // chained LW -> SW step (arc_rad_lwsw with device arrays): 1 = the LW call of the pair (no join, no sync at its end),
+  // 2 = the SW call (sunlit compaction, McICA and prep on `stream3` beside the LW kernels; joins and synchronises for both)
+  int chain = 0;
+  cudaStream_t stream3 = nullptr;
+  cudaEvent_t ev_pre = nullptr;
   HostTables H;
   DevTables D;
   std::vector<void *> table_allocs;
@@ -629,7 +634,10 @@ void arc_rad_finalize(void) {
   aer_finalize();
   if (g.stream) cudaStreamDestroy(g.stream);
   if (g.stream2) cudaStreamDestroy(g.stream2);
-  g.stream = g.stream2 = nullptr;
+  if (g.stream3) cudaStreamDestroy(g.stream3);
+  g.stream = g.stream2 = g.stream3 = nullptr;
+  if (g.ev_pre) cudaEventDestroy(g.ev_pre);
+  g.ev_pre = nullptr;
   if (g.ev_solved) cudaEventDestroy(g.ev_solved);
   for (int q = 0; q < 2; q++) if (g.ev_swept[q]) cudaEventDestroy(g.ev_swept[q]);
   g.ev_solved = g.ev_swept[0] = g.ev_swept[1] = nullptr;
@@ -660,6 +668,8 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
     g.overlap = !(e && atoi(e) == 0);
     const char *pr = getenv("ARC_RAD_SWEEP_PRIO");
     CK(cudaStreamCreateWithPriority(&g.stream2, cudaStreamNonBlocking, (pr && atoi(pr) == 0) ? lo : hi));
+    CK(cudaStreamCreateWithFlags(&g.stream3, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.ev_pre, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_solved, cudaEventDisableTiming));
     for (int q = 0; q < 2; q++) CK(cudaEventCreateWithFlags(&g.ev_swept[q], cudaEventDisableTiming));
   }
@@ -786,7 +796,9 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   const int nz = d->kte - d->kts + 1, nlay = nz + 1;
   if (nlay > 159) { g.err = "arc_rad_sw: too many layers (max 158 model layers)"; return ARC_ERR_BAD_ARG; }
 
-  CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
+  const bool chained = g.chain == 2;
+  cudaStream_t sp = chained ? g.stream3 : g.stream;       // stream of the column-parallel pre-kernels of the first outer chunk
+  if (!chained) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
   {
     const int fq[7] = {in->f_qv, in->f_qc, in->f_qr, in->f_qi, in->f_qs, in->f_qg, in->f_qndrop};
     const float *const p3[18] = {in->t3d, in->cldfra3d, in->lradius, in->iradius, in->qv3d, in->qc3d, in->qr3d, in->qi3d, in->qs3d,
@@ -847,12 +859,12 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   }
   int nsun = 0;
   {
-    Timed t("sw_compact");
-    launch_compact_sunlit(G, a.xcoszen, g.d_cols, g.d_count, g.stream);
-    launch_sw_night(a, g.stream);
+    Timed t("sw_compact", sp);
+    launch_compact_sunlit(G, a.xcoszen, g.d_cols, g.d_count, sp);
+    launch_sw_night(a, sp);
   }
-  CK(cudaMemcpyAsync(&nsun, g.d_count, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaMemcpyAsync(&nsun, g.d_count, sizeof(int), cudaMemcpyDeviceToHost, sp));
+  CK(cudaStreamSynchronize(sp));
   if (nsun > 0) {
     const size_t cap = std::min(outer_cap_default(), (size_t)((nsun + 255) / 256 * 256));
     const size_t pcap = std::min(chunk_cap_default(), cap);
@@ -866,12 +878,14 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
       m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGSW; m.permuteseed = 1; m.ncols = no; m.W = a.ws.W; m.icloud = in->icloud;
       m.cap = (int)cap; m.col0 = 0; m.lw_buffer = 0; m.cols = a.ws.cols; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
       m.mask = a.ws.mask; m.anyc = a.ws.anyc;
-      { Timed t("sw_mcica"); launch_mcica(m, g.stream); }
-      { Timed t("sw_prep"); launch_sw_prep(a, g.stream); }
+      cudaStream_t so = o0 == 0 ? sp : g.stream;
+      { Timed t("sw_mcica", so); launch_mcica(m, so); }
+      { Timed t("sw_prep", so); launch_sw_prep(a, so); }
       if (a.dbg.cldmask) {
-        k_unpack_mask<<<(no + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, a.ws.cols, 0, no, (int)cap, a.ws.W, nlay, NGSW, a.dbg.cldmask);
+        k_unpack_mask<<<(no + 127) / 128, 128, 0, so>>>(a.ws.mask, a.ws.cols, 0, no, (int)cap, a.ws.W, nlay, NGSW, a.dbg.cldmask);
         count_launch();
       }
+      if (so != g.stream) { CK(cudaEventRecord(g.ev_pre, so)); CK(cudaStreamWaitEvent(g.stream, g.ev_pre, 0)); }
       // inner chunks: column-indexed workspace pointers advance by c0, the partial buffers restart at 0
       cudaStream_t s2 = g.overlap ? g.stream2 : g.stream;
       int kc = 0;
@@ -892,6 +906,10 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
       }
       if (g.overlap) { CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0)); }
     }
+  }
+  if (chained) {   // join everything the pair queued: the night-column kernel on stream3, the sweeps of both calls on stream2
+    CK(cudaEventRecord(g.ev_pre, g.stream3)); CK(cudaStreamWaitEvent(g.stream, g.ev_pre, 0));
+    CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0));
   }
   return finish_call(dbglist);
 }
@@ -1022,8 +1040,13 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       { Timed t("lw_reduce", s2); launch_lw_reduce(b, s2); }
       if (g.overlap) CK(cudaEventRecord(g.ev_swept[buf], s2));
     }
-    if (g.overlap) { CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0)); }
+    // (the LW call of a chained pair leaves its last sweeps running: the SW call joins them)
+    const bool last_outer = o0 + (int)cap >= ncol;
+    if (g.overlap && !(g.chain == 1 && last_outer)) {
+      CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0));
+    }
   }
+  if (g.chain == 1) return 0;
   return finish_call(dbglist);
 }
 
@@ -1041,6 +1064,18 @@ int arc_rad_lwsw(const ArcDims *d, const ArcLwIn *lwin, ArcLwOut *lwout, const A
     const PipePart parts[2] = {lw_part(lwin, lwout), sw_part(swin, swout)};
     rc = run_pipelined(*d, parts, 2);
     if (rc != -1) return rc;
+  }
+  if (g.overlap && lwin->memspace == ARC_MEM_DEVICE && swin->memspace == ARC_MEM_DEVICE) {
+    // one continuous pipeline: the SW column kernels run beside the LW ones, the SW solver follows the LW solver on the main
+    // stream while the last LW sweep is still running; one join + synchronisation at the end
+    g.chain = 1;
+    rc = arc_rad_lw(d, lwin, lwout);
+    if (rc) { g.chain = 0; cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream); collect_times(); return rc; }
+    g.chain = 2;
+    rc = arc_rad_sw(d, swin, swout);
+    g.chain = 0;
+    if (rc) { cudaStreamSynchronize(g.stream3); cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream); }
+    return rc;
   }
   if ((rc = arc_rad_lw(d, lwin, lwout))) return rc;
   return arc_rad_sw(d, swin, swout);

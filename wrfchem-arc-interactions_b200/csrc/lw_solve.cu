@@ -11,13 +11,16 @@ namespace arc {
 
 static __constant__ LwBandDesc c_lw[16];
 static __constant__ int c_lw_ngb[NGLW];    // band index 0..15 of each LW g-point
+#ifndef LW_GMAX
+#define LW_GMAX 16
+#endif
 static SweepGroups h_lw_grp;               // sweep groups, see sw_solve.cu
 static __constant__ int c_lw_grp_band[SWEEP_MAXGRP];
 void upload_band_descs_lw(const HostTables &T) {
   cudaMemcpyToSymbol(c_lw, T.lw, sizeof(LwBandDesc) * 16);
   int ngs[16], g0s[16];
   for (int b = 0; b < 16; b++) { ngs[b] = T.lw[b].ng; g0s[b] = T.lw[b].g0; }
-  h_lw_grp = make_sweep_groups(ngs, g0s, 16, 16);
+  h_lw_grp = make_sweep_groups(ngs, g0s, 16, LW_GMAX);
   cudaMemcpyToSymbol(c_lw_grp_band, h_lw_grp.band, sizeof(int) * SWEEP_MAXGRP);
   int ngb[NGLW];
   for (int i = 0; i < NGLW; i++) ngb[i] = T.lw_ngb[i] - 1;

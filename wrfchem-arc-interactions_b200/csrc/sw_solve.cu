@@ -29,13 +29,16 @@ static __constant__ SwBandDesc c_sw[14];
 static __constant__ int c_sw_ngb[NGSW];    // band index 0..13 of each SW g-point
 // Sweep groups: the g-points of a band are swept by one thread per column in groups of at most SWEEP_GMAX consecutive
 // g-points (register state); bands with more g-points are cut into two equal groups.
+#ifndef SW_GMAX
+#define SW_GMAX 8
+#endif
 static SweepGroups h_sw_grp;
 static __constant__ int c_sw_grp_band[SWEEP_MAXGRP];
 void upload_band_descs_sw(const HostTables &T) {
   cudaMemcpyToSymbol(c_sw, T.sw, sizeof(SwBandDesc) * 14);
   int ngs[14], g0s[14];
   for (int b = 0; b < 14; b++) { ngs[b] = T.sw[b].ng; g0s[b] = T.sw[b].g0; }
-  h_sw_grp = make_sweep_groups(ngs, g0s, 14, 8);
+  h_sw_grp = make_sweep_groups(ngs, g0s, 14, SW_GMAX);
   cudaMemcpyToSymbol(c_sw_grp_band, h_sw_grp.band, sizeof(int) * SWEEP_MAXGRP);
   int ngb[NGSW];
   for (int i = 0; i < NGSW; i++) ngb[i] = T.sw_ngb[i] - 1;
