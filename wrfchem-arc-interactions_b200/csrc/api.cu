@@ -461,6 +461,11 @@ struct PipePart {
 };
 static inline const float *&fldv(void *st, size_t off) { return *reinterpret_cast<const float **>(reinterpret_cast<char *>(st) + off); }
 
+static int call_sw(const ArcDims *d, const void *in, void *out);
+static int call_lw(const ArcDims *d, const void *in, void *out);
+static int (*const call_sw_ptr)(const ArcDims *, const void *, void *) = call_sw;
+static int (*const call_lw_ptr)(const ArcDims *, const void *, void *) = call_lw;
+
 // Returns -1 when the call is not eligible (too few rows for more than one slab).
 static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
   const int nrows = d.jte - d.jts + 1;
@@ -555,6 +560,9 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
     ArcDims ds = d;
     ds.jms = j0; ds.jme = j1; ds.jts = j0; ds.jte = j1;
     CK(cudaStreamWaitEvent(g.stream, g.ev_in[set], 0));
+    // LW + SW on one slab run as one continuous multi-stream pipeline (see arc_rad_lwsw): no join / sync between the two
+    const bool chain = nparts == 2 && g.overlap && parts[0].call == call_lw_ptr && parts[1].call == call_sw_ptr;
+    if (chain) CK(cudaStreamWaitEvent(g.stream3, g.ev_in[set], 0));
     for (int p = 0; p < nparts && !status; p++) {
       din[p].assign((const char *)parts[p].in, (const char *)parts[p].in + parts[p].in_size);
       dout[p].assign((const char *)parts[p].out, (const char *)parts[p].out + parts[p].out_size);
@@ -566,10 +574,13 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
       for (int q = 0; q < parts[p].nalias; q++)
         if (fldv(din[p].data(), parts[p].alias[q][0])) fldv(din[p].data(), parts[p].alias[q][0]) = fldv(din[p].data(), parts[p].alias[q][1]);
       g.keep_ms = s > 0;
-      rc = parts[p].call(&ds, din[p].data(), dout[p].data());     // synchronises g.stream before returning
+      g.chain = chain ? p + 1 : 0;
+      rc = parts[p].call(&ds, din[p].data(), dout[p].data());     // synchronises g.stream before returning (chained: after SW)
+      g.chain = 0;
       g.keep_ms = false;
       if (rc && !status) status = rc;
     }
+    if (chain && status) { cudaStreamSynchronize(g.stream3); cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream); collect_times(); }
     if ((rc = download(s))) return rc;
     if (status) break;
   }
