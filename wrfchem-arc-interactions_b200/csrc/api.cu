@@ -99,6 +99,16 @@ size_t outer_cap_default() {
   return std::max(chunk_cap_default(), (size_t)((v + 255) / 256 * 256));
 }
 
+// Inner-chunk capacity bounded by the level-record budget (ARC_RAD_REC_GB per spectrum, default 40 GB for the two buffers):
+// the records are `bytes_per_col` per column and buffer, e.g. 84 B x 112 g x 52 levels (SW, 3 streams) at C2.
+size_t rec_limited_cap(size_t cap, size_t bytes_per_col) {
+  const char *e = getenv("ARC_RAD_REC_GB");
+  const double budget = (e ? atof(e) : 40.0) * 1e9;
+  size_t lim = (size_t)(budget / (2.0 * (double)bytes_per_col));
+  lim = std::max<size_t>(256, lim / 256 * 256);
+  return std::min(std::min(chunk_cap_default(), cap), lim);
+}
+
 struct Carver {
   char *base; size_t off = 0;
   template <class T> T *take(size_t n) {
@@ -878,7 +888,8 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   CK(cudaStreamSynchronize(sp));
   if (nsun > 0) {
     const size_t cap = std::min(outer_cap_default(), (size_t)((nsun + 255) / 256 * 256));
-    const size_t pcap = std::min(chunk_cap_default(), cap);
+    const int nstream = 2 + ((variants & ARC_VAR_CLEAN) ? 1 : 0) + ((variants & ARC_VAR_CLEANCLEAR) ? 1 : 0);
+    const size_t pcap = rec_limited_cap(cap, (size_t)28 * nstream * NGSW * (nlay + 1));
     if ((rc = ensure_sw_ws(nlay, cap, pcap, variants))) return rc;
     for (int o0 = 0; o0 < nsun; o0 += (int)cap) {
       const int no = std::min((int)cap, nsun - o0);
@@ -1015,7 +1026,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
 
   const int ncol = G.ncol_tile;
   const size_t cap = std::min(outer_cap_default(), (size_t)((ncol + 255) / 256 * 256));
-  const size_t pcap = std::min(chunk_cap_default(), cap);
+  const size_t pcap = rec_limited_cap(cap, (size_t)24 * ((variants & ARC_VAR_CLEAN) ? 2 : 1) * NGLW * (nlay + 1));
   if ((rc = ensure_lw_ws(nlay, cap, pcap, variants))) return rc;
   for (int o0 = 0; o0 < ncol; o0 += (int)cap) {
     const int no = std::min((int)cap, ncol - o0);

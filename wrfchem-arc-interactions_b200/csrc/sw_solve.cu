@@ -185,10 +185,15 @@ __device__ __forceinline__ float sw_expt(const float *__restrict__ exp_tbl, floa
 #define S_(a, b) __fsub_rn((a), (b))
 #define D_(a, b) div_rn((a), (b))
 
-// reftra_sw (kmodts = 2, PIFM) for one layer, SW:2540-2690.  Returns (ref, refd, tra, trad).
-__device__ __noinline__ float4 sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
+// reftra_sw (kmodts = 2, PIFM) for one layer, SW:2540-2690.  Returns (ref, refd, tra, trad) and, because both branches
+// evaluate it anyway, e = exp(-tau/mu0) through the table: the direct-beam transmittance spcvmc_sw computes again from the
+// same operands (SW:8560-8575), identical bit for bit as long as tau/mu0 <= 500 (reftra clamps its argument there).
+struct SwLayerRT { float4 p; float e; };
+__device__ __noinline__ SwLayerRT sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
   const float eps = 1.e-08f, zwcrit = 0.9999995f;
   float4 o;
+  const float zx = D_(zto1, prmuz);
+  const float zexp = sw_expt(exp_tbl, fminf(zx, 500.f), bpade);
   const float zg3 = M_(3.f, zg);
   const float zgamma1 = M_(S_(8.f, M_(zw, A_(5.f, zg3))), 0.25f);
   const float zgamma2 = M_(M_(3.f, M_(zw, S_(1.f, zg))), 0.25f);
@@ -201,8 +206,7 @@ __device__ __noinline__ float4 sw_reftra(const float *__restrict__ exp_tbl, floa
     const float za = M_(zgamma1, prmuz);
     const float za1 = S_(za, zgamma3);
     const float zgt = M_(zgamma1, zto1);
-    const float ze1 = fminf(D_(zto1, prmuz), 500.f);
-    const float ze2 = sw_expt(exp_tbl, ze1, bpade);
+    const float ze2 = zexp;
     o.x = D_(S_(zgt, M_(za1, S_(1.f, ze2))), A_(1.f, zgt));
     o.z = S_(1.f, o.x);
     o.y = D_(zgt, A_(1.f, zgt));
@@ -226,9 +230,8 @@ __device__ __noinline__ float4 sw_reftra(const float *__restrict__ exp_tbl, floa
     const float zt3 = M_(zrk2, A_(zgamma4, M_(za1, prmuz)));
     const float zbeta = D_(S_(zgamma1, zrk), zrkg);
     const float ze1 = fminf(M_(zrk, zto1), 500.f);
-    const float ze2 = fminf(D_(zto1, prmuz), 500.f);
     const float zem1 = sw_expt(exp_tbl, ze1, bpade), zep1 = D_(1.f, zem1);
-    const float zem2 = sw_expt(exp_tbl, ze2, bpade), zep2 = D_(1.f, zem2);
+    const float zem2 = zexp, zep2 = D_(1.f, zem2);
     const float zdenr = A_(M_(zr4, zep1), M_(zr5, zem1));
     const float zdent = zdenr;   // zt4 = zr4, zt5 = zr5
     if (zdenr >= -eps && zdenr <= eps) { o.x = eps; o.z = zem2; }
@@ -241,7 +244,10 @@ __device__ __noinline__ float4 sw_reftra(const float *__restrict__ exp_tbl, floa
     o.y = M_(M_(zgamma2, S_(1.f, zemm)), zdend);
     o.w = M_(M_(zrk2, zem1), zdend);
   }
-  return o;
+  SwLayerRT r;
+  r.p = o;
+  r.e = zx <= 500.f ? zexp : sw_expt(exp_tbl, zx, bpade);      // beyond the clamp the table is 0 or expeps
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -348,30 +354,35 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
 #pragma unroll
     for (int v = 0; v < 2; v++) {
       if (v == 1 && !noaer) break;
-      const float ta = v == 0 ? taua : 0.f;
-      float ztauc = A_(A_(taur, taug), ta);
-      float zomcc = A_(M_(taur, 1.0f), M_(ta, omga));
-      float zgcc = D_(M_(M_(asya, omga), ta), zomcc);
-      zomcc = D_(zomcc, ztauc);
+      float ztauc, zomcc, zgcc;
       if (v == 0) {
+        ztauc = A_(A_(taur, taug), taua);
+        zomcc = A_(M_(taur, 1.0f), M_(taua, omga));
+        zgcc = D_(M_(M_(asya, omga), taua), zomcc);
+        zomcc = D_(zomcc, ztauc);
         // direct beam without delta scaling (diagnostic surface direct flux of the FULL stream)
         const float tauorig = cloudy ? A_(ztauc, taormc) : ztauc;
         tdir_nodel = tdir_nodel * sw_expt(s_exp, D_(tauorig, prmu0), bpade);
+        const float zf = M_(zgcc, zgcc);
+        const float zwf = M_(zomcc, zf);
+        ztauc = M_(S_(1.0f, zwf), ztauc);
+        zomcc = D_(S_(zomcc, zwf), fmaxf(S_(1.0f, zwf), 1.0E-30f));
+        zgcc = D_(S_(zgcc, zf), fmaxf(S_(1.0f, zf), 1.0E-30f));
+      } else {
+        // zero aerosol: the same expressions with taua = 0 reduce exactly (x + 0, x * 1, 0 / x, x / 1) to
+        ztauc = A_(taur, taug);
+        zomcc = D_(taur, ztauc);
+        zgcc = 0.f;
       }
-      const float zf = M_(zgcc, zgcc);
-      const float zwf = M_(zomcc, zf);
-      ztauc = M_(S_(1.0f, zwf), ztauc);
-      zomcc = D_(S_(zomcc, zwf), fmaxf(S_(1.0f, zwf), 1.0E-30f));
-      zgcc = D_(S_(zgcc, zf), fmaxf(S_(1.0f, zf), 1.0E-30f));
-      pclr[v] = sw_reftra(s_exp, bpade, zgcc, prmu0, ztauc, zomcc);
-      eclr[v] = sw_expt(s_exp, D_(ztauc, prmu0), bpade);
+      const SwLayerRT rt = sw_reftra(s_exp, bpade, zgcc, prmu0, ztauc, zomcc);
+      pclr[v] = rt.p; eclr[v] = rt.e;
       if (cloudy) {
         const float ztauo = A_(ztauc, taucmc);
         float zomco = A_(M_(ztauc, zomcc), M_(taucmc, ssacmc));
         const float zgco = D_(A_(M_(M_(taucmc, ssacmc), asmcmc), M_(M_(ztauc, zomcc), zgcc)), zomco);
         zomco = D_(zomco, ztauo);
-        pcld[v] = sw_reftra(s_exp, bpade, zgco, prmu0, ztauo, zomco);
-        ecld[v] = sw_expt(s_exp, D_(ztauo, prmu0), bpade);
+        const SwLayerRT rc = sw_reftra(s_exp, bpade, zgco, prmu0, ztauo, zomco);
+        pcld[v] = rc.p; ecld[v] = rc.e;
       }
     }
     // ---- upward reflectances at the top of this layer (vrtqdr_sw bottom-up sweep)
