@@ -188,20 +188,31 @@ __device__ __forceinline__ float sw_expt(const float *__restrict__ exp_tbl, floa
 // reftra_sw (kmodts = 2, PIFM) for one layer, SW:2540-2690.  Returns (ref, refd, tra, trad) and, because both branches
 // evaluate it anyway, e = exp(-tau/mu0) through the table: the direct-beam transmittance spcvmc_sw computes again from the
 // same operands (SW:8560-8575), identical bit for bit as long as tau/mu0 <= 500 (reftra clamps its argument there).
+// ZG0: the asymmetry parameter is exactly zero (Rayleigh + gas layer of the aerosol-free streams); the expressions in zg
+// then reduce exactly (0 * x, x - 0, 0 / x, x / 1) and two divisions drop out.
 struct SwLayerRT { float4 p; float e; };
+template <bool ZG0>
 __device__ __noinline__ SwLayerRT sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
   const float eps = 1.e-08f, zwcrit = 0.9999995f;
   float4 o;
   const float zx = D_(zto1, prmuz);
   const float zexp = sw_expt(exp_tbl, fminf(zx, 500.f), bpade);
-  const float zg3 = M_(3.f, zg);
-  const float zgamma1 = M_(S_(8.f, M_(zw, A_(5.f, zg3))), 0.25f);
-  const float zgamma2 = M_(M_(3.f, M_(zw, S_(1.f, zg))), 0.25f);
-  const float zgamma3 = M_(S_(2.f, M_(zg3, prmuz)), 0.25f);
-  const float zgamma4 = S_(1.f, zgamma3);
-  const float q = D_(zg, S_(1.f, zg));
-  const float denom = fmaxf(S_(1.f, M_(S_(1.f, zw), M_(q, q))), 1.0E-30f);
-  const float zwo = D_(zw, denom);
+  float zgamma1, zgamma2, zgamma3, zgamma4, zwo;
+  if (ZG0) {
+    zgamma1 = M_(S_(8.f, M_(zw, 5.f)), 0.25f);
+    zgamma2 = M_(M_(3.f, zw), 0.25f);
+    zgamma3 = 0.5f; zgamma4 = 0.5f;
+    zwo = zw;
+  } else {
+    const float zg3 = M_(3.f, zg);
+    zgamma1 = M_(S_(8.f, M_(zw, A_(5.f, zg3))), 0.25f);
+    zgamma2 = M_(M_(3.f, M_(zw, S_(1.f, zg))), 0.25f);
+    zgamma3 = M_(S_(2.f, M_(zg3, prmuz)), 0.25f);
+    zgamma4 = S_(1.f, zgamma3);
+    const float q = D_(zg, S_(1.f, zg));
+    const float denom = fmaxf(S_(1.f, M_(S_(1.f, zw), M_(q, q))), 1.0E-30f);
+    zwo = D_(zw, denom);
+  }
   if (zwo >= zwcrit) {
     const float za = M_(zgamma1, prmuz);
     const float za1 = S_(za, zgamma3);
@@ -374,14 +385,15 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
         zomcc = D_(taur, ztauc);
         zgcc = 0.f;
       }
-      const SwLayerRT rt = sw_reftra(s_exp, bpade, zgcc, prmu0, ztauc, zomcc);
+      const SwLayerRT rt = v == 0 ? sw_reftra<false>(s_exp, bpade, zgcc, prmu0, ztauc, zomcc)
+                                  : sw_reftra<true>(s_exp, bpade, 0.f, prmu0, ztauc, zomcc);
       pclr[v] = rt.p; eclr[v] = rt.e;
       if (cloudy) {
         const float ztauo = A_(ztauc, taucmc);
         float zomco = A_(M_(ztauc, zomcc), M_(taucmc, ssacmc));
         const float zgco = D_(A_(M_(M_(taucmc, ssacmc), asmcmc), M_(M_(ztauc, zomcc), zgcc)), zomco);
         zomco = D_(zomco, ztauo);
-        const SwLayerRT rc = sw_reftra(s_exp, bpade, zgco, prmu0, ztauo, zomco);
+        const SwLayerRT rc = sw_reftra<false>(s_exp, bpade, zgco, prmu0, ztauo, zomco);
         pcld[v] = rc.p; ecld[v] = rc.e;
       }
     }
