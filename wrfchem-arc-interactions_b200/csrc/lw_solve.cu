@@ -144,13 +144,19 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
   const float *coefc = ws.coef + c, *aerc = ws.aer + c + (unsigned)b * ustf;
   float tz_up = coefc[(unsigned)LWC_TZ * ustf + (unsigned)(nlay - 1) * ucap];      // temperature of the interface above the layer
   float plev_up = planck_at(tz_up);
-  for (int lay = nlay - 1; lay >= 0; lay--) {
+  // Software pipeline: the workspace words of layer lay-1 are requested right after the gas optics of layer lay have
+  // consumed theirs (the registers are free then) and land while the radiative-transfer step of layer lay executes.
+  float fv[LWC_N], taua_nx, tz_nx;
+  auto load_layer = [&](int lay) {
     const float *p = coefc + (unsigned)lay * ucap;
-    float fv[LWC_N];
 #pragma unroll
     for (int f = 0; f < LWC_N; f++) fv[f] = ((need >> f) & 1u) ? p[(unsigned)f * ustf] : 0.f;
-    const float taua = aerc[(unsigned)lay * ucap];
-    const float tz_dn = lay > 0 ? p[(unsigned)LWC_TZ * ustf - ucap] : ws.colf[(size_t)LWF_TZ0 * cap + c];
+    taua_nx = aerc[(unsigned)lay * ucap];
+    tz_nx = lay > 0 ? p[(unsigned)LWC_TZ * ustf - ucap] : ws.colf[(size_t)LWF_TZ0 * cap + c];
+  };
+  load_layer(nlay - 1);
+  for (int lay = nlay - 1; lay >= 0; lay--) {
+    const float taua = taua_nx, tz_dn = tz_nx;
     auto F = [&](int f) { return fv[f]; };
     const int pk = __float_as_int(F(LWC_IDX));
     const int jp = IDX_JP(pk), jt = IDX_JT(pk), jt1 = IDX_JT1(pk), indself = IDX_SELF(pk), indfor = IDX_FOR(pk), indminor = IDX_MINOR(pk);
@@ -390,6 +396,7 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
 
     // ---- rtrnmc downward step for this layer (LW:3207-3300)
     const float blay = planck_at(F(LWC_TAVEL));
+    if (lay > 0) load_layer(lay - 1);          // prefetch (fv is dead from here on)
     const float plev_dn = planck_at(tz_dn);
     const float dplankup = plev_up - blay, dplankdn = plev_dn - blay;
     const float plfrac = fracs;
