@@ -21,6 +21,6 @@ for _ in range(steps):
     lib.RRTMG_LWRAD(dims, **R.lw_kwargs(ddom, o_lw, **flags))
     lib.RRTMG_SWRAD(dims, **R.sw_kwargs(ddom, o_sw, **flags))
 torch.cuda.synchronize()
-for n in ("sw_mcica", "sw_prep", "sw_solve", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_reduce"):
+for n in ("sw_mcica", "sw_prep", "sw_solve", "sw_sweep", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_sweep", "lw_reduce"):
     print(n, lib.lib.arc_rad_last_kernel_ms(n.encode()))
 print("swupt mean", float(o_sw["swupt"].mean()), "olr mean", float(o_lw["olr"].mean()))

@@ -7,6 +7,9 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-aer --no-cpu-baseline > gpurun_out/ncu_bench_$tag.log 2>&1
 python tools/prof_run.py 256 128 50 1 > gpurun_out/prof_plain_$tag.log 2>&1 || { tail -5 gpurun_out/prof_plain_$tag.log; exit 1; }
-ncu --set full --import-source on --clock-control none --kernel-name regex:"k_sw_solve|k_lw_solve|k_sw_sweep<8>|k_lw_sweep<16>|k_sw_reduce|k_lw_reduce" -c 12 \
+ncu --set full --import-source on --clock-control none --kernel-name regex:"k_sw_solve|k_lw_solve|k_sw_reduce|k_lw_reduce" -c 4 \
     -o gpurun_out/prof_${tag}_full -f python tools/prof_run.py 256 128 50 1 > gpurun_out/prof_ncu_$tag.log 2>&1
 tail -2 gpurun_out/prof_ncu_$tag.log
+ncu --set full --clock-control none --kernel-name regex:"k_sw_sweep<\(int\)(8|2)>|k_lw_sweep<\(int\)(16|8)>" -c 6 \
+    -o gpurun_out/prof_${tag}_sweep -f python tools/prof_run.py 256 128 50 1 > gpurun_out/prof_ncu_sweep_$tag.log 2>&1
+tail -2 gpurun_out/prof_ncu_sweep_$tag.log
