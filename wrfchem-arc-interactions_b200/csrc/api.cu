@@ -914,7 +914,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
       for (int c0 = 0; c0 < no; c0 += (int)pcap, kc++) {
         SwArgs b = a;
         b.ncols = std::min((int)pcap, no - c0);
-        b.ws.cols += c0; b.ws.coef += c0; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0;
+        b.ws.cols += c0; b.ws.coef += (size_t)c0 * SWC_N; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0;
         b.ws.laytrop += c0; b.ws.laysol += c0; b.ws.colf += c0;
         const int buf = kc & 1;
         b.ws.recP += buf * a.ws.rec_n; b.ws.recE += buf * a.ws.rec_n; b.ws.recR += buf * a.ws.rec_n;
@@ -1050,7 +1050,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       LwArgs b = a;
       b.ncols = std::min((int)pcap, no - c0);
       b.col0 = o0 + c0;
-      b.ws.coef += c0; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0; b.ws.laytrop += c0; b.ws.colf += c0;
+      b.ws.coef += (size_t)c0 * LWC_N; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0; b.ws.laytrop += c0; b.ws.colf += c0;
       b.ws.secdiff += c0;
       const int buf = kc & 1;
       b.ws.scrU += buf * a.ws.rec_n; b.ws.scrC += buf * a.ws.rec_n; b.ws.scrD += buf * a.ws.rec_n;

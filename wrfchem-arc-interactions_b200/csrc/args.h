@@ -57,7 +57,15 @@ inline SweepGroups make_sweep_groups(const int *ng, const int *g0, int nbands, i
 // flux "kinds" in the partial buffer: full up/down, clear up/down, clean up/down, clean-clear up/down
 enum { K_FU = 0, K_FD, K_CU, K_CD, K_NU, K_ND, K_XU, K_XD, NKIND };
 
-// ---- SW workspace fields [field][lay][c] -------------------------------------------------------------
+// Layout of the per-layer coefficient workspace: [layer][column tile of 32][field][32 lanes].  A thread's N fields of one
+// layer are N words 128 bytes apart, so the solver addresses them with immediate offsets from one pointer per layer
+// (a [field][layer][column] layout costs an address computation per load: 10 % of k_lw_solve's instructions).
+// `cap` (column capacity) is a multiple of 256.
+__host__ __device__ inline size_t coef_index(int f, int lay, size_t c, size_t cap, int nfields) {
+  return (((size_t)lay * (cap >> 5) + (c >> 5)) * nfields + f) * 32 + (c & 31);
+}
+
+// ---- SW workspace fields ---------------------------------------------------------------------------
 enum { SWC_FAC00 = 0, SWC_FAC01, SWC_FAC10, SWC_FAC11, SWC_H2O, SWC_CO2, SWC_O3, SWC_CH4, SWC_O2, SWC_MOL,
        SWC_SELFFAC, SWC_SELFFRAC, SWC_FORFAC, SWC_FORFRAC, SWC_IDX, SWC_N };
 // per-column floats [field][c]
@@ -69,7 +77,7 @@ struct SwWs {
   int nlay;                // kte-kts+2
   int W;                   // mask words per (g, column)
   int *cols;               // [cap] tile column id of each chunk column
-  float *coef;             // [SWC_N][nlay][cap]
+  float *coef;             // coef_index(field, layer, c, cap, SWC_N)
   float *aer;              // [14][3][nlay][cap]   tau, ssa, asy
   float *cld;              // [14][4][nlay][cap]   taucmc, ssacmc, asmcmc, taormc
   uint32_t *mask;          // [NGSW][W][cap]       McICA bits, bit (lay%32) of word lay/32
@@ -122,7 +130,7 @@ enum { LWF_TZ0 = 0, LWF_TBOUND, LWF_EMISS, LWF_N };
 struct LwWs {
   int cap, pcap, nlay, W;
   int *cols;               // nullable (identity)
-  float *coef;             // [LWC_N][nlay][cap]
+  float *coef;             // coef_index(field, layer, c, cap, LWC_N)
   float *aer;              // [16][nlay][cap]
   float *cld;              // [16][nlay][cap]  taucmc
   uint32_t *mask;          // [NGLW][W][cap]

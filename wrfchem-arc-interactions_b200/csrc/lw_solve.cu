@@ -141,18 +141,19 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
                                      H2O, H2O | O2 | SM | MF, H2O | CO2, H2O | N2O | CO2 | CO | O3 | MF | DRY, CO2, N2O | CO2 | BRD | SM | MF, H2O | CH4};
   constexpr unsigned need = COMMON | per_band[BAND - 1];
   const unsigned ucap = (unsigned)cap, ustf = (unsigned)nlay * (unsigned)cap;     // 32-bit offsets: LWC_N*nlay*cap < 2^31
-  const float *coefc = ws.coef + c, *aerc = ws.aer + c + (unsigned)b * ustf;
-  float tz_up = coefc[(unsigned)LWC_TZ * ustf + (unsigned)(nlay - 1) * ucap];      // temperature of the interface above the layer
+  const float *coefc = ws.coef + coef_index(0, 0, c, cap, LWC_N), *aerc = ws.aer + c + (unsigned)b * ustf;
+  const unsigned lstride = (unsigned)cap * LWC_N;                                  // coefficient words per layer
+  float tz_up = coefc[(size_t)((unsigned)(nlay - 1) * lstride) + LWC_TZ * 32];      // temperature of the interface above the layer
   float plev_up = planck_at(tz_up);
   // Software pipeline: the workspace words of layer lay-1 are requested right after the gas optics of layer lay have
   // consumed theirs (the registers are free then) and land while the radiative-transfer step of layer lay executes.
   float fv[LWC_N], taua_nx, tz_nx;
   auto load_layer = [&](int lay) {
-    const float *p = coefc + (unsigned)lay * ucap;
+    const float *p = coefc + (size_t)((unsigned)lay * lstride);      // fields at immediate offsets of 128 bytes
 #pragma unroll
-    for (int f = 0; f < LWC_N; f++) fv[f] = ((need >> f) & 1u) ? p[(unsigned)f * ustf] : 0.f;
+    for (int f = 0; f < LWC_N; f++) fv[f] = ((need >> f) & 1u) ? p[f * 32] : 0.f;
     taua_nx = aerc[(unsigned)lay * ucap];
-    tz_nx = lay > 0 ? p[(unsigned)LWC_TZ * ustf - ucap] : ws.colf[(size_t)LWF_TZ0 * cap + c];
+    tz_nx = lay > 0 ? *(p + LWC_TZ * 32 - (ptrdiff_t)lstride) : ws.colf[(size_t)LWF_TZ0 * cap + c];
   };
   load_layer(nlay - 1);
   for (int lay = nlay - 1; lay >= 0; lay--) {

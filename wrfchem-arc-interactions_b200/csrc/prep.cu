@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128) k_sw_prep(SwArgs a) {
   int inflg, iceflg, liqflg;
   cloud_flags(a.cf, inflg, iceflg, liqflg);
 
-  auto COEF = [&](int f, int l) -> float & { return ws.coef[((size_t)f * nlay + l) * cap + c]; };
+  auto COEF = [&](int f, int l) -> float & { return ws.coef[coef_index(f, l, c, cap, SWC_N)]; };
   auto AER = [&](int b, int q, int l) -> float & { return ws.aer[(((size_t)b * 3 + q) * nlay + l) * cap + c]; };
   auto CLD = [&](int b, int q, int l) -> float & { return ws.cld[(((size_t)b * 4 + q) * nlay + l) * cap + c]; };
 
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(128) k_lw_prep(LwArgs a) {
   int inflg, iceflg, liqflg;
   cloud_flags(a.cf, inflg, iceflg, liqflg);
 
-  auto COEF = [&](int f, int l) -> float & { return ws.coef[((size_t)f * nlay + l) * cap + c]; };
+  auto COEF = [&](int f, int l) -> float & { return ws.coef[coef_index(f, l, c, cap, LWC_N)]; };
 
   // temperature profile interpolated to a pressure level (LW:12220-12243)
   auto varint = [&](float p) {

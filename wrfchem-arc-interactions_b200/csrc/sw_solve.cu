@@ -327,15 +327,16 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
   float tdir_nodel = 1.f;     // product of the un-delta-scaled direct transmittances of the FULL stream
 
   // all workspace words of a layer are requested together at the top of the iteration (one wait per layer)
-  const float *coef = ws.coef + c;
+  const float *coef = ws.coef + coef_index(0, 0, c, cap, SWC_N);
+  const unsigned lstride = (unsigned)cap * SWC_N;                                  // coefficient words per layer
   const unsigned stf = (unsigned)nlay * (unsigned)cap, ucap = (unsigned)cap;      // 32-bit offsets: SWC_N*nlay*cap < 2^31
   auto load_layer = [&](int lay, SwLay &L, int &pk, float &ta, float &om, float &as) {
-    const float *p = coef + (unsigned)lay * ucap;
-    L.fac00 = p[SWC_FAC00 * stf]; L.fac01 = p[SWC_FAC01 * stf]; L.fac10 = p[SWC_FAC10 * stf]; L.fac11 = p[SWC_FAC11 * stf];
-    L.h2o = p[SWC_H2O * stf]; L.co2 = p[SWC_CO2 * stf]; L.o3 = p[SWC_O3 * stf]; L.ch4 = p[SWC_CH4 * stf]; L.o2 = p[SWC_O2 * stf];
-    L.mol = p[SWC_MOL * stf];
-    L.selffac = p[SWC_SELFFAC * stf]; L.selffrac = p[SWC_SELFFRAC * stf]; L.forfac = p[SWC_FORFAC * stf]; L.forfrac = p[SWC_FORFRAC * stf];
-    pk = __float_as_int(p[SWC_IDX * stf]);
+    const float *p = coef + (size_t)((unsigned)lay * lstride);       // fields at immediate offsets of 128 bytes
+    L.fac00 = p[SWC_FAC00 * 32]; L.fac01 = p[SWC_FAC01 * 32]; L.fac10 = p[SWC_FAC10 * 32]; L.fac11 = p[SWC_FAC11 * 32];
+    L.h2o = p[SWC_H2O * 32]; L.co2 = p[SWC_CO2 * 32]; L.o3 = p[SWC_O3 * 32]; L.ch4 = p[SWC_CH4 * 32]; L.o2 = p[SWC_O2 * 32];
+    L.mol = p[SWC_MOL * 32];
+    L.selffac = p[SWC_SELFFAC * 32]; L.selffrac = p[SWC_SELFFRAC * 32]; L.forfac = p[SWC_FORFAC * 32]; L.forfrac = p[SWC_FORFRAC * 32];
+    pk = __float_as_int(p[SWC_IDX * 32]);
     const float *pa = ws.aer + c + (unsigned)(b * 3) * stf + (unsigned)lay * ucap;
     ta = pa[0]; om = pa[stf]; as = pa[2u * stf];
   };
