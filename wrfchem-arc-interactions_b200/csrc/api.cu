@@ -131,10 +131,8 @@ void carve_sw(SwWs &w, char *base, size_t &bytes) {
   w.laysol = c.take<int>((size_t)NBSW * cap);
   w.colf = c.take<float>((size_t)SWF_N * cap);
   const size_t ns = w.nk / 2;                              // streams = pairs of flux kinds
-  w.rec_n = ns * NGSW * (nl + 1) * pcap;                  // two buffers of level records (solver k+1 overlaps sweep k)
-  w.recP = c.take<float4>(2 * w.rec_n);
-  w.recE = c.take<float>(2 * w.rec_n);
-  w.recR = c.take<float2>(2 * w.rec_n);
+  w.rec_n = (pcap / REC_TILE) * (nl + 1) * ns * NGSW * SW_REC;   // two buffers of level records (solver k+1 overlaps sweep k)
+  w.rec = c.take<float>(2 * w.rec_n);
   w.zinc = c.take<float>((size_t)2 * NGSW * pcap);
   w.bpart = c.take<float>((size_t)sw_sweep_groups() * (nl + 1) * w.nk * pcap);
   w.dirs = c.take<float>((size_t)2 * NGSW * pcap);
@@ -917,7 +915,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
         b.ws.cols += c0; b.ws.coef += (size_t)c0 * SWC_N; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0;
         b.ws.laytrop += c0; b.ws.laysol += c0; b.ws.colf += c0;
         const int buf = kc & 1;
-        b.ws.recP += buf * a.ws.rec_n; b.ws.recE += buf * a.ws.rec_n; b.ws.recR += buf * a.ws.rec_n;
+        b.ws.rec += buf * a.ws.rec_n;
         b.ws.zinc += (size_t)buf * NGSW * pcap; b.ws.dirs += (size_t)buf * NGSW * pcap;
         if (g.overlap && kc >= 2) CK(cudaStreamWaitEvent(g.stream, g.ev_swept[buf], 0));      // records of chunk k-2 consumed
         { Timed t("sw_solve"); launch_sw_solve(b, g.stream); }

@@ -54,6 +54,10 @@ inline SweepGroups make_sweep_groups(const int *ng, const int *g0, int nbands, i
   return G;
 }
 
+constexpr int REC_TILE = 128;                                     // columns per record tile = threads of a sweep block
+constexpr int SW_REC = 7 * REC_TILE, SW_REC_R = 4 * REC_TILE, SW_REC_E = 6 * REC_TILE;   // words per SW level record, offsets of R and E
+constexpr int LW_REC = 4 * REC_TILE, LW_REC_D = 2 * REC_TILE;     // LW: float2 U at 0, float2 D at LW_REC_D
+
 // flux "kinds" in the partial buffer: full up/down, clear up/down, clean up/down, clean-clear up/down
 enum { K_FU = 0, K_FD, K_CU, K_CD, K_NU, K_ND, K_XU, K_XD, NKIND };
 
@@ -85,12 +89,16 @@ struct SwWs {
   int *laytrop;            // [cap]
   int *laysol;             // [14][cap]            layer (0-based) where sfluxzen is taken, -1 = never
   float *colf;             // [SWF_N][cap]
-  // Level records handed from k_sw_solve (taumol, reftra, bottom-up sweep) to k_sw_sweep (top-down sweep + band sum):
-  // [stream slot][NGSW][nlay+1][pcap]; stream slots in the order clear, full [, clean][, clean-clear]
-  size_t rec_n;            // elements per buffer of the level records (host-side: two buffers are carved)
-  float4 *recP;            // (ref, refd, tra, trad) of the layer below the level (level 0 unused)
-  float *recE;             // direct-beam transmittance of that layer
-  float2 *recR;            // (rup, rupd) at the level; level 0 = surface albedos
+  // Level records handed from k_sw_solve (taumol, reftra, bottom-up sweep) to k_sw_sweep (top-down sweep + band sum),
+  // tiled [128-column tile][level][stream slot][g-point][SW_REC words]: one record = 128 lanes x (float4 P | float2 R | float E)
+  //   P = (ref, refd, tra, trad) of the layer below the level (level 0 unused), words 0..511
+  //   R = (rup, rupd) at the level (level 0 = surface albedos),                 words 512..767
+  //   E = direct-beam transmittance of that layer,                              words 768..895
+  // (128 columns = one sweep block: its loads are 2 KB / 1 KB / 512 B contiguous pieces)
+  // so the solver (one g, all streams) and the sweep (one stream, the g-points of a group) both address a level's records
+  // with immediate offsets from one pointer.  Stream slots in the order clear, full [, clean][, clean-clear].
+  size_t rec_n;            // words per buffer of the level records (host-side: two buffers are carved)
+  float *rec;
   float *zinc;             // [NGSW][pcap]        incident flux of the g-point (adjflux x sfluxzen x mu0)
   float *bpart;            // [sweep group][nlay+1][nk][pcap]  per-group sums of the fluxes; nk = kinds in use, slot of kind k = kslot[k]
   int nk; int kslot[NKIND];

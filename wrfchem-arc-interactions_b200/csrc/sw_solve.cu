@@ -312,16 +312,19 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
   // Level records handed to k_sw_sweep (layout in args.h): for every stream the two-stream solution (P, e) of the layer
   // below the level and the upward reflectances (rup, rupd) at the level.  Stream order: clear, full, clean, clean-clear.
   const size_t pcap = ws.pcap;
-  const size_t sstride = (size_t)NGSW * (nlay + 1) * pcap;            // stream stride of the records
-  const size_t rec0 = (size_t)g * (nlay + 1) * pcap + c;              // level 0 of stream 0
   const int slot[4] = {0, 1, 2, do_clean ? 3 : 2};                     // compact stream slots
+  const int nstream = 2 + (do_clean ? 1 : 0) + (do_clnc ? 1 : 0);
+  const unsigned lvstride = (unsigned)nstream * NGSW * SW_REC;         // words per (tile, level)
+  // record of (this tile, level 0, stream slot 0, g), lane part added per field
+  float *rec = ws.rec + ((size_t)(c / REC_TILE) * (nlay + 1) * nstream * NGSW + g) * SW_REC;
+  const int lane = c % REC_TILE;
   float rup[4], rupd[4];
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     rup[s] = albp; rupd[s] = albd;
     if (s == 2 && !do_clean) continue;
     if (s == 3 && !do_clnc) continue;
-    ws.recR[slot[s] * sstride + rec0] = make_float2(albp, albd);
+    reinterpret_cast<float2 *>(rec + slot[s] * (NGSW * SW_REC) + SW_REC_R)[lane] = make_float2(albp, albd);
   }
   float sfluxzen = 0.f;
   float tdir_nodel = 1.f;     // product of the un-delta-scaled direct transmittances of the FULL stream
@@ -414,8 +417,10 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
       const float nrup = fmaf(__fmul_rn(P.w, fmaf(e, rup[s], __fmul_rn(__fsub_rn(P.z, e), rupd[s]))), zreflect, P.x);
       const float nrupd = fmaf(__fmul_rn(__fmul_rn(P.w, P.w), rupd[s]), zreflect, P.y);
       rup[s] = nrup; rupd[s] = nrupd;
-      const size_t q = slot[s] * sstride + rec0 + (size_t)(lay + 1) * pcap;
-      ws.recP[q] = P; ws.recE[q] = e; ws.recR[q] = make_float2(nrup, nrupd);
+      float *q = rec + (size_t)((unsigned)(lay + 1) * lvstride) + slot[s] * (NGSW * SW_REC);
+      reinterpret_cast<float4 *>(q)[lane] = P;
+      reinterpret_cast<float2 *>(q + SW_REC_R)[lane] = make_float2(nrup, nrupd);
+      q[SW_REC_E + lane] = e;
     }
   }
   if (a.dbg.sfluxzen) a.dbg.sfluxzen[(size_t)ws.cols[c] * NGSW + g] = sfluxzen;
@@ -460,11 +465,9 @@ __global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0) {
   const int s = si < 2 ? si : (si == 2 && do_clean ? 2 : 3);      // 0 clear, 1 full, 2 clean, 3 clean-clear
   const int nlay = ws.nlay, nk = ws.nk;
   const size_t pcap = ws.pcap;
-  const size_t lstride = (size_t)(nlay + 1) * pcap;
-  const size_t base = ((size_t)si * NGSW + g0) * lstride + c;
-  const float4 *__restrict__ recP = ws.recP + base;
-  const float2 *__restrict__ recR = ws.recR + base;
-  const float *__restrict__ recE = ws.recE + base;
+  const int nstream = gridDim.y, lane = threadIdx.x;                   // block = one record tile
+  const unsigned lvstride = (unsigned)nstream * NGSW * SW_REC;         // words per (tile, level)
+  const float *__restrict__ rec = ws.rec + (((size_t)blockIdx.x * (nlay + 1) * nstream + si) * NGSW + g0) * SW_REC;
   const int ku = ws.kslot[s == 0 ? K_CU : s == 1 ? K_FU : s == 2 ? K_NU : K_XU];
   const int kd = ws.kslot[s == 0 ? K_CD : s == 1 ? K_FD : s == 2 ? K_ND : K_XD];
   float *__restrict__ bpart = ws.bpart + (size_t)grp * (nlay + 1) * nk * pcap + c;
@@ -473,12 +476,15 @@ __global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0) {
 #pragma unroll
   for (int i = 0; i < NG; i++) { zinc[i] = ws.zinc[(size_t)(g0 + i) * pcap + c]; tdbt[i] = 1.f; tdn[i] = 1.f; rdnd[i] = 0.f; }
   for (int lev = nlay; lev >= 0; lev--) {
-    const size_t lo = (size_t)lev * pcap;
+    const float *__restrict__ q = rec + (size_t)((unsigned)lev * lvstride);      // the group's records: immediate offsets
     float2 R[NG]; float4 P[NG]; float e[NG];
 #pragma unroll
     for (int i = 0; i < NG; i++) {
-      R[i] = __ldcs(recR + i * lstride + lo);
-      if (lev > 0) { P[i] = __ldcs(recP + i * lstride + lo); e[i] = __ldcs(recE + i * lstride + lo); }
+      R[i] = __ldcs(reinterpret_cast<const float2 *>(q + i * SW_REC + SW_REC_R) + lane);
+      if (lev > 0) {
+        P[i] = __ldcs(reinterpret_cast<const float4 *>(q + i * SW_REC) + lane);
+        e[i] = __ldcs(q + i * SW_REC + SW_REC_E + lane);
+      }
     }
     float su = 0.f, sd = 0.f;
 #pragma unroll
