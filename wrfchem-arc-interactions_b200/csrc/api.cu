@@ -150,10 +150,9 @@ void carve_lw(LwWs &w, char *base, size_t &bytes) {
   w.colf = c.take<float>((size_t)LWF_N * cap);
   w.secdiff = c.take<float>((size_t)NBLW * cap);
   const size_t nv = (w.kslot[K_NU] != 0) ? 2 : 1;          // streams: full (+ clear) [, clean (+ clean-clear)]
-  w.rec_n = nv * NGLW * (nl + 1) * pcap;                  // two buffers of level records (solver k+1 overlaps sweep k)
-  w.scrU = c.take<float2>(2 * w.rec_n);
-  w.scrC = c.take<float2>(2 * w.rec_n);
-  w.scrD = c.take<float2>(2 * w.rec_n);
+  w.rec_n = (pcap / REC_TILE) * (nl + 1) * nv * NGLW * LW_REC;   // two buffers of level records (solver k+1 overlaps sweep k)
+  w.rec = c.take<float>(2 * w.rec_n);
+  w.recC = c.take<float>(w.rec_n);
   w.scrS = c.take<float2>(2 * nv * NGLW * pcap);
   w.bpart = c.take<float>((size_t)lw_sweep_groups() * (nl + 1) * w.nk * pcap);
   bytes = c.off;
@@ -1051,8 +1050,8 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       b.ws.coef += (size_t)c0 * LWC_N; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0; b.ws.laytrop += c0; b.ws.colf += c0;
       b.ws.secdiff += c0;
       const int buf = kc & 1;
-      b.ws.scrU += buf * a.ws.rec_n; b.ws.scrC += buf * a.ws.rec_n; b.ws.scrD += buf * a.ws.rec_n;
-      b.ws.scrS += (size_t)buf * (a.ws.rec_n / (nlay + 1));
+      b.ws.rec += buf * a.ws.rec_n; b.ws.recC += buf * (a.ws.rec_n / 2);
+      b.ws.scrS += (size_t)buf * ((variants & ARC_VAR_CLEAN) ? 2 : 1) * NGLW * pcap;
       if (g.overlap && kc >= 2) CK(cudaStreamWaitEvent(g.stream, g.ev_swept[buf], 0));      // records of chunk k-2 consumed
       { Timed t("lw_solve"); launch_lw_solve(b, g.stream); }
       if (g.overlap) { CK(cudaEventRecord(g.ev_solved, g.stream)); CK(cudaStreamWaitEvent(s2, g.ev_solved, 0)); }

@@ -146,13 +146,13 @@ struct LwWs {
   int *laytrop;            // [cap]
   float *colf;             // [LWF_N][cap]
   float *secdiff;          // [16][cap]
-  // Level-indexed records handed from k_lw_solve (taumol + downward sweep) to k_lw_sweep (upward sweep + band sum):
-  // [stream v][NGLW][nlay+1][pcap] float2, v = 0 full (+ clear), 1 clean (+ clean-clear).  level = layer + 1 for the layer
-  // quantities, = the layer's lower interface for scrD.
-  size_t rec_n;            // elements per buffer of the level records (host-side: two buffers are carved)
-  float2 *scrU;            // (atrans, bbugas)
-  float2 *scrC;            // (X, Y) of radlu' = radlu - radlu X + Y; written only where the column has cloud in the layer
-  float2 *scrD;            // downward radiances at the level: (all-sky, clear-sky)
+  // Level-indexed records handed from k_lw_solve (taumol + downward sweep) to k_lw_sweep (upward sweep + band sum), tiled
+  // like the SW ones: [128-column tile][level][stream v][g-point][LW_REC words], v = 0 full (+ clear), 1 clean (+ clean-clear);
+  // one record = 128 lanes x (float2 U | float2 D):  U = (atrans, bbugas) of the layer below the level (level = layer + 1),
+  // D = downward radiances (all-sky, clear-sky) at the level.
+  size_t rec_n;            // words per buffer of `rec` (host-side: two buffers are carved); recC has rec_n / 2
+  float *rec;
+  float *recC;             // same tiling, 128 lanes x float2 (X, Y) of radlu' = radlu - radlu X + Y; written only where the column has cloud in the layer
   float2 *scrS;            // [v][NGLW][pcap] upward radiances leaving the surface: (all-sky, clear-sky)
   float *bpart;            // [sweep group][nlay+1][nk][pcap]  per-group sums of the radiances; nk = kinds in use, slot of kind k = kslot[k]
   int nk; int kslot[NKIND];

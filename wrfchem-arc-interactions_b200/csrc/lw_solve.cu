@@ -114,11 +114,14 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
   int iclddn = 0;
   float fracs_bot = 0.f;
   const size_t pcap = ws.pcap;
-  const size_t lvs = (size_t)g * (nlay + 1) * pcap + c;      // record of level 0, stream 0
-  const size_t vs = (size_t)NGLW * (nlay + 1) * pcap;        // stream stride
-  float2 *scrU = ws.scrU + lvs, *scrC = ws.scrC + lvs, *scrD = ws.scrD + lvs;
-  scrD[(size_t)nlay * pcap] = make_float2(0.f, 0.f);         // TOA downward radiance is zero
-  if (do_clean) scrD[vs + (size_t)nlay * pcap] = make_float2(0.f, 0.f);
+  const int nv = do_clean ? 2 : 1;
+  const unsigned lvstride = (unsigned)nv * NGLW;             // records per (tile, level)
+  const size_t r0 = (size_t)(c / REC_TILE) * (nlay + 1) * nv * NGLW + g;      // record (this tile, level 0, stream 0, g)
+  const int lane = c % REC_TILE;
+  float *rec = ws.rec + r0 * LW_REC;                          // U | D records, see args.h
+  float *recC = ws.recC + r0 * LW_REC_D;                      // cloudy-layer records
+  // record lay + 1 holds, per stream, U of layer lay and the downward radiances D at the layer's LOWER interface (level lay),
+  // so a layer writes one record and the sweep reads one record per step (the TOA downward radiance is zero: not stored)
 
   // Planck function at the top interface of the current layer; carried downwards
   auto planck_at = [&](float t) {
@@ -414,6 +417,8 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
       efclfrac = abscld * cldfmc;
     }
     if (icldlyr) iclddn = 1;
+    float *qrec = rec + (size_t)((unsigned)(lay + 1) * lvstride) * LW_REC;
+    float *qrecC = recC + (size_t)((unsigned)(lay + 1) * lvstride) * LW_REC_D;
 #pragma unroll
     for (int v = 0; v < 2; v++) {
       if (v == 1 && !do_clean) break;
@@ -471,7 +476,8 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
         radld[v] = radld[v] - radld[v] * (atrans + efclfrac * (1.f - atrans)) + gassrc + cldfmc * (bbdtot * atot - gassrc);
         // the same step for the upward radiance is radlu - radlu * X + Y (LW:3334-3338): hand over X and Y
         const float gassrcu = bbugas * atrans;
-        scrC[v * vs + (size_t)(lay + 1) * pcap] = make_float2(atrans + efclfrac * (1.f - atrans), gassrcu + cldfmc * (bbutot * atot - gassrcu));
+        reinterpret_cast<float2 *>(qrecC + v * (NGLW * LW_REC_D))[lane] =
+            make_float2(atrans + efclfrac * (1.f - atrans), gassrcu + cldfmc * (bbutot * atot - gassrcu));
       } else {
         if (odepth <= 0.06f) {
           atrans = odepth - 0.5f * odepth * odepth;
@@ -491,8 +497,8 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
       }
       if (iclddn == 1) radclrd[v] = radclrd[v] + (bbd - radclrd[v]) * atrans;
       else radclrd[v] = radld[v];
-      scrU[v * vs + (size_t)(lay + 1) * pcap] = make_float2(atrans, bbugas);
-      scrD[v * vs + (size_t)lay * pcap] = make_float2(radld[v], radclrd[v]);
+      reinterpret_cast<float2 *>(qrec + v * (NGLW * LW_REC))[lane] = make_float2(atrans, bbugas);
+      reinterpret_cast<float2 *>(qrec + v * (NGLW * LW_REC) + LW_REC_D)[lane] = make_float2(radld[v], radclrd[v]);
     }
     plev_up = plev_dn;
   }
@@ -604,9 +610,11 @@ __global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int grp, int g0) {
   const int v = blockIdx.y;                    // 0 full (+ clear), 1 clean (+ clean-clear)
   const int nlay = ws.nlay, nk = ws.nk;
   const size_t pcap = ws.pcap, cap = ws.cap;
-  const size_t lstride = (size_t)(nlay + 1) * pcap;            // g-point stride of the records
-  const size_t base = ((size_t)v * NGLW + g0) * lstride + c;
-  const float2 *__restrict__ scrU = ws.scrU + base, *__restrict__ scrC = ws.scrC + base, *__restrict__ scrD = ws.scrD + base;
+  const int nv = gridDim.y, lane = threadIdx.x;                // block = one record tile
+  const unsigned lvstride = (unsigned)nv * NGLW;               // records per (tile, level)
+  const size_t r0 = ((size_t)blockIdx.x * (nlay + 1) * nv + v) * NGLW + g0;
+  const float *__restrict__ rec = ws.rec + r0 * LW_REC;
+  const float *__restrict__ recC = ws.recC + r0 * LW_REC_D;
 
   bool iclddn = false;                         // the flag the downward sweep leaves behind (LW:3218): any cloud in the column
   for (int w = 0; w < ws.W; w++) iclddn = iclddn || ws.anyc[(size_t)w * cap + c] != 0u;
@@ -616,34 +624,36 @@ __global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int grp, int g0) {
   const int kU = ws.kslot[v == 0 ? K_FU : K_NU], kD = ws.kslot[v == 0 ? K_FD : K_ND];
   const int kCU = ws.kslot[v == 0 ? K_CU : K_XU], kCD = ws.kslot[v == 0 ? K_CD : K_XD];
   const bool clr = v == 0 || (a.variants & ARC_VAR_CLEANCLEAR) != 0;
-  {
-    float2 d[NG];
-    float sU = 0.f, sCU = 0.f, sD = 0.f, sCD = 0.f;
+  {   // level 0: the upward radiances leaving the surface
+    float sU = 0.f, sCU = 0.f;
 #pragma unroll
     for (int i = 0; i < NG; i++) {
       const float2 s0 = ws.scrS[((size_t)v * NGLW + g0 + i) * pcap + c];
       rl[i] = s0.x; rc[i] = s0.y;
-      d[i] = __ldcs(scrD + i * lstride);
     }
 #pragma unroll
-    for (int i = 0; i < NG; i++) { sU = sU + rl[i]; sCU = sCU + rc[i]; sD = sD + d[i].x; sCD = sCD + d[i].y; }
-    __stcs(bpart + (size_t)kU * pcap, sU); __stcs(bpart + (size_t)kD * pcap, sD);
-    if (clr) { __stcs(bpart + (size_t)kCU * pcap, sCU); __stcs(bpart + (size_t)kCD * pcap, sCD); }
+    for (int i = 0; i < NG; i++) { sU = sU + rl[i]; sCU = sCU + rc[i]; }
+    __stcs(bpart + (size_t)kU * pcap, sU);
+    if (clr) __stcs(bpart + (size_t)kCU * pcap, sCU);
   }
   uint32_t aw = 0u;
   for (int lev = 1; lev <= nlay; lev++) {
+    // record lev: U of layer lev-1 (-> upward radiances at level lev) and the downward radiances at level lev-1
     const int lay = lev - 1;
     if ((lay & 31) == 0) aw = ws.anyc[(size_t)(lay >> 5) * cap + c];
     const bool icldlyr = (aw >> (lay & 31)) & 1u;
     float2 u[NG], d[NG];
-    const size_t lo = (size_t)lev * pcap;
+    const float *__restrict__ q = rec + (size_t)((unsigned)lev * lvstride) * LW_REC;       // the group's records: immediate offsets
 #pragma unroll
-    for (int i = 0; i < NG; i++) { u[i] = __ldcs(scrU + i * lstride + lo); d[i] = __ldcs(scrD + i * lstride + lo); }
+    for (int i = 0; i < NG; i++) {
+      u[i] = __ldcs(reinterpret_cast<const float2 *>(q + i * LW_REC) + lane);
+      d[i] = __ldcs(reinterpret_cast<const float2 *>(q + i * LW_REC + LW_REC_D) + lane);
+    }
     float sU = 0.f, sCU = 0.f, sD = 0.f, sCD = 0.f;
     if (icldlyr) {
 #pragma unroll
       for (int i = 0; i < NG; i++) {
-        const float2 xy = __ldcs(scrC + i * lstride + lo);
+        const float2 xy = __ldcs(reinterpret_cast<const float2 *>(recC + ((size_t)((unsigned)lev * lvstride) + i) * LW_REC_D) + lane);
         rl[i] = rl[i] - rl[i] * xy.x + xy.y;
       }
     } else {
@@ -657,8 +667,13 @@ __global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int grp, int g0) {
       sU = sU + rl[i]; sCU = sCU + rc[i]; sD = sD + d[i].x; sCD = sCD + d[i].y;
     }
     float *bp = bpart + (size_t)lev * nk * pcap;
-    __stcs(bp + (size_t)kU * pcap, sU); __stcs(bp + (size_t)kD * pcap, sD);
-    if (clr) { __stcs(bp + (size_t)kCU * pcap, sCU); __stcs(bp + (size_t)kCD * pcap, sCD); }
+    __stcs(bp + (size_t)kU * pcap, sU); __stcs(bp - (size_t)nk * pcap + (size_t)kD * pcap, sD);
+    if (clr) { __stcs(bp + (size_t)kCU * pcap, sCU); __stcs(bp - (size_t)nk * pcap + (size_t)kCD * pcap, sCD); }
+  }
+  {   // TOA: no downward radiance
+    float *bp = bpart + (size_t)nlay * nk * pcap;
+    __stcs(bp + (size_t)kD * pcap, 0.f);
+    if (clr) __stcs(bp + (size_t)kCD * pcap, 0.f);
   }
 }
 
