@@ -30,7 +30,7 @@ static __constant__ int c_sw_ngb[NGSW];    // band index 0..13 of each SW g-poin
 // Sweep groups: the g-points of a band are swept by one thread per column in groups of at most SWEEP_GMAX consecutive
 // g-points (register state); bands with more g-points are cut into two equal groups.
 #ifndef SW_GMAX
-#define SW_GMAX 8
+#define SW_GMAX 12
 #endif
 static SweepGroups h_sw_grp;
 static __constant__ int c_sw_grp_band[SWEEP_MAXGRP];
@@ -524,6 +524,7 @@ void launch_sw_sweep(const SwArgs &a, cudaStream_t s) {
     switch (h_sw_grp.ng[q]) {
 #define SWEEP_CASE(N) case N: k_sw_sweep<N><<<grid, 128, 0, s>>>(a, q, g0); break;
       SWEEP_CASE(1) SWEEP_CASE(2) SWEEP_CASE(3) SWEEP_CASE(4) SWEEP_CASE(5) SWEEP_CASE(6) SWEEP_CASE(7) SWEEP_CASE(8)
+      SWEEP_CASE(9) SWEEP_CASE(10) SWEEP_CASE(11) SWEEP_CASE(12) SWEEP_CASE(13) SWEEP_CASE(14) SWEEP_CASE(15) SWEEP_CASE(16)
 #undef SWEEP_CASE
       default: break;
     }
