@@ -10,6 +10,7 @@ python tools/prof_run.py 256 128 50 1 > gpurun_out/prof_plain_$tag.log 2>&1 || {
 ncu --set full --import-source on --clock-control none --kernel-name regex:"k_sw_solve|k_lw_solve|k_sw_reduce|k_lw_reduce" -c 4 \
     -o gpurun_out/prof_${tag}_full -f python tools/prof_run.py 256 128 50 1 > gpurun_out/prof_ncu_$tag.log 2>&1
 tail -2 gpurun_out/prof_ncu_$tag.log
-ncu --set full --clock-control none --kernel-name regex:"k_sw_sweep<\(int\)(8|2)>|k_lw_sweep<\(int\)(16|8)>" -c 6 \
-    -o gpurun_out/prof_${tag}_sweep -f python tools/prof_run.py 256 128 50 1 > gpurun_out/prof_ncu_sweep_$tag.log 2>&1
-tail -2 gpurun_out/prof_ncu_sweep_$tag.log
+for k in k_lw_sweep k_sw_sweep; do
+  ncu --set full --clock-control none --kernel-name $k -c 3 -o gpurun_out/prof_${tag}_$k -f python tools/prof_run.py 256 128 50 1 > gpurun_out/prof_ncu_${k}_$tag.log 2>&1
+  tail -1 gpurun_out/prof_ncu_${k}_$tag.log
+done

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn gpurun_out/ ncu artefacts + a bench JSON line into the tracked summaries under profiles/.
-usage: tools/profile_summary.py <tag> <launches.csv> <full.ncu-rep> <bench.json>"""
+usage: tools/profile_summary.py <tag> <launches.csv> <full.ncu-rep> <bench.json> [more.ncu-rep ...]"""
 import collections, csv, json, os, subprocess, sys
 tag, launches, rep, bench = sys.argv[1:5]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -32,23 +32,26 @@ km = b.get("kernel_ms_per_step", {})
 if km:
     t = sum(km.values())
     W("Live CUDA-event shares inside bench.py (same command without ncu): " + ", ".join("%s %.1f %%" % (k, 100 * v / t) for k, v in km.items()) + "\n")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-h, u = rr[0], rr[1]
 want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
-W("## ncu --set full (one launch of each hot kernel, tile 256x128x50 = 32768 columns; report: gpurun_out/%s, not tracked)\n" % os.path.basename(rep))
-for r in rr[2:]:
-    W("### `%s`\n" % r[h.index("Kernel Name")])
-    W("| metric | value | unit |\n|---|---|---|")
-    for w in want:
-        if w in h:
-            W("| %s | %s | %s |" % (w, r[h.index(w)], u[h.index(w)]))
-    W()
-det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
+reps = [rep] + sys.argv[5:]
+W("## ncu --set full (launches of each hot kernel, tile 256x128x50 = 32768 columns; reports: %s under gpurun_out/, not tracked)\n" % ", ".join(os.path.basename(x) for x in reps))
+det = ""
+for rp in reps:
+    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h, u = rr[0], rr[1]
+    for r in rr[2:]:
+        W("### `%s`\n" % r[h.index("Kernel Name")])
+        W("| metric | value | unit |\n|---|---|---|")
+        for w in want:
+            if w in h:
+                W("| %s | %s | %s |" % (w, r[h.index(w)], u[h.index(w)]))
+        W()
+    det += subprocess.run(["ncu", "-i", rp, "--page", "details"], capture_output=True, text=True).stdout
 keep = [l for l in det.splitlines() if any(s in l for s in ("k_sw_solve", "k_lw_solve", "k_sw_sweep", "k_lw_sweep", "k_sw_reduce", "k_lw_reduce", "Stall", "stalled", "Issue Slots Busy", "No Eligible", "Warp Cycles Per Issued", "Achieved Occupancy", "L2 Hit Rate", "DRAM Throughput"))]
 W("## ncu details excerpts\n\n```\n" + "\n".join(keep) + "\n```")
 out.close()
