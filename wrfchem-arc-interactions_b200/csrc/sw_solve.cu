@@ -418,9 +418,9 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
       const float nrupd = fmaf(__fmul_rn(__fmul_rn(P.w, P.w), rupd[s]), zreflect, P.y);
       rup[s] = nrup; rupd[s] = nrupd;
       float *q = rec + (size_t)((unsigned)(lay + 1) * lvstride) + slot[s] * (NGSW * SW_REC);
-      reinterpret_cast<float4 *>(q)[lane] = P;
+      // (where its layer is not cloudy the FULL stream's two-stream solution IS the CLEAR one: k_sw_sweep reads it there)
+      if (s != 1 || cloudy) { reinterpret_cast<float4 *>(q)[lane] = P; q[SW_REC_E + lane] = e; }
       reinterpret_cast<float2 *>(q + SW_REC_R)[lane] = make_float2(nrup, nrupd);
-      q[SW_REC_E + lane] = e;
     }
   }
   if (a.dbg.sfluxzen) a.dbg.sfluxzen[(size_t)ws.cols[c] * NGSW + g] = sfluxzen;
@@ -456,18 +456,24 @@ void launch_sw_solve(const SwArgs &a, cudaStream_t s) {
 // kind.  No shared memory, no barriers, no atomics; lanes = neighbouring columns.  HBM-bound: 28 B per (column, g, level,
 // stream).
 template <int NG>
-__global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0) {
+__global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0, int nstream) {
   const SwWs &ws = a.ws;
-  const int c = blockIdx.x * 128 + threadIdx.x;
+  // blocks of the streams of one tile are neighbours in launch order: the FULL block re-reads the CLEAR records of its
+  // non-cloudy layers while they are still in L2
+  const int tile = blockIdx.x / nstream;
+  const int si = blockIdx.x % nstream;         // compact stream slot
+  const int c = tile * 128 + threadIdx.x;
   if (c >= a.ncols) return;
-  const int si = blockIdx.y;                   // compact stream slot
   const bool do_clean = (a.variants & ARC_VAR_CLEAN) != 0;
   const int s = si < 2 ? si : (si == 2 && do_clean ? 2 : 3);      // 0 clear, 1 full, 2 clean, 3 clean-clear
   const int nlay = ws.nlay, nk = ws.nk;
   const size_t pcap = ws.pcap;
-  const int nstream = gridDim.y, lane = threadIdx.x;                   // block = one record tile
+  const int lane = threadIdx.x;                                        // block = one record tile
   const unsigned lvstride = (unsigned)nstream * NGSW * SW_REC;         // words per (tile, level)
-  const float *__restrict__ rec = ws.rec + (((size_t)blockIdx.x * (nlay + 1) * nstream + si) * NGSW + g0) * SW_REC;
+  const float *__restrict__ rec = ws.rec + (((size_t)tile * (nlay + 1) * nstream + si) * NGSW + g0) * SW_REC;
+  const bool isfull = s == 1;
+  const int toclear = isfull ? -NGSW * SW_REC : 0;                     // FULL -> CLEAR record of the same (tile, level, g)
+  uint32_t mw[NG];                                                     // McICA bits of the current 32 layers (FULL stream only)
   const int ku = ws.kslot[s == 0 ? K_CU : s == 1 ? K_FU : s == 2 ? K_NU : K_XU];
   const int kd = ws.kslot[s == 0 ? K_CD : s == 1 ? K_FD : s == 2 ? K_ND : K_XD];
   float *__restrict__ bpart = ws.bpart + (size_t)grp * (nlay + 1) * nk * pcap + c;
@@ -478,12 +484,20 @@ __global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0) {
   for (int lev = nlay; lev >= 0; lev--) {
     const float *__restrict__ q = rec + (size_t)((unsigned)lev * lvstride);      // the group's records: immediate offsets
     float2 R[NG]; float4 P[NG]; float e[NG];
+    const int lay = lev - 1;
+    if (isfull && lev > 0 && ((lay & 31) == 31 || lev == nlay)) {
+#pragma unroll
+      for (int i = 0; i < NG; i++) mw[i] = ws.mask[((size_t)(g0 + i) * ws.W + (lay >> 5)) * ws.cap + c];
+    }
 #pragma unroll
     for (int i = 0; i < NG; i++) {
       R[i] = __ldcs(reinterpret_cast<const float2 *>(q + i * SW_REC + SW_REC_R) + lane);
       if (lev > 0) {
-        P[i] = __ldcs(reinterpret_cast<const float4 *>(q + i * SW_REC) + lane);
-        e[i] = __ldcs(q + i * SW_REC + SW_REC_E + lane);
+        // the layer's two-stream solution: own record, or the CLEAR stream's where this FULL layer is not cloudy
+        const bool own = !isfull || ((mw[i] >> (lay & 31)) & 1u);
+        const float *__restrict__ qs = q + i * SW_REC + (own ? 0 : toclear);
+        P[i] = __ldcs(reinterpret_cast<const float4 *>(qs) + lane);
+        e[i] = __ldcs(qs + SW_REC_E + lane);
       }
     }
     float su = 0.f, sd = 0.f;
@@ -518,11 +532,11 @@ __global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0) {
 int sw_sweep_groups() { return h_sw_grp.n; }
 void launch_sw_sweep(const SwArgs &a, cudaStream_t s) {
   const int nstream = 2 + ((a.variants & ARC_VAR_CLEAN) ? 1 : 0) + ((a.variants & ARC_VAR_CLEANCLEAR) ? 1 : 0);
-  const dim3 grid((a.ncols + 127) / 128, nstream);
+  const int grid = ((a.ncols + 127) / 128) * nstream;
   for (int q = 0; q < h_sw_grp.n; q++) {
     const int g0 = h_sw_grp.g0[q];
     switch (h_sw_grp.ng[q]) {
-#define SWEEP_CASE(N) case N: k_sw_sweep<N><<<grid, 128, 0, s>>>(a, q, g0); break;
+#define SWEEP_CASE(N) case N: k_sw_sweep<N><<<grid, 128, 0, s>>>(a, q, g0, nstream); break;
       SWEEP_CASE(1) SWEEP_CASE(2) SWEEP_CASE(3) SWEEP_CASE(4) SWEEP_CASE(5) SWEEP_CASE(6) SWEEP_CASE(7) SWEEP_CASE(8)
       SWEEP_CASE(9) SWEEP_CASE(10) SWEEP_CASE(11) SWEEP_CASE(12) SWEEP_CASE(13) SWEEP_CASE(14) SWEEP_CASE(15) SWEEP_CASE(16)
 #undef SWEEP_CASE
