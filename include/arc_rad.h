@@ -273,6 +273,13 @@ float arc_rad_last_kernel_ms(const char *name);
  * either way; off is for per-kernel timing.  Returns the previous setting. */
 int arc_rad_set_overlap(int on);
 
+/* Host-side layout logic exposed for the CPU tests (no CUDA device needed):
+ * arc_rad_test_sweep_groups: the sweep groups (consecutive g-points of one band, at most gmax each) for bands with ng[b] g-points;
+ *   writes band / first g-point (0-based, cumulative over the bands) / size of every group, returns the number of groups (<= 32).
+ * arc_rad_test_coef_index: word index of (field, layer, column) in the tiled coefficient workspace of column capacity cap. */
+int arc_rad_test_sweep_groups(const int *ng, int nbands, int gmax, int *band, int *g0, int *size);
+long long arc_rad_test_coef_index(int field, int layer, long long column, long long cap, int nfields);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,3 +71,49 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "libarc_oracle" not in txt and "import oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_sweep_groups_partition_the_g_points(lib):
+    """Sweep groups (k_sw_sweep / k_lw_sweep): consecutive g-points of one band, every g-point exactly once, sizes balanced and
+    <= gmax; with gmax >= the largest band the groups are the bands (the reference's per-band accumulation, LW:3365-3395)."""
+    L = lib.lib
+    L.arc_rad_test_sweep_groups.restype = C.c_int
+    sw = [6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12]            # ngc, module_ra_rrtmg_sw.F:4816
+    lw = [10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2]    # ngc, module_ra_rrtmg_lw.F:8146
+    for ng in (sw, lw):
+        for gmax in (16, 12, 8, 6, 5):
+            band, g0, size = (C.c_int * 32)(), (C.c_int * 32)(), (C.c_int * 32)()
+            n = L.arc_rad_test_sweep_groups((C.c_int * len(ng))(*ng), len(ng), gmax, band, g0, size)
+            if sum((x + gmax - 1) // gmax for x in ng) > 32:
+                assert n == -1          # more groups than the kernels' descriptor table holds: refused
+                continue
+            assert 0 < n <= 32
+            nxt = 0
+            per_band = {}
+            for q in range(n):
+                assert g0[q] == nxt and 1 <= size[q] <= gmax
+                nxt += size[q]
+                per_band.setdefault(band[q], []).append(size[q])
+            assert nxt == sum(ng)
+            assert sorted(per_band) == list(range(len(ng)))
+            for b, sizes in per_band.items():
+                assert sum(sizes) == ng[b] and max(sizes) - min(sizes) <= 1
+                assert len(sizes) == (ng[b] + gmax - 1) // gmax
+
+
+def test_tiled_coefficient_layout_is_a_bijection(lib):
+    """coef_index: [layer][32-column tile][field][lane] - every (field, layer, column) maps to its own word, a thread's fields of a
+    layer are exactly 32 words apart and the 32 lanes of a tile are contiguous."""
+    L = lib.lib
+    L.arc_rad_test_coef_index.restype = C.c_longlong
+    L.arc_rad_test_coef_index.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
+    cap, nf, nl = 512, 15, 7
+    seen = set()
+    for lay in range(nl):
+        for f in range(nf):
+            for c in range(cap):
+                seen.add(L.arc_rad_test_coef_index(f, lay, c, cap, nf))
+    assert len(seen) == cap * nf * nl and min(seen) == 0 and max(seen) == cap * nf * nl - 1
+    assert L.arc_rad_test_coef_index(3, 2, 70, cap, nf) - L.arc_rad_test_coef_index(2, 2, 70, cap, nf) == 32
+    assert L.arc_rad_test_coef_index(3, 2, 71, cap, nf) - L.arc_rad_test_coef_index(3, 2, 70, cap, nf) == 1
+    assert L.arc_rad_test_coef_index(0, 3, 5, cap, nf) - L.arc_rad_test_coef_index(0, 2, 5, cap, nf) == cap * nf

@@ -615,6 +615,18 @@ const char *arc_rad_last_error(void) { return g.err.c_str(); }
 int arc_rad_lw_nlayers(void) { return g.ready ? g.H.lw_nlayers : 0; }
 long long arc_rad_launch_count(void) { return launch_count(); }
 void *arc_rad_stream(void) { return (void *)g.stream; }
+int arc_rad_test_sweep_groups(const int *ng, int nbands, int gmax, int *band, int *g0, int *size) {
+  if (!ng || nbands <= 0 || nbands > 16 || gmax <= 0) return -1;
+  int g0s[16], acc = 0, need = 0;
+  for (int b = 0; b < nbands; b++) { g0s[b] = acc; acc += ng[b]; need += (ng[b] + gmax - 1) / gmax; }
+  if (need > SWEEP_MAXGRP) return -1;
+  const SweepGroups G = make_sweep_groups(ng, g0s, nbands, gmax);
+  for (int q = 0; q < G.n; q++) { band[q] = G.band[q]; g0[q] = G.g0[q]; size[q] = G.ng[q]; }
+  return G.n;
+}
+long long arc_rad_test_coef_index(int field, int layer, long long column, long long cap, int nfields) {
+  return (long long)coef_index(field, layer, (size_t)column, (size_t)cap, nfields);
+}
 int arc_rad_set_overlap(int on) { const int prev = g.overlap ? 1 : 0; g.overlap = on != 0; return prev; }
 float arc_rad_last_kernel_ms(const char *name) {
   auto it = g.last_ms.find(name ? name : "");
