@@ -148,8 +148,8 @@ struct LwWs {
   float *secdiff;          // [16][cap]
   // Level-indexed records handed from k_lw_solve (taumol + downward sweep) to k_lw_sweep (upward sweep + band sum), tiled
   // like the SW ones: [128-column tile][level][stream v][g-point][LW_REC words], v = 0 full (+ clear), 1 clean (+ clean-clear);
-  // one record = 128 lanes x (float2 U | float2 D):  U = (atrans, bbugas) of the layer below the level (level = layer + 1),
-  // D = downward radiances (all-sky, clear-sky) at the level.
+  // one record = 128 lanes x float4 (atrans, bbugas, radld, radclrd): record lay + 1 holds (atrans, bbugas) of layer lay and the
+  // downward radiances (all-sky, clear-sky) at the layer's LOWER interface, so a layer writes and a sweep step reads one 2 KB piece.
   size_t rec_n;            // words per buffer of `rec` (host-side: two buffers are carved); recC has rec_n / 2
   float *rec;
   float *recC;             // same tiling, 128 lanes x float2 (X, Y) of radlu' = radlu - radlu X + Y; written only where the column has cloud in the layer

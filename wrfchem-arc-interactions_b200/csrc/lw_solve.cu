@@ -497,8 +497,7 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
       }
       if (iclddn == 1) radclrd[v] = radclrd[v] + (bbd - radclrd[v]) * atrans;
       else radclrd[v] = radld[v];
-      reinterpret_cast<float2 *>(qrec + v * (NGLW * LW_REC))[lane] = make_float2(atrans, bbugas);
-      reinterpret_cast<float2 *>(qrec + v * (NGLW * LW_REC) + LW_REC_D)[lane] = make_float2(radld[v], radclrd[v]);
+      reinterpret_cast<float4 *>(qrec + v * (NGLW * LW_REC))[lane] = make_float4(atrans, bbugas, radld[v], radclrd[v]);
     }
     plev_up = plev_dn;
   }
@@ -646,8 +645,8 @@ __global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int grp, int g0) {
     const float *__restrict__ q = rec + (size_t)((unsigned)lev * lvstride) * LW_REC;       // the group's records: immediate offsets
 #pragma unroll
     for (int i = 0; i < NG; i++) {
-      u[i] = __ldcs(reinterpret_cast<const float2 *>(q + i * LW_REC) + lane);
-      d[i] = __ldcs(reinterpret_cast<const float2 *>(q + i * LW_REC + LW_REC_D) + lane);
+      const float4 r = __ldcs(reinterpret_cast<const float4 *>(q + i * LW_REC) + lane);
+      u[i] = make_float2(r.x, r.y); d[i] = make_float2(r.z, r.w);
     }
     float sU = 0.f, sCU = 0.f, sD = 0.f, sCD = 0.f;
     if (icldlyr) {
