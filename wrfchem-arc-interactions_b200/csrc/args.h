@@ -56,7 +56,7 @@ inline SweepGroups make_sweep_groups(const int *ng, const int *g0, int nbands, i
 
 constexpr int REC_TILE = 128;                                     // columns per record tile = threads of a sweep block
 constexpr int SW_REC = 7 * REC_TILE, SW_REC_R = 4 * REC_TILE, SW_REC_E = 6 * REC_TILE;   // words per SW level record, offsets of R and E
-constexpr int LW_REC = 4 * REC_TILE, LW_REC_D = 2 * REC_TILE;     // LW: float2 U at 0, float2 D at LW_REC_D
+constexpr int LW_REC = 4 * REC_TILE, LW_REC_D = 2 * REC_TILE;     // LW: words per level record (float4 per lane) / per cloudy-layer record (float2)
 
 // flux "kinds" in the partial buffer: full up/down, clear up/down, clean up/down, clean-clear up/down
 enum { K_FU = 0, K_FD, K_CU, K_CD, K_NU, K_ND, K_XU, K_XD, NKIND };
