@@ -280,10 +280,16 @@ def test_chunking_and_determinism(lib, ktab):
         c_sw, c_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
     finally:
         del os.environ["ARC_RAD_CHUNK"]; del os.environ["ARC_RAD_OUTER"]
+    # the level-record budget shrinks the inner chunk (here to 256 columns: 3 SW + 4 LW chunks of two buffers each)
+    os.environ["ARC_RAD_REC_GB"] = "0.25"
+    try:
+        d_sw, d_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    finally:
+        del os.environ["ARC_RAD_REC_GB"]
     for k in a_sw:
-        assert np.array_equal(a_sw[k], b_sw[k]) and np.array_equal(a_sw[k], c_sw[k]), k
+        assert np.array_equal(a_sw[k], b_sw[k]) and np.array_equal(a_sw[k], c_sw[k]) and np.array_equal(a_sw[k], d_sw[k]), k
     for k in a_lw:
-        assert np.array_equal(a_lw[k], b_lw[k]) and np.array_equal(a_lw[k], c_lw[k]), k
+        assert np.array_equal(a_lw[k], b_lw[k]) and np.array_equal(a_lw[k], c_lw[k]) and np.array_equal(a_lw[k], d_lw[k]), k
 
 
 @pytest.mark.parametrize("halo", [0, 2])
