@@ -481,6 +481,47 @@ def test_driver_post_and_domain_stats(lib, ktab):
         assert st[f, 2] == x.size and st[f, 3] == x.min() and st[f, 4] == x.max()
 
 
+def test_four_scenario_decomposition_from_device_statistics(lib, ktab):
+    """SURVEY 8(f)3 end to end: four scenarios (BASE, ALT = half the aerosol, and both without aerosol-radiation interaction)
+    through RRTMG_SWRAD / RRTMG_LWRAD, TOA fields reduced on the device (arc_rad_domain_stats), statistics columns and the
+    direct / semi-direct / indirect terms on the host (decomposition.py = the reference's RadDecomp_functions.py)."""
+    from wrfchem_arc_interactions_b200 import decomposition as D
+    dom = synth.make_domain(24, 16, 40, seed=41)
+    init(lib, dom, ktab)
+    L = lib.lib
+    L.arc_rad_domain_stats.restype = C.c_int
+    L.arc_rad_domain_stats.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_void_p]
+    dims = abi.make_dims(dom["dims"])
+    aer = [k for k in dom if k.startswith("tauaer")]
+
+    def scenario(scale):
+        d = dict(dom)
+        for k in aer:
+            d[k] = (dom[k] * np.float32(scale)).astype(np.float32)
+        sw, lw = run_pair("sw", lib, d), run_pair("lw", lib, d)
+        fields = {"SWUPT": sw["swupt"], "SWUPTCLN": sw["swuptcln"], "LWUPT": lw["lwupt"], "LWUPTC": lw["lwuptc"]}
+        names = list(fields)
+        ptrs = (abi.c_fp * len(names))(*[abi.fptr(fields[n]) for n in names])
+        st = np.zeros((len(names), 5))
+        lib.check(L.arc_rad_domain_stats(C.byref(dims), 0, len(names), ptrs, C.c_void_p(st.ctypes.data)))
+        return D.stats_from_sums(st, names=names), fields
+
+    (b, fb), (a, fa), (bn, fbn), (an, fan) = scenario(1.0), scenario(0.5), scenario(0.0), scenario(0.0)
+    B = dict(b); B.update({k + "_nA": v for k, v in bn.items()})
+    A = dict(a); A.update({k + "_nA": v for k, v in an.items()})
+    out = D.decompose(B, A, "standard_error", lw_indirect_fixed=True)
+    mean = lambda x: x.astype(np.float64).mean()
+    direct = (mean(fb["SWUPTCLN"]) - mean(fb["SWUPT"])) - (mean(fa["SWUPTCLN"]) - mean(fa["SWUPT"]))
+    assert np.isclose(out["SW_DIRECT"][0], direct, rtol=1e-9, atol=1e-9)
+    assert out["SW_DIRECT"][0] < 0.0            # BASE has twice ALT's aerosol: it reflects more sunlight at TOA than its clean twin
+    assert out["SW_DIRECT"][1] > 0.0
+    # without aerosol-radiation interaction clean == full, bit for bit, and the two such runs are identical: no indirect effect here
+    assert np.array_equal(fbn["SWUPT"], fbn["SWUPTCLN"]) and out["SW_INDIRECT"][0] == 0.0 and out["LW_INDIRECT"][0] == 0.0
+    ds = mean(fa["SWUPT"]) - mean(fb["SWUPT"])
+    assert np.isclose(out["Delta_S"][0], ds, rtol=1e-9, atol=1e-9)
+    assert np.isclose(out["SW_DIRECT"][0] + out["SW_SEMIDIRECT"][0] + (mean(fan["SWUPT"]) - mean(fbn["SWUPT"])), ds, rtol=1e-9, atol=1e-9)
+
+
 def test_coszen_and_accumulation(lib, orc, ktab):
     """calc_coszen (DRV:2640-2666) against the oracle, and AC* += flux*DT (DRV:2308-2377)."""
     dom = synth.make_domain(36, 9, 40, seed=23)

@@ -6,8 +6,9 @@ Sub-modules:
   abi        ctypes mirror of include/arc_rad.h
   ktables    synthetic RRTMG_SW_DATA / RRTMG_LW_DATA writer (real record layout)
   synth      seeded synthetic WRF-layout columns
+  decomposition  direct / semi-direct / indirect radiative effects from the domain statistics of four scenarios
 """
-from . import abi, ktables, partition, synth  # noqa: F401
+from . import abi, decomposition, ktables, partition, synth  # noqa: F401
 from . import radiation  # noqa: F401
 
-__all__ = ["abi", "ktables", "partition", "synth", "radiation"]
+__all__ = ["abi", "decomposition", "ktables", "partition", "synth", "radiation"]
