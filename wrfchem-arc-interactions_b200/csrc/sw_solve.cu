@@ -191,8 +191,11 @@ __device__ __forceinline__ float sw_expt(const float *__restrict__ exp_tbl, floa
 // ZG0: the asymmetry parameter is exactly zero (Rayleigh + gas layer of the aerosol-free streams); the expressions in zg
 // then reduce exactly (0 * x, x - 0, 0 / x, x / 1) and two divisions drop out.
 struct SwLayerRT { float4 p; float e; };
+#ifndef SW_REFTRA_INLINE
+#define SW_REFTRA_INLINE __forceinline__
+#endif
 template <bool ZG0>
-__device__ __noinline__ SwLayerRT sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
+__device__ SW_REFTRA_INLINE SwLayerRT sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
   const float eps = 1.e-08f, zwcrit = 0.9999995f;
   float4 o;
   const float zx = D_(zto1, prmuz);
