@@ -361,10 +361,10 @@ def main():
         return bytes_ / 1e9 / (ms * 1e-3) if ms > 0 else None
     roofline = {"kernel": "k_sw_solve", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak if fp32_peak > 0 else None,
-                # DRAM bytes of k_sw_solve: ncu --set full (profiles/r1_summary.md) measured 15.06 GB read+write for a
-                # 24,566-sunlit-column launch = 0.613 MB per sunlit column (the level records written for k_sw_sweep)
-                "traffic": 0.613e6 * nsun, "traffic_unit": "bytes per step (all k_sw_solve launches)",
-                "issue_slot_utilisation_ncu": 0.78,
+                # DRAM bytes of k_sw_solve: ncu --set full (profiles/r1_summary.md) measured 15.00 GB read+write for a
+                # 24,566-sunlit-column launch = 0.611 MB per sunlit column (the level records written for k_sw_sweep)
+                "traffic": 0.611e6 * nsun, "traffic_unit": "bytes per step (all k_sw_solve launches)",
+                "issue_slot_utilisation_ncu": 0.81,
                 "ms_per_step": sw_solve_ms,
                 "ms_per_step_alone": alone_ms,
                 "frac_alone": (f_solve * nsun / (alone_ms * 1e-3) / 1e12 / fp32_peak) if alone_ms > 0 and fp32_peak > 0 else None,
