@@ -595,12 +595,12 @@ void launch_lw_solve(const LwArgs &a, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------------
 // Upward sweep of rtrnmc (LW:3322-3356) + ordered sum over the g-points of a band (LW:3365-3395).
-// One thread per (column, band, stream): the NG upward radiances of the band's g-points are its register state; per
-// level it requests the 2 NG records of that level together (they were written by k_lw_solve; the addresses do not depend
-// on the recurrence, so the memory system sees 2 NG independent loads per thread), advances the NG two-term recurrences
-// and adds the NG up / down radiances in g order.  It writes ONE band partial [band][level][kind][c] per kind instead of
-// NG per-g partials.  No shared memory, no barriers, no atomics; lanes = neighbouring columns, so every access is a
-// full line.  HBM-bound: 16 B per (column, g, level, stream).
+// One thread per (column, band, stream), block = one 128-column record tile: the NG upward radiances of the band's
+// g-points are its register state; per step it requests the NG float4 records of that level together (written by
+// k_lw_solve; the addresses do not depend on the recurrence, so the memory system sees NG independent 2 KB loads per
+// block), advances the NG two-term recurrences and adds the NG up / down radiances in g order.  It writes ONE band partial
+// [band][level][kind][c] per kind; no per-g flux is ever stored.  No shared memory, no barriers, no atomics.
+// HBM-bound: 16 B per (column, g, level, stream).
 template <int NG>
 __global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int grp, int g0) {
   const LwWs &ws = a.ws;
@@ -693,8 +693,9 @@ void launch_lw_sweep(const LwArgs &a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Reduction: per band sum over its g-points in order, x wtdiff x delwave, sum over bands, x fluxfac
-// (LW:3365-3395); heating rates (LW:3397-3408); scatter (LW:12646-12692).  Block = 32 columns x 8 level-lanes.
+// Reduction: per band the sum of its sweep-group partials (its g-points were added in index order by k_lw_sweep),
+// x wtdiff x delwave, sum over bands, x fluxfac (LW:3365-3395); heating rates (LW:3397-3408); scatter (LW:12646-12692).
+// Block = 64 columns x 4 level-lanes.
 constexpr int RED_CX = 64, RED_LY = 4;
 __global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_lw_reduce(LwArgs a) {
   __shared__ float s_net[161][RED_CX];

@@ -550,10 +550,10 @@ void launch_sw_sweep(const SwArgs &a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Reduction over g-points (in index order = the reference's accumulation order SW:8617-8650), fluxes -> heating
-// rates (SW:9391-9434) and scatter to the WRF arrays (SW:11125-11172).  Block = 32 columns x 8 level-lanes; a thread sums
-// the 112 partials of its (column, level) sequentially, net fluxes meet in shared memory for the heating rates.  All
-// partial-buffer reads are 128-byte coalesced over columns.
+// Sum of the sweep-group (= band) partials in band order (the g-points inside a band were added in index order by
+// k_sw_sweep: the reference's accumulation SW:8617-8650), fluxes -> heating rates (SW:9391-9434) and scatter to the WRF
+// arrays (SW:11125-11172).  Block = 64 columns x 4 level-lanes; net fluxes meet in shared memory for the heating rates.
+// All partial-buffer reads are coalesced over columns.
 constexpr int RED_CX = 64, RED_LY = 4;
 __global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_sw_reduce(SwArgs a) {
   __shared__ float s_net[161][RED_CX];
