@@ -75,5 +75,5 @@ for which in ("sw", "lw"):
     hrg, hro = ag["hr"][w], ao["hr"][w]
     print("hr gpu", np.array2string(hrg, precision=3, max_line_width=200)); print("hr orc", np.array2string(hro, precision=3, max_line_width=200))
 print("launches", lib.lib.arc_rad_launch_count())
-for n in ("sw_mcica", "sw_prep", "sw_solve", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_reduce"):
+for n in ("sw_mcica", "sw_prep", "sw_solve", "sw_sweep", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_sweep", "lw_reduce"):
     print(n, lib.lib.arc_rad_last_kernel_ms(n.encode()))
