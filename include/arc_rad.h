@@ -205,6 +205,10 @@ int  arc_rad_accumulate(const ArcDims *d, int memspace, float dtaccum, int nfiel
  * Replaces calc_standard_stats' mean/SD/SE inputs (analysis_scripts/NCL_extraction_package/misc_stats_library.ncl:396-461);
  * partial results of several GPUs combine with one sum- and one max-all-reduce. */
 int  arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const float *const *fields, double *out);
+/* Moran's I of `nfields` 2-D (i,j) fields over the tile, out[f] in single precision, exactly as calc_morans_i_2D evaluates it
+ * for calc_standard_stats (neighbour + manhattan options: ordered pairs of edge-sharing cells, N-1 variance;
+ * misc_stats_library.ncl:196-371).  corrected SE = SE * I (misc_stats_library.ncl:449). */
+int  arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *const *fields, float *out);
 /* Host-only probe (no GPU needed): parse and g-point-reduce the table files as arc_rad_init does; returns the element count
  * of the reduced table `name` ("sw16.absa", "lw3.ka_mn2o", "lw_nlayers" ...) and copies it to buf when cap suffices;
  * name == NULL only validates the files.  Negative return = -ARC_ERR_*.  (sw_kgbNN / cmbgbNN, SW:5022-6065, 11315-12384) */

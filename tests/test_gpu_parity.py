@@ -8,6 +8,7 @@ input moves it by O(1)).  The oracle reports that conditioning per column (ArcDe
 are held to a looser bar and counted."""
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -479,6 +480,20 @@ def test_driver_post_and_domain_stats(lib, ktab):
         x = x.astype(np.float64)
         assert np.isclose(st[f, 0], x.sum(), rtol=1e-12) and np.isclose(st[f, 1], (x * x).sum(), rtol=1e-12)
         assert st[f, 2] == x.size and st[f, 3] == x.min() and st[f, 4] == x.max()
+    # Moran's I as calc_morans_i_2D evaluates it for calc_standard_stats (oracle/ncl_stats.py restates the NCL literally)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ncl_stats as N
+    L.arc_rad_morans_i.restype = C.c_int
+    L.arc_rad_morans_i.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_void_p]
+    mi = np.zeros(4, np.float32)
+    lib.check(L.arc_rad_morans_i(C.byref(dims), 0, 4, ptrs, C.c_void_p(mi.ctypes.data)))
+    for f, x in enumerate([sw[n] for n in names] + [lw["olr"]]):
+        want = float(N.calc_morans_i_2D(x))
+        assert abs(float(mi[f]) - want) <= 2e-6 * max(1.0, abs(want)), (f, mi[f], want)
+    from wrfchem_arc_interactions_b200 import decomposition as D
+    cols = D.stats_from_sums(st, morans_i=mi)
+    ref = N.calc_standard_stats(sw["swupt"])
+    assert np.isclose(cols["corrected_standard_error"][0], ref["corrected_standard_error"], rtol=1e-5, atol=1e-9)
 
 
 def test_four_scenario_decomposition_from_device_statistics(lib, ktab):

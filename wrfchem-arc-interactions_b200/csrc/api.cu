@@ -1295,6 +1295,77 @@ int arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const floa
   return 0;
 }
 
+// Moran's I of 2-D diagnostic fields over the tile as calc_morans_i_2D computes it with the options calc_standard_stats
+// passes (neighbour + manhattan; analysis_scripts/NCL_extraction_package/misc_stats_library.ncl:196-371, 401-404): the eight
+// raveled-index displacements with wrap-around, weight 1 where the Manhattan distance of the two cells is exactly 1 -
+// i.e. every ordered pair of edge-sharing cells once - deviations from the float mean, sums in double, normalised by
+// W_sum * stddev^2 with the N-1 stddev.  calc_standard_stats multiplies the standard error by it (its "corrected SE").
+// One block per field, fixed-order tree: reproducible.
+__global__ void __launch_bounds__(1024) k_morans_i(Geo G, int nfields, const float *const *__restrict__ fields, float *__restrict__ out) {
+  const int f = blockIdx.x;
+  const float *x = fields[f];
+  __shared__ double sh[2][1024];
+  __shared__ float s_mean, s_var;
+  const int ni = G.nci, nj = G.ncol_tile / G.nci;
+  double s = 0.0;
+  for (int tc = threadIdx.x; tc < G.ncol_tile; tc += blockDim.x) { int i, j; G.ij(tc, i, j); s += (double)x[G.at2(i, j)]; }
+  sh[0][threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) { if (threadIdx.x < off) sh[0][threadIdx.x] += sh[0][threadIdx.x + off]; __syncthreads(); }
+  if (threadIdx.x == 0) s_mean = (float)(sh[0][0] / (double)G.ncol_tile);
+  __syncthreads();
+  const float mean = s_mean;
+  // deviations are formed in single precision from the single-precision mean (X_diff = data - X_mean), products in double
+  double ss = 0.0, au = 0.0;
+  for (int tc = threadIdx.x; tc < G.ncol_tile; tc += blockDim.x) {
+    int i, j; G.ij(tc, i, j);
+    const float d0 = x[G.at2(i, j)] - mean;
+    ss += (double)d0 * (double)d0;
+    double nb = 0.0;
+    if (i < G.ite) nb += (double)(x[G.at2(i + 1, j)] - mean);
+    if (j < G.jte) nb += (double)(x[G.at2(i, j + 1)] - mean);
+    au += 2.0 * (double)d0 * nb;               // each edge-sharing pair counts in both directions
+  }
+  sh[0][threadIdx.x] = ss; sh[1][threadIdx.x] = au;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if (threadIdx.x < off) { sh[0][threadIdx.x] += sh[0][threadIdx.x + off]; sh[1][threadIdx.x] += sh[1][threadIdx.x + off]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = (double)G.ncol_tile;
+    const float sd = (float)sqrt(sh[0][0] / fmax(n - 1.0, 1.0));           // NCL stddev: N-1
+    const double wsum = 2.0 * ((double)nj * (ni - 1) + (double)ni * (nj - 1));
+    s_var = sd * sd;
+    out[f] = (sh[0][0] == 0.0 || wsum == 0.0) ? 0.f : (float)(sh[1][0] / (wsum * (double)s_var));
+  }
+}
+
+int arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *const *fields, float *out) {
+  if (!g.ready) { g.err = "arc_rad_morans_i: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !fields || !out || nfields < 1 || nfields > 64) { g.err = "arc_rad_morans_i: bad argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const float *dev[64];
+  for (int f = 0; f < nfields; f++) {
+    if (!fields[f]) { g.err = "arc_rad_morans_i: null field"; return ARC_ERR_BAD_ARG; }
+    if ((rc = in_arr(memspace, fields[f], G.n2(), &dev[f]))) return rc;
+  }
+  void *dptrs; if ((rc = stage_slot(sizeof(float *) * 64, &dptrs))) return rc;
+  CK(cudaMemcpyAsync(dptrs, dev, sizeof(float *) * nfields, cudaMemcpyHostToDevice, g.stream));
+  float *dout = out;
+  if (memspace != ARC_MEM_DEVICE) { void *p; if ((rc = stage_slot(sizeof(float) * 64, &p))) return rc; dout = (float *)p; }
+  k_morans_i<<<nfields, 1024, 0, g.stream>>>(G, nfields, (const float *const *)dptrs, dout);
+  count_launch();
+  if (memspace != ARC_MEM_DEVICE) CK(cudaMemcpyAsync(out, dout, sizeof(float) * nfields, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // Host-only probe used by the CPU test-suite: parse + reduce the k-distribution files exactly as arc_rad_init does
 // (no GPU needed) and return one reduced table ("sw16.absa", "lw3.ka_mn2o", ...) or, with name == NULL, only validate.
 int arc_rad_host_table(const char *inline_tables, const char *sw_data_path, const char *lw_data_path, float cp, float p_top,

@@ -12,7 +12,8 @@ The numbers come from the device: `arc_rad_domain_stats` reduces every TOA field
 {sum, sum of squares, count, min, max} (all-reduced over the GPUs of a run by `partition.combine_stats`), and
 `stats_from_sums` turns them into the columns calc_standard_stats writes
 (analysis_scripts/NCL_extraction_package/misc_stats_library.ncl:396-461): avg, stddev (NCL `stddev`: N-1 in the
-denominator), min, max, standard_error = stddev / sqrt(N), N.
+denominator), min, max, standard_error = stddev / sqrt(N), N; with Moran's I from `arc_rad_morans_i` also the
+corrected_standard_error = SE * I column.
 
 Reference quirk kept by default: calc_LW_INDIRECT (RadDecomp_functions.py:216-233) reads 'LWUPTC_nA' for BOTH the
 clear-sky and the all-sky operand, so its effect is identically zero and its error counts LWUPTC_nA four times.
@@ -26,15 +27,21 @@ import numpy as np
 ERROR_TYPES = ("standard_error", "corrected_standard_error")
 
 
-def stats_from_sums(sums, names=None):
+def stats_from_sums(sums, names=None, morans_i=None):
     """{sum, sum of squares, count, min, max} per field (the `out[f][5]` of arc_rad_domain_stats) -> the statistics columns of
-    calc_standard_stats that the decomposition uses.  `sums`: array (nfields, 5); `names`: field names (-> dict of dicts)."""
+    calc_standard_stats that the decomposition uses.  `sums`: array (nfields, 5); `names`: field names (-> dict of dicts);
+    `morans_i`: Moran's I per field (arc_rad_morans_i) -> also 'morans_i' and 'corrected_standard_error' = SE * I
+    (misc_stats_library.ncl:447-449)."""
     s = np.asarray(sums, dtype=np.float64)
     n = s[:, 2]
     avg = s[:, 0] / n
     var = (s[:, 1] - n * avg * avg) / np.maximum(n - 1.0, 1.0)
     sd = np.sqrt(np.maximum(var, 0.0))
     cols = {"avg": avg, "stddev": sd, "min": s[:, 3], "max": s[:, 4], "standard_error": sd / np.sqrt(n), "N": n}
+    if morans_i is not None:
+        mi = np.asarray(morans_i, dtype=np.float64)
+        cols["morans_i"] = mi
+        cols["corrected_standard_error"] = cols["standard_error"] * mi
     if names is None:
         return cols
     return {nm: {k: v[i] for k, v in cols.items()} for i, nm in enumerate(names)}
