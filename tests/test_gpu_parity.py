@@ -503,10 +503,6 @@ def test_four_scenario_decomposition_from_device_statistics(lib, ktab):
     from wrfchem_arc_interactions_b200 import decomposition as D
     dom = synth.make_domain(24, 16, 40, seed=41)
     init(lib, dom, ktab)
-    L = lib.lib
-    L.arc_rad_domain_stats.restype = C.c_int
-    L.arc_rad_domain_stats.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_void_p]
-    dims = abi.make_dims(dom["dims"])
     aer = [k for k in dom if k.startswith("tauaer")]
 
     def scenario(scale):
@@ -516,15 +512,14 @@ def test_four_scenario_decomposition_from_device_statistics(lib, ktab):
         sw, lw = run_pair("sw", lib, d), run_pair("lw", lib, d)
         fields = {"SWUPT": sw["swupt"], "SWUPTCLN": sw["swuptcln"], "LWUPT": lw["lwupt"], "LWUPTC": lw["lwuptc"]}
         names = list(fields)
-        ptrs = (abi.c_fp * len(names))(*[abi.fptr(fields[n]) for n in names])
-        st = np.zeros((len(names), 5))
-        lib.check(L.arc_rad_domain_stats(C.byref(dims), 0, len(names), ptrs, C.c_void_p(st.ctypes.data)))
-        return D.stats_from_sums(st, names=names), fields
+        return lib.domain_statistics(dom["dims"], [fields[n] for n in names], names=names), fields
 
     (b, fb), (a, fa), (bn, fbn), (an, fan) = scenario(1.0), scenario(0.5), scenario(0.0), scenario(0.0)
     B = dict(b); B.update({k + "_nA": v for k, v in bn.items()})
     A = dict(a); A.update({k + "_nA": v for k, v in an.items()})
     out = D.decompose(B, A, "standard_error", lw_indirect_fixed=True)
+    outc = D.decompose(B, A, "corrected_standard_error", lw_indirect_fixed=True)      # SE * Moran's I (ncl:449)
+    assert outc["SW_DIRECT"][0] == out["SW_DIRECT"][0] and 0.0 < outc["SW_DIRECT"][1] != out["SW_DIRECT"][1]
     mean = lambda x: x.astype(np.float64).mean()
     direct = (mean(fb["SWUPTCLN"]) - mean(fb["SWUPT"])) - (mean(fa["SWUPTCLN"]) - mean(fa["SWUPT"]))
     assert np.isclose(out["SW_DIRECT"][0], direct, rtol=1e-9, atol=1e-9)

@@ -171,6 +171,38 @@ class RadLib:
 
 
     # optical_averaging (WRF-Chem chem/module_optical_averaging.F; restated)
+    def domain_statistics(self, dims, fields, names=None, morans=True):
+        """Statistics columns of calc_standard_stats (misc_stats_library.ncl:396-461) for 2-D fields, reduced on the device:
+        avg, stddev (N-1), min, max, standard_error, N and, with `morans`, morans_i and corrected_standard_error = SE * I.
+        `fields`: list of numpy arrays (host) or torch CUDA tensors (device); returns decomposition.stats_from_sums(...)."""
+        from . import decomposition
+        d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        dev = [_is_device(f) for f in fields]
+        if any(dev) and not all(dev):
+            raise ValueError("mix of host and device arrays")
+        ms = abi.ARC_MEM_DEVICE if dev[0] else abi.ARC_MEM_HOST
+        n = len(fields)
+        ptrs = (abi.c_fp * n)(*[abi.fptr(int(f.data_ptr())) if dev[0] else abi.fptr(f) for f in fields])
+        L = self.lib
+        L.arc_rad_domain_stats.restype = C.c_int
+        L.arc_rad_domain_stats.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_void_p]
+        L.arc_rad_morans_i.restype = C.c_int
+        L.arc_rad_morans_i.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_void_p]
+        if dev[0]:
+            import torch
+            st = torch.zeros(n, 5, dtype=torch.float64, device=fields[0].device)
+            mi = torch.zeros(n, dtype=torch.float32, device=fields[0].device)
+            self.check(L.arc_rad_domain_stats(C.byref(d), ms, n, ptrs, C.c_void_p(int(st.data_ptr()))))
+            if morans:
+                self.check(L.arc_rad_morans_i(C.byref(d), ms, n, ptrs, C.c_void_p(int(mi.data_ptr()))))
+            st, mi = st.cpu().numpy(), mi.cpu().numpy()
+        else:
+            st, mi = np.zeros((n, 5)), np.zeros(n, np.float32)
+            self.check(L.arc_rad_domain_stats(C.byref(d), ms, n, ptrs, C.c_void_p(st.ctypes.data)))
+            if morans:
+                self.check(L.arc_rad_morans_i(C.byref(d), ms, n, ptrs, C.c_void_p(mi.ctypes.data)))
+        return decomposition.stats_from_sums(st, names=names, morans_i=mi if morans else None)
+
     def optical_averaging(self, dims, mode, bins, alt, dz8w, outs, sigmag=None):
         """bins: list (one per size section, or per mode) of dicts {species_name: array, ..., "num": array}; a species name
         starts with its class (so4, no3, cl, nh4, na, oin, oc, bc, water), e.g. "oc_orgaro1j".  outs: dict with
