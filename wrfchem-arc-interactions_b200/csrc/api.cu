@@ -38,6 +38,11 @@ struct Ctx {
   int chain = 0;
   cudaStream_t stream3 = nullptr;
   cudaEvent_t ev_pre = nullptr;
+  // asynchronous slab pipeline (host arrays): the chained pair of slab s ends without join / synchronisation, so the LW
+  // kernels of slab s+1 start while the last SW sweep of slab s is still running.  ev_lw_done / ev_sw_done (recorded on
+  // stream2 after the last LW / SW reduce of a pair) order the reuse of the LW / SW workspaces and the download.
+  bool async_pair = false; int slab_index = 0;
+  cudaEvent_t ev_lw_done = nullptr, ev_sw_done = nullptr;
   HostTables H;
   DevTables D;
   std::vector<void *> table_allocs;
@@ -567,7 +572,8 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
     ArcDims ds = d;
     ds.jms = j0; ds.jme = j1; ds.jts = j0; ds.jte = j1;
     CK(cudaStreamWaitEvent(g.stream, g.ev_in[set], 0));
-    // LW + SW on one slab run as one continuous multi-stream pipeline (see arc_rad_lwsw): no join / sync between the two
+    // LW + SW on one slab run as one continuous multi-stream pipeline (see arc_rad_lwsw): no join / sync between the two,
+    // and none at the end of the slab either - the next slab's LW kernels start while this slab's last SW sweep runs
     const bool chain = nparts == 2 && g.overlap && parts[0].call == call_lw_ptr && parts[1].call == call_sw_ptr;
     if (chain) CK(cudaStreamWaitEvent(g.stream3, g.ev_in[set], 0));
     for (int p = 0; p < nparts && !status; p++) {
@@ -582,14 +588,29 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
         if (fldv(din[p].data(), parts[p].alias[q][0])) fldv(din[p].data(), parts[p].alias[q][0]) = fldv(din[p].data(), parts[p].alias[q][1]);
       g.keep_ms = s > 0;
       g.chain = chain ? p + 1 : 0;
-      rc = parts[p].call(&ds, din[p].data(), dout[p].data());     // synchronises g.stream before returning (chained: after SW)
-      g.chain = 0;
+      g.async_pair = chain; g.slab_index = s;
+      rc = parts[p].call(&ds, din[p].data(), dout[p].data());     // synchronises g.stream before returning (chained: not at all)
+      g.chain = 0; g.async_pair = false;
       g.keep_ms = false;
       if (rc && !status) status = rc;
     }
     if (chain && status) { cudaStreamSynchronize(g.stream3); cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream); collect_times(); }
+    if (chain && !status) {       // the download of this slab waits for its last reduce (stream2) and the night-column kernel (stream3)
+      CK(cudaStreamWaitEvent(g.d2h, g.ev_sw_done, 0));
+      CK(cudaStreamWaitEvent(g.d2h, g.ev_pre, 0));
+    }
     if ((rc = download(s))) return rc;
     if (status) break;
+  }
+  if (!status && nparts == 2 && g.overlap && parts[0].call == call_lw_ptr && parts[1].call == call_sw_ptr) {
+    // end of the asynchronous pipeline: drain the compute streams, fetch the device status word, collect the kernel times
+    int dev_status = 0;
+    CK(cudaStreamSynchronize(g.stream3)); CK(cudaStreamSynchronize(g.stream2));
+    CK(cudaMemcpyAsync(&dev_status, g.d_status, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    collect_times();
+    if (dev_status) { g.err = code_msg(dev_status); status = dev_status; }
   }
   CK(cudaStreamSynchronize(g.d2h));
   CK(cudaStreamSynchronize(g.h2d));
@@ -666,6 +687,9 @@ void arc_rad_finalize(void) {
   if (g.stream2) cudaStreamDestroy(g.stream2);
   if (g.stream3) cudaStreamDestroy(g.stream3);
   g.stream = g.stream2 = g.stream3 = nullptr;
+  if (g.ev_lw_done) cudaEventDestroy(g.ev_lw_done);
+  if (g.ev_sw_done) cudaEventDestroy(g.ev_sw_done);
+  g.ev_lw_done = g.ev_sw_done = nullptr;
   if (g.ev_pre) cudaEventDestroy(g.ev_pre);
   g.ev_pre = nullptr;
   if (g.ev_solved) cudaEventDestroy(g.ev_solved);
@@ -700,6 +724,8 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
     CK(cudaStreamCreateWithPriority(&g.stream2, cudaStreamNonBlocking, (pr && atoi(pr) == 0) ? lo : hi));
     CK(cudaStreamCreateWithFlags(&g.stream3, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_pre, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_lw_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_sw_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_solved, cudaEventDisableTiming));
     for (int q = 0; q < 2; q++) CK(cudaEventCreateWithFlags(&g.ev_swept[q], cudaEventDisableTiming));
   }
@@ -829,6 +855,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   const bool chained = g.chain == 2;
   cudaStream_t sp = chained ? g.stream3 : g.stream;       // stream of the column-parallel pre-kernels of the first outer chunk
   if (!chained) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
+  if (chained && g.async_pair) CK(cudaStreamWaitEvent(g.stream3, g.ev_sw_done, 0));    // the SW workspace of the previous slab is free
   {
     const int fq[7] = {in->f_qv, in->f_qc, in->f_qr, in->f_qi, in->f_qs, in->f_qg, in->f_qndrop};
     const float *const p3[18] = {in->t3d, in->cldfra3d, in->lradius, in->iradius, in->qv3d, in->qc3d, in->qr3d, in->qi3d, in->qs3d,
@@ -938,6 +965,11 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
       if (g.overlap) { CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0)); }
     }
   }
+  if (chained && g.async_pair) {   // slab pipeline: no join here; run_pipelined orders the download on these events
+    CK(cudaEventRecord(g.ev_pre, g.stream3));
+    CK(cudaEventRecord(g.ev_sw_done, g.stream2));
+    return 0;
+  }
   if (chained) {   // join everything the pair queued: the night-column kernel on stream3, the sweeps of both calls on stream2
     CK(cudaEventRecord(g.ev_pre, g.stream3)); CK(cudaStreamWaitEvent(g.stream, g.ev_pre, 0));
     CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0));
@@ -993,7 +1025,8 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   const int nlay = g.H.lw_nlayers - d->kts + 1;
   if (nlay > 159 || nlay < nz + 1) { g.err = "arc_rad_lw: bad LW layer count (nlayers from init vs kte)"; return ARC_ERR_BAD_ARG; }
 
-  CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
+  if (!(g.chain == 1 && g.async_pair && g.slab_index > 0)) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
+  if (g.chain == 1 && g.async_pair) CK(cudaStreamWaitEvent(g.stream, g.ev_lw_done, 0));     // the LW workspace of the previous slab is free
   {
     const int fq[7] = {in->f_qv, in->f_qc, in->f_qr, in->f_qi, in->f_qs, in->f_qg, in->f_qndrop};
     const float *const p3[18] = {in->t3d, in->cldfra3d, in->lradius, in->iradius, in->qv3d, in->qc3d, in->qr3d, in->qi3d, in->qs3d,
@@ -1077,7 +1110,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       CK(cudaStreamWaitEvent(g.stream, g.ev_swept[0], 0)); CK(cudaStreamWaitEvent(g.stream, g.ev_swept[1], 0));
     }
   }
-  if (g.chain == 1) return 0;
+  if (g.chain == 1) { if (g.async_pair) CK(cudaEventRecord(g.ev_lw_done, g.stream2)); return 0; }
   return finish_call(dbglist);
 }
 
