@@ -42,7 +42,7 @@ struct Ctx {
   // kernels of slab s+1 start while the last SW sweep of slab s is still running.  ev_lw_done / ev_sw_done (recorded on
   // stream2 after the last LW / SW reduce of a pair) order the reuse of the LW / SW workspaces and the download.
   bool async_pair = false; int slab_index = 0;
-  cudaEvent_t ev_lw_done = nullptr, ev_sw_done = nullptr;
+  cudaEvent_t ev_lw_done = nullptr, ev_sw_done = nullptr, ev_pre_lw = nullptr;
   HostTables H;
   DevTables D;
   std::vector<void *> table_allocs;
@@ -484,7 +484,24 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
   const int ni = d.ime - d.ims + 1, nk = d.kme - d.kms + 1;
   const int rows_per = slab_rows_default(nrows, d.ite - d.its + 1);
   if (rows_per >= nrows) return -1;
-  const int nslab = (nrows + rows_per - 1) / rows_per;
+  // Slab boundaries: a short first slab (the pipeline cannot compute before its upload has finished) and a short last slab
+  // (nothing hides its download) of ARC_RAD_SLAB_EDGE columns each can be requested (default 0 = uniform slabs: measured no gain).
+  std::vector<int> slab_j0;      // first row of every slab (relative to jts), plus the end
+  {
+    const char *e = getenv("ARC_RAD_SLAB_EDGE");
+    const long edge_cols = e ? atol(e) : 0;
+    int edge = (int)std::min<long>(rows_per, std::max<long>(0, edge_cols / std::max(d.ite - d.its + 1, 1)));
+    if (nrows < 2 * edge + rows_per) edge = 0;
+    int j = 0;
+    if (edge > 0) { slab_j0.push_back(0); j = edge; }
+    const int mid_end = nrows - edge;
+    const int nmid = (mid_end - j + rows_per - 1) / rows_per;
+    const int each = (mid_end - j + nmid - 1) / nmid;
+    while (j < mid_end) { slab_j0.push_back(j); j = std::min(mid_end, j + each); }
+    if (edge > 0) slab_j0.push_back(mid_end);
+    slab_j0.push_back(nrows);
+  }
+  const int nslab = (int)slab_j0.size() - 1;
   const bool ihalo = d.its != d.ims || d.ite != d.ime;
   const int nz = d.kte - d.kts + 1;
   const size_t row3 = (size_t)ni * nk, row2 = (size_t)ni, rowp = (size_t)ni * (nk + 2);
@@ -511,7 +528,7 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
 
   auto upload = [&](int s) -> int {
     const int set = s & 1;
-    const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1), nr = j1 - j0 + 1;
+    const int j0 = d.jts + slab_j0[s], j1 = d.jts + slab_j0[s + 1] - 1, nr = j1 - j0 + 1;
     CK(cudaStreamWaitEvent(g.h2d, g.ev_out[set], 0));          // the previous user of this set has been downloaded
     std::vector<bool> done(nslots, false);
     for (int p = 0; p < nparts; p++) {
@@ -539,7 +556,7 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
   };
   auto download = [&](int s) -> int {
     const int set = s & 1;
-    const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1), nr = j1 - j0 + 1;
+    const int j0 = d.jts + slab_j0[s], j1 = d.jts + slab_j0[s + 1] - 1, nr = j1 - j0 + 1;
     for (int p = 0; p < nparts; p++)
       for (int f = 0; f < parts[p].nouts; f++) {
         const int slot = maps[p].out_slot[f];
@@ -568,7 +585,7 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
   for (int s = 0; s < nslab; s++) {
     const int set = s & 1;
     if (s + 1 < nslab && (rc = upload(s + 1))) return rc;
-    const int j0 = d.jts + s * rows_per, j1 = std::min(d.jte, j0 + rows_per - 1);
+    const int j0 = d.jts + slab_j0[s], j1 = d.jts + slab_j0[s + 1] - 1;
     ArcDims ds = d;
     ds.jms = j0; ds.jme = j1; ds.jts = j0; ds.jte = j1;
     CK(cudaStreamWaitEvent(g.stream, g.ev_in[set], 0));
@@ -687,6 +704,8 @@ void arc_rad_finalize(void) {
   if (g.stream2) cudaStreamDestroy(g.stream2);
   if (g.stream3) cudaStreamDestroy(g.stream3);
   g.stream = g.stream2 = g.stream3 = nullptr;
+  if (g.ev_pre_lw) cudaEventDestroy(g.ev_pre_lw);
+  g.ev_pre_lw = nullptr;
   if (g.ev_lw_done) cudaEventDestroy(g.ev_lw_done);
   if (g.ev_sw_done) cudaEventDestroy(g.ev_sw_done);
   g.ev_lw_done = g.ev_sw_done = nullptr;
@@ -725,6 +744,7 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
     CK(cudaStreamCreateWithFlags(&g.stream3, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_pre, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_lw_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_pre_lw, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_sw_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_solved, cudaEventDisableTiming));
     for (int q = 0; q < 2; q++) CK(cudaEventCreateWithFlags(&g.ev_swept[q], cudaEventDisableTiming));
@@ -1026,7 +1046,10 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   if (nlay > 159 || nlay < nz + 1) { g.err = "arc_rad_lw: bad LW layer count (nlayers from init vs kte)"; return ARC_ERR_BAD_ARG; }
 
   if (!(g.chain == 1 && g.async_pair && g.slab_index > 0)) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
-  if (g.chain == 1 && g.async_pair) CK(cudaStreamWaitEvent(g.stream, g.ev_lw_done, 0));     // the LW workspace of the previous slab is free
+  // Slab pipeline: from the second slab on the LW column kernels (McICA, prep) run on stream3 beside the SW solver of the
+  // previous slab (at one slab's worth of columns they are latency-bound and would otherwise sit exposed on the main stream)
+  cudaStream_t spl = (g.chain == 1 && g.async_pair && g.slab_index > 0) ? g.stream3 : g.stream;
+  if (g.chain == 1 && g.async_pair) CK(cudaStreamWaitEvent(spl, g.ev_lw_done, 0));     // the LW workspace of the previous slab is free
   {
     const int fq[7] = {in->f_qv, in->f_qc, in->f_qr, in->f_qi, in->f_qs, in->f_qg, in->f_qndrop};
     const float *const p3[18] = {in->t3d, in->cldfra3d, in->lradius, in->iradius, in->qv3d, in->qc3d, in->qr3d, in->qi3d, in->qs3d,
@@ -1080,12 +1103,14 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
     m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGLW; m.permuteseed = 150; m.ncols = no; m.W = a.ws.W; m.icloud = in->icloud;
     m.cap = (int)cap; m.col0 = o0; m.lw_buffer = 1; m.cols = nullptr; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
     m.mask = a.ws.mask; m.anyc = a.ws.anyc;
-    { Timed t("lw_mcica"); launch_mcica(m, g.stream); }
-    { Timed t("lw_prep"); launch_lw_prep(a, g.stream); }
+    cudaStream_t so = o0 == 0 ? spl : g.stream;
+    { Timed t("lw_mcica", so); launch_mcica(m, so); }
+    { Timed t("lw_prep", so); launch_lw_prep(a, so); }
     if (a.dbg.cldmask) {
-      k_unpack_mask<<<(no + 127) / 128, 128, 0, g.stream>>>(a.ws.mask, nullptr, o0, no, (int)cap, a.ws.W, nlay, NGLW, a.dbg.cldmask);
+      k_unpack_mask<<<(no + 127) / 128, 128, 0, so>>>(a.ws.mask, nullptr, o0, no, (int)cap, a.ws.W, nlay, NGLW, a.dbg.cldmask);
       count_launch();
     }
+    if (so != g.stream) { CK(cudaEventRecord(g.ev_pre_lw, so)); CK(cudaStreamWaitEvent(g.stream, g.ev_pre_lw, 0)); }
     cudaStream_t s2 = g.overlap ? g.stream2 : g.stream;
     int kc = 0;
     for (int c0 = 0; c0 < no; c0 += (int)pcap, kc++) {
