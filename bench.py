@@ -319,7 +319,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": ncol * world * n_e2e / float(te[0]), "unit": "columns/s",
                "h2d_bytes_per_step": int(in_sw + in_lw + inout_b), "d2h_bytes_per_step": int(out_b),
-               "steps": n_e2e, "note": "host pinned WRF-layout arrays through one RRTMG_LWSW step (arc_rad_lwsw: LW then SW) + statistics; the library pipelines j-slabs: upload / compute / download overlap on three streams, shared inputs uploaded once"}
+               "steps": n_e2e, "note": "host pinned WRF-layout arrays through one RRTMG_LWSW step (arc_rad_lwsw: LW then SW) + statistics; the library pipelines j-slabs: upload / compute / download overlap on copy streams, shared inputs uploaded once, LW and SW of a slab chained and slabs not joined (the next slab's LW kernels start under the last SW sweep)"}
 
     # ---- aerosol optical-property stage (MOSAIC 8-bin sectional), reported separately ------------------
     aer = None
