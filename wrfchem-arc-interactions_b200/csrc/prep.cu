@@ -165,9 +165,12 @@ __global__ void __launch_bounds__(256) k_mcica(McicaArgs a, const KissJump *__re
   }
   float prev = 0.f, omc_prev = 1.f;
   uint32_t word = 0u;
+  const bool havecf = a.icloud != 0 && a.cldfra3d;
+  const float *pcf = havecf ? a.cldfra3d + a.geo.at3(i, kts, j) : nullptr;      // level stride = ni
+  const int kstride = a.geo.ni;
   for (int l = 0; l < a.nlay; l++) {
     float cf = 0.f;
-    if (l < a.nz && a.icloud != 0 && a.cldfra3d) cf = a.cldfra3d[a.geo.at3(i, kts + l, j)];
+    if (l < a.nz && havecf) { cf = *pcf; pcf += kstride; }
     if (cf < 1.0e-20f) cf = 0.f;
     const float omc = 1.0f - cf;
     float x = K.next();
@@ -752,16 +755,24 @@ __global__ void __launch_bounds__(128) k_lw_prep(LwArgs a) {
       a.dbg.fac00[q] = pc.fac00; a.dbg.fac01[q] = pc.fac01; a.dbg.fac10[q] = pc.fac10; a.dbg.fac11[q] = pc.fac11;
     }
     // ---- aerosol (LW:12576-12615)
-    bool chem = false;
+    // all 16 band fields of the layer are requested together (one memory latency per layer, not one per band)
+    float tv[NBLW];
+#pragma unroll
+    for (int b = 0; b < NBLW; b++) tv[b] = 0.f;
     if (model && a.aer_ra_feedback == 1) {
       const size_t q = G.at3(i, k, j);
-      chem = a.tauaerlw[0][q] > thresh && a.tauaerlw[15][q] > thresh;
+#pragma unroll
+      for (int b = 0; b < NBLW; b++) tv[b] = a.tauaerlw[b][q];
+      const bool chem = tv[0] > thresh && tv[15] > thresh;
+      if (!chem) {
+#pragma unroll
+        for (int b = 0; b < NBLW; b++) tv[b] = 0.f;
+      }
     }
+#pragma unroll
     for (int b = 0; b < NBLW; b++) {
-      float taua = 0.f;
-      if (chem) taua = a.tauaerlw[b][G.at3(i, k, j)];
-      ws.aer[((size_t)b * nlay + l) * cap + c] = taua;
-      if (model) aersum[b] = aersum[b] + taua;
+      ws.aer[((size_t)b * nlay + l) * cap + c] = tv[b];
+      if (model) aersum[b] = aersum[b] + tv[b];
     }
     // ---- clouds
     const bool anycld = (ws.anyc[(size_t)(l >> 5) * cap + c] >> (l & 31)) & 1u;
