@@ -92,3 +92,8 @@ def test_two_rank_statistics_match_single_rank(orc, ktab):
     x = sw["swupt"].astype(np.float64)
     assert np.isclose(got["mean"][0], x.mean()) and np.isclose(got["sd"][0], x.std(ddof=1)) and np.isclose(got["se"][0], x.std(ddof=1) / np.sqrt(x.size))
     assert slabs[0][0] == 1 and slabs[-1][1] == 8
+    # the all-reduced sums feed the decomposition's statistics columns directly (decomposition.stats_from_sums)
+    from wrfchem_arc_interactions_b200 import decomposition as D
+    cols = D.stats_from_sums(np.column_stack([sums, -ext[:, 0], ext[:, 1]]))
+    assert np.allclose(cols["avg"], got["mean"], rtol=1e-14) and np.allclose(cols["stddev"], got["sd"], rtol=1e-9)
+    assert np.allclose(cols["standard_error"], got["se"], rtol=1e-9) and np.array_equal(cols["N"], sums[:, 2])
