@@ -216,6 +216,10 @@ int  arc_rad_host_table(const char *inline_tables, const char *sw_data_path, con
                         int kme, const char *name, float *buf, int cap);
 /* Self-test (GPU): setcoef's jp | jt << 8 | jt1 << 12 for n host (p hPa, T K) pairs (SW:2854-2887), same device code as the prep kernels */
 int  arc_rad_selftest_pt(const float *p, const float *t, int n, int *packed);
+/* Self-test of the glibc-compatible logf / expf / powf the device path uses for LOG, EXP and ** of the reference
+ * (which = 0 logf(x), 1 expf(x), 2 powf(x, y)): out[i] from the host instantiation (on_device = 0; needs no GPU and no init)
+ * or the device instantiation (on_device = 1); the caller compares with the C library (SW:2854, 11004-11008; LW:3650). */
+int  arc_rad_selftest_libm(int which, const float *x, const float *y, int n, float *out, int on_device);
 /* Self-test (GPU): mismatches of the kernels' branch-free division against IEEE division over n random operand pairs */
 int  arc_rad_selftest_div(int n, unsigned seed);
 /* FP32 FMA throughput of the device in TFLOP/s (microbenchmark; roofline denominator of the solver kernels) */

@@ -84,6 +84,13 @@ int arc_oracle_pt(const float *p, const float *t, int n, int *packed) {
   return 0;
 }
 
+// The C library's own logf / expf / powf (what gfortran's LOG / EXP / ** call): which = 0 logf(x), 1 expf(x), 2 powf(x, y).
+// Checker for the product's glibc-compatible device functions (csrc/glibc_math.cuh).
+int arc_oracle_libm(int which, const float *x, const float *y, int n, float *out) {
+  for (int q = 0; q < n; q++) out[q] = which == 0 ? logf(x[q]) : which == 1 ? expf(x[q]) : powf(x[q], y[q]);
+  return 0;
+}
+
 // radconst + calc_coszen, module_radiation_driver.F:2595-2666 (scalar restatement)
 void arc_oracle_radconst(float xtime, float julian, float degrad, float dpd, float *declin, float *solcon) {
   (void)xtime;

@@ -99,3 +99,32 @@ def test_record_layout_sizes(ktab):
     n0 = struct.unpack("<i", raw[:4])[0]
     assert n0 == 4 * (2 + 1 + 9 * 5 * 13 * 16 + 5 * 47 * 16 + 10 * 16 + 3 * 16 + 16)
     assert struct.unpack("<i", raw[4 + n0:8 + n0])[0] == n0
+
+
+def _to_big_endian(src, dst):
+    """Rewrite a little-endian Fortran sequential-unformatted file of 4-byte items as WRF's big-endian flavour
+    (-fconvert=big-endian: record markers and REAL*4 / INTEGER*4 payload byte-swapped)."""
+    raw = np.fromfile(src, dtype="<u4")
+    raw.astype(">u4").tofile(dst)
+
+
+def test_big_endian_files_give_the_same_tables(lib, ktab, tmp_path):
+    """The data files WRF ships are big-endian (WRF is compiled with -fconvert=big-endian); the reader detects the byte
+    order from the first record's markers (csrc/tables.cpp FileCursor)."""
+    be = (str(tmp_path / "RRTMG_SW_DATA"), str(tmp_path / "RRTMG_LW_DATA"))
+    _to_big_endian(ktab[0], be[0]); _to_big_endian(ktab[1], be[1])
+    assert open(be[0], "rb").read(4) != open(ktab[0], "rb").read(4)
+    assert host_table(lib, be, None) == 0
+    n = 0
+    for name in ("sw16.absa", "sw17.absb", "sw24.rayla", "sw29.absco2", "sw22.sflux", "lw1.ka_mn2", "lw3.absa", "lw5.absb", "lw13.ka_mco", "lw8.cfc22adj",
+                 "lw16.fracrefa"):
+        a, b = host_table(lib, ktab, name), host_table(lib, be, name)
+        assert a.shape == b.shape and np.array_equal(a, b), name
+        n += a.size
+    assert n > 40000
+    # mixed byte order inside one file is an error, not garbage
+    bad = str(tmp_path / "mixed")
+    raw = bytearray(open(be[1], "rb").read())
+    raw[0:4] = raw[0:4][::-1]
+    open(bad, "wb").write(raw)
+    assert host_table(lib, (ktab[0], bad), None) == -3          # -ARC_ERR_IO

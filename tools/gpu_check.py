@@ -51,7 +51,8 @@ for which in ("sw", "lw"):
         a_, b_ = ag[k][m].astype(np.float64), ao[k][m].astype(np.float64)
         err = np.abs(a_ - b_); rel = err / np.maximum(np.abs(b_), 1e-30)
         sel = np.abs(b_) > 1e-12 * max(np.abs(b_).max() if b_.size else 0, 1e-30)
-        print("%-10s maxabs %.3e  maxrel %.3e  (ref absmax %.4g)" % (k, err.max() if err.size else 0, rel[sel].max() if sel.any() else 0, np.abs(b_).max() if b_.size else 0))
+        nbit = int((ag[k][m].view(np.uint32) != ao[k][m].view(np.uint32)).sum())
+        print("%-10s maxabs %.3e  maxrel %.3e  (ref absmax %.4g)  bitwise different %d / %d" % (k, err.max() if err.size else 0, rel[sel].max() if sel.any() else 0, np.abs(b_).max() if b_.size else 0, nbit, a_.size))
     for k in og:
         stats(k, og[k], oo[k])
     if which == "sw":
@@ -74,6 +75,19 @@ for which in ("sw", "lw"):
           "aod400", float(dom["tauaer400"].reshape(nj, nk + 1, ni)[w // ni, :, w % ni].sum()))
     hrg, hro = ag["hr"][w], ao["hr"][w]
     print("hr gpu", np.array2string(hrg, precision=3, max_line_width=200)); print("hr orc", np.array2string(hro, precision=3, max_line_width=200))
+# device logf / expf / powf against the C library
+import ctypes as C
+L, Ol = lib.lib, orc.lib
+L.arc_rad_selftest_libm.argtypes = [C.c_int, abi.c_fp, abi.c_fp, C.c_int, abi.c_fp, C.c_int]
+Ol.arc_oracle_libm.argtypes = [C.c_int, abi.c_fp, abi.c_fp, C.c_int, abi.c_fp]
+rng = np.random.default_rng(3)
+for which, x, y in ((0, np.exp(rng.uniform(np.log(1e-3), np.log(1200.), 1 << 22)), None), (1, rng.uniform(-87, 87, 1 << 22), None),
+                    (2, np.exp(rng.uniform(-10, 10, 1 << 22)), rng.uniform(-4, 4, 1 << 22))):
+    x = x.astype(np.float32); y = (y if y is not None else x).astype(np.float32)
+    a = np.empty_like(x); b = np.empty_like(x)
+    assert L.arc_rad_selftest_libm(which, abi.fptr(x), abi.fptr(y), x.size, abi.fptr(a), 1) == 0
+    Ol.arc_oracle_libm(which, abi.fptr(x), abi.fptr(y), x.size, abi.fptr(b))
+    print("libm device fn %d: %d of %d differ from the C library" % (which, int((a.view(np.uint32) != b.view(np.uint32)).sum()), x.size))
 print("launches", lib.lib.arc_rad_launch_count())
 for n in ("sw_mcica", "sw_prep", "sw_solve", "sw_sweep", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_sweep", "lw_reduce"):
     print(n, lib.lib.arc_rad_last_kernel_ms(n.encode()))

@@ -6,6 +6,7 @@
 // setcoef_sw SW:2734-2990, setcoef LW:3444-3809.
 #pragma once
 #include "args.h"
+#include "glibc_math.cuh"
 
 namespace arc {
 
@@ -99,7 +100,7 @@ __device__ inline void layer_cloud(const CloudFields &cf, const Geo &G, const De
     reliq = 10.f;
     if (cf.f_qndrop > 0) {
       if (qc * pdel > 3.e-5f && qnd > 1000.f) {
-        reliq = powf(relconst * qc / qnd, 1.f / 3.f);
+        reliq = glm::powf_(relconst * qc / qnd, 1.f / 3.f);
         reliq = 1.1f * reliq;
         reliq = reliq * 1.e6f;
         reliq = fminf(fmaxf(reliq, 4.f), 20.f);
@@ -154,9 +155,8 @@ __device__ inline float o3_clim(const DevTables &tb, float pb, float pt) {
 struct PTCoef { int jp, jt, jt1; float fac00, fac01, fac10, fac11, plog; };
 
 __device__ inline void pt_coef(const float *__restrict__ preflog, const float *__restrict__ tref, float pavel, float tavel, PTCoef &c) {
-  // double-precision log rounded to float: agrees with glibc's correctly-rounded logf (used by the CPU
-  // reference) in all but ~0.2% of inputs, where CUDA's 1-ulp logf would not
-  const float plog = (float)log((double)pavel);
+  // glibc's logf bit for bit (glibc_math.cuh): plog defines jp and, through fp, every interpolation weight
+  const float plog = glm::logf_(pavel);
   int jp = (int)(36.f - 5 * (plog + 0.04f));
   jp = min(max(jp, 1), 58);
   const int jp1 = jp + 1;

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/arc_rad.h"
+#include "glibc_math.cuh"
 #include "aer.h"
 #include "args.h"
 
@@ -104,6 +105,14 @@ size_t outer_cap_default() {
   return std::max(chunk_cap_default(), (size_t)((v + 255) / 256 * 256));
 }
 
+// LW inner chunk (ARC_RAD_LW_CHUNK, default 65536 columns): bounds the group-partial buffer (47 KB per column and buffer at C2)
+size_t lw_chunk_cap_default() {
+  const char *e = getenv("ARC_RAD_LW_CHUNK");
+  long v = e ? atol(e) : 65536;
+  if (v < 256) v = 256;
+  return (size_t)((v + 255) / 256 * 256);
+}
+
 // Inner-chunk capacity bounded by the level-record budget (ARC_RAD_REC_GB per spectrum, default 40 GB for the two buffers):
 // the records are `bytes_per_col` per column and buffer, e.g. 84 B x 112 g x 52 levels (SW, 3 streams) at C2.
 size_t rec_limited_cap(size_t cap, size_t bytes_per_col) {
@@ -154,12 +163,8 @@ void carve_lw(LwWs &w, char *base, size_t &bytes) {
   w.laytrop = c.take<int>(cap);
   w.colf = c.take<float>((size_t)LWF_N * cap);
   w.secdiff = c.take<float>((size_t)NBLW * cap);
-  const size_t nv = (w.kslot[K_NU] != 0) ? 2 : 1;          // streams: full (+ clear) [, clean (+ clean-clear)]
-  w.rec_n = (pcap / REC_TILE) * (nl + 1) * nv * NGLW * LW_REC;   // two buffers of level records (solver k+1 overlaps sweep k)
-  w.rec = c.take<float>(2 * w.rec_n);
-  w.recC = c.take<float>(w.rec_n);
-  w.scrS = c.take<float2>(2 * nv * NGLW * pcap);
-  w.bpart = c.take<float>((size_t)lw_sweep_groups() * (nl + 1) * w.nk * pcap);
+  // two buffers of group partials: k_lw_band of inner chunk k+1 runs beside k_lw_reduce of chunk k
+  w.bpart = c.take<float>((size_t)2 * lw_sweep_groups() * (nl + 1) * w.nk * pcap);
   bytes = c.off;
 }
 
@@ -616,8 +621,8 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
       CK(cudaStreamWaitEvent(g.d2h, g.ev_sw_done, 0));
       CK(cudaStreamWaitEvent(g.d2h, g.ev_pre, 0));
     }
+    if (status) break;            // a failed slab leaves the caller's arrays as they were (nothing of it is copied back)
     if ((rc = download(s))) return rc;
-    if (status) break;
   }
   if (!status && nparts == 2 && g.overlap && parts[0].call == call_lw_ptr && parts[1].call == call_sw_ptr) {
     // end of the asynchronous pipeline: drain the compute streams, fetch the device status word, collect the kernel times
@@ -813,6 +818,7 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
   }
   D.lw_nlayers = H.lw_nlayers;
   upload_band_descs(H);
+  if (!lw_layout_ok()) { g.err = "RRTMG_LW_DATA: table shapes differ from the RRTMG layout the longwave kernel is compiled for"; return ARC_ERR_IO; }
   CK(cudaDeviceSynchronize());
   g.ready = true;
   return 0;
@@ -855,10 +861,14 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
       !(out->swupflx && out->swupflxc && out->swupflxcln && out->swdnflx && out->swdnflxc && out->swdnflxcln)) {
     g.err = "arc_rad_sw: flux profile outputs must be passed all together"; return ARC_ERR_BAD_ARG;
   }
-  if (out->swupt && !(out->swuptc && out->swuptcln && out->swdnt && out->swdntc && out->swdntcln && out->swupb && out->swupbc &&
-                      out->swupbcln && out->swdnb && out->swdnbc && out->swdnbcln && out->swvisdir && out->swvisdif &&
-                      out->swnirdir && out->swnirdif)) {
-    g.err = "arc_rad_sw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG;
+  {   // optional output groups are all-or-nothing: every array the caller passes is written (the host path relies on it)
+    float *const grp[16] = {out->swupt, out->swuptc, out->swuptcln, out->swdnt, out->swdntc, out->swdntcln, out->swupb, out->swupbc,
+                            out->swupbcln, out->swdnb, out->swdnbc, out->swdnbcln, out->swvisdir, out->swvisdif, out->swnirdir, out->swnirdif};
+    int n = 0; for (float *p : grp) n += p != nullptr;
+    if (n != 0 && n != 16) { g.err = "arc_rad_sw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG; }
+    float *const ex[4] = {out->swuptclnc, out->swdntclnc, out->swupbclnc, out->swdnbclnc};
+    n = 0; for (float *p : ex) n += p != nullptr;
+    if (n != 0 && n != 4) { g.err = "arc_rad_sw: the four clean-clear outputs must be passed all together"; return ARC_ERR_BAD_ARG; }
   }
   CK(cudaSetDevice(g.device));
   if (!g.keep_ms) for (auto it = g.last_ms.begin(); it != g.last_ms.end();) { if (it->first.compare(0, 3, "sw_") == 0) it = g.last_ms.erase(it); else ++it; }
@@ -1028,9 +1038,17 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       !(out->lwupflx && out->lwupflxc && out->lwupflxcln && out->lwdnflx && out->lwdnflxc && out->lwdnflxcln)) {
     g.err = "arc_rad_lw: flux profile outputs must be passed all together"; return ARC_ERR_BAD_ARG;
   }
-  if (out->lwupt && !(out->lwuptc && out->lwuptcln && out->lwdnt && out->lwdntc && out->lwdntcln && out->lwupb && out->lwupbc &&
-                      out->lwupbcln && out->lwdnb && out->lwdnbc && out->lwdnbcln)) {
-    g.err = "arc_rad_lw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG;
+  {   // optional output groups are all-or-nothing (see arc_rad_sw)
+    float *const grp[12] = {out->lwupt, out->lwuptc, out->lwuptcln, out->lwdnt, out->lwdntc, out->lwdntcln, out->lwupb, out->lwupbc,
+                            out->lwupbcln, out->lwdnb, out->lwdnbc, out->lwdnbcln};
+    int n = 0; for (float *p : grp) n += p != nullptr;
+    if (n != 0 && n != 12) { g.err = "arc_rad_lw: TOA/surface flux outputs must be passed all together"; return ARC_ERR_BAD_ARG; }
+    float *const ex[4] = {out->lwuptclnc, out->lwdntclnc, out->lwupbclnc, out->lwdnbclnc};
+    n = 0; for (float *p : ex) n += p != nullptr;
+    if (n != 0 && n != 4) { g.err = "arc_rad_lw: the four clean-clear outputs must be passed all together"; return ARC_ERR_BAD_ARG; }
+  }
+  if (in->variant_mask != 0 && (in->variant_mask & ~(ARC_VAR_FULL | ARC_VAR_CLEAR | ARC_VAR_CLEAN | ARC_VAR_CLEANCLEAR))) {
+    g.err = "arc_rad_lw: unknown bits in variant_mask"; return ARC_ERR_BAD_ARG;
   }
   CK(cudaSetDevice(g.device));
   if (!g.keep_ms) for (auto it = g.last_ms.begin(); it != g.last_ms.end();) { if (it->first.compare(0, 3, "lw_") == 0) it = g.last_ms.erase(it); else ++it; }
@@ -1042,7 +1060,10 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   const Geo &G = a.geo;
   const size_t n3 = G.n3(), n2 = G.n2(), np = G.np();
   const int nz = d->kte - d->kts + 1;
-  const int nlay = g.H.lw_nlayers - d->kts + 1;
+  // nlay = nlayers = kme + nint(p_top/4 hPa) - 1 as rrtmg_lwinit fixed it (LW:12861, 12050): the reference's layer count does
+  // not depend on the tile, which presumes the WRF convention kts = 1
+  if (d->kts != 1) { g.err = "arc_rad_lw: kts must be 1 (the layer count nlayers of rrtmg_lwinit assumes it, LW:12861)"; return ARC_ERR_BAD_ARG; }
+  const int nlay = g.H.lw_nlayers;
   if (nlay > 159 || nlay < nz + 1) { g.err = "arc_rad_lw: bad LW layer count (nlayers from init vs kte)"; return ARC_ERR_BAD_ARG; }
 
   if (!(g.chain == 1 && g.async_pair && g.slab_index > 0)) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
@@ -1080,8 +1101,13 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
 #undef OUT3
 #undef OUT2
 #undef OUTP
-  int variants = ARC_VAR_FULL | ARC_VAR_CLEAR;
-  if (in->clean_atm_diag > 0) variants |= ARC_VAR_CLEAN | (ext ? ARC_VAR_CLEANCLEAR : 0);   // clean call: LW:11022-11027
+  // call variants: as arc_rad_sw (full + clear always; clean from clean_atm_diag, LW:11022-11027, unless variant_mask narrows it)
+  int variants = in->variant_mask;
+  if (variants == 0) variants = ARC_VAR_FULL | ARC_VAR_CLEAR | (in->clean_atm_diag > 0 ? ARC_VAR_CLEAN : 0);
+  variants |= ARC_VAR_FULL | ARC_VAR_CLEAR;
+  if (in->clean_atm_diag <= 0) variants &= ~(ARC_VAR_CLEAN | ARC_VAR_CLEANCLEAR);
+  if (ext && (variants & ARC_VAR_CLEAN)) variants |= ARC_VAR_CLEANCLEAR;
+  if (!ext) variants &= ~ARC_VAR_CLEANCLEAR;
   a.variants = variants;
   a.ngroups = lw_sweep_groups();
   a.status = g.d_status;
@@ -1091,7 +1117,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
 
   const int ncol = G.ncol_tile;
   const size_t cap = std::min(outer_cap_default(), (size_t)((ncol + 255) / 256 * 256));
-  const size_t pcap = rec_limited_cap(cap, (size_t)24 * ((variants & ARC_VAR_CLEAN) ? 2 : 1) * NGLW * (nlay + 1));
+  const size_t pcap = std::min(lw_chunk_cap_default(), cap);
   if ((rc = ensure_lw_ws(nlay, cap, pcap, variants))) return rc;
   for (int o0 = 0; o0 < ncol; o0 += (int)cap) {
     const int no = std::min((int)cap, ncol - o0);
@@ -1119,13 +1145,11 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       b.col0 = o0 + c0;
       b.ws.coef += (size_t)c0 * LWC_N; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0; b.ws.laytrop += c0; b.ws.colf += c0;
       b.ws.secdiff += c0;
-      const int buf = kc & 1;
-      b.ws.rec += buf * a.ws.rec_n; b.ws.recC += buf * (a.ws.rec_n / 2);
-      b.ws.scrS += (size_t)buf * ((variants & ARC_VAR_CLEAN) ? 2 : 1) * NGLW * pcap;
-      if (g.overlap && kc >= 2) CK(cudaStreamWaitEvent(g.stream, g.ev_swept[buf], 0));      // records of chunk k-2 consumed
-      { Timed t("lw_solve"); launch_lw_solve(b, g.stream); }
+      const int buf = g.overlap ? (kc & 1) : 0;
+      b.ws.bpart += (size_t)buf * lw_sweep_groups() * (nlay + 1) * a.ws.nk * pcap;
+      if (g.overlap && kc >= 2) CK(cudaStreamWaitEvent(g.stream, g.ev_swept[buf], 0));      // partials of chunk k-2 consumed
+      { Timed t("lw_solve"); launch_lw_band(b, g.stream); }
       if (g.overlap) { CK(cudaEventRecord(g.ev_solved, g.stream)); CK(cudaStreamWaitEvent(s2, g.ev_solved, 0)); }
-      { Timed t("lw_sweep", s2); launch_lw_sweep(b, s2); }
       { Timed t("lw_reduce", s2); launch_lw_reduce(b, s2); }
       if (g.overlap) CK(cudaEventRecord(g.ev_swept[buf], s2));
     }
@@ -1457,6 +1481,35 @@ int arc_rad_selftest_pt(const float *p, const float *t, int n, int *packed) {
   if ((rc = stage_slot((size_t)n * 4, &dout))) return rc;
   launch_selftest_pt(g.D, dp, dt, n, (int *)dout, g.stream);
   CK(cudaMemcpyAsync(packed, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Self-test of glibc_math.cuh: which = 0 logf(x), 1 expf(x), 2 powf(x, y); on_device = 0 evaluates the host instantiation
+// (no GPU, no init needed), 1 the device instantiation.  The caller compares with the C library.
+__global__ void k_selftest_libm(int which, const float *__restrict__ x, const float *__restrict__ y, int n, float *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  out[t] = which == 0 ? glm::logf_(x[t]) : which == 1 ? glm::expf_(x[t]) : glm::powf_(x[t], y[t]);
+}
+int arc_rad_selftest_libm(int which, const float *x, const float *y, int n, float *out, int on_device) {
+  if (which < 0 || which > 2 || !x || !out || (which == 2 && !y) || n < 0) { g.err = "arc_rad_selftest_libm: bad argument"; return ARC_ERR_BAD_ARG; }
+  if (!on_device) {
+    for (int t = 0; t < n; t++) out[t] = which == 0 ? glm::logf_(x[t]) : which == 1 ? glm::expf_(x[t]) : glm::powf_(x[t], y[t]);
+    return 0;
+  }
+  if (!g.ready) { g.err = "arc_rad_selftest_libm: not initialised"; return ARC_ERR_NOT_INIT; }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  const float *dx, *dy = nullptr; void *dout;
+  int rc;
+  if ((rc = in_arr(ARC_MEM_HOST, x, n, &dx))) return rc;
+  if (which == 2 && (rc = in_arr(ARC_MEM_HOST, y, n, &dy))) return rc;
+  if ((rc = stage_slot((size_t)n * 4, &dout))) return rc;
+  k_selftest_libm<<<(n + 255) / 256, 256, 0, g.stream>>>(which, dx, dy, n, (float *)dout);
+  count_launch();
+  CK(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());
   return 0;

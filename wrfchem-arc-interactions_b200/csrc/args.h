@@ -56,7 +56,6 @@ inline SweepGroups make_sweep_groups(const int *ng, const int *g0, int nbands, i
 
 constexpr int REC_TILE = 128;                                     // columns per record tile = threads of a sweep block
 constexpr int SW_REC = 7 * REC_TILE, SW_REC_R = 4 * REC_TILE, SW_REC_E = 6 * REC_TILE;   // words per SW level record, offsets of R and E
-constexpr int LW_REC = 4 * REC_TILE, LW_REC_D = 2 * REC_TILE;     // LW: words per level record (float4 per lane) / per cloudy-layer record (float2)
 
 // flux "kinds" in the partial buffer: full up/down, clear up/down, clean up/down, clean-clear up/down
 enum { K_FU = 0, K_FD, K_CU, K_CD, K_NU, K_ND, K_XU, K_XD, NKIND };
@@ -146,15 +145,7 @@ struct LwWs {
   int *laytrop;            // [cap]
   float *colf;             // [LWF_N][cap]
   float *secdiff;          // [16][cap]
-  // Level-indexed records handed from k_lw_solve (taumol + downward sweep) to k_lw_sweep (upward sweep + band sum), tiled
-  // like the SW ones: [128-column tile][level][stream v][g-point][LW_REC words], v = 0 full (+ clear), 1 clean (+ clean-clear);
-  // one record = 128 lanes x float4 (atrans, bbugas, radld, radclrd): record lay + 1 holds (atrans, bbugas) of layer lay and the
-  // downward radiances (all-sky, clear-sky) at the layer's LOWER interface, so a layer writes and a sweep step reads one 2 KB piece.
-  size_t rec_n;            // words per buffer of `rec` (host-side: two buffers are carved); recC has rec_n / 2
-  float *rec;
-  float *recC;             // same tiling, 128 lanes x float2 (X, Y) of radlu' = radlu - radlu X + Y; written only where the column has cloud in the layer
-  float2 *scrS;            // [v][NGLW][pcap] upward radiances leaving the surface: (all-sky, clear-sky)
-  float *bpart;            // [sweep group][nlay+1][nk][pcap]  per-group sums of the radiances; nk = kinds in use, slot of kind k = kslot[k]
+  float *bpart;            // [band group][nlay+1][nk][pcap]  sums of the radiances over a group's g-points (k_lw_band -> k_lw_reduce); nk = kinds in use, slot of kind k = kslot[k]
   int nk; int kslot[NKIND];
 };
 
@@ -199,8 +190,8 @@ int sw_sweep_groups();
 int lw_sweep_groups();
 void launch_sw_reduce(const SwArgs &a, cudaStream_t s);
 void launch_lw_prep(const LwArgs &a, cudaStream_t s);
-void launch_lw_solve(const LwArgs &a, cudaStream_t s);
-void launch_lw_sweep(const LwArgs &a, cudaStream_t s);
+void launch_lw_band(const LwArgs &a, cudaStream_t s);
+bool lw_layout_ok();
 void launch_lw_reduce(const LwArgs &a, cudaStream_t s);
 void upload_band_descs(const HostTables &T);
 void launch_selftest_pt(const DevTables &tb, const float *p, const float *t, int n, int *packed, cudaStream_t s);

@@ -1,10 +1,26 @@
-// Longwave spectral solver: k_lw_solve = taumol (taugb1..16) + downward sweep of rtrnmc for the full and the clean
-// (aerosol-free) call, k_lw_sweep = upward sweep + ordered sum over the g-points of a band, k_lw_reduce = band sum,
-// heating rates and scatter.
+// Longwave spectral solver.  k_lw_band = taumol (taugb1..16) + both sweeps of rtrnmc for the full and the clean (aerosol-free)
+// call, one thread per (column, band group); k_lw_reduce = band sum, heating rates and scatter.
 //
 // Reference (module_ra_rrtmg_lw.F v3.9.1): taumol 4712-7828, rtrnmc 2974-3410, rrtmg_lw 10984-11044
 // (taut = taug + taua; clean rtrnmc(taug) then rtrnmc(taut)), RRTMG_LWRAD output scatter 12646-12692.
+//
+// Mapping.  The reference evaluates, per layer, everything that depends on the band only (the binary-species parameter eta,
+// its table indices js / ind0 / ind1, the interpolation weights, minor-gas columns, Planck-fraction abscissa) once and then
+// loops over the band's g-points (LW:5185-5349).  So does this kernel: a thread owns one column and the NG <= 8 consecutive
+// g-points of one band ("band group"), walks the layers, computes the band-level values once per layer and then the NG gas
+// optical depths / Planck fractions with table addresses that differ between g-points by compile-time constants only
+// (the slice layout of every band is a compile-time constant, LWK below).  Lanes = 32 neighbouring columns.
+//
+// No level records.  rtrnmc's downward and upward sweeps each need the layer transmittance and source of every layer; the
+// radiances themselves are two-term recurrences.  Instead of handing the layer quantities of the first sweep to the second
+// through memory (the round-1 design: 32 B per column x g-point x level written and read back, 73 GB per C2 step), the
+// thread makes two passes over the layers and recomputes the gas optics in the second one: top-down (downward radiances,
+// kept in registers: NG x streams x {all-sky, clear-sky}) then, from the surface, bottom-up.  The recomputation is ~35
+// instructions per (g-point, layer); the record traffic, the 19 GB of record buffers and the separate sweep kernels are gone.
+// Sums over the group's g-points are formed in index order at every level (the reference's accumulation order,
+// LW:3365-3395) and written as one partial per (group, level, kind); k_lw_reduce adds the groups in band order.
 #include "args.h"
+#include "glibc_math.cuh"
 #include "../../include/arc_rad.h"
 
 namespace arc {
@@ -12,20 +28,60 @@ namespace arc {
 static __constant__ LwBandDesc c_lw[16];
 static __constant__ int c_lw_ngb[NGLW];    // band index 0..15 of each LW g-point
 #ifndef LW_GMAX
-#define LW_GMAX 16
+#define LW_GMAX 8
 #endif
-static SweepGroups h_lw_grp;               // sweep groups, see sw_solve.cu
+static SweepGroups h_lw_grp;               // band groups: consecutive g-points of one band, at most LW_GMAX
 static __constant__ int c_lw_grp_band[SWEEP_MAXGRP];
+static __constant__ int c_lw_grp_g0[SWEEP_MAXGRP];
+static bool h_lw_layout_ok = true;
+
+// Compile-time slice layout of each band (floats inside one g-point's slice, tables.cpp; oA = 0).  The layout follows from
+// RRTMG's fixed table shapes (nspa / nspb and the minor-gas tables of each band); upload_band_descs_lw checks it against the
+// descriptors the host table builder produced.
+struct LwK { int sf, oB, oSelf, oFor, oFracA, oFracB, oCfc, mA[M_COUNT], mB[M_COUNT]; };
+#define NONE6 {-1, -1, -1, -1, -1, -1}
+static constexpr LwK LWK[16] = {
+    {408, 80, 328, 340, 344, 356, 404, {364, -1, -1, -1, -1, -1}, {384, -1, -1, -1, -1, -1}},
+    {368, 80, 328, 340, 344, 356, 364, NONE6, NONE6},
+    {2096, 600, 1788, 1800, 1804, 1816, 2092, {-1, 1824, -1, -1, -1, -1}, {-1, 1996, -1, -1, -1, -1}},
+    {1828, 600, 1788, 1800, 1804, 1816, 1824, NONE6, NONE6},
+    {2000, 600, 1788, 1800, 1804, 1816, 1996, {-1, -1, 1824, -1, -1, -1}, NONE6},
+    {152, 80, 92, 104, 108, 120, 148, {-1, -1, -1, 128, -1, -1}, NONE6},
+    {1080, 600, 848, 860, 864, 876, 1076, {-1, -1, -1, 884, -1, -1}, {-1, -1, -1, 1056, -1, -1}},
+    {468, 80, 328, 340, 344, 356, 464, {-1, 364, 404, 424, -1, -1}, {-1, 384, -1, 444, -1, -1}},
+    {1080, 600, 848, 860, 864, 876, 1076, {-1, 884, -1, -1, -1, -1}, {-1, 1056, -1, -1, -1, -1}},
+    {368, 80, 328, 340, 344, 356, 364, NONE6, NONE6},
+    {408, 80, 328, 340, 344, 356, 404, {-1, -1, -1, -1, -1, 364}, {-1, -1, -1, -1, -1, 384}},
+    {652, 600, 612, 624, 628, 640, 648, NONE6, NONE6},
+    {1016, 600, 612, 624, 628, 640, 1012, {-1, -1, -1, 668, 840, -1}, {-1, -1, 648, -1, -1, -1}},
+    {368, 80, 328, 340, 344, 356, 364, NONE6, NONE6},
+    {824, 600, 612, 624, 628, 640, 820, {648, -1, -1, -1, -1, -1}, NONE6},
+    {888, 600, 848, 860, 864, 876, 884, NONE6, NONE6}};
+#undef NONE6
+constexpr int LW_SLICE_MAX = 2096;
+
 void upload_band_descs_lw(const HostTables &T) {
   cudaMemcpyToSymbol(c_lw, T.lw, sizeof(LwBandDesc) * 16);
   int ngs[16], g0s[16];
   for (int b = 0; b < 16; b++) { ngs[b] = T.lw[b].ng; g0s[b] = T.lw[b].g0; }
   h_lw_grp = make_sweep_groups(ngs, g0s, 16, LW_GMAX);
   cudaMemcpyToSymbol(c_lw_grp_band, h_lw_grp.band, sizeof(int) * SWEEP_MAXGRP);
+  cudaMemcpyToSymbol(c_lw_grp_g0, h_lw_grp.g0, sizeof(int) * SWEEP_MAXGRP);
   int ngb[NGLW];
   for (int i = 0; i < NGLW; i++) ngb[i] = T.lw_ngb[i] - 1;
   cudaMemcpyToSymbol(c_lw_ngb, ngb, sizeof(int) * NGLW);
+  h_lw_layout_ok = true;
+  const int ngc[16] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
+  for (int b = 0; b < 16; b++) {
+    const LwBandDesc &D = T.lw[b];
+    const LwK &K = LWK[b];
+    bool ok = D.slice_floats == K.sf && D.oA == 0 && D.oB == K.oB && D.oSelf == K.oSelf && D.oFor == K.oFor && D.oFracA == K.oFracA &&
+              D.oFracB == K.oFracB && D.oCfc == K.oCfc && D.ng == ngc[b];
+    for (int m = 0; m < M_COUNT; m++) ok = ok && D.oMinA[m] == K.mA[m] && D.oMinB[m] == K.mB[m];
+    if (!ok) h_lw_layout_ok = false;
+  }
 }
+bool lw_layout_ok() { return h_lw_layout_ok; }
 
 struct LwEta { float speccomb, specparm, f; int j; };
 
@@ -41,89 +97,437 @@ __device__ __forceinline__ LwEta lw_eta(float cola, float ratio, float colb, flo
 }
 __device__ __forceinline__ float pow4f(float p) { const float p2 = p * p; return p2 * p2; }
 
-// lower-atmosphere major-species term of the binary bands for one pressure level (LW:5219-5349)
-__device__ __forceinline__ float lw_major_lower(const float *__restrict__ A, const LwEta &e, int ind, float fa, float fb) {
-  const float *p = A + ind - 1;
+// Stencil of the lower-atmosphere major-species interpolation in eta at one pressure level (LW:5219-5349): three table
+// entries from offset `o` (relative to the (p, T) row) with weights w[0..2]; the usual 2-point interpolation has w[2] = 0.
+struct LwStencil { int o; float w0, w1, w2; bool three; };
+__device__ __forceinline__ LwStencil lw_stencil(const LwEta &e) {
+  LwStencil s;
   if (e.specparm < 0.125f) {
     const float q = e.f - 1;
     const float p4 = pow4f(q);
-    const float fk0 = p4, fk1 = 1 - q - 2.0f * p4, fk2 = q + p4;
-    return e.speccomb * ((fk0 * fa) * p[0] + (fk1 * fa) * p[1] + (fk2 * fa) * p[2] + (fk0 * fb) * p[9] + (fk1 * fb) * p[10] + (fk2 * fb) * p[11]);
+    s.o = e.j - 1; s.w0 = p4; s.w1 = 1 - q - 2.0f * p4; s.w2 = q + p4; s.three = true;
   } else if (e.specparm > 0.875f) {
     const float q = -e.f;
     const float p4 = pow4f(q);
-    const float fk0 = p4, fk1 = 1 - q - 2.0f * p4, fk2 = q + p4;
-    return e.speccomb * ((fk2 * fa) * p[-1] + (fk1 * fa) * p[0] + (fk0 * fa) * p[1] + (fk2 * fb) * p[8] + (fk1 * fb) * p[9] + (fk0 * fb) * p[10]);
+    s.o = e.j - 2; s.w0 = q + p4; s.w1 = 1 - q - 2.0f * p4; s.w2 = p4; s.three = true;
   } else {
-    const float f1 = 1.f - e.f;
-    return e.speccomb * ((f1 * fa) * p[0] + (e.f * fa) * p[1] + (f1 * fb) * p[9] + (e.f * fb) * p[10]);
+    s.o = e.j - 1; s.w0 = 1.f - e.f; s.w1 = e.f; s.w2 = 0.f; s.three = false;
   }
+  return s;
 }
 
 #ifndef LW_BLOCK_SZ
 #define LW_BLOCK_SZ 512
 #endif
-constexpr int LW_BLOCK = LW_BLOCK_SZ;   // 91 KB of staged tables per block: two blocks per SM
+constexpr int LW_BLOCK = LW_BLOCK_SZ;   // one block per SM: 80 KB exp / tfn table + up to 67 KB of g-point slices
 struct LwSmem { const float2 *et; const float *S, *plk, *rat, *chi; };
 
-// One (column, g-point) of band BAND: taumol + both rtrnmc calls.  BAND is a template parameter so that each band's
-// instantiation only contains (and requests up front) the workspace loads and the table arithmetic of that band.
-template <int NL, int BAND>
-__device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm, const LwBandDesc &D, int g, int c) {
-  const float2 *s_et = sm.et;
-  const float *S = sm.S, *s_plk = sm.plk, *s_rat = sm.rat, *s_chi = sm.chi;
-  const DevTables &tb = a.tb;
-  constexpr int band = BAND;
+// Band-level values of one layer: everything taumol computes before its loop over g-points (LW:5185-5230 and the
+// corresponding lines of every taugbN).  Pointers address g-point 0 of the group; g-point i is `+ i * slice floats`.
+struct LwBL {
+  bool low, three, any3;       // three: this lane uses the 3-point eta stencil; any3: some lane of the warp does
+  float fac00, fac01, fac10, fac11;
+  const float *pA0, *pA1;                  // major-species rows at (jp, jt) and (jp+1, jt1), eta stencil offset included
+  float a0, a1, a2, b0, b1, b2, c0, c1, c2, d0, d1, d2;   // eta stencil weights x fac00 / fac10 (level jp) and x fac01 / fac11 (level jp+1)
+  float sc0, sc1;                          // speccomb at the two levels (binary bands) / key-species column (others)
+  const float *pSelf, *pFor, *pM0, *pM1, *pM2, *pFrac, *pCfc;
+  float selffac, selffrac, forfac, forfrac, minorfrac, fm0, fm1, fFrac;
+  float x0, x1, x2, x3, x4;                // band-specific scalars (rescaled minor columns, CFC columns, pressure correction)
+};
+
+// Gas optical depth and Planck fraction of g-point i of the group (off = i * slice floats, ig = 1-based g-point inside the
+// band).  Expressions and operation order are those of taugb1..16 (LW:4961-7826).
+template <int BAND>
+__device__ __forceinline__ void lw_gas(const LwBL &L, const int off, const int ig, float &taug, float &fracs) {
+  auto selfk = [&]() { const float *r = L.pSelf + off; return L.selffac * (r[0] + L.selffrac * (r[1] - r[0])); };
+  auto fork = [&]() { const float *r = L.pFor + off; return L.forfac * (r[0] + L.forfrac * (r[1] - r[0])); };
+  auto minor1 = [&](const float *p) { const float *r = p + off; return r[0] + L.minorfrac * (r[1] - r[0]); };
+  auto minor2 = [&](const float *p, int ne, float fm) {
+    const float *r = p + off;
+    const float m1 = r[0] + fm * (r[1] - r[0]);
+    const float m2 = r[ne] + fm * (r[ne + 1] - r[ne]);
+    return m1 + L.minorfrac * (m2 - m1);
+  };
+  auto k4 = [&]() { const float *q0 = L.pA0 + off, *q1 = L.pA1 + off; return L.fac00 * q0[0] + L.fac10 * q0[1] + L.fac01 * q1[0] + L.fac11 * q1[1]; };
+  // binary bands, lower atmosphere: eta stencil at both pressure levels, T stride 9 (LW:5219-5349)
+  auto major_lower2 = [&]() {
+    const float *p = L.pA0 + off, *q = L.pA1 + off;
+    if (L.any3)     // warp-uniform: some lane sits in the 3-point region (eta < 0.125 or > 0.875); the others carry a zero weight
+      return L.sc0 * (L.a0 * p[0] + L.a1 * p[1] + L.a2 * p[2] + L.b0 * p[9] + L.b1 * p[10] + L.b2 * p[11]) +
+             L.sc1 * (L.c0 * q[0] + L.c1 * q[1] + L.c2 * q[2] + L.d0 * q[9] + L.d1 * q[10] + L.d2 * q[11]);
+    return L.sc0 * (L.a0 * p[0] + L.a1 * p[1] + L.b0 * p[9] + L.b1 * p[10]) + L.sc1 * (L.c0 * q[0] + L.c1 * q[1] + L.d0 * q[9] + L.d1 * q[10]);
+  };
+  // binary bands, upper atmosphere: 2-point eta interpolation, T stride 5
+  auto major_upper = [&]() {
+    const float *p = L.pA0 + off, *q = L.pA1 + off;
+    return L.sc0 * (L.a0 * p[0] + L.a1 * p[1] + L.b0 * p[5] + L.b1 * p[6]) + L.sc1 * (L.c0 * q[0] + L.c1 * q[1] + L.d0 * q[5] + L.d1 * q[6]);
+  };
+  auto frac_eta = [&]() { const float *r = L.pFrac + off; return r[0] + L.fFrac * (r[1] - r[0]); };
+  auto frac1 = [&]() { return L.pFrac[off]; };
+  auto cfc = [&](int k) { return L.pCfc[off + k]; };
+
+  taug = 0.f; fracs = 0.f;
+  if (BAND == 1) {                           // x0 = colbrd * scaleminorn2, x4 = corradj
+    if (L.low) taug = L.x4 * (L.sc0 * k4() + selfk() + fork() + L.x0 * minor1(L.pM0));
+    else taug = L.x4 * (L.sc0 * k4() + fork() + L.x0 * minor1(L.pM0));
+    fracs = frac1();
+  } else if (BAND == 2) {
+    if (L.low) taug = L.x4 * (L.sc0 * k4() + selfk() + fork());
+    else taug = L.sc0 * k4() + fork();
+    fracs = frac1();
+  } else if (BAND == 3) {                    // x0 = adjcoln2o
+    if (L.low) taug = major_lower2() + selfk() + fork() + L.x0 * minor2(L.pM0, 9, L.fm0);
+    else taug = major_upper() + fork() + L.x0 * minor2(L.pM0, 5, L.fm0);
+    fracs = frac_eta();
+  } else if (BAND == 4) {
+    if (L.low) taug = major_lower2() + selfk() + fork();
+    else {
+      taug = major_upper();
+      if (ig == 8) taug = taug * 0.92f; else if (ig == 9) taug = taug * 0.88f; else if (ig == 10) taug = taug * 1.07f;
+      else if (ig == 11) taug = taug * 1.1f; else if (ig == 12) taug = taug * 0.99f; else if (ig == 13) taug = taug * 0.88f;
+      else if (ig == 14) taug = taug * 0.943f;
+    }
+    fracs = frac_eta();
+  } else if (BAND == 5) {                    // x0 = wx(ccl4), x1 = colo3
+    if (L.low) taug = major_lower2() + selfk() + fork() + minor2(L.pM0, 9, L.fm0) * L.x1 + L.x0 * cfc(0);
+    else taug = major_upper() + L.x0 * cfc(0);
+    fracs = frac_eta();
+  } else if (BAND == 6) {                    // x0 = wx(cfc11), x1 = wx(cfc12), x2 = adjcolco2
+    if (L.low) taug = L.sc0 * k4() + selfk() + fork() + L.x2 * minor1(L.pM0) + L.x0 * cfc(1) + L.x1 * cfc(2);
+    else taug = 0.0f + L.x0 * cfc(1) + L.x1 * cfc(2);
+    fracs = frac1();
+  } else if (BAND == 7) {                    // x0 = adjcolco2
+    if (L.low) { taug = major_lower2() + selfk() + fork() + L.x0 * minor2(L.pM0, 9, L.fm0); fracs = frac_eta(); }
+    else {
+      taug = L.sc0 * k4() + L.x0 * minor1(L.pM0);
+      fracs = frac1();
+      if (ig == 6) taug = taug * 0.92f; else if (ig == 7) taug = taug * 0.88f; else if (ig == 8) taug = taug * 1.07f;
+      else if (ig == 9) taug = taug * 1.1f; else if (ig == 10) taug = taug * 0.99f; else if (ig == 11) taug = taug * 0.855f;
+    }
+  } else if (BAND == 8) {                    // x0 = adjcolco2, x1 = colo3, x2 = coln2o, x3 = wx(cfc12), x4 = wx(cfc22); pM0 CO2, pM1 O3, pM2 N2O
+    if (L.low) taug = L.sc0 * k4() + selfk() + fork() + L.x0 * minor1(L.pM0) + L.x1 * minor1(L.pM1) + L.x2 * minor1(L.pM2) + L.x3 * cfc(2) + L.x4 * cfc(3);
+    else taug = L.sc0 * k4() + L.x0 * minor1(L.pM0) + L.x2 * minor1(L.pM2) + L.x3 * cfc(2) + L.x4 * cfc(3);
+    fracs = frac1();
+  } else if (BAND == 9) {                    // x0 = adjcoln2o
+    if (L.low) { taug = major_lower2() + selfk() + fork() + L.x0 * minor2(L.pM0, 9, L.fm0); fracs = frac_eta(); }
+    else { taug = L.sc0 * k4() + L.x0 * minor1(L.pM0); fracs = frac1(); }
+  } else if (BAND == 10) {
+    if (L.low) taug = L.sc0 * k4() + selfk() + fork();
+    else taug = L.sc0 * k4() + fork();
+    fracs = frac1();
+  } else if (BAND == 11) {                   // x0 = colo2 * scaleminor
+    float t;
+    if (L.low) t = L.sc0 * k4() + selfk() + fork();
+    else t = L.sc0 * k4() + fork();
+    taug = t + L.x0 * minor1(L.pM0);
+    fracs = frac1();
+  } else if (BAND == 12) {
+    if (L.low) { taug = major_lower2() + selfk() + fork(); fracs = frac_eta(); }
+  } else if (BAND == 13) {                   // x0 = adjcolco2 (lower) / colo3 (upper), x1 = colco; pM0 CO2 / O3, pM1 CO
+    if (L.low) {
+      taug = major_lower2() + selfk() + fork() + L.x0 * minor2(L.pM0, 9, L.fm0) + L.x1 * minor2(L.pM1, 9, L.fm1);
+      fracs = frac_eta();
+    } else { taug = L.x0 * minor1(L.pM0); fracs = frac1(); }
+  } else if (BAND == 14) {
+    if (L.low) taug = L.sc0 * k4() + selfk() + fork();
+    else taug = L.sc0 * k4();
+    fracs = frac1();
+  } else if (BAND == 15) {                   // x0 = colbrd * scaleminor
+    if (L.low) { taug = major_lower2() + selfk() + fork() + L.x0 * minor2(L.pM0, 9, L.fm0); fracs = frac_eta(); }
+  } else {                                   // 16
+    if (L.low) { taug = major_lower2() + selfk() + fork(); fracs = frac_eta(); }
+    else { taug = L.sc0 * k4(); fracs = frac1(); }
+  }
+}
+
+// Band-level setup of one layer from the layer's workspace fields fv[] (prep.cu).  S0 = slice of the group's first g-point.
+template <int BAND>
+__device__ __forceinline__ void lw_setup(const float (&fv)[LWC_N], const LwSmem &sm, const float *__restrict__ S0, const bool low, const float oneminus,
+                                         const float (&rc)[5], LwBL &L) {
+  constexpr LwK K = LWK[BAND - 1];
+  const float *s_rat = sm.rat, *s_chi = sm.chi;
+  auto CHI = [&](int imol, int jp) { return s_chi[(imol - 1) + 7 * (jp - 1)]; };   // 1-based like the reference
+  auto RAT = [&](int r, int jpp) { return s_rat[r * 60 + jpp - 1]; };
+  const int pk = __float_as_int(fv[LWC_IDX]);
+  const int jp = IDX_JP(pk), jt = IDX_JT(pk), jt1 = IDX_JT1(pk), indself = IDX_SELF(pk), indfor = IDX_FOR(pk), indminor = IDX_MINOR(pk);
+  L.low = low; L.three = false; L.any3 = false;
+  L.fac00 = fv[LWC_FAC00]; L.fac01 = fv[LWC_FAC01]; L.fac10 = fv[LWC_FAC10]; L.fac11 = fv[LWC_FAC11];
+  L.selffac = fv[LWC_SELFFAC]; L.selffrac = fv[LWC_SELFFRAC]; L.forfac = fv[LWC_FORFAC]; L.forfrac = fv[LWC_FORFRAC];
+  L.minorfrac = fv[LWC_MINORFRAC];
+  L.pSelf = S0 + K.oSelf + indself - 1;
+  L.pFor = S0 + K.oFor + indfor - 1;
+  L.pCfc = S0 + K.oCfc;
+  L.pM0 = L.pM1 = L.pM2 = S0; L.fm0 = L.fm1 = 0.f; L.fFrac = 0.f;
+  L.x0 = L.x1 = L.x2 = L.x3 = L.x4 = 0.f; L.sc0 = L.sc1 = 0.f;
+  // single-key-species rows (k4): 4 points, the two T rows are neighbours
+  auto rows4 = [&]() {
+    if (low) { L.pA0 = S0 + ((jp - 1) * 5 + (jt - 1)); L.pA1 = S0 + (jp * 5 + (jt1 - 1)); }
+    else { L.pA0 = S0 + K.oB + ((jp - 13) * 5 + (jt - 1)); L.pA1 = S0 + K.oB + ((jp - 12) * 5 + (jt1 - 1)); }
+  };
+  // binary-species rows: eta at the two pressure levels
+  auto rows_bin = [&](const LwEta &e, const LwEta &e1) {
+    L.sc0 = e.speccomb; L.sc1 = e1.speccomb;
+    if (low) {
+      const LwStencil s0 = lw_stencil(e), s1 = lw_stencil(e1);
+      L.pA0 = S0 + ((jp - 1) * 5 + (jt - 1)) * 9 + s0.o;
+      L.pA1 = S0 + (jp * 5 + (jt1 - 1)) * 9 + s1.o;
+      L.a0 = s0.w0 * L.fac00; L.a1 = s0.w1 * L.fac00; L.a2 = s0.w2 * L.fac00;
+      L.b0 = s0.w0 * L.fac10; L.b1 = s0.w1 * L.fac10; L.b2 = s0.w2 * L.fac10;
+      L.c0 = s1.w0 * L.fac01; L.c1 = s1.w1 * L.fac01; L.c2 = s1.w2 * L.fac01;
+      L.d0 = s1.w0 * L.fac11; L.d1 = s1.w1 * L.fac11; L.d2 = s1.w2 * L.fac11;
+      L.three = s0.three || s1.three;
+    } else {
+      const float f0 = 1.f - e.f, f1 = 1.f - e1.f;
+      L.pA0 = S0 + K.oB + ((jp - 13) * 5 + (jt - 1)) * 5 + e.j - 1;
+      L.pA1 = S0 + K.oB + ((jp - 12) * 5 + (jt1 - 1)) * 5 + e1.j - 1;
+      L.a0 = f0 * L.fac00; L.a1 = e.f * L.fac00; L.b0 = f0 * L.fac10; L.b1 = e.f * L.fac10;
+      L.c0 = f1 * L.fac01; L.c1 = e1.f * L.fac01; L.d0 = f1 * L.fac11; L.d1 = e1.f * L.fac11;
+    }
+  };
+  auto set_frac_eta = [&](int o, const LwEta &ep) { L.pFrac = S0 + o + ep.j - 1; L.fFrac = ep.f; };
+  auto set_minor1 = [&](const float *&p, int o) { p = S0 + o + indminor - 1; };
+  auto set_minor2 = [&](const float *&p, float &fm, int o, int ne, const LwEta &em) { p = S0 + o + (em.j - 1) + ne * (indminor - 1); fm = em.f; };
+  // empirical column rescaling of a minor gas (e.g. LW:5208-5216)
+  auto adjcol = [&](float col, int imol, float thresh, float base, float expo) {
+    const float coldry = fv[LWC_COLDRY];
+    const float chim = CHI(imol, jp + 1);
+    const float chi = col / coldry;
+    const float rat = 1.e20f * chi / chim;
+    if (rat > thresh) {
+      const float adjfac = base + glm::powf_(rat - base, expo);
+      return adjfac * chim * coldry * 1.e-20f;
+    }
+    return col;
+  };
+  auto WX = [&](float vmr) { return fv[LWC_COLDRY] * vmr * 1.e-20f; };
+  const float vccl4 = 0.093e-9f, vcfc11 = 0.251e-9f, vcfc12 = 0.538e-9f, vcfc22 = 0.169e-9f;
+  // rc[] = reference ratios at fixed pressure levels: 0 rp_a, 1 rp_b, 2 rm_a, 3 rm_b, 4 rm_a3
+  L.pFrac = S0 + (low ? K.oFracA : K.oFracB);
+
+  if (BAND == 1) {
+    const float pp = fv[LWC_PAVEL];
+    L.x0 = fv[LWC_BRD] * fv[LWC_SCALEMINORN2];
+    L.sc0 = fv[LWC_H2O]; rows4();
+    if (low) { float corradj = 1.f; if (pp < 250.f) corradj = 1.f - 0.15f * (250.f - pp) / 154.4f; L.x4 = corradj; set_minor1(L.pM0, K.mA[M_N2]); }
+    else { L.x4 = 1.f - 0.15f * (pp / 95.6f); set_minor1(L.pM0, K.mB[M_N2]); }
+  } else if (BAND == 2) {
+    L.sc0 = fv[LWC_H2O]; rows4();
+    if (low) { const float pp = fv[LWC_PAVEL]; L.x4 = 1.f - .05f * (pp - 100.f) / 900.f; }
+  } else if (BAND == 3) {
+    const float h2o = fv[LWC_H2O], co2 = fv[LWC_CO2];
+    const float mult = low ? 8.f : 4.f;
+    const LwEta e = lw_eta(h2o, RAT(0, jp), co2, mult, oneminus), e1 = lw_eta(h2o, RAT(0, jp + 1), co2, mult, oneminus);
+    const LwEta em = lw_eta(h2o, low ? rc[2] : rc[3], co2, mult, oneminus);
+    const LwEta ep = lw_eta(h2o, low ? rc[0] : rc[1], co2, mult, oneminus);
+    L.x0 = adjcol(fv[LWC_N2O], 4, 1.5f, 0.5f, 0.65f);
+    rows_bin(e, e1);
+    if (low) { set_minor2(L.pM0, L.fm0, K.mA[M_N2O], 9, em); set_frac_eta(K.oFracA, ep); }
+    else { set_minor2(L.pM0, L.fm0, K.mB[M_N2O], 5, em); set_frac_eta(K.oFracB, ep); }
+  } else if (BAND == 4) {
+    const float co2 = fv[LWC_CO2];
+    if (low) {
+      const float h2o = fv[LWC_H2O];
+      const LwEta e = lw_eta(h2o, RAT(0, jp), co2, 8.f, oneminus), e1 = lw_eta(h2o, RAT(0, jp + 1), co2, 8.f, oneminus);
+      const LwEta ep = lw_eta(h2o, rc[0], co2, 8.f, oneminus);
+      rows_bin(e, e1); set_frac_eta(K.oFracA, ep);
+    } else {
+      const float o3 = fv[LWC_O3];
+      const LwEta e = lw_eta(o3, RAT(5, jp), co2, 4.f, oneminus), e1 = lw_eta(o3, RAT(5, jp + 1), co2, 4.f, oneminus);
+      const LwEta ep = lw_eta(o3, rc[1], co2, 4.f, oneminus);
+      rows_bin(e, e1); set_frac_eta(K.oFracB, ep);
+    }
+  } else if (BAND == 5) {
+    const float co2 = fv[LWC_CO2];
+    L.x0 = WX(vccl4);
+    if (low) {
+      const float h2o = fv[LWC_H2O];
+      const LwEta e = lw_eta(h2o, RAT(0, jp), co2, 8.f, oneminus), e1 = lw_eta(h2o, RAT(0, jp + 1), co2, 8.f, oneminus);
+      const LwEta em = lw_eta(h2o, rc[2], co2, 8.f, oneminus), ep = lw_eta(h2o, rc[0], co2, 8.f, oneminus);
+      L.x1 = fv[LWC_O3];
+      rows_bin(e, e1); set_minor2(L.pM0, L.fm0, K.mA[M_O3], 9, em); set_frac_eta(K.oFracA, ep);
+    } else {
+      const float o3 = fv[LWC_O3];
+      const LwEta e = lw_eta(o3, RAT(5, jp), co2, 4.f, oneminus), e1 = lw_eta(o3, RAT(5, jp + 1), co2, 4.f, oneminus);
+      const LwEta ep = lw_eta(o3, rc[1], co2, 4.f, oneminus);
+      rows_bin(e, e1); set_frac_eta(K.oFracB, ep);
+    }
+  } else if (BAND == 6) {
+    L.x0 = WX(vcfc11); L.x1 = WX(vcfc12);
+    L.pFrac = S0 + K.oFracA;
+    if (low) { L.x2 = adjcol(fv[LWC_CO2], 2, 3.0f, 2.0f, 0.77f); L.sc0 = fv[LWC_H2O]; rows4(); set_minor1(L.pM0, K.mA[M_CO2]); }
+    else { L.pA0 = L.pA1 = S0; }
+  } else if (BAND == 7) {
+    if (low) {
+      const float h2o = fv[LWC_H2O], o3 = fv[LWC_O3];
+      const LwEta e = lw_eta(h2o, RAT(1, jp), o3, 8.f, oneminus), e1 = lw_eta(h2o, RAT(1, jp + 1), o3, 8.f, oneminus);
+      const LwEta em = lw_eta(h2o, rc[2], o3, 8.f, oneminus), ep = lw_eta(h2o, rc[0], o3, 8.f, oneminus);
+      L.x0 = adjcol(fv[LWC_CO2], 2, 3.0f, 3.0f, 0.79f);
+      rows_bin(e, e1); set_minor2(L.pM0, L.fm0, K.mA[M_CO2], 9, em); set_frac_eta(K.oFracA, ep);
+    } else {
+      L.x0 = adjcol(fv[LWC_CO2], 2, 3.0f, 2.0f, 0.79f);
+      L.sc0 = fv[LWC_O3]; rows4(); set_minor1(L.pM0, K.mB[M_CO2]);
+    }
+  } else if (BAND == 8) {
+    L.x0 = adjcol(fv[LWC_CO2], 2, 3.0f, 2.0f, 0.65f);
+    L.x1 = fv[LWC_O3]; L.x2 = fv[LWC_N2O]; L.x3 = WX(vcfc12); L.x4 = WX(vcfc22);
+    rows4();
+    if (low) { L.sc0 = fv[LWC_H2O]; set_minor1(L.pM0, K.mA[M_CO2]); set_minor1(L.pM1, K.mA[M_O3]); set_minor1(L.pM2, K.mA[M_N2O]); }
+    else { L.sc0 = fv[LWC_O3]; set_minor1(L.pM0, K.mB[M_CO2]); set_minor1(L.pM2, K.mB[M_N2O]); }
+  } else if (BAND == 9) {
+    L.x0 = adjcol(fv[LWC_N2O], 4, 1.5f, 0.5f, 0.65f);
+    if (low) {
+      const float h2o = fv[LWC_H2O], ch4 = fv[LWC_CH4];
+      const LwEta e = lw_eta(h2o, RAT(3, jp), ch4, 8.f, oneminus), e1 = lw_eta(h2o, RAT(3, jp + 1), ch4, 8.f, oneminus);
+      const LwEta em = lw_eta(h2o, rc[2], ch4, 8.f, oneminus), ep = lw_eta(h2o, rc[0], ch4, 8.f, oneminus);
+      rows_bin(e, e1); set_minor2(L.pM0, L.fm0, K.mA[M_N2O], 9, em); set_frac_eta(K.oFracA, ep);
+    } else { L.sc0 = fv[LWC_CH4]; rows4(); set_minor1(L.pM0, K.mB[M_N2O]); }
+  } else if (BAND == 10) {
+    L.sc0 = fv[LWC_H2O]; rows4();
+  } else if (BAND == 11) {
+    L.sc0 = fv[LWC_H2O]; rows4();
+    L.x0 = fv[LWC_O2] * fv[LWC_SCALEMINOR];
+    set_minor1(L.pM0, low ? K.mA[M_O2] : K.mB[M_O2]);
+  } else if (BAND == 12) {
+    if (low) {
+      const float h2o = fv[LWC_H2O], co2 = fv[LWC_CO2];
+      const LwEta e = lw_eta(h2o, RAT(0, jp), co2, 8.f, oneminus), e1 = lw_eta(h2o, RAT(0, jp + 1), co2, 8.f, oneminus);
+      const LwEta ep = lw_eta(h2o, rc[0], co2, 8.f, oneminus);
+      rows_bin(e, e1); set_frac_eta(K.oFracA, ep);
+    } else { L.pA0 = L.pA1 = S0; }
+  } else if (BAND == 13) {
+    if (low) {
+      const float h2o = fv[LWC_H2O], n2o = fv[LWC_N2O], co2 = fv[LWC_CO2], coldry = fv[LWC_COLDRY];
+      const LwEta e = lw_eta(h2o, RAT(2, jp), n2o, 8.f, oneminus), e1 = lw_eta(h2o, RAT(2, jp + 1), n2o, 8.f, oneminus);
+      const LwEta em = lw_eta(h2o, rc[2], n2o, 8.f, oneminus), eco = lw_eta(h2o, rc[4], n2o, 8.f, oneminus);
+      const LwEta ep = lw_eta(h2o, rc[0], n2o, 8.f, oneminus);
+      const float chi_co2 = co2 / coldry;
+      const float ratco2 = 1.e20f * chi_co2 / 3.55e-4f;
+      if (ratco2 > 3.0f) { const float adjfac = 2.0f + glm::powf_(ratco2 - 2.0f, 0.68f); L.x0 = adjfac * 3.55e-4f * coldry * 1.e-20f; }
+      else L.x0 = co2;
+      L.x1 = fv[LWC_CO];
+      rows_bin(e, e1);
+      set_minor2(L.pM0, L.fm0, K.mA[M_CO2], 9, em); set_minor2(L.pM1, L.fm1, K.mA[M_CO], 9, eco); set_frac_eta(K.oFracA, ep);
+    } else { L.x0 = fv[LWC_O3]; L.pA0 = L.pA1 = S0; set_minor1(L.pM0, K.mB[M_O3]); }
+  } else if (BAND == 14) {
+    L.sc0 = fv[LWC_CO2]; rows4();
+  } else if (BAND == 15) {
+    if (low) {
+      const float n2o = fv[LWC_N2O], co2 = fv[LWC_CO2];
+      const LwEta e = lw_eta(n2o, RAT(4, jp), co2, 8.f, oneminus), e1 = lw_eta(n2o, RAT(4, jp + 1), co2, 8.f, oneminus);
+      const LwEta em = lw_eta(n2o, rc[2], co2, 8.f, oneminus), ep = lw_eta(n2o, rc[0], co2, 8.f, oneminus);
+      L.x0 = fv[LWC_BRD] * fv[LWC_SCALEMINOR];
+      rows_bin(e, e1); set_minor2(L.pM0, L.fm0, K.mA[M_N2], 9, em); set_frac_eta(K.oFracA, ep);
+    } else { L.pA0 = L.pA1 = S0; }
+  } else {  // 16
+    if (low) {
+      const float h2o = fv[LWC_H2O], ch4 = fv[LWC_CH4];
+      const LwEta e = lw_eta(h2o, RAT(3, jp), ch4, 8.f, oneminus), e1 = lw_eta(h2o, RAT(3, jp + 1), ch4, 8.f, oneminus);
+      const LwEta ep = lw_eta(h2o, rc[0], ch4, 8.f, oneminus);
+      rows_bin(e, e1); set_frac_eta(K.oFracA, ep);
+    } else { L.sc0 = fv[LWC_CH4]; rows4(); }
+  }
+}
+
+// One layer of rtrnmc for one g-point and stream (LW:3207-3300 downward with dplank = dplankdn, 3322-3356 upward with
+// dplank = dplankup): gas-only transmittance `atrans` and source function `bb`, and where the column has cloud in the layer
+// the terms of  rad' = rad - rad * X + src + Z.  The exponentials are table look-ups as in the reference.
+template <bool UP>
+__device__ __forceinline__ void lw_rt(const float2 *__restrict__ s_et, const float bpade, float odepth, const bool icldlyr, const float odcld,
+                                      const float efclfrac, const float cldfmc, const float plfrac, const float blay, const float dplank,
+                                      float &atrans, float &bb, float &X, float &src, float &Z) {
+  if (icldlyr) {
+    float odtot = odepth + odcld;
+    float bbtot, atot;
+    if (odtot < 0.06f) {
+      atrans = odepth - 0.5f * odepth * odepth;
+      const float odepth_rec = 0.166667f * odepth;
+      bb = plfrac * (blay + dplank * odepth_rec);
+      src = bb * atrans;
+      atot = odtot - 0.5f * odtot * odtot;
+      const float odtot_rec = 0.166667f * odtot;
+      bbtot = plfrac * (blay + dplank * odtot_rec);
+    } else if (odepth <= 0.06f) {
+      atrans = odepth - 0.5f * odepth * odepth;
+      const float odepth_rec = 0.166667f * odepth;
+      bb = plfrac * (blay + dplank * odepth_rec);
+      src = bb * atrans;
+      const float tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
+      const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
+      const float2 et = s_et[ittot];
+      bbtot = plfrac * (blay + et.y * dplank);
+      atot = 1.f - et.x;
+    } else {
+      float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
+      const int itgas = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
+      // tau_tbl(itgas) recomputed with the table generator's arithmetic (LW:7944-7950)
+      if (itgas >= 10000) odepth = 1.e10f;
+      else { const float tfn = div_rn((float)itgas, 10000.0f); odepth = div_rn(__fmul_rn(bpade, tfn), __fsub_rn(1.0f, tfn)); }
+      const float2 eg = s_et[itgas];
+      atrans = 1.f - eg.x;
+      const float tfacgas = eg.y;
+      bb = plfrac * (blay + tfacgas * dplank);
+      src = UP ? bb * atrans : atrans * plfrac * (blay + tfacgas * dplank);
+      odtot = odepth + odcld;
+      tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
+      const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
+      const float2 et = s_et[ittot];
+      bbtot = plfrac * (blay + et.y * dplank);
+      atot = 1.f - et.x;
+    }
+    X = atrans + efclfrac * (1.f - atrans);
+    Z = cldfmc * (bbtot * atot - src);
+  } else {
+    if (odepth <= 0.06f) {
+      atrans = odepth - 0.5f * odepth * odepth;
+      odepth = 0.166667f * odepth;
+      bb = plfrac * (blay + dplank * odepth);
+    } else {
+      const float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
+      const int itr = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
+      const float2 et = s_et[itr];
+      atrans = 1.f - et.x;
+      bb = plfrac * (blay + et.y * dplank);
+    }
+    X = 0.f; src = 0.f; Z = 0.f;
+  }
+}
+
+// One (column, band group): NG consecutive g-points of band BAND starting at g-point g0 (absolute index).
+template <int BAND, int NG>
+__device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, const int grp, const int g0, const int c, const bool live) {
+  constexpr LwK K = LWK[BAND - 1];
+  constexpr int SF = K.sf;
   constexpr int b = BAND - 1;
+  const float2 *s_et = sm.et;
+  const float *S0 = sm.S, *s_plk = sm.plk, *s_chi = sm.chi;
+  const DevTables &tb = a.tb;
   const LwWs &ws = a.ws;
-  const int nlay = ws.nlay;
-  const size_t cap = ws.cap;
+  const int nlay = ws.nlay, nk = ws.nk;
+  const size_t cap = ws.cap, pcap = ws.pcap;
   const float bpade = tb.bpade, oneminus = tb.oneminus;
   const bool do_clean = (a.variants & ARC_VAR_CLEAN) != 0;
+  const bool do_clnc = (a.variants & ARC_VAR_CLEANCLEAR) != 0;
   const int laytrop = ws.laytrop[c];
   const float secdiff = ws.secdiff[(size_t)b * cap + c];
-  auto CHI = [&](int imol, int jp) { return s_chi[(imol - 1) + 7 * (jp - 1)]; };   // 1-based like the reference
+  const int ig0 = g0 - c_lw[b].g0 + 1;                                              // 1-based g-point of the group's first member inside the band
+  auto CHI = [&](int imol, int jp) { return s_chi[(imol - 1) + 7 * (jp - 1)]; };
 
-  // band constants (reference ratios at fixed pressure levels)
-  float rp_a = 0.f, rp_b = 0.f, rm_a = 0.f, rm_b = 0.f, rm_a3 = 0.f;
-  switch (band) {
-    case 3: rp_a = div_rn(CHI(1, 9), CHI(2, 9)); rp_b = div_rn(CHI(1, 13), CHI(2, 13));
-            rm_a = div_rn(CHI(1, 3), CHI(2, 3)); rm_b = div_rn(CHI(1, 13), CHI(2, 13)); break;
-    case 4: rp_a = div_rn(CHI(1, 11), CHI(2, 11)); rp_b = div_rn(CHI(3, 13), CHI(2, 13)); break;
-    case 5: rp_a = div_rn(CHI(1, 5), CHI(2, 5)); rp_b = div_rn(CHI(3, 43), CHI(2, 43)); rm_a = div_rn(CHI(1, 7), CHI(2, 7)); break;
-    case 7: rp_a = div_rn(CHI(1, 3), CHI(3, 3)); rm_a = div_rn(CHI(1, 3), CHI(3, 3)); break;
-    case 9: rp_a = div_rn(CHI(1, 9), CHI(6, 9)); rm_a = div_rn(CHI(1, 3), CHI(6, 3)); break;
-    case 12: rp_a = div_rn(CHI(1, 10), CHI(2, 10)); break;
-    case 13: rp_a = div_rn(CHI(1, 5), CHI(4, 5)); rm_a = div_rn(CHI(1, 1), CHI(4, 1)); rm_a3 = div_rn(CHI(1, 3), CHI(4, 3)); break;
-    case 15: rp_a = div_rn(CHI(4, 1), CHI(2, 1)); rm_a = div_rn(CHI(4, 1), CHI(2, 1)); break;
-    case 16: rp_a = div_rn(CHI(1, 6), CHI(6, 6)); break;
+  // band constants: reference ratios at fixed pressure levels (0 rp_a, 1 rp_b, 2 rm_a, 3 rm_b, 4 rm_a3)
+  float rc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  switch (BAND) {
+    case 3: rc[0] = div_rn(CHI(1, 9), CHI(2, 9)); rc[1] = div_rn(CHI(1, 13), CHI(2, 13));
+            rc[2] = div_rn(CHI(1, 3), CHI(2, 3)); rc[3] = div_rn(CHI(1, 13), CHI(2, 13)); break;
+    case 4: rc[0] = div_rn(CHI(1, 11), CHI(2, 11)); rc[1] = div_rn(CHI(3, 13), CHI(2, 13)); break;
+    case 5: rc[0] = div_rn(CHI(1, 5), CHI(2, 5)); rc[1] = div_rn(CHI(3, 43), CHI(2, 43)); rc[2] = div_rn(CHI(1, 7), CHI(2, 7)); break;
+    case 7: rc[0] = div_rn(CHI(1, 3), CHI(3, 3)); rc[2] = div_rn(CHI(1, 3), CHI(3, 3)); break;
+    case 9: rc[0] = div_rn(CHI(1, 9), CHI(6, 9)); rc[2] = div_rn(CHI(1, 3), CHI(6, 3)); break;
+    case 12: rc[0] = div_rn(CHI(1, 10), CHI(2, 10)); break;
+    case 13: rc[0] = div_rn(CHI(1, 5), CHI(4, 5)); rc[2] = div_rn(CHI(1, 1), CHI(4, 1)); rc[4] = div_rn(CHI(1, 3), CHI(4, 3)); break;
+    case 15: rc[0] = div_rn(CHI(4, 1), CHI(2, 1)); rc[2] = div_rn(CHI(4, 1), CHI(2, 1)); break;
+    case 16: rc[0] = div_rn(CHI(1, 6), CHI(6, 6)); break;
     default: break;
   }
 
-  uint32_t mw[NL / 32], aw[NL / 32];
-#pragma unroll
-  for (int w = 0; w < NL / 32; w++) {
-    mw[w] = w < ws.W ? ws.mask[((size_t)g * ws.W + w) * cap + c] : 0u;
-    aw[w] = w < ws.W ? ws.anyc[(size_t)w * cap + c] : 0u;
-  }
-
-  // Per-layer results of the downward sweep that the upward sweep (k_lw_sweep) needs go to level-indexed scratch
-  // records (layout in args.h): level = layer + 1 for the layer quantities, level = the layer's lower interface for the
-  // downward fluxes.  v = 0 full (taug + taua), 1 clean (taug).
-  float radld[2] = {0.f, 0.f}, radclrd[2] = {0.f, 0.f};
-  int iclddn = 0;
-  float fracs_bot = 0.f;
-  const size_t pcap = ws.pcap;
-  const int nv = do_clean ? 2 : 1;
-  const unsigned lvstride = (unsigned)nv * NGLW;             // records per (tile, level)
-  const size_t r0 = (size_t)(c / REC_TILE) * (nlay + 1) * nv * NGLW + g;      // record (this tile, level 0, stream 0, g)
-  const int lane = c % REC_TILE;
-  float *rec = ws.rec + r0 * LW_REC;                          // U | D records, see args.h
-  float *recC = ws.recC + r0 * LW_REC_D;                      // cloudy-layer records
-  // record lay + 1 holds, per stream, U of layer lay and the downward radiances D at the layer's LOWER interface (level lay),
-  // so a layer writes one record and the sweep reads one record per step (the TOA downward radiance is zero: not stored)
-
-  // Planck function at the top interface of the current layer; carried downwards
   auto planck_at = [&](float t) {
     int ind = (int)(t - 159.f);
     ind = min(max(ind, 1), 180);
@@ -132,8 +536,7 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
     return p0 + frac * (p1 - p0);
   };
 
-  // Every workspace field this band reads is requested at the top of the layer iteration (one wait per layer instead of
-  // one per field); BAND is a compile-time constant, so the other loads do not exist in this instantiation.
+  // workspace fields this band reads (BAND is a compile-time constant: the other loads do not exist in this instantiation)
   constexpr unsigned COMMON = (1u << LWC_FAC00) | (1u << LWC_FAC01) | (1u << LWC_FAC10) | (1u << LWC_FAC11) | (1u << LWC_SELFFAC) |
                               (1u << LWC_SELFFRAC) | (1u << LWC_FORFAC) | (1u << LWC_FORFRAC) | (1u << LWC_TAVEL) | (1u << LWC_IDX);
   constexpr unsigned H2O = 1u << LWC_H2O, CO2 = 1u << LWC_CO2, O3 = 1u << LWC_O3, N2O = 1u << LWC_N2O, CO = 1u << LWC_CO, CH4 = 1u << LWC_CH4,
@@ -145,402 +548,200 @@ __device__ __forceinline__ void lw_solve_band(const LwArgs &a, const LwSmem &sm,
   constexpr unsigned need = COMMON | per_band[BAND - 1];
   const unsigned ucap = (unsigned)cap, ustf = (unsigned)nlay * (unsigned)cap;     // 32-bit offsets: LWC_N*nlay*cap < 2^31
   const float *coefc = ws.coef + coef_index(0, 0, c, cap, LWC_N), *aerc = ws.aer + c + (unsigned)b * ustf;
+  const float *cldc = ws.cld + c + (unsigned)b * ustf;
   const unsigned lstride = (unsigned)cap * LWC_N;                                  // coefficient words per layer
-  float tz_up = coefc[(size_t)((unsigned)(nlay - 1) * lstride) + LWC_TZ * 32];      // temperature of the interface above the layer
-  float plev_up = planck_at(tz_up);
-  // Software pipeline: the workspace words of layer lay-1 are requested right after the gas optics of layer lay have
-  // consumed theirs (the registers are free then) and land while the radiative-transfer step of layer lay executes.
-  float fv[LWC_N], taua_nx, tz_nx;
+  float fv[LWC_N];
   auto load_layer = [&](int lay) {
     const float *p = coefc + (size_t)((unsigned)lay * lstride);      // fields at immediate offsets of 128 bytes
 #pragma unroll
     for (int f = 0; f < LWC_N; f++) fv[f] = ((need >> f) & 1u) ? p[f * 32] : 0.f;
-    taua_nx = aerc[(unsigned)lay * ucap];
-    tz_nx = lay > 0 ? *(p + LWC_TZ * 32 - (ptrdiff_t)lstride) : ws.colf[(size_t)LWF_TZ0 * cap + c];
   };
-  load_layer(nlay - 1);
-  for (int lay = nlay - 1; lay >= 0; lay--) {
-    const float taua = taua_nx, tz_dn = tz_nx;
-    auto F = [&](int f) { return fv[f]; };
-    const int pk = __float_as_int(F(LWC_IDX));
-    const int jp = IDX_JP(pk), jt = IDX_JT(pk), jt1 = IDX_JT1(pk), indself = IDX_SELF(pk), indfor = IDX_FOR(pk), indminor = IDX_MINOR(pk);
-    const float fac00 = F(LWC_FAC00), fac01 = F(LWC_FAC01), fac10 = F(LWC_FAC10), fac11 = F(LWC_FAC11);
-    const bool low = lay < laytrop;
-    const float *A = S + D.oA, *B = S + D.oB;
-    auto selfk = [&]() { const float *r = S + D.oSelf + indself - 1; return F(LWC_SELFFAC) * (r[0] + F(LWC_SELFFRAC) * (r[1] - r[0])); };
-    auto fork = [&]() { const float *r = S + D.oFor + indfor - 1; return F(LWC_FORFAC) * (r[0] + F(LWC_FORFRAC) * (r[1] - r[0])); };
-    auto minor1 = [&](int off) { const float *r = S + off + indminor - 1; return r[0] + F(LWC_MINORFRAC) * (r[1] - r[0]); };
-    auto minor2 = [&](int off, int ne, int jm, float fm) {
-      const float *r = S + off + (jm - 1) + ne * (indminor - 1);
-      const float m1 = r[0] + fm * (r[1] - r[0]);
-      const float m2 = r[ne] + fm * (r[ne + 1] - r[ne]);
-      return m1 + F(LWC_MINORFRAC) * (m2 - m1);
-    };
-    auto k4 = [&](const float *ab, bool lower) {
-      int ind0, ind1;
-      if (lower) { ind0 = ((jp - 1) * 5 + (jt - 1)); ind1 = (jp * 5 + (jt1 - 1)); }
-      else { ind0 = ((jp - 13) * 5 + (jt - 1)); ind1 = ((jp - 12) * 5 + (jt1 - 1)); }
-      return fac00 * ab[ind0] + fac10 * ab[ind0 + 1] + fac01 * ab[ind1] + fac11 * ab[ind1 + 1];
-    };
-    auto RAT = [&](int r, int jpp) { return s_rat[r * 60 + jpp - 1]; };
-    auto major_lower2 = [&](const LwEta &e, const LwEta &e1) {
-      const int ind0 = ((jp - 1) * 5 + (jt - 1)) * 9 + e.j, ind1 = (jp * 5 + (jt1 - 1)) * 9 + e1.j;
-      return lw_major_lower(A, e, ind0, fac00, fac10) + lw_major_lower(A, e1, ind1, fac01, fac11);
-    };
-    auto major_upper = [&](const LwEta &e, const LwEta &e1) {
-      const int ind0 = ((jp - 13) * 5 + (jt - 1)) * 5 + e.j, ind1 = ((jp - 12) * 5 + (jt1 - 1)) * 5 + e1.j;
-      const float *q0 = B + ind0 - 1, *q1 = B + ind1 - 1;
-      const float f0 = 1.f - e.f, f1 = 1.f - e1.f;
-      return e.speccomb * ((f0 * fac00) * q0[0] + (e.f * fac00) * q0[1] + (f0 * fac10) * q0[5] + (e.f * fac10) * q0[6]) +
-             e1.speccomb * ((f1 * fac01) * q1[0] + (e1.f * fac01) * q1[1] + (f1 * fac11) * q1[5] + (e1.f * fac11) * q1[6]);
-    };
-    auto frac_eta = [&](int off, const LwEta &ep) { const float *r = S + off + ep.j - 1; return r[0] + ep.f * (r[1] - r[0]); };
-    // empirical column rescaling of a minor gas (e.g. LW:5208-5216)
-    auto adjcol = [&](float col, int imol, float thresh, float base, float expo) {
-      const float coldry = F(LWC_COLDRY);
-      const float chim = CHI(imol, jp + 1);
-      const float chi = col / coldry;
-      const float rat = 1.e20f * chi / chim;
-      if (rat > thresh) {
-        const float adjfac = base + powf(rat - base, expo);
-        return adjfac * chim * coldry * 1.e-20f;
-      }
-      return col;
-    };
-    auto WX = [&](float vmr) { return F(LWC_COLDRY) * vmr * 1.e-20f; };
-    const float vccl4 = 0.093e-9f, vcfc11 = 0.251e-9f, vcfc12 = 0.538e-9f, vcfc22 = 0.169e-9f;
+  auto tz_at = [&](int lev) {     // interface temperature: level 0 = surface
+    return lev > 0 ? coefc[(size_t)((unsigned)(lev - 1) * lstride) + LWC_TZ * 32] : ws.colf[(size_t)LWF_TZ0 * cap + c];
+  };
+  float *__restrict__ bpart = ws.bpart + (size_t)grp * (nlay + 1) * nk * pcap + c;
+  const unsigned oFU = ws.kslot[K_FU] * (unsigned)pcap, oFD = ws.kslot[K_FD] * (unsigned)pcap, oCU = ws.kslot[K_CU] * (unsigned)pcap,
+                 oCD = ws.kslot[K_CD] * (unsigned)pcap, oNU = ws.kslot[K_NU] * (unsigned)pcap, oND = ws.kslot[K_ND] * (unsigned)pcap,
+                 oXU = ws.kslot[K_XU] * (unsigned)pcap, oXD = ws.kslot[K_XD] * (unsigned)pcap;
+  const size_t lvs = (size_t)nk * pcap;                                            // partial-buffer words per level
 
-    float taug = 0.f, fracs = 0.f;
-    switch (band) {
-      case 1: {
-        const float pp = F(LWC_PAVEL);
-        const float scalen2 = F(LWC_BRD) * F(LWC_SCALEMINORN2);
-        if (low) {
-          float corradj = 1.f; if (pp < 250.f) corradj = 1.f - 0.15f * (250.f - pp) / 154.4f;
-          taug = corradj * (F(LWC_H2O) * k4(A, true) + selfk() + fork() + scalen2 * minor1(D.oMinA[M_N2]));
-          fracs = S[D.oFracA];
-        } else {
-          const float corradj = 1.f - 0.15f * (pp / 95.6f);
-          taug = corradj * (F(LWC_H2O) * k4(B, false) + fork() + scalen2 * minor1(D.oMinB[M_N2]));
-          fracs = S[D.oFracB];
-        }
-        break; }
-      case 2: {
-        if (low) {
-          const float pp = F(LWC_PAVEL);
-          const float corradj = 1.f - .05f * (pp - 100.f) / 900.f;
-          taug = corradj * (F(LWC_H2O) * k4(A, true) + selfk() + fork());
-          fracs = S[D.oFracA];
-        } else { taug = F(LWC_H2O) * k4(B, false) + fork(); fracs = S[D.oFracB]; }
-        break; }
-      case 3: {
-        const float h2o = F(LWC_H2O), co2 = F(LWC_CO2);
-        const float mult = low ? 8.f : 4.f;
-        const LwEta e = lw_eta(h2o, RAT(0, jp), co2, mult, oneminus), e1 = lw_eta(h2o, RAT(0, jp + 1), co2, mult, oneminus);
-        const LwEta em = lw_eta(h2o, low ? rm_a : rm_b, co2, mult, oneminus);
-        const LwEta ep = lw_eta(h2o, low ? rp_a : rp_b, co2, mult, oneminus);
-        const float adjcoln2o = adjcol(F(LWC_N2O), 4, 1.5f, 0.5f, 0.65f);
-        if (low) {
-          taug = major_lower2(e, e1) + selfk() + fork() + adjcoln2o * minor2(D.oMinA[M_N2O], 9, em.j, em.f);
-          fracs = frac_eta(D.oFracA, ep);
-        } else {
-          taug = major_upper(e, e1) + fork() + adjcoln2o * minor2(D.oMinB[M_N2O], 5, em.j, em.f);
-          fracs = frac_eta(D.oFracB, ep);
-        }
-        break; }
-      case 4: {
-        const float co2 = F(LWC_CO2);
-        if (low) {
-          const float h2o = F(LWC_H2O);
-          const LwEta e = lw_eta(h2o, RAT(0, jp), co2, 8.f, oneminus), e1 = lw_eta(h2o, RAT(0, jp + 1), co2, 8.f, oneminus);
-          const LwEta ep = lw_eta(h2o, rp_a, co2, 8.f, oneminus);
-          taug = major_lower2(e, e1) + selfk() + fork();
-          fracs = frac_eta(D.oFracA, ep);
-        } else {
-          const float o3 = F(LWC_O3);
-          const LwEta e = lw_eta(o3, RAT(5, jp), co2, 4.f, oneminus), e1 = lw_eta(o3, RAT(5, jp + 1), co2, 4.f, oneminus);
-          const LwEta ep = lw_eta(o3, rp_b, co2, 4.f, oneminus);
-          taug = major_upper(e, e1);
-          fracs = frac_eta(D.oFracB, ep);
-          const int ig = g - D.g0 + 1;
-          if (ig == 8) taug = taug * 0.92f; else if (ig == 9) taug = taug * 0.88f; else if (ig == 10) taug = taug * 1.07f;
-          else if (ig == 11) taug = taug * 1.1f; else if (ig == 12) taug = taug * 0.99f; else if (ig == 13) taug = taug * 0.88f;
-          else if (ig == 14) taug = taug * 0.943f;
-        }
-        break; }
-      case 5: {
-        const float co2 = F(LWC_CO2);
-        const float wx1 = WX(vccl4);
-        if (low) {
-          const float h2o = F(LWC_H2O);
-          const LwEta e = lw_eta(h2o, RAT(0, jp), co2, 8.f, oneminus), e1 = lw_eta(h2o, RAT(0, jp + 1), co2, 8.f, oneminus);
-          const LwEta em = lw_eta(h2o, rm_a, co2, 8.f, oneminus), ep = lw_eta(h2o, rp_a, co2, 8.f, oneminus);
-          taug = major_lower2(e, e1) + selfk() + fork() + minor2(D.oMinA[M_O3], 9, em.j, em.f) * F(LWC_O3) + wx1 * S[D.oCfc + 0];
-          fracs = frac_eta(D.oFracA, ep);
-        } else {
-          const float o3 = F(LWC_O3);
-          const LwEta e = lw_eta(o3, RAT(5, jp), co2, 4.f, oneminus), e1 = lw_eta(o3, RAT(5, jp + 1), co2, 4.f, oneminus);
-          const LwEta ep = lw_eta(o3, rp_b, co2, 4.f, oneminus);
-          taug = major_upper(e, e1) + wx1 * S[D.oCfc + 0];
-          fracs = frac_eta(D.oFracB, ep);
-        }
-        break; }
-      case 6: {
-        const float wx2 = WX(vcfc11), wx3 = WX(vcfc12);
-        if (low) {
-          const float adjcolco2 = adjcol(F(LWC_CO2), 2, 3.0f, 2.0f, 0.77f);
-          taug = F(LWC_H2O) * k4(A, true) + selfk() + fork() + adjcolco2 * minor1(D.oMinA[M_CO2]) + wx2 * S[D.oCfc + 1] + wx3 * S[D.oCfc + 2];
-        } else taug = 0.0f + wx2 * S[D.oCfc + 1] + wx3 * S[D.oCfc + 2];
-        fracs = S[D.oFracA];
-        break; }
-      case 7: {
-        if (low) {
-          const float h2o = F(LWC_H2O), o3 = F(LWC_O3);
-          const LwEta e = lw_eta(h2o, RAT(1, jp), o3, 8.f, oneminus), e1 = lw_eta(h2o, RAT(1, jp + 1), o3, 8.f, oneminus);
-          const LwEta em = lw_eta(h2o, rm_a, o3, 8.f, oneminus), ep = lw_eta(h2o, rp_a, o3, 8.f, oneminus);
-          const float adjcolco2 = adjcol(F(LWC_CO2), 2, 3.0f, 3.0f, 0.79f);
-          taug = major_lower2(e, e1) + selfk() + fork() + adjcolco2 * minor2(D.oMinA[M_CO2], 9, em.j, em.f);
-          fracs = frac_eta(D.oFracA, ep);
-        } else {
-          const float adjcolco2 = adjcol(F(LWC_CO2), 2, 3.0f, 2.0f, 0.79f);
-          taug = F(LWC_O3) * k4(B, false) + adjcolco2 * minor1(D.oMinB[M_CO2]);
-          fracs = S[D.oFracB];
-          const int ig = g - D.g0 + 1;
-          if (ig == 6) taug = taug * 0.92f; else if (ig == 7) taug = taug * 0.88f; else if (ig == 8) taug = taug * 1.07f;
-          else if (ig == 9) taug = taug * 1.1f; else if (ig == 10) taug = taug * 0.99f; else if (ig == 11) taug = taug * 0.855f;
-        }
-        break; }
-      case 8: {
-        const float adjcolco2 = adjcol(F(LWC_CO2), 2, 3.0f, 2.0f, 0.65f);
-        const float wx3 = WX(vcfc12), wx4 = WX(vcfc22);
-        if (low) {
-          taug = F(LWC_H2O) * k4(A, true) + selfk() + fork() + adjcolco2 * minor1(D.oMinA[M_CO2]) + F(LWC_O3) * minor1(D.oMinA[M_O3]) +
-                 F(LWC_N2O) * minor1(D.oMinA[M_N2O]) + wx3 * S[D.oCfc + 2] + wx4 * S[D.oCfc + 3];
-          fracs = S[D.oFracA];
-        } else {
-          taug = F(LWC_O3) * k4(B, false) + adjcolco2 * minor1(D.oMinB[M_CO2]) + F(LWC_N2O) * minor1(D.oMinB[M_N2O]) +
-                 wx3 * S[D.oCfc + 2] + wx4 * S[D.oCfc + 3];
-          fracs = S[D.oFracB];
-        }
-        break; }
-      case 9: {
-        const float adjcoln2o = adjcol(F(LWC_N2O), 4, 1.5f, 0.5f, 0.65f);
-        if (low) {
-          const float h2o = F(LWC_H2O), ch4 = F(LWC_CH4);
-          const LwEta e = lw_eta(h2o, RAT(3, jp), ch4, 8.f, oneminus), e1 = lw_eta(h2o, RAT(3, jp + 1), ch4, 8.f, oneminus);
-          const LwEta em = lw_eta(h2o, rm_a, ch4, 8.f, oneminus), ep = lw_eta(h2o, rp_a, ch4, 8.f, oneminus);
-          taug = major_lower2(e, e1) + selfk() + fork() + adjcoln2o * minor2(D.oMinA[M_N2O], 9, em.j, em.f);
-          fracs = frac_eta(D.oFracA, ep);
-        } else {
-          taug = F(LWC_CH4) * k4(B, false) + adjcoln2o * minor1(D.oMinB[M_N2O]);
-          fracs = S[D.oFracB];
-        }
-        break; }
-      case 10: case 11: {
-        float t;
-        if (low) { t = F(LWC_H2O) * k4(A, true) + selfk() + fork(); fracs = S[D.oFracA]; }
-        else { t = F(LWC_H2O) * k4(B, false) + fork(); fracs = S[D.oFracB]; }
-        if (band == 11) { const float scaleo2 = F(LWC_O2) * F(LWC_SCALEMINOR); t = t + scaleo2 * minor1(low ? D.oMinA[M_O2] : D.oMinB[M_O2]); }
-        taug = t;
-        break; }
-      case 12: {
-        if (low) {
-          const float h2o = F(LWC_H2O), co2 = F(LWC_CO2);
-          const LwEta e = lw_eta(h2o, RAT(0, jp), co2, 8.f, oneminus), e1 = lw_eta(h2o, RAT(0, jp + 1), co2, 8.f, oneminus);
-          const LwEta ep = lw_eta(h2o, rp_a, co2, 8.f, oneminus);
-          taug = major_lower2(e, e1) + selfk() + fork();
-          fracs = frac_eta(D.oFracA, ep);
-        }
-        break; }
-      case 13: {
-        if (low) {
-          const float h2o = F(LWC_H2O), n2o = F(LWC_N2O), co2 = F(LWC_CO2), coldry = F(LWC_COLDRY);
-          const LwEta e = lw_eta(h2o, RAT(2, jp), n2o, 8.f, oneminus), e1 = lw_eta(h2o, RAT(2, jp + 1), n2o, 8.f, oneminus);
-          const LwEta em = lw_eta(h2o, rm_a, n2o, 8.f, oneminus), eco = lw_eta(h2o, rm_a3, n2o, 8.f, oneminus);
-          const LwEta ep = lw_eta(h2o, rp_a, n2o, 8.f, oneminus);
-          const float chi_co2 = co2 / coldry;
-          const float ratco2 = 1.e20f * chi_co2 / 3.55e-4f;
-          float adjcolco2;
-          if (ratco2 > 3.0f) { const float adjfac = 2.0f + powf(ratco2 - 2.0f, 0.68f); adjcolco2 = adjfac * 3.55e-4f * coldry * 1.e-20f; }
-          else adjcolco2 = co2;
-          taug = major_lower2(e, e1) + selfk() + fork() + adjcolco2 * minor2(D.oMinA[M_CO2], 9, em.j, em.f) +
-                 F(LWC_CO) * minor2(D.oMinA[M_CO], 9, eco.j, eco.f);
-          fracs = frac_eta(D.oFracA, ep);
-        } else { taug = F(LWC_O3) * minor1(D.oMinB[M_O3]); fracs = S[D.oFracB]; }
-        break; }
-      case 14: {
-        if (low) { taug = F(LWC_CO2) * k4(A, true) + selfk() + fork(); fracs = S[D.oFracA]; }
-        else { taug = F(LWC_CO2) * k4(B, false); fracs = S[D.oFracB]; }
-        break; }
-      case 15: {
-        if (low) {
-          const float n2o = F(LWC_N2O), co2 = F(LWC_CO2);
-          const LwEta e = lw_eta(n2o, RAT(4, jp), co2, 8.f, oneminus), e1 = lw_eta(n2o, RAT(4, jp + 1), co2, 8.f, oneminus);
-          const LwEta em = lw_eta(n2o, rm_a, co2, 8.f, oneminus), ep = lw_eta(n2o, rp_a, co2, 8.f, oneminus);
-          const float scalen2 = F(LWC_BRD) * F(LWC_SCALEMINOR);
-          taug = major_lower2(e, e1) + selfk() + fork() + scalen2 * minor2(D.oMinA[M_N2], 9, em.j, em.f);
-          fracs = frac_eta(D.oFracA, ep);
-        }
-        break; }
-      default: {  // 16
-        if (low) {
-          const float h2o = F(LWC_H2O), ch4 = F(LWC_CH4);
-          const LwEta e = lw_eta(h2o, RAT(3, jp), ch4, 8.f, oneminus), e1 = lw_eta(h2o, RAT(3, jp + 1), ch4, 8.f, oneminus);
-          const LwEta ep = lw_eta(h2o, rp_a, ch4, 8.f, oneminus);
-          taug = major_lower2(e, e1) + selfk() + fork();
-          fracs = frac_eta(D.oFracA, ep);
-        } else { taug = F(LWC_CH4) * k4(B, false); fracs = S[D.oFracB]; }
-        break; }
-    }
-    if (a.dbg.taug) {
-      const size_t q = ((size_t)(a.col0 + c) * nlay + lay) * NGLW + g;
-      a.dbg.taug[q] = taug; a.dbg.taur[q] = fracs;
-    }
-    if (lay == 0) fracs_bot = fracs;
-
-    // ---- rtrnmc downward step for this layer (LW:3207-3300)
-    const float blay = planck_at(F(LWC_TAVEL));
-    if (lay > 0) load_layer(lay - 1);          // prefetch (fv is dead from here on)
-    const float plev_dn = planck_at(tz_dn);
-    const float dplankup = plev_up - blay, dplankdn = plev_dn - blay;
-    const float plfrac = fracs;
-    const bool icldlyr = (aw[lay >> 5] >> (lay & 31)) & 1u;
-    const bool cloudy = (mw[lay >> 5] >> (lay & 31)) & 1u;
-    float odcld = 0.f, efclfrac = 0.f;
-    const float cldfmc = cloudy ? 1.f : 0.f;
-    if (cloudy) {
-      const float taucmc = ws.cld[(size_t)((unsigned)b * ustf + (unsigned)lay * ucap) + c];
-      if (a.dbg.taucmc) a.dbg.taucmc[((size_t)(a.col0 + c) * nlay + lay) * NGLW + g] = taucmc;
-      odcld = secdiff * taucmc;
-      const float transcld = expf(-odcld);
-      const float abscld = 1.f - transcld;
-      efclfrac = abscld * cldfmc;
-    }
-    if (icldlyr) iclddn = 1;
-    float *qrec = rec + (size_t)((unsigned)(lay + 1) * lvstride) * LW_REC;
-    float *qrecC = recC + (size_t)((unsigned)(lay + 1) * lvstride) * LW_REC_D;
+  // rad[i][v]: all-sky radiance, radc[i][v]: clear-sky radiance of g-point i, stream v (0 full, 1 clean)
+  float rad[NG][2], radc[NG][2], fracs_bot[NG];
 #pragma unroll
-    for (int v = 0; v < 2; v++) {
-      if (v == 1 && !do_clean) break;
-      const float taut = v == 0 ? taug + taua : taug;
-      float odepth = secdiff * taut;
-      if (odepth < 0.0f) odepth = 0.0f;
-      float atrans, bbd, bbugas;
-      if (icldlyr) {
-        float odtot = odepth + odcld;
-        float gassrc, bbdtot, atot, bbutot;
-        if (odtot < 0.06f) {
-          atrans = odepth - 0.5f * odepth * odepth;
-          const float odepth_rec = 0.166667f * odepth;
-          gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
-          atot = odtot - 0.5f * odtot * odtot;
-          const float odtot_rec = 0.166667f * odtot;
-          bbdtot = plfrac * (blay + dplankdn * odtot_rec);
-          bbd = plfrac * (blay + dplankdn * odepth_rec);
-          bbugas = plfrac * (blay + dplankup * odepth_rec);
-          bbutot = plfrac * (blay + dplankup * odtot_rec);
-        } else if (odepth <= 0.06f) {
-          atrans = odepth - 0.5f * odepth * odepth;
-          const float odepth_rec = 0.166667f * odepth;
-          gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
-          const float tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
-          const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-          const float2 et = s_et[ittot];
-          const float tfactot = et.y;
-          bbdtot = plfrac * (blay + tfactot * dplankdn);
-          bbd = plfrac * (blay + dplankdn * odepth_rec);
-          atot = 1.f - et.x;
-          bbugas = plfrac * (blay + dplankup * odepth_rec);
-          bbutot = plfrac * (blay + tfactot * dplankup);
-        } else {
-          float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
-          const int itgas = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-          // tau_tbl(itgas) recomputed with the table generator's arithmetic (LW:7944-7950)
-          if (itgas >= 10000) odepth = 1.e10f;
-          else { const float tfn = div_rn((float)itgas, 10000.0f); odepth = div_rn(__fmul_rn(bpade, tfn), __fsub_rn(1.0f, tfn)); }
-          const float2 eg = s_et[itgas];
-          atrans = 1.f - eg.x;
-          const float tfacgas = eg.y;
-          gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
-          odtot = odepth + odcld;
-          tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
-          const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-          const float2 et = s_et[ittot];
-          const float tfactot = et.y;
-          bbdtot = plfrac * (blay + tfactot * dplankdn);
-          bbd = plfrac * (blay + tfacgas * dplankdn);
-          atot = 1.f - et.x;
-          bbugas = plfrac * (blay + tfacgas * dplankup);
-          bbutot = plfrac * (blay + tfactot * dplankup);
-        }
-        radld[v] = radld[v] - radld[v] * (atrans + efclfrac * (1.f - atrans)) + gassrc + cldfmc * (bbdtot * atot - gassrc);
-        // the same step for the upward radiance is radlu - radlu * X + Y (LW:3334-3338): hand over X and Y
-        const float gassrcu = bbugas * atrans;
-        reinterpret_cast<float2 *>(qrecC + v * (NGLW * LW_REC_D))[lane] =
-            make_float2(atrans + efclfrac * (1.f - atrans), gassrcu + cldfmc * (bbutot * atot - gassrcu));
-      } else {
-        if (odepth <= 0.06f) {
-          atrans = odepth - 0.5f * odepth * odepth;
-          odepth = 0.166667f * odepth;
-          bbd = plfrac * (blay + dplankdn * odepth);
-          bbugas = plfrac * (blay + dplankup * odepth);
-        } else {
-          const float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
-          const int itr = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-          const float2 et = s_et[itr];
-          atrans = 1.f - et.x;
-          const float tausfac = et.y;
-          bbd = plfrac * (blay + tausfac * dplankdn);
-          bbugas = plfrac * (blay + tausfac * dplankup);
-        }
-        radld[v] = radld[v] + (bbd - radld[v]) * atrans;
-      }
-      if (iclddn == 1) radclrd[v] = radclrd[v] + (bbd - radclrd[v]) * atrans;
-      else radclrd[v] = radld[v];
-      reinterpret_cast<float4 *>(qrec + v * (NGLW * LW_REC))[lane] = make_float4(atrans, bbugas, radld[v], radclrd[v]);
+  for (int i = 0; i < NG; i++) { rad[i][0] = rad[i][1] = 0.f; radc[i][0] = radc[i][1] = 0.f; fracs_bot[i] = 0.f; }
+  uint32_t mwc[NG];                   // McICA bits of the current 32 layers
+  uint32_t awc = 0u;
+  int iclddn = 0;
+  LwBL L;
+
+  // ---------------- pass 1: downward (LW:3207-3300), top layer first
+  if (live) { bpart[(size_t)nlay * lvs + oFD] = 0.f; bpart[(size_t)nlay * lvs + oCD] = 0.f;
+              if (do_clean) bpart[(size_t)nlay * lvs + oND] = 0.f;
+              if (do_clnc) bpart[(size_t)nlay * lvs + oXD] = 0.f; }
+  for (int lay = nlay - 1; lay >= 0; lay--) {
+    if ((lay & 31) == 31 || lay == nlay - 1) {
+      awc = ws.anyc[(size_t)(lay >> 5) * cap + c];
+#pragma unroll
+      for (int i = 0; i < NG; i++) mwc[i] = ws.mask[((size_t)(g0 + i) * ws.W + (lay >> 5)) * cap + c];
     }
-    plev_up = plev_dn;
+    load_layer(lay);
+    const float taua = aerc[(unsigned)lay * ucap];
+    const float tz_dn = tz_at(lay);
+    const bool low = lay < laytrop;
+    lw_setup<BAND>(fv, sm, S0, low, oneminus, rc, L);
+    L.any3 = __any_sync(0xffffffffu, L.three);      // all 32 lanes are here: the layer loop has no early exit
+    const float blay = planck_at(fv[LWC_TAVEL]);
+    const float dplankdn = planck_at(tz_dn) - blay;
+    const bool icldlyr = (awc >> (lay & 31)) & 1u;
+    float odcld = 0.f, abscld = 0.f;
+    if (icldlyr) {
+      const float taucmc = cldc[(unsigned)lay * ucap];
+      odcld = secdiff * taucmc;
+      abscld = 1.f - glm::expf_(-odcld);
+      if (a.dbg.taucmc && live) {
+#pragma unroll
+        for (int i = 0; i < NG; i++)
+          if ((mwc[i] >> (lay & 31)) & 1u) a.dbg.taucmc[((size_t)(a.col0 + c) * nlay + lay) * NGLW + g0 + i] = taucmc;
+      }
+      iclddn = 1;
+    }
+#pragma unroll
+    for (int i = 0; i < NG; i++) {
+      float taug, fracs;
+      lw_gas<BAND>(L, i * SF, ig0 + i, taug, fracs);
+      if (a.dbg.taug && live) {
+        const size_t q = ((size_t)(a.col0 + c) * nlay + lay) * NGLW + g0 + i;
+        a.dbg.taug[q] = taug; a.dbg.taur[q] = fracs;
+      }
+      fracs_bot[i] = fracs;                       // the last iteration (lay = 0) leaves the surface value
+      const float cldfmc = ((mwc[i] >> (lay & 31)) & 1u) ? 1.f : 0.f;
+      const float efclfrac = abscld * cldfmc;
+#pragma unroll
+      for (int v = 0; v < 2; v++) {
+        if (v == 1 && !do_clean) break;
+        const float taut = v == 0 ? taug + taua : taug;
+        float odepth = secdiff * taut;
+        if (odepth < 0.0f) odepth = 0.0f;
+        float atrans, bbd, X, src, Z;
+        lw_rt<false>(s_et, bpade, odepth, icldlyr, odcld, efclfrac, cldfmc, fracs, blay, dplankdn, atrans, bbd, X, src, Z);
+        if (icldlyr) rad[i][v] = rad[i][v] - rad[i][v] * X + src + Z;
+        else rad[i][v] = rad[i][v] + (bbd - rad[i][v]) * atrans;
+        if (iclddn == 1) radc[i][v] = radc[i][v] + (bbd - radc[i][v]) * atrans;
+        else radc[i][v] = rad[i][v];
+      }
+    }
+    // downward radiances at the lower interface of the layer, summed over the group's g-points in index order
+    if (live) {
+      float *bp = bpart + (size_t)lay * lvs;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NG; i++) { s0 = s0 + rad[i][0]; s1 = s1 + radc[i][0]; s2 = s2 + rad[i][1]; s3 = s3 + radc[i][1]; }
+      __stcs(bp + oFD, s0); __stcs(bp + oCD, s1);
+      if (do_clean) __stcs(bp + oND, s2);
+      if (do_clnc) __stcs(bp + oXD, s3);
+    }
   }
-  // ---- surface (LW:3303-3320)
-  const float emis = ws.colf[(size_t)LWF_EMISS * cap + c];
-  float plankbnd;
+  // ---------------- surface (LW:3303-3320)
   {
+    const float emis = ws.colf[(size_t)LWF_EMISS * cap + c];
     const float tbound = ws.colf[(size_t)LWF_TBOUND * cap + c];
     int ind = (int)(tbound - 159.f);
     ind = min(max(ind, 1), 180);
     const float frac = tbound - 159.f - (float)ind;
     const float dbdtlev = s_plk[ind] - s_plk[ind - 1];
-    plankbnd = emis * (s_plk[ind - 1] + frac * dbdtlev);
+    const float plankbnd = emis * (s_plk[ind - 1] + frac * dbdtlev);
+    const float reflect = 1.f - emis;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NG; i++) {
+      const float rad0 = fracs_bot[i] * plankbnd;
+#pragma unroll
+      for (int v = 0; v < 2; v++) { rad[i][v] = rad0 + reflect * rad[i][v]; radc[i][v] = rad0 + reflect * radc[i][v]; }
+      s0 = s0 + rad[i][0]; s1 = s1 + radc[i][0]; s2 = s2 + rad[i][1]; s3 = s3 + radc[i][1];
+    }
+    if (live) {
+      __stcs(bpart + oFU, s0); __stcs(bpart + oCU, s1);
+      if (do_clean) __stcs(bpart + oNU, s2);
+      if (do_clnc) __stcs(bpart + oXU, s3);
+    }
   }
-  const float rad0 = fracs_bot * plankbnd;
-  const float reflect = 1.f - emis;
-  // upward radiances leaving the surface; the upward sweep itself runs in k_lw_sweep
-  ws.scrS[(size_t)g * pcap + c] = make_float2(rad0 + reflect * radld[0], rad0 + reflect * radclrd[0]);
-  if (do_clean) ws.scrS[(size_t)(NGLW + g) * pcap + c] = make_float2(rad0 + reflect * radld[1], rad0 + reflect * radclrd[1]);
+  // ---------------- pass 2: upward (LW:3322-3356), bottom layer first; the gas optics are recomputed
+  for (int lay = 0; lay < nlay; lay++) {
+    if ((lay & 31) == 0) {
+      awc = ws.anyc[(size_t)(lay >> 5) * cap + c];
+#pragma unroll
+      for (int i = 0; i < NG; i++) mwc[i] = ws.mask[((size_t)(g0 + i) * ws.W + (lay >> 5)) * cap + c];
+    }
+    load_layer(lay);
+    const float taua = aerc[(unsigned)lay * ucap];
+    const float plev_up = planck_at(tz_at(lay + 1));
+    const bool low = lay < laytrop;
+    lw_setup<BAND>(fv, sm, S0, low, oneminus, rc, L);
+    L.any3 = __any_sync(0xffffffffu, L.three);      // all 32 lanes are here: the layer loop has no early exit
+    const float blay = planck_at(fv[LWC_TAVEL]);
+    const float dplankup = plev_up - blay;
+    const bool icldlyr = (awc >> (lay & 31)) & 1u;
+    float odcld = 0.f, abscld = 0.f;
+    if (icldlyr) {
+      odcld = secdiff * cldc[(unsigned)lay * ucap];
+      abscld = 1.f - glm::expf_(-odcld);
+    }
+#pragma unroll
+    for (int i = 0; i < NG; i++) {
+      float taug, fracs;
+      lw_gas<BAND>(L, i * SF, ig0 + i, taug, fracs);
+      const float cldfmc = ((mwc[i] >> (lay & 31)) & 1u) ? 1.f : 0.f;
+      const float efclfrac = abscld * cldfmc;
+#pragma unroll
+      for (int v = 0; v < 2; v++) {
+        if (v == 1 && !do_clean) break;
+        const float taut = v == 0 ? taug + taua : taug;
+        float odepth = secdiff * taut;
+        if (odepth < 0.0f) odepth = 0.0f;
+        float atrans, bbu, X, src, Z;
+        lw_rt<true>(s_et, bpade, odepth, icldlyr, odcld, efclfrac, cldfmc, fracs, blay, dplankup, atrans, bbu, X, src, Z);
+        if (icldlyr) rad[i][v] = rad[i][v] - rad[i][v] * X + src + Z;
+        else rad[i][v] = rad[i][v] + (bbu - rad[i][v]) * atrans;
+        if (iclddn == 1) radc[i][v] = radc[i][v] + (bbu - radc[i][v]) * atrans;      // iclddn as the downward sweep left it: any cloud in the column
+        else radc[i][v] = rad[i][v];
+      }
+    }
+    if (live) {
+      float *bp = bpart + (size_t)(lay + 1) * lvs;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NG; i++) { s0 = s0 + rad[i][0]; s1 = s1 + radc[i][0]; s2 = s2 + rad[i][1]; s3 = s3 + radc[i][1]; }
+      __stcs(bp + oFU, s0); __stcs(bp + oCU, s1);
+      if (do_clean) __stcs(bp + oNU, s2);
+      if (do_clnc) __stcs(bp + oXU, s3);
+    }
+  }
 }
 
-template <int NL>
-__global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
+// Block = LW_BLOCK columns x one band group.  Blocks of one column tile are neighbours in launch order (its coefficient lines
+// are re-read from L2 by the 25 groups); thread 0 stages the exp / tfn table, the group's NG table slices and the band's Planck
+// column with TMA bulk copies.
+__global__ void __launch_bounds__(LW_BLOCK, 1) k_lw_band(LwArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *s_et = reinterpret_cast<float2 *>(smem_raw);                // 10002 x (exp_tbl, tfn_tbl)
-  float *S = reinterpret_cast<float *>(s_et + 10002);                 // slice
-  float *s_plk = S + SLICE_MAX;                                       // totplnk(1:181, band), padded to 184
+  float *S = reinterpret_cast<float *>(s_et + 10002);                 // NG slices
+  float *s_plk = S + LW_GMAX * LW_SLICE_MAX;                          // totplnk(1:181, band), padded to 184
   float *s_rat = s_plk + 184;                                         // [6][60] chi_mls ratios by jp
   float *s_chi = s_rat + 6 * 60;                                      // chi_mls(7,59)
   uint64_t *bar = reinterpret_cast<uint64_t *>(s_chi + 416);
 
-  // block order: band-major, then column tile, then g-point within the band (see k_sw_solve)
-  const int ntiles = (a.ncols + LW_BLOCK - 1) / LW_BLOCK;
-  int b = 0;
-  while (b < NBLW - 1 && (int)blockIdx.x >= c_lw[b + 1].g0 * ntiles) b++;
+  const int ngrp = a.ngroups;
+  const int tile = blockIdx.x / ngrp, grp = blockIdx.x % ngrp;
+  const int b = c_lw_grp_band[grp];
+  const int g0 = c_lw_grp_g0[grp];
   const LwBandDesc &D = c_lw[b];
-  const int rblk = blockIdx.x - D.g0 * ntiles;
-  const int tile = rblk / D.ng;
-  const int g = D.g0 + rblk % D.ng;
+  // number of g-points of this group = distance to the next group's first g-point (or the band's end)
+  const int gend = (grp + 1 < ngrp && c_lw_grp_band[grp + 1] == b) ? c_lw_grp_g0[grp + 1] : D.g0 + D.ng;
+  const int ng = gend - g0;
   const DevTables &tb = a.tb;
   {
     StageReq req[3] = {{s_et, tb.lw_exptfn, 10002 * 8},
-                       {S, tb.lw_tab + D.slice_base + (size_t)D.slice_floats * (g - D.g0), (uint32_t)D.slice_floats * 4},
+                       {S, tb.lw_tab + D.slice_base + (size_t)D.slice_floats * (g0 - D.g0), (uint32_t)(D.slice_floats * ng) * 4},
                        {s_plk, tb.totplnk + 184 * b, 184 * 4}};
     stage_tables(bar, req, 3);
   }
@@ -553,143 +754,33 @@ __global__ void __launch_bounds__(LW_BLOCK, 2) k_lw_solve(LwArgs a) {
   }
   for (int t = threadIdx.x; t < 7 * 59; t += blockDim.x) s_chi[t] = tb.chi_mls[t];
   __syncthreads();
-  const int c = tile * LW_BLOCK + threadIdx.x;
-  if (c >= a.ncols) return;
+  int c = tile * LW_BLOCK + threadIdx.x;
+  const bool live = c < a.ncols;              // every lane stays: the band bodies use warp votes
+  if (!live) c = a.ncols - 1;
   const LwSmem sm{s_et, S, s_plk, s_rat, s_chi};
-  switch (b) {
-    case 0: lw_solve_band<NL, 1>(a, sm, D, g, c); break;
-    case 1: lw_solve_band<NL, 2>(a, sm, D, g, c); break;
-    case 2: lw_solve_band<NL, 3>(a, sm, D, g, c); break;
-    case 3: lw_solve_band<NL, 4>(a, sm, D, g, c); break;
-    case 4: lw_solve_band<NL, 5>(a, sm, D, g, c); break;
-    case 5: lw_solve_band<NL, 6>(a, sm, D, g, c); break;
-    case 6: lw_solve_band<NL, 7>(a, sm, D, g, c); break;
-    case 7: lw_solve_band<NL, 8>(a, sm, D, g, c); break;
-    case 8: lw_solve_band<NL, 9>(a, sm, D, g, c); break;
-    case 9: lw_solve_band<NL, 10>(a, sm, D, g, c); break;
-    case 10: lw_solve_band<NL, 11>(a, sm, D, g, c); break;
-    case 11: lw_solve_band<NL, 12>(a, sm, D, g, c); break;
-    case 12: lw_solve_band<NL, 13>(a, sm, D, g, c); break;
-    case 13: lw_solve_band<NL, 14>(a, sm, D, g, c); break;
-    case 14: lw_solve_band<NL, 15>(a, sm, D, g, c); break;
-    default: lw_solve_band<NL, 16>(a, sm, D, g, c); break;
+#define LWB(B_, N_) lw_band_body<B_, N_>(a, sm, grp, g0, c, live)
+  // (band, group size) pairs that make_sweep_groups(LW_GMAX = 8) produces from ngc = 10,12,16,14,16,8,12,8,12,6,8,8,4,2,2,2
+  switch (b * 32 + ng) {
+    case 0 * 32 + 5: LWB(1, 5); break;    case 1 * 32 + 6: LWB(2, 6); break;    case 2 * 32 + 8: LWB(3, 8); break;
+    case 3 * 32 + 7: LWB(4, 7); break;    case 4 * 32 + 8: LWB(5, 8); break;    case 5 * 32 + 8: LWB(6, 8); break;
+    case 6 * 32 + 6: LWB(7, 6); break;    case 7 * 32 + 8: LWB(8, 8); break;    case 8 * 32 + 6: LWB(9, 6); break;
+    case 9 * 32 + 6: LWB(10, 6); break;   case 10 * 32 + 8: LWB(11, 8); break;  case 11 * 32 + 8: LWB(12, 8); break;
+    case 12 * 32 + 4: LWB(13, 4); break;  case 13 * 32 + 2: LWB(14, 2); break;  case 14 * 32 + 2: LWB(15, 2); break;
+    case 15 * 32 + 2: LWB(16, 2); break;
+    default: break;
   }
+#undef LWB
 }
 
-static int lw_solve_smem() { return 10002 * 8 + (SLICE_MAX + 184 + 6 * 60 + 416) * 4 + 16; }
-
-void launch_lw_solve(const LwArgs &a, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_lw_solve<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, lw_solve_smem());
-    cudaFuncSetAttribute(k_lw_solve<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lw_solve_smem());
-    cudaFuncSetAttribute(k_lw_solve<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, lw_solve_smem());
-    attr = true;
-  }
-  dim3 grid(NGLW * ((a.ncols + LW_BLOCK - 1) / LW_BLOCK));
-  if (a.ws.nlay <= 64) k_lw_solve<64><<<grid, LW_BLOCK, lw_solve_smem(), s>>>(a);
-  else if (a.ws.nlay <= 128) k_lw_solve<128><<<grid, LW_BLOCK, lw_solve_smem(), s>>>(a);
-  else k_lw_solve<160><<<grid, LW_BLOCK, lw_solve_smem(), s>>>(a);
-  count_launch();
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Upward sweep of rtrnmc (LW:3322-3356) + ordered sum over the g-points of a band (LW:3365-3395).
-// One thread per (column, band, stream), block = one 128-column record tile: the NG upward radiances of the band's
-// g-points are its register state; per step it requests the NG float4 records of that level together (written by
-// k_lw_solve; the addresses do not depend on the recurrence, so the memory system sees NG independent 2 KB loads per
-// block), advances the NG two-term recurrences and adds the NG up / down radiances in g order.  It writes ONE band partial
-// [band][level][kind][c] per kind; no per-g flux is ever stored.  No shared memory, no barriers, no atomics.
-// HBM-bound: 16 B per (column, g, level, stream).
-template <int NG>
-__global__ void __launch_bounds__(128) k_lw_sweep(LwArgs a, int grp, int g0) {
-  const LwWs &ws = a.ws;
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= a.ncols) return;
-  const int v = blockIdx.y;                    // 0 full (+ clear), 1 clean (+ clean-clear)
-  const int nlay = ws.nlay, nk = ws.nk;
-  const size_t pcap = ws.pcap, cap = ws.cap;
-  const int nv = gridDim.y, lane = threadIdx.x;                // block = one record tile
-  const unsigned lvstride = (unsigned)nv * NGLW;               // records per (tile, level)
-  const size_t r0 = ((size_t)blockIdx.x * (nlay + 1) * nv + v) * NGLW + g0;
-  const float *__restrict__ rec = ws.rec + r0 * LW_REC;
-  const float *__restrict__ recC = ws.recC + r0 * LW_REC_D;
-
-  bool iclddn = false;                         // the flag the downward sweep leaves behind (LW:3218): any cloud in the column
-  for (int w = 0; w < ws.W; w++) iclddn = iclddn || ws.anyc[(size_t)w * cap + c] != 0u;
-
-  float rl[NG], rc[NG];
-  float *__restrict__ bpart = ws.bpart + (size_t)grp * (nlay + 1) * nk * pcap + c;
-  const int kU = ws.kslot[v == 0 ? K_FU : K_NU], kD = ws.kslot[v == 0 ? K_FD : K_ND];
-  const int kCU = ws.kslot[v == 0 ? K_CU : K_XU], kCD = ws.kslot[v == 0 ? K_CD : K_XD];
-  const bool clr = v == 0 || (a.variants & ARC_VAR_CLEANCLEAR) != 0;
-  {   // level 0: the upward radiances leaving the surface
-    float sU = 0.f, sCU = 0.f;
-#pragma unroll
-    for (int i = 0; i < NG; i++) {
-      const float2 s0 = ws.scrS[((size_t)v * NGLW + g0 + i) * pcap + c];
-      rl[i] = s0.x; rc[i] = s0.y;
-    }
-#pragma unroll
-    for (int i = 0; i < NG; i++) { sU = sU + rl[i]; sCU = sCU + rc[i]; }
-    __stcs(bpart + (size_t)kU * pcap, sU);
-    if (clr) __stcs(bpart + (size_t)kCU * pcap, sCU);
-  }
-  uint32_t aw = 0u;
-  for (int lev = 1; lev <= nlay; lev++) {
-    // record lev: U of layer lev-1 (-> upward radiances at level lev) and the downward radiances at level lev-1
-    const int lay = lev - 1;
-    if ((lay & 31) == 0) aw = ws.anyc[(size_t)(lay >> 5) * cap + c];
-    const bool icldlyr = (aw >> (lay & 31)) & 1u;
-    float2 u[NG], d[NG];
-    const float *__restrict__ q = rec + (size_t)((unsigned)lev * lvstride) * LW_REC;       // the group's records: immediate offsets
-#pragma unroll
-    for (int i = 0; i < NG; i++) {
-      const float4 r = __ldcs(reinterpret_cast<const float4 *>(q + i * LW_REC) + lane);
-      u[i] = make_float2(r.x, r.y); d[i] = make_float2(r.z, r.w);
-    }
-    float sU = 0.f, sCU = 0.f, sD = 0.f, sCD = 0.f;
-    if (icldlyr) {
-#pragma unroll
-      for (int i = 0; i < NG; i++) {
-        const float2 xy = __ldcs(reinterpret_cast<const float2 *>(recC + ((size_t)((unsigned)lev * lvstride) + i) * LW_REC_D) + lane);
-        rl[i] = rl[i] - rl[i] * xy.x + xy.y;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NG; i++) rl[i] = rl[i] + (u[i].y - rl[i]) * u[i].x;
-    }
-#pragma unroll
-    for (int i = 0; i < NG; i++) {
-      if (iclddn) rc[i] = rc[i] + (u[i].y - rc[i]) * u[i].x;
-      else rc[i] = rl[i];
-      sU = sU + rl[i]; sCU = sCU + rc[i]; sD = sD + d[i].x; sCD = sCD + d[i].y;
-    }
-    float *bp = bpart + (size_t)lev * nk * pcap;
-    __stcs(bp + (size_t)kU * pcap, sU); __stcs(bp - (size_t)nk * pcap + (size_t)kD * pcap, sD);
-    if (clr) { __stcs(bp + (size_t)kCU * pcap, sCU); __stcs(bp - (size_t)nk * pcap + (size_t)kCD * pcap, sCD); }
-  }
-  {   // TOA: no downward radiance
-    float *bp = bpart + (size_t)nlay * nk * pcap;
-    __stcs(bp + (size_t)kD * pcap, 0.f);
-    if (clr) __stcs(bp + (size_t)kCD * pcap, 0.f);
-  }
-}
+static int lw_band_smem() { return 10002 * 8 + (LW_GMAX * LW_SLICE_MAX + 184 + 6 * 60 + 416) * 4 + 16; }
 
 int lw_sweep_groups() { return h_lw_grp.n; }
-void launch_lw_sweep(const LwArgs &a, cudaStream_t s) {
-  const dim3 grid((a.ncols + 127) / 128, (a.variants & ARC_VAR_CLEAN) ? 2 : 1);
-  for (int q = 0; q < h_lw_grp.n; q++) {
-    const int g0 = h_lw_grp.g0[q];
-    switch (h_lw_grp.ng[q]) {
-#define SWEEP_CASE(N) case N: k_lw_sweep<N><<<grid, 128, 0, s>>>(a, q, g0); break;
-      SWEEP_CASE(1) SWEEP_CASE(2) SWEEP_CASE(3) SWEEP_CASE(4) SWEEP_CASE(5) SWEEP_CASE(6) SWEEP_CASE(7) SWEEP_CASE(8)
-      SWEEP_CASE(9) SWEEP_CASE(10) SWEEP_CASE(11) SWEEP_CASE(12) SWEEP_CASE(13) SWEEP_CASE(14) SWEEP_CASE(15) SWEEP_CASE(16)
-#undef SWEEP_CASE
-      default: break;
-    }
-  }
-  count_launch(h_lw_grp.n);
+void launch_lw_band(const LwArgs &a, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_lw_band, cudaFuncAttributeMaxDynamicSharedMemorySize, lw_band_smem()); attr = true; }
+  const int ntiles = (a.ncols + LW_BLOCK - 1) / LW_BLOCK;
+  k_lw_band<<<ntiles * h_lw_grp.n, LW_BLOCK, lw_band_smem(), s>>>(a);
+  count_launch();
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -411,6 +411,11 @@ __global__ void __launch_bounds__(128) k_sw_prep(SwArgs a) {
     ws.colf[(size_t)SWF_ADJFLUX * cap + c] = 1.0f * solvar;
   }
 
+  // log2 of the 14 Angstrom bases 0.4 / wavemid (the level-independent half of the reference's ** , SW:11008)
+  double l2wave[NBSW];
+#pragma unroll
+  for (int b = 0; b < NBSW; b++) l2wave[b] = glm::powf_log2(0.4f / tb.wavemid[b]);
+
   unsigned char jps[PREP_MAXLAY];
   float o3top_ref = 0.f, o31d_top = 0.f;   // o3mmr(nz), o31d(nz) for the shifted climatology above the model top
   float h2o_prev = 0.f;
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(128) k_sw_prep(SwArgs a) {
       if (t300 > thresh && t999 > thresh) {
         chem = true;
         t400 = a.tauaer400[q]; w4 = a.waer400[q]; w6 = a.waer600[q]; g4 = a.gaer400[q]; g6 = a.gaer600[q];
-        lograt = logf(t300 / t999) / logf(999.f / 300.f);
+        lograt = glm::logf_(t300 / t999) / glm::logf_(999.f / 300.f);
       }
     }
     for (int b = 0; b < NBSW; b++) {
@@ -516,7 +521,7 @@ __global__ void __launch_bounds__(128) k_sw_prep(SwArgs a) {
       }
       if (chem) {
         const float wavemid = tb.wavemid[b];
-        taua = t400 * powf(0.4f / wavemid, lograt);
+        taua = t400 * glm::powf_with(0.4f / wavemid, lograt, l2wave[b]);
         float slope = (w6 - w4) / .2f;
         ssaa = slope * (wavemid - .6f) + w6;
         if (ssaa < 0.4f) ssaa = 0.4f;
@@ -804,7 +809,7 @@ __global__ void __launch_bounds__(128) k_lw_prep(LwArgs a) {
     const int ibnd = b + 1;
     if (ibnd == 1 || ibnd == 4 || ibnd >= 10) sd = 1.66f;
     else {
-      sd = tb.a0[b] + tb.a1[b] * expf(tb.a2[b] * pwvcm);
+      sd = tb.a0[b] + tb.a1[b] * glm::expf_(tb.a2[b] * pwvcm);
       if (sd > 1.80f) sd = 1.80f;
       if (sd < 1.50f) sd = 1.50f;
     }

@@ -102,27 +102,48 @@ const char *LW_SCHEMA[16] = {
 
 struct Raw { std::vector<float> v; bool g_first = false; int lead = 1; };   // lead = elements per g (g last) or columns (g first)
 
+// Fortran sequential unformatted file: every record is <int32 n> n bytes <int32 n>.  WRF is built with
+// -fconvert=big-endian / -convert big_endian, so the RRTMG_*_DATA files it ships are big-endian; files written by a
+// native little-endian program (ktables.py) are not.  The byte order is detected from the first record (the leading and
+// trailing markers must agree and fit the file in exactly one of the two readings) and every 4-byte word
+// (REAL*4 / INTEGER*4 payload, markers) is swapped when it is not the host's.
 struct FileCursor {
   std::vector<char> buf; size_t pos = 0, rec_end = 0;
+  uint32_t rec_len = 0;
+  bool swap = false;
+  static uint32_t bswap(uint32_t x) { return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24); }
+  uint32_t word(size_t at) const { uint32_t x; memcpy(&x, &buf[at], 4); return swap ? bswap(x) : x; }
   bool open(const std::string &p, std::string &err) {
     std::ifstream f(p, std::ios::binary);
     if (!f) { err = "cannot open " + p; return false; }
     buf.assign((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (buf.size() < 8) { err = p + ": not a Fortran unformatted file"; return false; }
+    bool ok[2] = {false, false};
+    for (int q = 0; q < 2; q++) {
+      swap = q == 1;
+      const uint64_t n = word(0);
+      ok[q] = n > 0 && n % 4 == 0 && n + 8 <= buf.size() && word(4 + (size_t)n) == n;
+    }
+    if (ok[0] == ok[1]) { err = p + ": cannot determine the byte order of the record markers"; return false; }
+    swap = ok[1];
     return true;
   }
   bool begin(std::string &err) {
     if (pos + 4 > buf.size()) { err = "unexpected end of file"; return false; }
-    int32_t n; memcpy(&n, &buf[pos], 4); pos += 4; rec_end = pos + (size_t)n;
+    const int32_t n = (int32_t)word(pos); pos += 4; rec_end = pos + (size_t)n; rec_len = (uint32_t)n;
     if (n < 0 || rec_end + 4 > buf.size()) { err = "truncated record"; return false; }
     return true;
   }
   bool take(void *dst, size_t bytes, std::string &err) {
     if (pos + bytes > rec_end) { err = "record shorter than its schema"; return false; }
-    memcpy(dst, &buf[pos], bytes); pos += bytes; return true;
+    memcpy(dst, &buf[pos], bytes); pos += bytes;
+    if (swap) { uint32_t *w = (uint32_t *)dst; for (size_t i = 0; i < bytes / 4; i++) w[i] = bswap(w[i]); }
+    return true;
   }
   bool end(std::string &err) {
     if (pos != rec_end) { err = "record longer than its schema"; return false; }
-    int32_t tail; memcpy(&tail, &buf[pos], 4); pos += 4;
+    if (word(pos) != rec_len) { err = "record markers disagree"; return false; }
+    pos += 4;
     return true;
   }
 };
