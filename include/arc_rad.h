@@ -28,6 +28,16 @@
  * New relative to the reference: `memspace` (pointers are host or device
  * memory) and `variant_mask`, which hands the whole tile over once with a
  * call-variant axis instead of the reference's two internal solver calls.
+ *
+ * Streams (memspace = ARC_MEM_DEVICE).  The library enqueues its kernels on
+ * private non-blocking CUDA streams (the main one is arc_rad_stream()) and does
+ * NOT order them against any stream of the caller.  Contract: every input array,
+ * and every INOUT output array the caller pre-filled, must be complete before
+ * the call - cudaStreamSynchronize / cudaDeviceSynchronize on the producing
+ * streams, or an event the producer recorded that the caller has waited on with
+ * cudaStreamWaitEvent on arc_rad_stream() BEFORE calling.  On return every output
+ * is complete: each entry point synchronises its own streams before it returns.
+ * With ARC_MEM_HOST the call is synchronous in the ordinary host sense.
  */
 #ifndef ARC_RAD_H
 #define ARC_RAD_H
@@ -209,6 +219,19 @@ int  arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const flo
  * for calc_standard_stats (neighbour + manhattan options: ordered pairs of edge-sharing cells, N-1 variance;
  * misc_stats_library.ncl:196-371).  corrected SE = SE * I (misc_stats_library.ncl:449). */
 int  arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *const *fields, float *out);
+/* cal_cldfra1 (module_radiation_driver.F:2886-3122; radiation_driver calls it for icloud = 1, DRV:1104-1118): cloud fraction
+ * CLDFRA(i,k,j) from QV, QC, QI, QS, T, p, tile levels kts..kte.  f_q*: 1 = .TRUE., 0 = .FALSE., < 0 = argument not PRESENT;
+ * f_ice_phy and cldfra1_flag (INTEGER(i,k,j): 1 no condensate, 2 saturated, 3 partial) may be NULL.  Bit-exact with the
+ * reference's arithmetic (unfused, glibc EXP and **). */
+int  arc_rad_cal_cldfra1(const ArcDims *d, int memspace, const float *qv, const float *qc, const float *qi, const float *qs, int f_qv,
+                         int f_qc, int f_qi, int f_qs, const float *t_phy, const float *p_phy, const float *f_ice_phy, int mp_physics,
+                         float *cldfra, int *cldfra1_flag);
+/* Order statistics of `nfields` 2-D (i,j) fields over the tile: out[f * nperc + q] = sorted(field f)[round(0.01 * perc[q] * (N - 1))],
+ * the element calc_boxplot_stats picks (misc_stats_library.ncl:145-189); perc = {50, 25, 75, 5, 95} gives calc_standard_stats'
+ * median, lower / upper quartile, 5th / 95th percentile (ncl:439-445).  Exact (radix selection, no interpolation).  The 5-cell
+ * domain trim of calculate_domain_stats (data_extraction_library.ncl:318-322) is a matter of the tile bounds in `d`.
+ * With several GPUs the field must be gathered first (an order statistic does not combine from partial results). */
+int  arc_rad_percentiles(const ArcDims *d, int memspace, int nfields, const float *const *fields, int nperc, const float *perc, float *out);
 /* Host-only probe (no GPU needed): parse and g-point-reduce the table files as arc_rad_init does; returns the element count
  * of the reduced table `name` ("sw16.absa", "lw3.ka_mn2o", "lw_nlayers" ...) and copies it to buf when cap suffices;
  * name == NULL only validates the files.  Negative return = -ARC_ERR_*.  (sw_kgbNN / cmbgbNN, SW:5022-6065, 11315-12384) */
@@ -269,7 +292,9 @@ int  arc_aer_mie_direct(int wl, float radius_cm, float refr, float refi, float *
 
 /* Kernel launch counter (number of this library's CUDA kernels launched since init) */
 long long arc_rad_launch_count(void);
-/* CUDA stream used for all work (cudaStream_t as void*), for event timing by the caller */
+/* The library's main CUDA stream (cudaStream_t as void*): for event timing by the caller and for ordering the library behind
+ * a producer (cudaStreamWaitEvent(arc_rad_stream(), ev) before a call, see "Streams" at the top).  Every call also uses two
+ * more private streams that fork from and join this one inside the call. */
 void *arc_rad_stream(void);
 /* time (ms, CUDA events on the launching stream) spent in the named kernel class during the last call:
  * "sw_mcica", "sw_prep", "sw_solve", "sw_sweep", "sw_reduce", "lw_mcica", "lw_prep", "lw_solve", "lw_sweep", "lw_reduce",

@@ -1,4 +1,5 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.hpp).  C entry points for ctypes.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -81,6 +82,64 @@ int arc_oracle_pt(const float *p, const float *t, int n, int *packed) {
     if (jt1 < 1) jt1 = 1; else if (jt1 > 4) jt1 = 4;
     packed[q] = jp | (jt << 8) | (jt1 << 12);
   }
+  return 0;
+}
+
+// cal_cldfra1, module_radiation_driver.F:2886-3122 (scalar restatement; f_q*: 1 true, 0 false, < 0 not PRESENT)
+int arc_oracle_cal_cldfra1(const ArcDims *d, const float *QV, const float *QC, const float *QI, const float *QS, int f_qv, int f_qc, int f_qi,
+                           int f_qs, const float *t_phy, const float *p_phy, const float *F_ICE_PHY, int mp_physics, float *CLDFRA, int *flag) {
+  (void)f_qv;
+  const float ALPHA0 = 100.f, GAMMA = 0.49f, QCLDMIN = 1.E-12f, PEXP = 0.25f, RHGRID = 1.0f;
+  const float SVP1 = 0.61078f, SVP2 = 17.2693882f, SVPI2 = 21.8745584f, SVP3 = 35.86f, SVPI3 = 7.66f, SVPT0 = 273.15f;
+  const float r_d = 287.f, r_v = 461.6f, ep_2 = r_d / r_v;
+  const int ni = d->ime - d->ims + 1, nk = d->kme - d->kms + 1;
+  for (int j = d->jts; j <= d->jte; j++)
+    for (int k = d->kts; k <= d->kte; k++)
+      for (int i = d->its; i <= d->ite; i++) {
+        const size_t q = (size_t)(i - d->ims) + (size_t)ni * ((size_t)(k - d->kms) + (size_t)nk * (size_t)(j - d->jms));
+        float tc = t_phy[q] - SVPT0;
+        float esw = 1000.0f * SVP1 * expf(SVP2 * tc / (t_phy[q] - SVP3));
+        float esi = 1000.0f * SVP1 * expf(SVPI2 * tc / (t_phy[q] - SVPI3));
+        float QVSW = ep_2 * esw / (p_phy[q] - esw);
+        float QVSI = ep_2 * esi / (p_phy[q] - esi);
+        float weight = 0.f, QCLD = 0.f;
+        const bool present = f_qi >= 0 && f_qc >= 0 && f_qs >= 0;
+        if (present) {
+          const bool F_QI = f_qi > 0, F_QC = f_qc > 0, F_QS = f_qs > 0;
+          const float qi = QI ? QI[q] : 0.f, qc = QC ? QC[q] : 0.f, qs = QS ? QS[q] : 0.f;
+          if (F_QI && F_QC && F_QS) { QCLD = qi + qc + qs; if (QCLD < QCLDMIN) weight = 0.f; else weight = (qi + qs) / QCLD; }
+          if (F_QI && F_QC && !F_QS) { QCLD = qi + qc; if (QCLD < QCLDMIN) weight = 0.f; else weight = qi / QCLD; }
+          if (F_QC && !F_QI && !F_QS) {
+            QCLD = qc;
+            if (QCLD < QCLDMIN) weight = 0.f; else { if (t_phy[q] > 273.15f) weight = 0.f; if (t_phy[q] <= 273.15f) weight = 1.f; }
+          }
+          if (F_QC && !F_QI && F_QS && F_ICE_PHY) {
+            float QIMID = qs, QWMID = qc;
+            QCLD = QWMID + QIMID;
+            if (QCLD < QCLDMIN) weight = 0.f; else weight = F_ICE_PHY[q];
+          }
+          if (mp_physics == 5 || mp_physics == 15) {
+            float QIMID = qi, QWMID = qc;
+            QCLD = QWMID + QIMID;
+            if (QCLD < QCLDMIN) weight = 0.f; else { weight = QIMID / QCLD; if (tc < -40.f) weight = 1.f; }
+          }
+        }
+        float QVS_WEIGHT = (1 - weight) * QVSW + weight * QVSI;
+        float RHUM = QV[q] / QVS_WEIGHT;
+        int fl;
+        if (!present || QCLD < QCLDMIN) { CLDFRA[q] = 0.f; fl = 1; }
+        else if (RHUM >= RHGRID) { CLDFRA[q] = 1.f; fl = 2; }
+        else {
+          fl = 3;
+          float SUBSAT = std::max(1.E-10f, RHGRID * QVS_WEIGHT - QV[q]);
+          float DENOM = powf(SUBSAT, GAMMA);
+          float ARG = std::max(-6.9f, -ALPHA0 * QCLD / DENOM);
+          RHUM = std::max(1.E-10f, RHUM);
+          CLDFRA[q] = powf(RHUM / RHGRID, PEXP) * (1.f - expf(ARG));
+          if (CLDFRA[q] < .01f) CLDFRA[q] = 0.f;
+        }
+        if (flag) flag[q] = fl;
+      }
   return 0;
 }
 

@@ -50,3 +50,41 @@ def test_calc_coszen_oracle(orc):
     assert abs(lon[j0, i_noon]) <= 10.0 and cz[j0].max() > 0.99
     assert np.allclose(cz[:, i_noon], np.cos(np.radians(lat[:, i_noon])), atol=2e-3)
     assert (cz < 0).mean() > 0.35 and (cz > 0).mean() > 0.35          # half the globe is dark
+
+
+def test_cal_cldfra1_oracle_known_answers(orc):
+    """cal_cldfra1 (module_radiation_driver.F:2886-3122) restated in the oracle: no condensate -> 0 (flag 1); condensate at or above
+    saturation -> 1 (flag 2); subsaturated -> (RH)^0.25 (1 - exp(-100 q / subsat^0.49)) with the 0.01 floor (flag 3); the
+    ice / water weighting of the saturation mixing ratio; OPTIONAL flags not PRESENT -> 0."""
+    from wrfchem_arc_interactions_b200 import synth
+    dom = synth.make_domain(12, 5, 40, seed=3, cloudy_frac=1.0)
+    shp = dom["t3d"].shape
+    cf = np.full(shp, -9.0, np.float32); fl = np.full(shp, -9, np.int32)
+    p = dom["p3d"]; t = dom["t3d"]
+    orc.cal_cldfra1(dom["dims"], cf, dom["qv3d"], dom["qc3d"], dom["qi3d"], dom["qs3d"], t, p, cldfra1_flag=fl)
+    tile = (slice(None), slice(0, 40), slice(None))
+    assert np.all(cf[:, 40, :] == -9.0)                              # the level kme is not part of the tile
+    c, f = cf[tile], fl[tile]
+    qcld = (dom["qi3d"] + dom["qc3d"] + dom["qs3d"])[tile]
+    assert np.all(c[qcld < 1e-12] == 0) and np.all(f[qcld < 1e-12] == 1)
+    assert set(np.unique(f)) <= {1, 2, 3} and (f == 3).any()
+    assert np.all((c == 0) | (c >= 0.01)) and c.max() <= 1.0
+    assert np.all(c[f == 2] == 1.0)
+    # closed form of one partially cloudy cell, in float64 (the oracle runs float32)
+    jj, kk, ii = [x[0] for x in np.nonzero((f == 3) & (c > 0.05) & (c < 0.95))]
+    tk, pp = float(t[jj, kk, ii]), float(p[jj, kk, ii])
+    esw = 610.78 * np.exp(17.2693882 * (tk - 273.15) / (tk - 35.86)); esi = 610.78 * np.exp(21.8745584 * (tk - 273.15) / (tk - 7.66))
+    qvsw, qvsi = 287.0 / 461.6 * esw / (pp - esw), 287.0 / 461.6 * esi / (pp - esi)
+    qi, qc, qs, qv = (float(dom[k][jj, kk, ii]) for k in ("qi3d", "qc3d", "qs3d", "qv3d"))
+    w = (qi + qs) / (qi + qc + qs)
+    qvs = (1 - w) * qvsw + w * qvsi
+    want = (qv / qvs) ** 0.25 * (1 - np.exp(max(-6.9, -100.0 * (qi + qc + qs) / max(1e-10, qvs - qv) ** 0.49)))
+    assert abs(float(c[jj, kk, ii]) - want) < 2e-5
+    # OPTIONAL flags not PRESENT: zero everywhere
+    cf2 = np.full(shp, -9.0, np.float32)
+    orc.cal_cldfra1(dom["dims"], cf2, dom["qv3d"], dom["qc3d"], dom["qi3d"], dom["qs3d"], t, p, F_QI=None)
+    assert np.all(cf2[tile] == 0)
+    # qc only (MP options 1 / 3): ice saturation at and below freezing
+    cf3 = np.zeros(shp, np.float32)
+    orc.cal_cldfra1(dom["dims"], cf3, dom["qv3d"], dom["qc3d"], None, None, t, p, F_QI=False, F_QS=False)
+    assert (cf3[tile] > 0).any()

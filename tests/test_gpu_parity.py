@@ -1,11 +1,13 @@
 """Parity of the CUDA path (through the C ABI) against the oracle on identical synthetic columns and identical synthetic
 k-tables.  Bars (BASELINE.json north_star): jp / jt / jt1 / indfor / indself (+ laytrop, indminor) and the McICA masks
-bit-exact; fluxes within 1e-4 relative or 0.01 W/m2 absolute; heating rates within 1e-4 relative or 0.01 K/day.
+bit-exact; fluxes within 1e-4 relative or 0.01 W/m2 absolute; heating rates within 1e-4 relative or 0.01 K/day - ONE
+tolerance for EVERY column.
 
-One documented exception (DESIGN.md "Parity"): reftra_sw evaluates a removable 0/0 at k*mu0 = 1 through a 10,001-entry
-exp table (SW:2629-2660); within |1-(k*mu0)^2| < 1e-3 the reference's own result is rounding noise (a 1-ulp change of an
-input moves it by O(1)).  The oracle reports that conditioning per column (ArcDebug.sw_cond); columns below the threshold
-are held to a looser bar and counted."""
+Round 1 held the columns that touch reftra_sw's removable singularity k*mu0 = 1 (SW:2629-2660) to a looser bar because the
+inputs of reftra differed from the oracle's in the last bit.  They no longer do: LOG / ** go through glibc-identical
+device functions (csrc/glibc_math.cuh) and taumol_sw is evaluated unfused, so the interpolation weights, the gas / Rayleigh /
+cloud optical depths and the solar source are BIT-EXACT (asserted below) and reftra_sw, itself unfused IEEE, sees the
+oracle's operands."""
 import ctypes as C
 import os
 import sys
@@ -14,10 +16,10 @@ import numpy as np
 import pytest
 
 from conftest import init, interior, run_pair
+from parity_cases import FULL_CASES, compare_outputs, run_case
 from wrfchem_arc_interactions_b200 import abi, radiation as R, synth
 
 pytestmark = pytest.mark.gpu
-COND_THR = 1.0e-3
 SW2D = ("gsw", "swcf", "swupt", "swuptc", "swuptcln", "swdnt", "swdntc", "swdntcln", "swupb", "swupbc", "swupbcln", "swdnb", "swdnbc",
         "swdnbcln", "swvisdir", "swvisdif", "swnirdir", "swnirdif", "swddir", "swddni", "swddif", "swuptclnc", "swdntclnc", "swupbclnc", "swdnbclnc")
 SWPROF = ("swupflx", "swupflxc", "swupflxcln", "swdnflx", "swdnflxc", "swdnflxcln")
@@ -46,33 +48,25 @@ def both(which, lib, orc, dom, ktab, **over):
     return og, oo, tg, to
 
 
+def bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
 def check_sw(dom, og, oo, tg, to):
     sun = to["laytrop"] >= 0
     assert np.array_equal(tg["laytrop"], to["laytrop"])
     for k in ("jp", "jt", "jt1", "indfor", "indself", "cldmask"):
         assert np.array_equal(tg[k][sun], to[k][sun]), "%s not bit-exact" % k
-    for k, tol in (("taug", 2e-5), ("taur", 1e-6), ("sfluxzen", 1e-6), ("taucmc", 1e-6), ("fac00", 2e-3)):
-        a, b = tg[k][sun].astype(np.float64), to[k][sun].astype(np.float64)
-        assert np.all(np.abs(a - b) <= tol * np.abs(b) + 1e-6 * np.abs(b).max()), k
-    good = sun & (to["sw_cond"] >= COND_THR)
-    illc = sun & ~good
-    nbad_ill = np.zeros(sun.size, bool)
-    for k in SW2D + SWPROF:
-        a, b = per_column(dom, og[k]), per_column(dom, oo[k])
-        ok = within(a, b)
-        okc = ok if ok.ndim == 1 else ok.all(axis=1)
-        assert okc[good].all(), "%s: %d well-conditioned columns out of tolerance" % (k, (~okc[good]).sum())
-        assert okc[~sun].all(), k
-        nbad_ill |= ~okc & illc
-        dev = np.abs(a.astype(np.float64) - b) / np.maximum(np.abs(b), 10.0)
-        assert dev.max() < 0.05, "%s: gross deviation %.3g" % (k, dev.max())
-    if illc.sum() >= 50:
-        assert nbad_ill.sum() <= 0.05 * illc.sum(), "ill-conditioned columns out of tolerance: %d of %d" % (nbad_ill.sum(), illc.sum())
-    ok = within(tg["hr"], to["hr"])          # K/day
-    assert ok[good].all(), "heating rate"
-    a, b = per_column(dom, og["rthratensw"]), per_column(dom, oo["rthratensw"])
-    assert within(a * 86400.0, b * 86400.0)[good].all()
-    return dict(sunlit=int(sun.sum()), well_conditioned=int(good.sum()), ill_out_of_tol=int(nbad_ill.sum()))
+    # the operands of reftra_sw: bit-exact, not merely close
+    for k in ("fac00", "fac01", "fac10", "fac11", "taug", "taur", "sfluxzen", "taucmc"):
+        assert bits_equal(tg[k][sun], to[k][sun]), "%s not bit-exact (%d words differ)" % (
+            k, int((tg[k][sun].view(np.uint32) != to[k][sun].view(np.uint32)).sum()))
+    info = compare_outputs(dom, og, oo)
+    assert info["out_of_tolerance"] == 0, "SW: %d of %d columns out of tolerance (worst %.3g W/m2)" % (
+        info["out_of_tolerance"], info["columns"], info["worst_abs"])
+    assert within(tg["hr"], to["hr"]).all(), "heating rate"          # K/day, every RRTMG layer
+    info["sunlit"] = int(sun.sum())
+    return info
 
 
 def check_lw(dom, lib, og, oo, tg, to):
@@ -96,7 +90,7 @@ def test_sw_c1(lib, orc, ktab):
     dom = synth.make_domain(32, 32, 40)
     info = check_sw(dom, *both("sw", lib, orc, dom, ktab))
     print("SW C1:", info)
-    assert info["well_conditioned"] > 100
+    assert info["sunlit"] > 700
 
 
 def test_lw_c1(lib, orc, ktab):
@@ -496,6 +490,40 @@ def test_driver_post_and_domain_stats(lib, ktab):
     assert np.isclose(cols["corrected_standard_error"][0], ref["corrected_standard_error"], rtol=1e-5, atol=1e-9)
 
 
+def test_percentiles_and_trim_match_the_ncl_statistics(lib, ktab):
+    """Median, quartiles, 5th / 95th percentile of calc_standard_stats (radix selection on the device) and the 5-cell domain
+    trim of calculate_domain_stats: exactly the elements the restated NCL picks, on host and device arrays, with ties, negative
+    values and a one-row tile."""
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ncl_stats as N
+    dom = synth.make_domain(45, 31, 40, seed=29, halo=2)
+    init(lib, dom, ktab)
+    sw, lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    rng = np.random.default_rng(8)
+    ties = np.round(rng.normal(0, 3, sw["swupt"].shape)).astype(np.float32)        # many equal values, both signs, zeros
+    fields = {"SWUPT": sw["swupt"], "SWCF": sw["swcf"], "OLR": lw["olr"], "LWCF": lw["lwcf"], "TIES": ties}
+    names = list(fields)
+    for trim in (0, 5):
+        host = lib.domain_statistics(dom["dims"], [fields[n] for n in names], names=names, trim=trim)
+        devf = [torch.from_numpy(fields[n]).cuda() for n in names]
+        devs = lib.domain_statistics(dom["dims"], devf, names=names, trim=trim)
+        for n in names:
+            ref = N.calc_standard_stats(interior(dom, fields[n]), trim=trim)
+            for k in ("median", "lower_quartile", "upper_quartile", "p05", "p95", "min", "max", "N"):
+                assert host[n][k] == ref[k] and devs[n][k] == ref[k], (trim, n, k, host[n][k], ref[k])
+            assert np.isclose(host[n]["avg"], ref["avg"], rtol=1e-12) and np.isclose(host[n]["stddev"], ref["stddev"], rtol=1e-9)
+            assert abs(host[n]["morans_i"] - ref["morans_i"]) <= 2e-6 * max(1.0, abs(ref["morans_i"]))
+    # arbitrary percentile list, one-row tile
+    L = lib.lib
+    d1 = abi.make_dims(dict(dom["dims"], jts=3, jte=3))
+    perc = np.array([0.0, 33.0, 100.0], np.float32); out = np.zeros(3, np.float32)
+    ptr = (abi.c_fp * 1)(abi.fptr(lw["olr"]))
+    lib.check(L.arc_rad_percentiles(C.byref(d1), 0, 1, ptr, 3, abi.fptr(perc), C.c_void_p(out.ctypes.data)))
+    row = np.sort(interior(dom, lw["olr"])[2])
+    assert out[0] == row[0] and out[2] == row[-1] and out[1] == row[N.ncl_round(np.float32(np.float32(0.01) * np.float32(33.0)) * np.float32(row.size - 1))]
+
+
 def test_four_scenario_decomposition_from_device_statistics(lib, ktab):
     """SURVEY 8(f)3 end to end: four scenarios (BASE, ALT = half the aerosol, and both without aerosol-radiation interaction)
     through RRTMG_SWRAD / RRTMG_LWRAD, TOA fields reduced on the device (arc_rad_domain_stats), statistics columns and the
@@ -563,6 +591,31 @@ def test_coszen_and_accumulation(lib, orc, ktab):
         assert np.array_equal(x, r)
 
 
+def test_cal_cldfra1_bit_exact(lib, orc, ktab):
+    """cal_cldfra1 on the device (DRV:2886-3122) against the oracle: CLDFRA and cldfra1_flag bit-exact for the
+    microphysics families the routine distinguishes, host and device arrays, halo untouched."""
+    import torch
+    dom = synth.make_domain(40, 9, 40, seed=31, cloudy_frac=1.0, halo=1)
+    init(lib, dom, ktab)
+    rng = np.random.default_rng(5)
+    fice = rng.uniform(0, 1, dom["t3d"].shape).astype(np.float32)
+    cases = [dict(), dict(F_QS=False), dict(F_QI=False, F_QS=False), dict(F_QI=False, F_ICE_PHY=fice), dict(mp_physics=5), dict(F_QC=None)]
+    for kw in cases:
+        a = [np.full(dom["t3d"].shape, -7.0, np.float32), np.full(dom["t3d"].shape, -7, np.int32)]
+        b = [np.full(dom["t3d"].shape, -7.0, np.float32), np.full(dom["t3d"].shape, -7, np.int32)]
+        args = (dom["qv3d"], dom["qc3d"], dom["qi3d"], dom["qs3d"], dom["t3d"], dom["p3d"])
+        lib.cal_cldfra1(dom["dims"], a[0], *args, cldfra1_flag=a[1], **kw)
+        orc.cal_cldfra1(dom["dims"], b[0], *args, cldfra1_flag=b[1], **kw)
+        assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1]), kw
+        assert np.all(a[0][0] == -7.0) and np.all(a[0][:, 40] == -7.0) and np.all(a[0][:, :, 0] == -7.0)       # halo rows / level kme / halo columns
+        if "F_ICE_PHY" not in kw:
+            dv = [torch.from_numpy(x).cuda() for x in args]
+            dc = torch.full(dom["t3d"].shape, -7.0, dtype=torch.float32, device="cuda")
+            lib.cal_cldfra1(dom["dims"], dc, *dv, **kw)
+            assert np.array_equal(dc.cpu().numpy().view(np.uint32), b[0].view(np.uint32)), kw
+    assert (interior(dom, b[0]) == 0).all()                       # the last case: an OPTIONAL flag absent -> no cloud
+
+
 def test_full_size_properties(lib, ktab):
     """BASELINE config C2 at full size (127,500 columns x 50 levels), checked through size-independent properties:
     energy bounds, clean == full where the aerosol is zero, clear == full in cloud-free columns, night gate."""
@@ -588,3 +641,17 @@ def test_full_size_properties(lib, ktab):
     assert (sw["swdnbc"][day & e] < sw["swdnbclnc"][day & e]).mean() > 0.999
     assert np.all(lw["olr"] > 50) and np.all(lw["olr"] < 500) and np.all(lw["glw"] > 20)
     assert np.all(lw["lwdnt"] == 0)
+
+
+@pytest.mark.parametrize("case", FULL_CASES, ids=[c[0].replace(" ", "_") for c in FULL_CASES])
+def test_full_size_against_oracle(lib, ktab, case):
+    """Every BASELINE configuration at full size (C1, C2) or on a >= 20,000-column slice of its grid (C3, C4, C5) against the
+    oracle run on all host threads: every output, every column, one tolerance.  tools/parity_report.py writes the same
+    numbers to profiles/r2_parity.md."""
+    import oracle as O
+    res = run_case(case, lib, O.oracle_mt(0), ktab, run_pair, init)
+    print(case[0], res)
+    for which in ("sw", "lw"):
+        r = res[which]
+        assert r["columns"] >= 1024 and r["out_of_tolerance"] == 0, "%s %s: %d of %d columns out of tolerance, worst %.3g W/m2 / %.3g K/day" % (
+            case[0], which, r["out_of_tolerance"], r["columns"], r["worst_abs"], r["worst_hr"])

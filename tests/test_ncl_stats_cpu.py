@@ -50,3 +50,20 @@ def test_corrected_standard_error_column():
     st = N.calc_standard_stats(f)
     assert st["N"] == f.size and np.isclose(st["standard_error"], f.astype(np.float64).std(ddof=1) / np.sqrt(f.size))
     assert np.isclose(st["corrected_standard_error"], st["standard_error"] * st["morans_i"])   # ncl:449
+
+
+def test_boxplot_stats_are_order_statistics():
+    """calc_boxplot_stats (ncl:145-189): sorted(x)[round(.01 p (N-1))], p = 5, 25, 50, 75, 95 - no interpolation."""
+    x = np.arange(101, dtype=np.float32)[::-1].copy()                   # 100 .. 0
+    assert np.array_equal(N.calc_boxplot_stats(x), np.array([5, 25, 50, 75, 95], np.float32))
+    y = np.array([3.0, -1.0, 7.0, 7.0, 2.0, 9.5, -4.0, 0.0], np.float32)      # N = 8: indices round(.35)=0, round(1.75)=2, round(3.5)=4, 5, 7
+    assert np.array_equal(N.calc_boxplot_stats(y), np.sort(y)[[0, 2, 4, 5, 7]])
+    assert N.ncl_round(2.5) == 3 and N.ncl_round(3.5) == 4 and N.ncl_round(0.49) == 0          # halves away from zero, not to even
+    rng = np.random.default_rng(4)
+    z = rng.normal(300, 40, (37, 53)).astype(np.float32)
+    bp = N.calc_boxplot_stats(z)
+    for p, v in zip((5, 25, 50, 75, 95), bp):
+        assert abs((z < v).mean() - p / 100.0) < 2.0 / z.size + 1e-3
+    st = N.calc_standard_stats(z, trim=5)
+    assert st["N"] == 27 * 43 and st["p05"] <= st["lower_quartile"] <= st["median"] <= st["upper_quartile"] <= st["p95"]
+    assert st["median"] == float(N.calc_boxplot_stats(z[5:-5, 5:-5])[2])

@@ -97,3 +97,47 @@ def test_two_rank_statistics_match_single_rank(orc, ktab):
     cols = D.stats_from_sums(np.column_stack([sums, -ext[:, 0], ext[:, 1]]))
     assert np.allclose(cols["avg"], got["mean"], rtol=1e-14) and np.allclose(cols["stddev"], got["sd"], rtol=1e-9)
     assert np.allclose(cols["standard_error"], got["se"], rtol=1e-9) and np.array_equal(cols["N"], sums[:, 2])
+
+
+def _gather_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(33)
+    nf, nj, ni = 5, 23, 7
+    cz = rng.uniform(-0.5, 1.0, (nj, ni)).astype(np.float32)
+    cz[:9] = -1.0                                             # unequal slabs: the night band is cheap
+    glob = rng.normal(300.0, 40.0, (nf, nj, ni)).astype(np.float32)
+    slabs = partition.jslabs(cz, world)
+    a, b = slabs[rank]
+    g = partition.SlabGather(dist, slabs, rank, nf, ni, torch.device("cpu"))
+    mine = [torch.from_numpy(glob[f, a - 1:b].copy()) for f in range(nf)]
+    out1 = g(mine).clone()
+    out2 = g(mine)                                            # buffers are reused step after step
+    ok = bool(np.array_equal(out1.numpy(), glob) and np.array_equal(out2.numpy(), glob))
+    # what the gathered fields are for: an order statistic of the whole field, identical on every rank
+    med = float(np.sort(out2[0].numpy().ravel())[int(np.floor(np.float32(0.5) * np.float32(nj * ni - 1) + 0.5))])
+    q.put((rank, ok, [tuple(s) for s in slabs], med, float(np.sort(glob[0].ravel())[int(np.floor(np.float32(0.5) * np.float32(nj * ni - 1) + 0.5))])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_field_gather_rebuilds_the_global_fields():
+    """partition.SlabGather (the all-gather of the 2-D diagnostic fields bench.py runs every step over NCCL) on a
+    world-size-2 gloo group with unequal slabs: every rank ends up with the global fields, bit for bit."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, slabs, med, want in res:
+        assert ok and med == want
+        assert slabs[0][1] - slabs[0][0] != slabs[1][1] - slabs[1][0]          # the slabs really are unequal

@@ -5,7 +5,7 @@ cd /root/repo/wrfchem-arc-interactions_b200/csrc
 tag=$1; shift
 NV="/usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fno-strict-aliasing"
 mkdir -p var/$tag
-$NV "$@" -c sw_solve.cu -o var/$tag/sw_solve.o &
+$NV -fmad=false "$@" -c sw_solve.cu -o var/$tag/sw_solve.o &
 $NV "$@" -c lw_solve.cu -o var/$tag/lw_solve.o &
 wait
 $NV -shared -o var/libarcrad_$tag.so api.o prep.o var/$tag/sw_solve.o var/$tag/lw_solve.o tables.o aer_optics.o aer_tables.o -lcudart_static -lpthread -ldl -lrt

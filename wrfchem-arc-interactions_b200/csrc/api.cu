@@ -34,10 +34,12 @@ struct Ctx {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_solved = nullptr, ev_swept[2] = {nullptr, nullptr};
   bool overlap = true;
+  bool bucket = true;           // cloud bucketing of the sunlit column list (ARC_RAD_BUCKET=0: plain tile order)
   // chained LW -> SW step (arc_rad_lwsw with device arrays): 1 = the LW call of the pair (no join, no sync at its end),
   // 2 = the SW call (sunlit compaction, McICA and prep on `stream3` beside the LW kernels; joins and synchronises for both)
   int chain = 0;
   cudaStream_t stream3 = nullptr;
+  cudaEvent_t ev_entry = nullptr;      // call entry on `stream`: stream3 starts behind whatever the caller ordered before `stream`
   cudaEvent_t ev_pre = nullptr;
   // asynchronous slab pipeline (host arrays): the chained pair of slab s ends without join / synchronisation, so the LW
   // kernels of slab s+1 start while the last SW sweep of slab s is still running.  ev_lw_done / ev_sw_done (recorded on
@@ -49,6 +51,7 @@ struct Ctx {
   std::vector<void *> table_allocs;
   int *d_status = nullptr, *d_count = nullptr;
   int *d_cols = nullptr; size_t cols_cap = 0;
+  int *d_cols_lw = nullptr; size_t cols_lw_cap = 0;      // LW column list (every column, cloud-bucketed)
   // workspaces (grow-only)
   SwWs sw{}; size_t sw_bytes = 0; void *sw_arena = nullptr;
   LwWs lw{}; size_t lw_bytes = 0; void *lw_arena = nullptr;
@@ -105,10 +108,11 @@ size_t outer_cap_default() {
   return std::max(chunk_cap_default(), (size_t)((v + 255) / 256 * 256));
 }
 
-// LW inner chunk (ARC_RAD_LW_CHUNK, default 65536 columns): bounds the group-partial buffer (47 KB per column and buffer at C2)
+// LW inner chunk (ARC_RAD_LW_CHUNK, default 32768 columns): bounds the pass records (2 x 141 KB per column at C2's 63 layers)
+// and the group-partial buffers (2 x 47 KB per column)
 size_t lw_chunk_cap_default() {
   const char *e = getenv("ARC_RAD_LW_CHUNK");
-  long v = e ? atol(e) : 65536;
+  long v = e ? atol(e) : 32768;
   if (v < 256) v = 256;
   return (size_t)((v + 255) / 256 * 256);
 }
@@ -163,6 +167,8 @@ void carve_lw(LwWs &w, char *base, size_t &bytes) {
   w.laytrop = c.take<int>(cap);
   w.colf = c.take<float>((size_t)LWF_N * cap);
   w.secdiff = c.take<float>((size_t)NBLW * cap);
+  w.rec = c.take<float4>((size_t)nl * NGLW * pcap);
+  w.recC = c.take<float4>((size_t)nl * NGLW * pcap);
   // two buffers of group partials: k_lw_band of inner chunk k+1 runs beside k_lw_reduce of chunk k
   w.bpart = c.take<float>((size_t)2 * lw_sweep_groups() * (nl + 1) * w.nk * pcap);
   bytes = c.off;
@@ -699,6 +705,8 @@ void arc_rad_finalize(void) {
   g.h2d = g.d2h = nullptr;
   if (g.d_cols) cudaFree(g.d_cols);
   g.d_cols = nullptr; g.cols_cap = 0;
+  if (g.d_cols_lw) cudaFree(g.d_cols_lw);
+  g.d_cols_lw = nullptr; g.cols_lw_cap = 0;
   if (g.d_status) cudaFree(g.d_status);
   if (g.d_count) cudaFree(g.d_count);
   g.d_status = g.d_count = nullptr;
@@ -742,11 +750,13 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
   {
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // hi = numerically lowest = greatest priority
+    if (const char *eb = getenv("ARC_RAD_BUCKET")) g.bucket = atoi(eb) != 0;
     const char *e = getenv("ARC_RAD_OVERLAP");
     g.overlap = !(e && atoi(e) == 0);
     const char *pr = getenv("ARC_RAD_SWEEP_PRIO");
     CK(cudaStreamCreateWithPriority(&g.stream2, cudaStreamNonBlocking, (pr && atoi(pr) == 0) ? lo : hi));
     CK(cudaStreamCreateWithFlags(&g.stream3, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.ev_entry, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_pre, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_lw_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_pre_lw, cudaEventDisableTiming));
@@ -758,7 +768,7 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
   CK(cudaStreamCreateWithFlags(&g.d2h, cudaStreamNonBlocking));
   for (int q = 0; q < 2; q++) { CK(cudaEventCreateWithFlags(&g.ev_in[q], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.ev_out[q], cudaEventDisableTiming)); }
   CK(cudaMalloc(&g.d_status, sizeof(int)));
-  CK(cudaMalloc(&g.d_count, sizeof(int)));
+  CK(cudaMalloc(&g.d_count, 2 * sizeof(int)));
 
   const HostTables &H = g.H;
   DevTables &D = g.D;
@@ -947,7 +957,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   int nsun = 0;
   {
     Timed t("sw_compact", sp);
-    launch_compact_sunlit(G, a.xcoszen, g.d_cols, g.d_count, sp);
+    launch_compact_sunlit(G, a.xcoszen, (in->icloud != 0 && g.bucket) ? a.cf.cldfra3d : nullptr, g.d_cols, g.d_count, 0, sp);
     launch_sw_night(a, sp);
   }
   CK(cudaMemcpyAsync(&nsun, g.d_count, sizeof(int), cudaMemcpyDeviceToHost, sp));
@@ -1119,21 +1129,33 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   const size_t cap = std::min(outer_cap_default(), (size_t)((ncol + 255) / 256 * 256));
   const size_t pcap = std::min(lw_chunk_cap_default(), cap);
   if ((rc = ensure_lw_ws(nlay, cap, pcap, variants))) return rc;
+  // column order: cloud-free columns first, then the columns with cloud (see launch_compact_sunlit): the cloudy-layer branch of
+  // rtrnmc then runs in warps whose columns all have cloud instead of in every warp that holds one such column
+  const bool lw_bucket = g.bucket && in->icloud != 0 && a.cf.cldfra3d != nullptr;
+  if (lw_bucket) {
+    if ((size_t)ncol > g.cols_lw_cap) {
+      if (g.d_cols_lw) cudaFree(g.d_cols_lw);
+      g.d_cols_lw = nullptr; g.cols_lw_cap = 0;
+      CK(cudaMalloc(&g.d_cols_lw, sizeof(int) * (size_t)ncol));
+      g.cols_lw_cap = (size_t)ncol;
+    }
+    launch_compact_sunlit(G, nullptr, a.cf.cldfra3d, g.d_cols_lw, g.d_count + 1, 1, spl);
+  }
   for (int o0 = 0; o0 < ncol; o0 += (int)cap) {
     const int no = std::min((int)cap, ncol - o0);
     a.ws = g.lw;
-    a.ws.cols = nullptr;
+    a.ws.cols = lw_bucket ? g.d_cols_lw + o0 : nullptr;
     a.col0 = o0;
     a.ncols = no;
     McicaArgs m{};
     m.geo = G; m.nlay = nlay; m.nz = nz; m.ngpt = NGLW; m.permuteseed = 150; m.ncols = no; m.W = a.ws.W; m.icloud = in->icloud;
-    m.cap = (int)cap; m.col0 = o0; m.lw_buffer = 1; m.cols = nullptr; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
+    m.cap = (int)cap; m.col0 = o0; m.lw_buffer = 1; m.cols = a.ws.cols; m.p3d = a.p3d; m.p8w = a.p8w; m.cldfra3d = a.cf.cldfra3d;
     m.mask = a.ws.mask; m.anyc = a.ws.anyc;
     cudaStream_t so = o0 == 0 ? spl : g.stream;
     { Timed t("lw_mcica", so); launch_mcica(m, so); }
     { Timed t("lw_prep", so); launch_lw_prep(a, so); }
     if (a.dbg.cldmask) {
-      k_unpack_mask<<<(no + 127) / 128, 128, 0, so>>>(a.ws.mask, nullptr, o0, no, (int)cap, a.ws.W, nlay, NGLW, a.dbg.cldmask);
+      k_unpack_mask<<<(no + 127) / 128, 128, 0, so>>>(a.ws.mask, a.ws.cols, o0, no, (int)cap, a.ws.W, nlay, NGLW, a.dbg.cldmask);
       count_launch();
     }
     if (so != g.stream) { CK(cudaEventRecord(g.ev_pre_lw, so)); CK(cudaStreamWaitEvent(g.stream, g.ev_pre_lw, 0)); }
@@ -1143,6 +1165,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
       LwArgs b = a;
       b.ncols = std::min((int)pcap, no - c0);
       b.col0 = o0 + c0;
+      if (b.ws.cols) b.ws.cols += c0;
       b.ws.coef += (size_t)c0 * LWC_N; b.ws.aer += c0; b.ws.cld += c0; b.ws.mask += c0; b.ws.anyc += c0; b.ws.laytrop += c0; b.ws.colf += c0;
       b.ws.secdiff += c0;
       const int buf = g.overlap ? (kc & 1) : 0;
@@ -1181,6 +1204,7 @@ int arc_rad_lwsw(const ArcDims *d, const ArcLwIn *lwin, ArcLwOut *lwout, const A
   if (g.overlap && lwin->memspace == ARC_MEM_DEVICE && swin->memspace == ARC_MEM_DEVICE) {
     // one continuous pipeline: the SW column kernels run beside the LW ones, the SW solver follows the LW solver on the main
     // stream while the last LW sweep is still running; one join + synchronisation at the end
+    CK(cudaEventRecord(g.ev_entry, g.stream)); CK(cudaStreamWaitEvent(g.stream3, g.ev_entry, 0));
     g.chain = 1;
     rc = arc_rad_lw(d, lwin, lwout);
     if (rc) { g.chain = 0; cudaStreamSynchronize(g.stream2); cudaStreamSynchronize(g.stream); collect_times(); return rc; }
@@ -1443,6 +1467,106 @@ int arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *c
   k_morans_i<<<nfields, 1024, 0, g.stream>>>(G, nfields, (const float *const *)dptrs, dout);
   count_launch();
   if (memspace != ARC_MEM_DEVICE) CK(cudaMemcpyAsync(out, dout, sizeof(float) * nfields, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// cal_cldfra1 (module_radiation_driver.F:2886-3122, called for icloud = 1 at DRV:1104-1118): the cloud fraction radiation_driver
+// computes before the RRTMG calls, here on the device so that CLDFRA need not be produced on the host.
+int arc_rad_cal_cldfra1(const ArcDims *d, int memspace, const float *qv, const float *qc, const float *qi, const float *qs, int f_qv, int f_qc,
+                        int f_qi, int f_qs, const float *t_phy, const float *p_phy, const float *f_ice_phy, int mp_physics, float *cldfra,
+                        int *cldfra1_flag) {
+  if (!g.ready) { g.err = "arc_rad_cal_cldfra1: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !qv || !t_phy || !p_phy || !cldfra) { g.err = "arc_rad_cal_cldfra1: null argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if ((f_qc > 0 && !qc) || (f_qi > 0 && !qi) || (f_qs > 0 && !qs)) { g.err = "arc_rad_cal_cldfra1: F_Qx set but array missing"; return ARC_ERR_BAD_ARG; }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const size_t n3 = G.n3();
+  const float *dqv, *dqc = nullptr, *dqi = nullptr, *dqs = nullptr, *dt, *dp, *dfi = nullptr;
+  if ((rc = in_arr(memspace, qv, n3, &dqv)) || (rc = in_arr(memspace, t_phy, n3, &dt)) || (rc = in_arr(memspace, p_phy, n3, &dp))) return rc;
+  if (qc && (rc = in_arr(memspace, qc, n3, &dqc))) return rc;
+  if (qi && (rc = in_arr(memspace, qi, n3, &dqi))) return rc;
+  if (qs && (rc = in_arr(memspace, qs, n3, &dqs))) return rc;
+  if (f_ice_phy && (rc = in_arr(memspace, f_ice_phy, n3, &dfi))) return rc;
+  float *dcf; int *dfl = nullptr;
+  if ((rc = out_arr(memspace, cldfra, n3, &dcf))) return rc;
+  if (cldfra1_flag && (rc = out_arr(memspace, (float *)cldfra1_flag, n3, (float **)&dfl))) return rc;
+  launch_cal_cldfra1(G, dqv, dqc, dqi, dqs, f_qv, f_qc, f_qi, f_qs, dt, dp, dfi, mp_physics, dcf, dfl, g.stream);
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Order statistics of 2-D diagnostic fields over the tile: calc_boxplot_stats picks sorted(x)[round(0.01 * p * (N - 1))] for
+// p = 5, 25, 50, 75, 95 (misc_stats_library.ncl:145-189; calc_standard_stats stores them as median, quartiles and 5th / 95th
+// percentile, ncl:439-445).  No sort: one block per (field, percentile) selects the element of that rank by four 8-bit radix
+// passes over the order-preserving integer image of the floats (histogram in shared memory, digit by digit from the top), so
+// the result is exactly the value the reference's qsort + index gives.
+__device__ __forceinline__ uint32_t f2key(float x) { const uint32_t u = __float_as_uint(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__global__ void __launch_bounds__(1024) k_percentiles(Geo G, int nperc, const float *const *__restrict__ fields, const int *__restrict__ ranks,
+                                                       float *__restrict__ out) {
+  const int f = blockIdx.x, q = blockIdx.y;
+  const float *x = fields[f];
+  __shared__ unsigned hist[256];
+  __shared__ uint32_t s_prefix; __shared__ unsigned s_rank;
+  if (threadIdx.x == 0) { s_prefix = 0u; s_rank = (unsigned)ranks[q]; }
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 24 - 8 * pass;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int tc = threadIdx.x; tc < G.ncol_tile; tc += blockDim.x) {
+      int i, j; G.ij(tc, i, j);
+      const uint32_t k = f2key(x[G.at2(i, j)]);
+      if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned r = s_rank, cum = 0u; int dsel = 255;
+      for (int dgt = 0; dgt < 256; dgt++) { if (r < cum + hist[dgt]) { dsel = dgt; break; } cum += hist[dgt]; }
+      s_rank = r - cum; s_prefix = (prefix << 8) | (uint32_t)dsel;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[f * nperc + q] = key2f(s_prefix);
+}
+
+int arc_rad_percentiles(const ArcDims *d, int memspace, int nfields, const float *const *fields, int nperc, const float *perc, float *out) {
+  if (!g.ready) { g.err = "arc_rad_percentiles: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !fields || !out || !perc || nfields < 1 || nfields > 64 || nperc < 1 || nperc > 16) { g.err = "arc_rad_percentiles: bad argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  int ranks[16];
+  for (int q = 0; q < nperc; q++) {
+    if (!(perc[q] >= 0.f && perc[q] <= 100.f)) { g.err = "arc_rad_percentiles: percentile outside 0..100"; return ARC_ERR_BAD_ARG; }
+    // pt_x = round(.01 * perc_point * (numel - 1), 3): single-precision product left to right, round half away from zero (ncl:176)
+    const float ptx = 0.01f * perc[q] * (float)(G.ncol_tile - 1);
+    long r = (long)floorf(ptx + 0.5f);
+    ranks[q] = (int)std::min<long>(std::max<long>(r, 0), G.ncol_tile - 1);
+  }
+  const float *dev[64];
+  for (int f = 0; f < nfields; f++) {
+    if (!fields[f]) { g.err = "arc_rad_percentiles: null field"; return ARC_ERR_BAD_ARG; }
+    if ((rc = in_arr(memspace, fields[f], G.n2(), &dev[f]))) return rc;
+  }
+  void *dptrs; if ((rc = stage_slot(sizeof(float *) * 64, &dptrs))) return rc;
+  CK(cudaMemcpyAsync(dptrs, dev, sizeof(float *) * nfields, cudaMemcpyHostToDevice, g.stream));
+  void *dranks; if ((rc = stage_slot(sizeof(int) * 16, &dranks))) return rc;
+  CK(cudaMemcpyAsync(dranks, ranks, sizeof(int) * nperc, cudaMemcpyHostToDevice, g.stream));
+  float *dout = out;
+  if (memspace != ARC_MEM_DEVICE) { void *p; if ((rc = stage_slot(sizeof(float) * 64 * 16, &p))) return rc; dout = (float *)p; }
+  k_percentiles<<<dim3(nfields, nperc), 1024, 0, g.stream>>>(G, nperc, (const float *const *)dptrs, (const int *)dranks, dout);
+  count_launch();
+  if (memspace != ARC_MEM_DEVICE) CK(cudaMemcpyAsync(out, dout, sizeof(float) * nfields * nperc, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());
   return 0;

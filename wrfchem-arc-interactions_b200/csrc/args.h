@@ -136,7 +136,7 @@ enum { LWF_TZ0 = 0, LWF_TBOUND, LWF_EMISS, LWF_N };
 
 struct LwWs {
   int cap, pcap, nlay, W;
-  int *cols;               // nullable (identity)
+  int *cols;               // [cap] tile column id of each chunk column (cloud-bucketed list); nullable = identity from col0
   float *coef;             // coef_index(field, layer, c, cap, LWC_N)
   float *aer;              // [16][nlay][cap]
   float *cld;              // [16][nlay][cap]  taucmc
@@ -145,6 +145,11 @@ struct LwWs {
   int *laytrop;            // [cap]
   float *colf;             // [LWF_N][cap]
   float *secdiff;          // [16][cap]
+  // Records k_lw_band's downward pass leaves for its upward pass, [layer][g-point][pcap] float4 (a warp = 512 contiguous bytes):
+  //   rec  (atrans, bbu) of the full stream, (atrans, bbu) of the clean stream: radlu' = radlu + (bbu - radlu) atrans
+  //   recC (X, Y) x (full, clean) of radlu' = radlu - radlu X + Y; written and read only where the column has cloud in the layer
+  // One buffer: the thread that wrote a record is the one that reads it.
+  float4 *rec, *recC;
   float *bpart;            // [band group][nlay+1][nk][pcap]  sums of the radiances over a group's g-points (k_lw_band -> k_lw_reduce); nk = kinds in use, slot of kind k = kslot[k]
   int nk; int kslot[NKIND];
 };
@@ -180,7 +185,7 @@ struct McicaArgs {
 };
 
 // launchers (defined in the .cu files); every launcher bumps the launch counter
-void launch_compact_sunlit(const Geo &g, const float *xcoszen, int *cols, int *count, cudaStream_t s);
+void launch_compact_sunlit(const Geo &g, const float *xcoszen, const float *cldfra3d, int *cols, int *count, int slot, cudaStream_t s);
 void launch_sw_night(const SwArgs &a, cudaStream_t s);
 void launch_mcica(const McicaArgs &a, cudaStream_t s);
 void launch_sw_prep(const SwArgs &a, cudaStream_t s);
@@ -190,6 +195,8 @@ int sw_sweep_groups();
 int lw_sweep_groups();
 void launch_sw_reduce(const SwArgs &a, cudaStream_t s);
 void launch_lw_prep(const LwArgs &a, cudaStream_t s);
+void launch_cal_cldfra1(const Geo &G, const float *qv, const float *qc, const float *qi, const float *qs, int f_qv, int f_qc, int f_qi, int f_qs,
+                        const float *t_phy, const float *p_phy, const float *f_ice_phy, int mp_physics, float *cldfra, int *flag, cudaStream_t s);
 void launch_lw_band(const LwArgs &a, cudaStream_t s);
 bool lw_layout_ok();
 void launch_lw_reduce(const LwArgs &a, cudaStream_t s);

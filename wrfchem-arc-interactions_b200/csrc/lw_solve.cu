@@ -428,76 +428,90 @@ __device__ __forceinline__ void lw_setup(const float (&fv)[LWC_N], const LwSmem 
   }
 }
 
-// One layer of rtrnmc for one g-point and stream (LW:3207-3300 downward with dplank = dplankdn, 3322-3356 upward with
-// dplank = dplankup): gas-only transmittance `atrans` and source function `bb`, and where the column has cloud in the layer
-// the terms of  rad' = rad - rad * X + src + Z.  The exponentials are table look-ups as in the reference.
-template <bool UP>
-__device__ __forceinline__ void lw_rt(const float2 *__restrict__ s_et, const float bpade, float odepth, const bool icldlyr, const float odcld,
-                                      const float efclfrac, const float cldfmc, const float plfrac, const float blay, const float dplank,
-                                      float &atrans, float &bb, float &X, float &src, float &Z) {
-  if (icldlyr) {
-    float odtot = odepth + odcld;
-    float bbtot, atot;
-    if (odtot < 0.06f) {
-      atrans = odepth - 0.5f * odepth * odepth;
-      const float odepth_rec = 0.166667f * odepth;
-      bb = plfrac * (blay + dplank * odepth_rec);
-      src = bb * atrans;
-      atot = odtot - 0.5f * odtot * odtot;
-      const float odtot_rec = 0.166667f * odtot;
-      bbtot = plfrac * (blay + dplank * odtot_rec);
-    } else if (odepth <= 0.06f) {
-      atrans = odepth - 0.5f * odepth * odepth;
-      const float odepth_rec = 0.166667f * odepth;
-      bb = plfrac * (blay + dplank * odepth_rec);
-      src = bb * atrans;
-      const float tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
-      const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-      const float2 et = s_et[ittot];
-      bbtot = plfrac * (blay + et.y * dplank);
-      atot = 1.f - et.x;
-    } else {
-      float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
-      const int itgas = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-      // tau_tbl(itgas) recomputed with the table generator's arithmetic (LW:7944-7950)
-      if (itgas >= 10000) odepth = 1.e10f;
-      else { const float tfn = div_rn((float)itgas, 10000.0f); odepth = div_rn(__fmul_rn(bpade, tfn), __fsub_rn(1.0f, tfn)); }
-      const float2 eg = s_et[itgas];
-      atrans = 1.f - eg.x;
-      const float tfacgas = eg.y;
-      bb = plfrac * (blay + tfacgas * dplank);
-      src = UP ? bb * atrans : atrans * plfrac * (blay + tfacgas * dplank);
-      odtot = odepth + odcld;
-      tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
-      const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-      const float2 et = s_et[ittot];
-      bbtot = plfrac * (blay + et.y * dplank);
-      atot = 1.f - et.x;
-    }
-    X = atrans + efclfrac * (1.f - atrans);
-    Z = cldfmc * (bbtot * atot - src);
+// One layer of rtrnmc for one g-point and stream, both directions at once (LW:3207-3300 downward, 3322-3356 upward): the
+// gas-only transmittance `atrans`, the source functions towards the lower (bbd) and upper (bbu) interface - they share the
+// table look-up - and, where the column has cloud in the layer, the terms of  rad' = rad - rad * X + src + Z  (downward:
+// srcd, Zd; upward: Yu = srcu + Zu).  The exponentials are table look-ups as in the reference.
+struct LwRT { float atrans, bbd, bbu, X, srcd, Zd, Yu; };
+// clear layer (no sub-column of the column is cloudy in it): series below 0.06, table above; both are evaluated and selected
+// (the table index of a small optical depth is valid), no divergence
+__device__ __forceinline__ void lw_rt_clear(const float2 *__restrict__ s_et, const float bpade, const float odepth, const float plfrac,
+                                            const float blay, const float dplankdn, const float dplankup, float &atrans, float &bbd, float &bbu) {
+  const float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
+  const int itr = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
+  const float2 et = s_et[itr];
+  const bool ser = odepth <= 0.06f;
+  atrans = ser ? odepth - 0.5f * odepth * odepth : 1.f - et.x;
+  const float tf = ser ? 0.166667f * odepth : et.y;
+  bbd = plfrac * (blay + tf * dplankdn);
+  bbu = plfrac * (blay + tf * dplankup);
+}
+// layer in which the column has cloud in some sub-column (icldlyr, LW:3218-3290): three optical-depth regimes, gas-only and
+// gas + cloud quantities
+__device__ __forceinline__ void lw_rt_cloudy(const float2 *__restrict__ s_et, const float bpade, float odepth, const float odcld,
+                                             const float efclfrac, const float cldfmc, const float plfrac, const float blay, const float dplankdn,
+                                             const float dplankup, LwRT &o) {
+  float odtot = odepth + odcld;
+  float tf, tftot, atot;
+  bool table_gas = false;
+  if (odtot < 0.06f) {
+    o.atrans = odepth - 0.5f * odepth * odepth;
+    tf = 0.166667f * odepth;
+    atot = odtot - 0.5f * odtot * odtot;
+    tftot = 0.166667f * odtot;
+  } else if (odepth <= 0.06f) {
+    o.atrans = odepth - 0.5f * odepth * odepth;
+    tf = 0.166667f * odepth;
+    const float tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
+    const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
+    const float2 et = s_et[ittot];
+    tftot = et.y; atot = 1.f - et.x;
   } else {
-    if (odepth <= 0.06f) {
-      atrans = odepth - 0.5f * odepth * odepth;
-      odepth = 0.166667f * odepth;
-      bb = plfrac * (blay + dplank * odepth);
-    } else {
-      const float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
-      const int itr = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
-      const float2 et = s_et[itr];
-      atrans = 1.f - et.x;
-      bb = plfrac * (blay + et.y * dplank);
-    }
-    X = 0.f; src = 0.f; Z = 0.f;
+    float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
+    const int itgas = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
+    // tau_tbl(itgas) recomputed with the table generator's arithmetic (LW:7944-7950)
+    if (itgas >= 10000) odepth = 1.e10f;
+    else { const float tfn = div_rn((float)itgas, 10000.0f); odepth = div_rn(__fmul_rn(bpade, tfn), __fsub_rn(1.0f, tfn)); }
+    const float2 eg = s_et[itgas];
+    o.atrans = 1.f - eg.x;
+    tf = eg.y;
+    table_gas = true;
+    odtot = odepth + odcld;
+    tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
+    const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
+    const float2 et = s_et[ittot];
+    tftot = et.y; atot = 1.f - et.x;
   }
+  o.bbd = plfrac * (blay + tf * dplankdn);
+  o.bbu = plfrac * (blay + tf * dplankup);
+  const float bbdtot = plfrac * (blay + tftot * dplankdn), bbutot = plfrac * (blay + tftot * dplankup);
+  o.srcd = table_gas ? o.atrans * plfrac * (blay + tf * dplankdn) : o.bbd * o.atrans;
+  const float srcu = o.bbu * o.atrans;
+  o.X = o.atrans + efclfrac * (1.f - o.atrans);
+  o.Zd = cldfmc * (bbdtot * atot - o.srcd);
+  o.Yu = srcu + cldfmc * (bbutot * atot - srcu);
 }
 
-// One (column, band group): NG consecutive g-points of band BAND starting at g-point g0 (absolute index).
-template <int BAND, int NG>
-__device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, const int grp, const int g0, const int c, const bool live) {
+// One (column, band group): the ng consecutive g-points of band BAND that start at g-point g0 (absolute index).
+//
+// Pass 1 walks the layers top-down: band-level setup, then a real (LW_UNROLL_G-fold unrolled) loop over the group's g-points -
+// gas optics, layer transmittance and sources, downward radiances, whose running values live in shared memory
+// [g-point][4][thread].  (A fully unrolled g-point loop with the radiances in registers was measured twice: 77 KB of code per
+// pass with everything inline was instruction-fetch-bound - the SM's instruction cache holds 32 KB - and a compact version
+// that called the cloudy-layer routine out of line spilled around every call.)  Pass 1 adds the downward radiances of the
+// group in g order into the partial buffer and leaves, per (g-point, layer), ONE 16-byte record (atrans, bbu) x (full, clean)
+// for the way back up - half of round 1's record, and the thread that wrote it reads it.  Pass 2 walks bottom-up over the
+// records only: two fused multiply-adds per stream and g-point.
+#ifndef LW_UNROLL_G
+#define LW_UNROLL_G 1
+#endif
+template <int BAND>
+__device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, float *__restrict__ st, const int grp, const int g0, const int ng,
+                                             const int c, const bool live) {
   constexpr LwK K = LWK[BAND - 1];
   constexpr int SF = K.sf;
   constexpr int b = BAND - 1;
+  constexpr int UG = LW_UNROLL_G;
   const float2 *s_et = sm.et;
   const float *S0 = sm.S, *s_plk = sm.plk, *s_chi = sm.chi;
   const DevTables &tb = a.tb;
@@ -511,6 +525,8 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
   const float secdiff = ws.secdiff[(size_t)b * cap + c];
   const int ig0 = g0 - c_lw[b].g0 + 1;                                              // 1-based g-point of the group's first member inside the band
   auto CHI = [&](int imol, int jp) { return s_chi[(imol - 1) + 7 * (jp - 1)]; };
+  // state of g-point i: 0 all-sky full, 1 clear-sky full, 2 all-sky clean, 3 clear-sky clean
+  auto ST = [&](int i, int f) -> float & { return st[(i * 4 + f) * LW_BLOCK]; };
 
   // band constants: reference ratios at fixed pressure levels (0 rp_a, 1 rp_b, 2 rm_a, 3 rm_b, 4 rm_a3)
   float rc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -549,12 +565,18 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
   const unsigned ucap = (unsigned)cap, ustf = (unsigned)nlay * (unsigned)cap;     // 32-bit offsets: LWC_N*nlay*cap < 2^31
   const float *coefc = ws.coef + coef_index(0, 0, c, cap, LWC_N), *aerc = ws.aer + c + (unsigned)b * ustf;
   const float *cldc = ws.cld + c + (unsigned)b * ustf;
+  const uint32_t *maskc = ws.mask + (size_t)g0 * ws.W * cap + c;
+  const unsigned mstride = (unsigned)ws.W * ucap;                                  // mask words between consecutive g-points
   const unsigned lstride = (unsigned)cap * LWC_N;                                  // coefficient words per layer
-  float fv[LWC_N];
+  // the layer's workspace words are requested one layer ahead (fvn, taua_n, tz_n) and land while the g-point loop of the
+  // current layer runs: with 16 warps per SM an exposed L2 / HBM round trip per layer was 25 % of all stall samples
+  float fv[LWC_N], fvn[LWC_N], taua_n = 0.f, tz_n = 0.f;
   auto load_layer = [&](int lay) {
     const float *p = coefc + (size_t)((unsigned)lay * lstride);      // fields at immediate offsets of 128 bytes
 #pragma unroll
-    for (int f = 0; f < LWC_N; f++) fv[f] = ((need >> f) & 1u) ? p[f * 32] : 0.f;
+    for (int f = 0; f < LWC_N; f++) fvn[f] = ((need >> f) & 1u) ? p[f * 32] : 0.f;
+    taua_n = aerc[(unsigned)lay * ucap];
+    tz_n = lay > 0 ? *(p + LWC_TZ * 32 - (ptrdiff_t)lstride) : ws.colf[(size_t)LWF_TZ0 * cap + c];     // interface below the layer
   };
   auto tz_at = [&](int lev) {     // interface temperature: level 0 = surface
     return lev > 0 ? coefc[(size_t)((unsigned)(lev - 1) * lstride) + LWC_TZ * 32] : ws.colf[(size_t)LWF_TZ0 * cap + c];
@@ -564,84 +586,18 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
                  oCD = ws.kslot[K_CD] * (unsigned)pcap, oNU = ws.kslot[K_NU] * (unsigned)pcap, oND = ws.kslot[K_ND] * (unsigned)pcap,
                  oXU = ws.kslot[K_XU] * (unsigned)pcap, oXD = ws.kslot[K_XD] * (unsigned)pcap;
   const size_t lvs = (size_t)nk * pcap;                                            // partial-buffer words per level
+  // records [layer][g-point][column]: float4 per lane, a warp writes / reads 512 contiguous bytes
+  float4 *__restrict__ rec = ws.rec + (size_t)g0 * pcap + c;
+  float4 *__restrict__ recC = ws.recC + (size_t)g0 * pcap + c;
+  const size_t rls = (size_t)NGLW * pcap;                                          // records per layer
 
-  // rad[i][v]: all-sky radiance, radc[i][v]: clear-sky radiance of g-point i, stream v (0 full, 1 clean)
-  float rad[NG][2], radc[NG][2], fracs_bot[NG];
-#pragma unroll
-  for (int i = 0; i < NG; i++) { rad[i][0] = rad[i][1] = 0.f; radc[i][0] = radc[i][1] = 0.f; fracs_bot[i] = 0.f; }
-  uint32_t mwc[NG];                   // McICA bits of the current 32 layers
+  for (int i = 0; i < ng; i++) { ST(i, 0) = 0.f; ST(i, 1) = 0.f; ST(i, 2) = 0.f; ST(i, 3) = 0.f; }
   uint32_t awc = 0u;
+  uint32_t mw[LW_GMAX];                      // McICA bits of the group's g-points for the current 32 layers
   int iclddn = 0;
   LwBL L;
 
-  // ---------------- pass 1: downward (LW:3207-3300), top layer first
-  if (live) { bpart[(size_t)nlay * lvs + oFD] = 0.f; bpart[(size_t)nlay * lvs + oCD] = 0.f;
-              if (do_clean) bpart[(size_t)nlay * lvs + oND] = 0.f;
-              if (do_clnc) bpart[(size_t)nlay * lvs + oXD] = 0.f; }
-  for (int lay = nlay - 1; lay >= 0; lay--) {
-    if ((lay & 31) == 31 || lay == nlay - 1) {
-      awc = ws.anyc[(size_t)(lay >> 5) * cap + c];
-#pragma unroll
-      for (int i = 0; i < NG; i++) mwc[i] = ws.mask[((size_t)(g0 + i) * ws.W + (lay >> 5)) * cap + c];
-    }
-    load_layer(lay);
-    const float taua = aerc[(unsigned)lay * ucap];
-    const float tz_dn = tz_at(lay);
-    const bool low = lay < laytrop;
-    lw_setup<BAND>(fv, sm, S0, low, oneminus, rc, L);
-    L.any3 = __any_sync(0xffffffffu, L.three);      // all 32 lanes are here: the layer loop has no early exit
-    const float blay = planck_at(fv[LWC_TAVEL]);
-    const float dplankdn = planck_at(tz_dn) - blay;
-    const bool icldlyr = (awc >> (lay & 31)) & 1u;
-    float odcld = 0.f, abscld = 0.f;
-    if (icldlyr) {
-      const float taucmc = cldc[(unsigned)lay * ucap];
-      odcld = secdiff * taucmc;
-      abscld = 1.f - glm::expf_(-odcld);
-      if (a.dbg.taucmc && live) {
-#pragma unroll
-        for (int i = 0; i < NG; i++)
-          if ((mwc[i] >> (lay & 31)) & 1u) a.dbg.taucmc[((size_t)(a.col0 + c) * nlay + lay) * NGLW + g0 + i] = taucmc;
-      }
-      iclddn = 1;
-    }
-#pragma unroll
-    for (int i = 0; i < NG; i++) {
-      float taug, fracs;
-      lw_gas<BAND>(L, i * SF, ig0 + i, taug, fracs);
-      if (a.dbg.taug && live) {
-        const size_t q = ((size_t)(a.col0 + c) * nlay + lay) * NGLW + g0 + i;
-        a.dbg.taug[q] = taug; a.dbg.taur[q] = fracs;
-      }
-      fracs_bot[i] = fracs;                       // the last iteration (lay = 0) leaves the surface value
-      const float cldfmc = ((mwc[i] >> (lay & 31)) & 1u) ? 1.f : 0.f;
-      const float efclfrac = abscld * cldfmc;
-#pragma unroll
-      for (int v = 0; v < 2; v++) {
-        if (v == 1 && !do_clean) break;
-        const float taut = v == 0 ? taug + taua : taug;
-        float odepth = secdiff * taut;
-        if (odepth < 0.0f) odepth = 0.0f;
-        float atrans, bbd, X, src, Z;
-        lw_rt<false>(s_et, bpade, odepth, icldlyr, odcld, efclfrac, cldfmc, fracs, blay, dplankdn, atrans, bbd, X, src, Z);
-        if (icldlyr) rad[i][v] = rad[i][v] - rad[i][v] * X + src + Z;
-        else rad[i][v] = rad[i][v] + (bbd - rad[i][v]) * atrans;
-        if (iclddn == 1) radc[i][v] = radc[i][v] + (bbd - radc[i][v]) * atrans;
-        else radc[i][v] = rad[i][v];
-      }
-    }
-    // downward radiances at the lower interface of the layer, summed over the group's g-points in index order
-    if (live) {
-      float *bp = bpart + (size_t)lay * lvs;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int i = 0; i < NG; i++) { s0 = s0 + rad[i][0]; s1 = s1 + radc[i][0]; s2 = s2 + rad[i][1]; s3 = s3 + radc[i][1]; }
-      __stcs(bp + oFD, s0); __stcs(bp + oCD, s1);
-      if (do_clean) __stcs(bp + oND, s2);
-      if (do_clnc) __stcs(bp + oXD, s3);
-    }
-  }
-  // ---------------- surface (LW:3303-3320)
+  float plankbnd, reflect;                   // surface (LW:3303-3320)
   {
     const float emis = ws.colf[(size_t)LWF_EMISS * cap + c];
     const float tbound = ws.colf[(size_t)LWF_TBOUND * cap + c];
@@ -649,68 +605,159 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
     ind = min(max(ind, 1), 180);
     const float frac = tbound - 159.f - (float)ind;
     const float dbdtlev = s_plk[ind] - s_plk[ind - 1];
-    const float plankbnd = emis * (s_plk[ind - 1] + frac * dbdtlev);
-    const float reflect = 1.f - emis;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NG; i++) {
-      const float rad0 = fracs_bot[i] * plankbnd;
-#pragma unroll
-      for (int v = 0; v < 2; v++) { rad[i][v] = rad0 + reflect * rad[i][v]; radc[i][v] = rad0 + reflect * radc[i][v]; }
-      s0 = s0 + rad[i][0]; s1 = s1 + radc[i][0]; s2 = s2 + rad[i][1]; s3 = s3 + radc[i][1];
-    }
-    if (live) {
-      __stcs(bpart + oFU, s0); __stcs(bpart + oCU, s1);
-      if (do_clean) __stcs(bpart + oNU, s2);
-      if (do_clnc) __stcs(bpart + oXU, s3);
-    }
+    plankbnd = emis * (s_plk[ind - 1] + frac * dbdtlev);
+    reflect = 1.f - emis;
   }
-  // ---------------- pass 2: upward (LW:3322-3356), bottom layer first; the gas optics are recomputed
-  for (int lay = 0; lay < nlay; lay++) {
-    if ((lay & 31) == 0) {
+
+  // ---------------- pass 1: downward (LW:3207-3300), top layer first
+  if (live) { bpart[(size_t)nlay * lvs + oFD] = 0.f; bpart[(size_t)nlay * lvs + oCD] = 0.f;
+              if (do_clean) bpart[(size_t)nlay * lvs + oND] = 0.f;
+              if (do_clnc) bpart[(size_t)nlay * lvs + oXD] = 0.f; }
+  float plev_up = planck_at(tz_at(nlay));
+  load_layer(nlay - 1);
+  for (int lay = nlay - 1; lay >= 0; lay--) {
+    if ((lay & 31) == 31 || lay == nlay - 1) {
       awc = ws.anyc[(size_t)(lay >> 5) * cap + c];
 #pragma unroll
-      for (int i = 0; i < NG; i++) mwc[i] = ws.mask[((size_t)(g0 + i) * ws.W + (lay >> 5)) * cap + c];
+      for (int i = 0; i < LW_GMAX; i++) mw[i] = i < ng ? maskc[(unsigned)i * mstride + (unsigned)(lay >> 5) * ucap] : 0u;
     }
-    load_layer(lay);
-    const float taua = aerc[(unsigned)lay * ucap];
-    const float plev_up = planck_at(tz_at(lay + 1));
+#pragma unroll
+    for (int f = 0; f < LWC_N; f++) fv[f] = fvn[f];
+    const float taua = taua_n, tz_dn = tz_n;
+    if (lay > 0) load_layer(lay - 1);
     const bool low = lay < laytrop;
     lw_setup<BAND>(fv, sm, S0, low, oneminus, rc, L);
     L.any3 = __any_sync(0xffffffffu, L.three);      // all 32 lanes are here: the layer loop has no early exit
     const float blay = planck_at(fv[LWC_TAVEL]);
-    const float dplankup = plev_up - blay;
+    const float plev_dn = planck_at(tz_dn);
+    const float dplankdn = plev_dn - blay, dplankup = plev_up - blay;
+    plev_up = plev_dn;
     const bool icldlyr = (awc >> (lay & 31)) & 1u;
-    float odcld = 0.f, abscld = 0.f;
+    float odcld = 0.f, abscld = 0.f, taucmc = 0.f;
+    unsigned gbits = 0u;                             // bit i: g-point i of the group is cloudy in this layer
     if (icldlyr) {
-      odcld = secdiff * cldc[(unsigned)lay * ucap];
+      taucmc = cldc[(unsigned)lay * ucap];
+      odcld = secdiff * taucmc;
       abscld = 1.f - glm::expf_(-odcld);
-    }
+      iclddn = 1;
 #pragma unroll
-    for (int i = 0; i < NG; i++) {
+      for (int i = 0; i < LW_GMAX; i++) gbits |= ((mw[i] >> (lay & 31)) & 1u) << i;
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;          // upward radiances leaving the surface (lay == 0 only)
+    float4 *rl = rec + (size_t)lay * rls, *rlC = recC + (size_t)lay * rls;
+#pragma unroll UG
+    for (int i = 0; i < ng; i++) {
       float taug, fracs;
       lw_gas<BAND>(L, i * SF, ig0 + i, taug, fracs);
-      const float cldfmc = ((mwc[i] >> (lay & 31)) & 1u) ? 1.f : 0.f;
-      const float efclfrac = abscld * cldfmc;
-#pragma unroll
-      for (int v = 0; v < 2; v++) {
-        if (v == 1 && !do_clean) break;
-        const float taut = v == 0 ? taug + taua : taug;
-        float odepth = secdiff * taut;
-        if (odepth < 0.0f) odepth = 0.0f;
-        float atrans, bbu, X, src, Z;
-        lw_rt<true>(s_et, bpade, odepth, icldlyr, odcld, efclfrac, cldfmc, fracs, blay, dplankup, atrans, bbu, X, src, Z);
-        if (icldlyr) rad[i][v] = rad[i][v] - rad[i][v] * X + src + Z;
-        else rad[i][v] = rad[i][v] + (bbu - rad[i][v]) * atrans;
-        if (iclddn == 1) radc[i][v] = radc[i][v] + (bbu - radc[i][v]) * atrans;      // iclddn as the downward sweep left it: any cloud in the column
-        else radc[i][v] = rad[i][v];
+      const float cldfmc = ((gbits >> i) & 1u) ? 1.f : 0.f;
+      if (a.dbg.taug && live) {
+        const size_t q = ((size_t)(ws.cols ? ws.cols[c] : a.col0 + c) * nlay + lay) * NGLW + g0 + i;
+        a.dbg.taug[q] = taug; a.dbg.taur[q] = fracs;
+        if (a.dbg.taucmc && cldfmc != 0.f) a.dbg.taucmc[q] = taucmc;
       }
+      const float efclfrac = abscld * cldfmc;
+      float r[2] = {ST(i, 0), ST(i, 2)}, rcl[2] = {ST(i, 1), ST(i, 3)};
+      float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float od[2];
+      od[0] = fmaxf(secdiff * (taug + taua), 0.f); od[1] = fmaxf(secdiff * taug, 0.f);
+      if (!icldlyr) {
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+          if (v == 1 && !do_clean) break;
+          float atrans, bbd, bbu;
+          lw_rt_clear(s_et, bpade, od[v], fracs, blay, dplankdn, dplankup, atrans, bbd, bbu);
+          r[v] = r[v] + (bbd - r[v]) * atrans;
+          if (iclddn == 1) rcl[v] = rcl[v] + (bbd - rcl[v]) * atrans;
+          else rcl[v] = r[v];
+          if (v == 0) { q4.x = atrans; q4.y = bbu; } else { q4.z = atrans; q4.w = bbu; }
+        }
+      } else {
+        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+          if (v == 1 && !do_clean) break;
+          LwRT t;
+          lw_rt_cloudy(s_et, bpade, od[v], odcld, efclfrac, cldfmc, fracs, blay, dplankdn, dplankup, t);
+          r[v] = r[v] - r[v] * t.X + t.srcd + t.Zd;
+          rcl[v] = rcl[v] + (t.bbd - rcl[v]) * t.atrans;          // iclddn == 1 here
+          if (v == 0) { q4.x = t.atrans; q4.y = t.bbu; c4.x = t.X; c4.y = t.Yu; }
+          else { q4.z = t.atrans; q4.w = t.bbu; c4.z = t.X; c4.w = t.Yu; }
+        }
+        __stcs(rlC + (size_t)i * pcap, c4);
+      }
+      __stcs(rl + (size_t)i * pcap, q4);
+      // downward radiances at the lower interface of the layer, summed over the group's g-points in index order
+      s0 = s0 + r[0]; s1 = s1 + rcl[0]; s2 = s2 + r[1]; s3 = s3 + rcl[1];
+      if (lay == 0) {
+        const float rad0 = fracs * plankbnd;            // fracs of the lowest layer (LW:3305)
+#pragma unroll
+        for (int v = 0; v < 2; v++) { r[v] = rad0 + reflect * r[v]; rcl[v] = rad0 + reflect * rcl[v]; }
+        z0 = z0 + r[0]; z1 = z1 + rcl[0]; z2 = z2 + r[1]; z3 = z3 + rcl[1];
+      }
+      ST(i, 0) = r[0]; ST(i, 1) = rcl[0]; ST(i, 2) = r[1]; ST(i, 3) = rcl[1];
     }
     if (live) {
-      float *bp = bpart + (size_t)(lay + 1) * lvs;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float *bp = bpart + (size_t)lay * lvs;
+      __stcs(bp + oFD, s0); __stcs(bp + oCD, s1);
+      if (do_clean) __stcs(bp + oND, s2);
+      if (do_clnc) __stcs(bp + oXD, s3);
+      if (lay == 0) {
+        __stcs(bp + oFU, z0); __stcs(bp + oCU, z1);
+        if (do_clean) __stcs(bp + oNU, z2);
+        if (do_clnc) __stcs(bp + oXU, z3);
+      }
+    }
+  }
+  // ---------------- pass 2: upward (LW:3322-3356), bottom layer first, from the records of pass 1 (requested one layer ahead)
+  float ru[LW_GMAX][2], rcu[LW_GMAX][2];
+  float4 qn[LW_GMAX];
+  {
+    const float4 *p = rec;
 #pragma unroll
-      for (int i = 0; i < NG; i++) { s0 = s0 + rad[i][0]; s1 = s1 + radc[i][0]; s2 = s2 + rad[i][1]; s3 = s3 + radc[i][1]; }
+    for (int i = 0; i < LW_GMAX; i++) {
+      ru[i][0] = i < ng ? ST(i, 0) : 0.f; rcu[i][0] = i < ng ? ST(i, 1) : 0.f;
+      ru[i][1] = i < ng ? ST(i, 2) : 0.f; rcu[i][1] = i < ng ? ST(i, 3) : 0.f;
+      qn[i] = i < ng ? __ldcs(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      p += pcap;
+    }
+  }
+  const float4 *rl = rec, *rlC = recC;
+  float *bp = bpart;
+  for (int lay = 0; lay < nlay; lay++) {
+    if ((lay & 31) == 0) awc = ws.anyc[(size_t)(lay >> 5) * cap + c];
+    const bool icldlyr = (awc >> (lay & 31)) & 1u;
+    float4 q4[LW_GMAX];
+#pragma unroll
+    for (int i = 0; i < LW_GMAX; i++) q4[i] = qn[i];
+    if (lay + 1 < nlay) {
+      const float4 *p = rl + rls;
+#pragma unroll
+      for (int i = 0; i < LW_GMAX; i++) { if (i < ng) qn[i] = __ldcs(p); p += pcap; }
+    }
+    if (icldlyr) {          // rad' = rad - rad X + Y
+      const float4 *p = rlC;
+#pragma unroll
+      for (int i = 0; i < LW_GMAX; i++) {
+        if (i < ng) { const float4 c4 = __ldcs(p); ru[i][0] = ru[i][0] - ru[i][0] * c4.x + c4.y; ru[i][1] = ru[i][1] - ru[i][1] * c4.z + c4.w; }
+        p += pcap;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LW_GMAX; i++) { ru[i][0] = ru[i][0] + (q4[i].y - ru[i][0]) * q4[i].x; ru[i][1] = ru[i][1] + (q4[i].w - ru[i][1]) * q4[i].z; }
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // upward radiances at the top of the layer; g-points beyond ng hold zeros
+    if (iclddn == 1) {      // iclddn as the downward sweep left it: any cloud in the column
+#pragma unroll
+      for (int i = 0; i < LW_GMAX; i++) { rcu[i][0] = rcu[i][0] + (q4[i].y - rcu[i][0]) * q4[i].x; rcu[i][1] = rcu[i][1] + (q4[i].w - rcu[i][1]) * q4[i].z; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LW_GMAX; i++) { rcu[i][0] = ru[i][0]; rcu[i][1] = ru[i][1]; }
+    }
+#pragma unroll
+    for (int i = 0; i < LW_GMAX; i++) { s0 = s0 + ru[i][0]; s1 = s1 + rcu[i][0]; s2 = s2 + ru[i][1]; s3 = s3 + rcu[i][1]; }
+    rl += rls; rlC += rls; bp += lvs;
+    if (live) {
       __stcs(bp + oFU, s0); __stcs(bp + oCU, s1);
       if (do_clean) __stcs(bp + oNU, s2);
       if (do_clnc) __stcs(bp + oXU, s3);
@@ -719,16 +766,17 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
 }
 
 // Block = LW_BLOCK columns x one band group.  Blocks of one column tile are neighbours in launch order (its coefficient lines
-// are re-read from L2 by the 25 groups); thread 0 stages the exp / tfn table, the group's NG table slices and the band's Planck
+// are re-read from L2 by the 23 groups); thread 0 stages the exp / tfn table, the group's table slices and the band's Planck
 // column with TMA bulk copies.
 __global__ void __launch_bounds__(LW_BLOCK, 1) k_lw_band(LwArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *s_et = reinterpret_cast<float2 *>(smem_raw);                // 10002 x (exp_tbl, tfn_tbl)
-  float *S = reinterpret_cast<float *>(s_et + 10002);                 // NG slices
+  float *S = reinterpret_cast<float *>(s_et + 10002);                 // the group's slices
   float *s_plk = S + LW_GMAX * LW_SLICE_MAX;                          // totplnk(1:181, band), padded to 184
   float *s_rat = s_plk + 184;                                         // [6][60] chi_mls ratios by jp
   float *s_chi = s_rat + 6 * 60;                                      // chi_mls(7,59)
-  uint64_t *bar = reinterpret_cast<uint64_t *>(s_chi + 416);
+  float *s_state = s_chi + 416;                                       // [LW_GMAX][4][LW_BLOCK] radiances
+  uint64_t *bar = reinterpret_cast<uint64_t *>(s_state + LW_GMAX * 4 * LW_BLOCK);
 
   const int ngrp = a.ngroups;
   const int tile = blockIdx.x / ngrp, grp = blockIdx.x % ngrp;
@@ -758,21 +806,16 @@ __global__ void __launch_bounds__(LW_BLOCK, 1) k_lw_band(LwArgs a) {
   const bool live = c < a.ncols;              // every lane stays: the band bodies use warp votes
   if (!live) c = a.ncols - 1;
   const LwSmem sm{s_et, S, s_plk, s_rat, s_chi};
-#define LWB(B_, N_) lw_band_body<B_, N_>(a, sm, grp, g0, c, live)
-  // (band, group size) pairs that make_sweep_groups(LW_GMAX = 8) produces from ngc = 10,12,16,14,16,8,12,8,12,6,8,8,4,2,2,2
-  switch (b * 32 + ng) {
-    case 0 * 32 + 5: LWB(1, 5); break;    case 1 * 32 + 6: LWB(2, 6); break;    case 2 * 32 + 8: LWB(3, 8); break;
-    case 3 * 32 + 7: LWB(4, 7); break;    case 4 * 32 + 8: LWB(5, 8); break;    case 5 * 32 + 8: LWB(6, 8); break;
-    case 6 * 32 + 6: LWB(7, 6); break;    case 7 * 32 + 8: LWB(8, 8); break;    case 8 * 32 + 6: LWB(9, 6); break;
-    case 9 * 32 + 6: LWB(10, 6); break;   case 10 * 32 + 8: LWB(11, 8); break;  case 11 * 32 + 8: LWB(12, 8); break;
-    case 12 * 32 + 4: LWB(13, 4); break;  case 13 * 32 + 2: LWB(14, 2); break;  case 14 * 32 + 2: LWB(15, 2); break;
-    case 15 * 32 + 2: LWB(16, 2); break;
+  float *st = s_state + threadIdx.x;
+#define LWB(B_) case B_ - 1: lw_band_body<B_>(a, sm, st, grp, g0, ng, c, live); break;
+  switch (b) {
+    LWB(1) LWB(2) LWB(3) LWB(4) LWB(5) LWB(6) LWB(7) LWB(8) LWB(9) LWB(10) LWB(11) LWB(12) LWB(13) LWB(14) LWB(15) LWB(16)
     default: break;
   }
 #undef LWB
 }
 
-static int lw_band_smem() { return 10002 * 8 + (LW_GMAX * LW_SLICE_MAX + 184 + 6 * 60 + 416) * 4 + 16; }
+static int lw_band_smem() { return 10002 * 8 + (LW_GMAX * LW_SLICE_MAX + 184 + 6 * 60 + 416 + LW_GMAX * 4 * LW_BLOCK) * 4 + 16; }
 
 int lw_sweep_groups() { return h_lw_grp.n; }
 void launch_lw_band(const LwArgs &a, cudaStream_t s) {
@@ -797,7 +840,7 @@ __global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_lw_reduce(LwArgs a) {
   const int nlay = ws.nlay, nz = G.kte - G.kts + 1;
   const size_t cap = ws.pcap;      // the reduce only touches the partial buffer
   const bool active = c < a.ncols;
-  const int tc = a.col0 + c;
+  const int tc = active ? (ws.cols ? ws.cols[c] : a.col0 + c) : 0;
   int i = 0, j = 0; size_t ij = 0;
   if (active) { G.ij(tc, i, j); ij = G.at2(i, j); }
   const bool do_clean = (a.variants & ARC_VAR_CLEAN) != 0;

@@ -36,18 +36,29 @@ __device__ __forceinline__ void set_status(int *status, int code) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Sunlit compaction (SW:10336 "if (coszrs.le.0.0) dorrsw = .false.").  Order-preserving: one block scans
-// a 1024-column segment, segment offsets come from a first counting pass, so the chunk-local ordering (and
-// with it every memory address) is deterministic.
-__global__ void k_count_sunlit(Geo G, const float *__restrict__ xcoszen, int *__restrict__ segcount) {
-  int tc = blockIdx.x * blockDim.x + threadIdx.x;
-  bool sun = false;
-  if (tc < G.ncol_tile) { int i, j; G.ij(tc, i, j); sun = !(xcoszen[G.at2(i, j)] <= 0.0f); }
-  int n = __syncthreads_count(sun);
-  if (threadIdx.x == 0) segcount[blockIdx.x] = n;
+// Sunlit compaction (SW:10336 "if (coszrs.le.0.0) dorrsw = .false.") with cloud bucketing: the list holds first the
+// cloud-free sunlit columns, then the sunlit columns with cloud (cldfra > 0 in some layer), each in tile order.  Columns are
+// independent, so the order changes no result; it puts columns that take the cloudy-layer path of the solver (two extra
+// two-stream evaluations per cloudy layer) into the same warps instead of idling 31 lanes for one.  Deterministic: one block
+// scans a 1024-column segment, segment offsets come from a first counting pass.
+__device__ __forceinline__ void sunlit_class(const Geo &G, const float *__restrict__ xcoszen, const float *__restrict__ cldfra3d, int tc,
+                                             bool &sun, bool &cloudy) {
+  sun = false; cloudy = false;
+  if (tc >= G.ncol_tile) return;
+  int i, j; G.ij(tc, i, j);
+  sun = xcoszen ? !(xcoszen[G.at2(i, j)] <= 0.0f) : true;     // no xcoszen: every column (the LW list)
+  if (sun && cldfra3d)
+    for (int k = G.kts; k <= G.kte; k++) cloudy = cloudy || cldfra3d[G.at3(i, k, j)] > 0.f;
+}
+__global__ void k_count_sunlit(Geo G, const float *__restrict__ xcoszen, const float *__restrict__ cldfra3d, int nseg, int *__restrict__ segcount) {
+  const int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  bool sun, cloudy;
+  sunlit_class(G, xcoszen, cldfra3d, tc, sun, cloudy);
+  const int n0 = __syncthreads_count(sun && !cloudy), n1 = __syncthreads_count(sun && cloudy);
+  if (threadIdx.x == 0) { segcount[blockIdx.x] = n0; segcount[nseg + blockIdx.x] = n1; }
 }
 __global__ void k_scan_segments(int nseg, int *__restrict__ segcount, int *__restrict__ total) {
-  // single thread block; nseg is small (ncol/1024)
+  // single thread block; nseg is small (2 * ncol/1024)
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
@@ -71,27 +82,32 @@ __global__ void k_scan_segments(int nseg, int *__restrict__ segcount, int *__res
   }
   if (threadIdx.x == 0) *total = carry;
 }
-__global__ void k_fill_sunlit(Geo G, const float *__restrict__ xcoszen, const int *__restrict__ segoff, int *__restrict__ cols) {
-  int tc = blockIdx.x * blockDim.x + threadIdx.x;
-  bool sun = false;
-  if (tc < G.ncol_tile) { int i, j; G.ij(tc, i, j); sun = !(xcoszen[G.at2(i, j)] <= 0.0f); }
-  __shared__ int wcount[32];
-  unsigned b = __ballot_sync(0xffffffffu, sun);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) wcount[w] = __popc(b);
+__global__ void k_fill_sunlit(Geo G, const float *__restrict__ xcoszen, const float *__restrict__ cldfra3d, int nseg, const int *__restrict__ segoff,
+                              int *__restrict__ cols) {
+  const int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  bool sun, cloudy;
+  sunlit_class(G, xcoszen, cldfra3d, tc, sun, cloudy);
+  __shared__ int wcount[2][32];
+  const unsigned b0 = __ballot_sync(0xffffffffu, sun && !cloudy), b1 = __ballot_sync(0xffffffffu, sun && cloudy);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { wcount[0][w] = __popc(b0); wcount[1][w] = __popc(b1); }
   __syncthreads();
-  int off = segoff[blockIdx.x];
-  for (int q = 0; q < w; q++) off += wcount[q];
-  if (sun) cols[off + __popc(b & ((1u << lane) - 1u))] = tc;
+  if (!sun) return;
+  const int q = cloudy ? 1 : 0;
+  int off = segoff[q * nseg + blockIdx.x];
+  for (int v = 0; v < w; v++) off += wcount[q][v];
+  cols[off + __popc((q ? b1 : b0) & ((1u << lane) - 1u))] = tc;
 }
 
-static int *g_seg = nullptr; static int g_seg_cap = 0;
-void launch_compact_sunlit(const Geo &g, const float *xcoszen, int *cols, int *count, cudaStream_t s) {
+// `slot` selects one of two scratch buffers: the SW list (0) and the LW list (1) of a chained radiation step are built on
+// different streams at the same time
+static int *g_seg[2] = {nullptr, nullptr}; static int g_seg_cap[2] = {0, 0};
+void launch_compact_sunlit(const Geo &g, const float *xcoszen, const float *cldfra3d, int *cols, int *count, int slot, cudaStream_t s) {
   int nseg = (g.ncol_tile + 1023) / 1024;
-  if (nseg > g_seg_cap) { if (g_seg) cudaFree(g_seg); cudaMalloc(&g_seg, sizeof(int) * nseg); g_seg_cap = nseg; }
-  k_count_sunlit<<<nseg, 1024, 0, s>>>(g, xcoszen, g_seg);
-  k_scan_segments<<<1, 1024, 0, s>>>(nseg, g_seg, count);
-  k_fill_sunlit<<<nseg, 1024, 0, s>>>(g, xcoszen, g_seg, cols);
+  if (2 * nseg > g_seg_cap[slot]) { if (g_seg[slot]) cudaFree(g_seg[slot]); cudaMalloc(&g_seg[slot], sizeof(int) * 2 * nseg); g_seg_cap[slot] = 2 * nseg; }
+  k_count_sunlit<<<nseg, 1024, 0, s>>>(g, xcoszen, cldfra3d, nseg, g_seg[slot]);
+  k_scan_segments<<<1, 1024, 0, s>>>(2 * nseg, g_seg[slot], count);
+  k_fill_sunlit<<<nseg, 1024, 0, s>>>(g, xcoszen, cldfra3d, nseg, g_seg[slot], cols);
   count_launch(3);
 }
 
@@ -596,6 +612,73 @@ void launch_sw_prep(const SwArgs &a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// cal_cldfra1 (module_radiation_driver.F:2886-3122; icloud = 1): Randall-1994 / Hong-1998 cloud fraction from the grid-scale
+// condensate and the relative humidity with respect to a water / ice weighted saturation mixing ratio.  One thread per cell,
+// i fastest.  EXP and ** are glibc's (glibc_math.cuh) and this file is compiled without FMA contraction: bit-exact with the
+// reference's arithmetic.  f_q* : 1 = .TRUE., 0 = .FALSE., < 0 = not PRESENT.
+struct CldfraArgs {
+  Geo geo;
+  const float *qv, *qc, *qi, *qs, *t_phy, *p_phy, *f_ice_phy;
+  int f_qv, f_qc, f_qi, f_qs, mp_physics;
+  float *cldfra; int *flag;
+};
+__global__ void __launch_bounds__(256) k_cal_cldfra1(CldfraArgs a) {
+  const Geo &G = a.geo;
+  const int nz = G.kte - G.kts + 1;
+  const long n = (long)G.ncol_tile * nz;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int ii = (int)(t % G.nci), k = G.kts + (int)((t / G.nci) % nz), j = G.jts + (int)(t / ((long)G.nci * nz));
+  const size_t q = G.at3(G.its + ii, k, j);
+  const float ALPHA0 = 100.f, GAMMA = 0.49f, QCLDMIN = 1.E-12f, PEXP = 0.25f, RHGRID = 1.0f;
+  const float SVP1 = 0.61078f, SVP2 = 17.2693882f, SVPI2 = 21.8745584f, SVP3 = 35.86f, SVPI3 = 7.66f, SVPT0 = 273.15f;
+  const float ep_2 = 287.f / 461.6f;
+  const float tk = a.t_phy[q], pp = a.p_phy[q];
+  const float tc = tk - SVPT0;
+  const float esw = 1000.0f * SVP1 * glm::expf_(SVP2 * tc / (tk - SVP3));
+  const float esi = 1000.0f * SVP1 * glm::expf_(SVPI2 * tc / (tk - SVPI3));
+  const float qvsw = ep_2 * esw / (pp - esw);
+  const float qvsi = ep_2 * esi / (pp - esi);
+  float weight = 0.f, qcld = 0.f;
+  const bool present = a.f_qi >= 0 && a.f_qc >= 0 && a.f_qs >= 0;
+  if (present) {
+    const bool fqi = a.f_qi > 0, fqc = a.f_qc > 0, fqs = a.f_qs > 0;
+    const float qi = a.qi ? a.qi[q] : 0.f, qc = a.qc ? a.qc[q] : 0.f, qs = a.qs ? a.qs[q] : 0.f;
+    if (fqi && fqc && fqs) { qcld = qi + qc + qs; weight = qcld < QCLDMIN ? 0.f : (qi + qs) / qcld; }
+    if (fqi && fqc && !fqs) { qcld = qi + qc; weight = qcld < QCLDMIN ? 0.f : qi / qcld; }
+    if (fqc && !fqi && !fqs) { qcld = qc; weight = qcld < QCLDMIN ? 0.f : (tk > 273.15f ? 0.f : 1.f); }
+    if (fqc && !fqi && fqs && a.f_ice_phy) { qcld = qc + qs; weight = qcld < QCLDMIN ? 0.f : a.f_ice_phy[q]; }
+    if (a.mp_physics == 5 || a.mp_physics == 15) {          // FER_MP_HIRES, FER_MP_HIRES_ADVECT (Registry.EM_COMMON)
+      qcld = qc + qi;
+      if (qcld < QCLDMIN) weight = 0.f; else { weight = qi / qcld; if (tc < -40.f) weight = 1.f; }
+    }
+  }
+  const float qvs_weight = (1 - weight) * qvsw + weight * qvsi;
+  float rhum = a.qv[q] / qvs_weight;
+  float cf; int fl;
+  if (!present || qcld < QCLDMIN) { cf = 0.f; fl = 1; }
+  else if (rhum >= RHGRID) { cf = 1.f; fl = 2; }
+  else {
+    fl = 3;
+    const float subsat = fmaxf(1.E-10f, RHGRID * qvs_weight - a.qv[q]);
+    const float denom = glm::powf_(subsat, GAMMA);
+    const float arg = fmaxf(-6.9f, -ALPHA0 * qcld / denom);
+    rhum = fmaxf(1.E-10f, rhum);
+    cf = glm::powf_(rhum / RHGRID, PEXP) * (1.f - glm::expf_(arg));
+    if (cf < .01f) cf = 0.f;
+  }
+  a.cldfra[q] = cf;
+  if (a.flag) a.flag[q] = fl;
+}
+void launch_cal_cldfra1(const Geo &G, const float *qv, const float *qc, const float *qi, const float *qs, int f_qv, int f_qc, int f_qi, int f_qs,
+                        const float *t_phy, const float *p_phy, const float *f_ice_phy, int mp_physics, float *cldfra, int *flag, cudaStream_t s) {
+  CldfraArgs a{G, qv, qc, qi, qs, t_phy, p_phy, f_ice_phy, f_qv, f_qc, f_qi, f_qs, mp_physics, cldfra, flag};
+  const long n = (long)G.ncol_tile * (G.kte - G.kts + 1);
+  k_cal_cldfra1<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------------
 // LW column preparation.  One thread per column (all columns; LW has no day/night gate).
 __global__ void __launch_bounds__(128) k_lw_prep(LwArgs a) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -603,7 +686,7 @@ __global__ void __launch_bounds__(128) k_lw_prep(LwArgs a) {
   const Geo &G = a.geo;
   const DevTables &tb = a.tb;
   const LwWs &ws = a.ws;
-  const int tc = a.col0 + c;
+  const int tc = a.ws.cols ? a.ws.cols[c] : a.col0 + c;
   int i, j; G.ij(tc, i, j);
   const size_t ij = G.at2(i, j);
   const int kts = G.kts, nz = G.kte - G.kts + 1, nlay = ws.nlay;

@@ -27,11 +27,12 @@ import numpy as np
 ERROR_TYPES = ("standard_error", "corrected_standard_error")
 
 
-def stats_from_sums(sums, names=None, morans_i=None):
+def stats_from_sums(sums, names=None, morans_i=None, percentiles=None):
     """{sum, sum of squares, count, min, max} per field (the `out[f][5]` of arc_rad_domain_stats) -> the statistics columns of
     calc_standard_stats that the decomposition uses.  `sums`: array (nfields, 5); `names`: field names (-> dict of dicts);
     `morans_i`: Moran's I per field (arc_rad_morans_i) -> also 'morans_i' and 'corrected_standard_error' = SE * I
-    (misc_stats_library.ncl:447-449)."""
+    (misc_stats_library.ncl:447-449); `percentiles`: array (nfields, 5) = median, lower / upper quartile, 5th / 95th
+    percentile (arc_rad_percentiles with perc = 50, 25, 75, 5, 95; ncl:439-445)."""
     s = np.asarray(sums, dtype=np.float64)
     n = s[:, 2]
     avg = s[:, 0] / n
@@ -42,6 +43,10 @@ def stats_from_sums(sums, names=None, morans_i=None):
         mi = np.asarray(morans_i, dtype=np.float64)
         cols["morans_i"] = mi
         cols["corrected_standard_error"] = cols["standard_error"] * mi
+    if percentiles is not None:
+        pc = np.asarray(percentiles, dtype=np.float64)
+        for q, nm in enumerate(("median", "lower_quartile", "upper_quartile", "p05", "p95")):
+            cols[nm] = pc[:, q]
     if names is None:
         return cols
     return {nm: {k: v[i] for k, v in cols.items()} for i, nm in enumerate(names)}

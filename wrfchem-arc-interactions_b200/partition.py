@@ -43,3 +43,40 @@ def finalize_stats(s, s2, n, mn, mx):
     var = np.maximum(s2 / n - mean * mean, 0.0) * n / np.maximum(n - 1, 1)      # sample variance like NCL's stddev
     sd = np.sqrt(var)
     return dict(mean=mean, sd=sd, se=sd / np.sqrt(n), min=mn, max=mx, n=n)
+
+
+class SlabGather:
+    """All-gather of 2-D (j, i) fields that are partitioned into j-slabs: every rank ends up with the global fields
+    (the diagnostic-field gather of SURVEY.md section 8e; order statistics and Moran's I need the whole field).
+
+    One collective per step: the `nf` fields of a slab are stacked into one send buffer, padded to the tallest slab, and
+    all-gathered (torch.distributed.all_gather_into_tensor: NCCL on GPUs, gloo on the CPU); the valid rows of every rank
+    are then copied to their place in the global array.  Buffers are allocated once."""
+
+    def __init__(self, dist, slabs, rank, nf, ni, device, dtype=None):
+        import torch
+        self.dist, self.slabs, self.rank, self.nf, self.ni = dist, list(slabs), rank, nf, ni
+        self.world = len(self.slabs)
+        self.rows = self.slabs[rank][1] - self.slabs[rank][0] + 1
+        self.maxrows = max(b - a + 1 for a, b in self.slabs)
+        self.nj = self.slabs[-1][1]
+        dtype = dtype or torch.float32
+        self.send = torch.zeros(nf, self.maxrows, ni, dtype=dtype, device=device)
+        self.recv = torch.zeros(self.world * nf, self.maxrows, ni, dtype=dtype, device=device)     # rank-major concatenation
+        self.glob = torch.zeros(nf, self.nj, ni, dtype=dtype, device=device)
+
+    def bytes_per_step(self):
+        return self.recv.numel() * self.recv.element_size()
+
+    def __call__(self, fields):
+        """fields: list of nf tensors (rows, ni) of this rank's slab -> (nf, nj, ni) global fields (a view of self.glob)."""
+        for f, t in enumerate(fields):
+            self.send[f, :self.rows].copy_(t)
+        return self.exchange()
+
+    def exchange(self):
+        self.dist.all_gather_into_tensor(self.recv, self.send)
+        recv = self.recv.view(self.world, self.nf, self.maxrows, self.ni)
+        for r, (a, b) in enumerate(self.slabs):
+            self.glob[:, a - 1:b].copy_(recv[r, :, :b - a + 1])
+        return self.glob

@@ -38,6 +38,17 @@ def _is_device(a):
     return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
 
 
+def _sync_producers(arrays):
+    """Stream contract of the C ABI for device arrays (include/arc_rad.h, "Streams"): the library works on its own
+    non-blocking streams and does not order itself against the caller's, so everything that produces the arrays must have
+    finished before the call.  The arrays here are torch tensors: wait for the current torch stream of their device."""
+    for a in arrays:
+        if _is_device(a):
+            import torch
+            torch.cuda.current_stream(a.device).synchronize()
+            return
+
+
 def _ptr(a):
     if a is None:
         return None
@@ -98,6 +109,7 @@ class RadLib:
         """kw: Fortran dummy names -> arrays / scalars.  F_Qx flags: True/False or omitted (= not PRESENT)."""
         d = abi.make_dims(dims) if isinstance(dims, dict) else dims
         si, so = self._build_sw(kw)
+        _sync_producers(kw.values())
         self.check(self._sw(C.byref(d), C.byref(si), C.byref(so), C.byref(debug) if debug is not None else None))
 
     def _build_sw(self, kw):
@@ -128,6 +140,7 @@ class RadLib:
     def RRTMG_LWRAD(self, dims, debug=None, **kw):
         d = abi.make_dims(dims) if isinstance(dims, dict) else dims
         li, lo = self._build_lw(kw)
+        _sync_producers(kw.values())
         self.check(self._lw(C.byref(d), C.byref(li), C.byref(lo), C.byref(debug) if debug is not None else None))
 
     def RRTMG_LWSW(self, dims, lw_kw, sw_kw):
@@ -139,6 +152,7 @@ class RadLib:
         fn = self.lib.arc_rad_lwsw
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(abi.ArcDims), C.POINTER(abi.ArcLwIn), C.POINTER(abi.ArcLwOut), C.POINTER(abi.ArcSwIn), C.POINTER(abi.ArcSwOut)]
+        _sync_producers(list(lw_kw.values()) + list(sw_kw.values()))
         self.check(fn(C.byref(d), C.byref(li), C.byref(lo), C.byref(si), C.byref(so)))
 
     def _build_lw(self, kw):
@@ -171,12 +185,16 @@ class RadLib:
 
 
     # optical_averaging (WRF-Chem chem/module_optical_averaging.F; restated)
-    def domain_statistics(self, dims, fields, names=None, morans=True):
-        """Statistics columns of calc_standard_stats (misc_stats_library.ncl:396-461) for 2-D fields, reduced on the device:
-        avg, stddev (N-1), min, max, standard_error, N and, with `morans`, morans_i and corrected_standard_error = SE * I.
+    def domain_statistics(self, dims, fields, names=None, morans=True, percentiles=True, trim=0):
+        """The 13 statistics of calc_standard_stats (misc_stats_library.ncl:396-461) for 2-D fields, reduced on the device:
+        avg, stddev (N-1), min, max, median, lower_quartile, upper_quartile, p05, p95 (with `percentiles`), standard_error,
+        morans_i and corrected_standard_error = SE * I (with `morans`), N.  `trim` cells are cut from every edge of the tile
+        first, as calculate_domain_stats does with domain_trim@trim = 5 (data_extraction_library.ncl:318-322).
         `fields`: list of numpy arrays (host) or torch CUDA tensors (device); returns decomposition.stats_from_sums(...)."""
         from . import decomposition
-        d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        d = abi.make_dims(dims) if isinstance(dims, dict) else abi.ArcDims.from_buffer_copy(dims)
+        if trim:
+            d.its += trim; d.ite -= trim; d.jts += trim; d.jte -= trim
         dev = [_is_device(f) for f in fields]
         if any(dev) and not all(dev):
             raise ValueError("mix of host and device arrays")
@@ -188,20 +206,58 @@ class RadLib:
         L.arc_rad_domain_stats.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_void_p]
         L.arc_rad_morans_i.restype = C.c_int
         L.arc_rad_morans_i.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_void_p]
+        L.arc_rad_percentiles.restype = C.c_int
+        L.arc_rad_percentiles.argtypes = [C.POINTER(abi.ArcDims), C.c_int, C.c_int, C.POINTER(abi.c_fp), C.c_int, abi.c_fp, C.c_void_p]
+        perc = np.array([50.0, 25.0, 75.0, 5.0, 95.0], np.float32)          # median, quartiles, 5th / 95th (ncl:441-445)
         if dev[0]:
             import torch
             st = torch.zeros(n, 5, dtype=torch.float64, device=fields[0].device)
             mi = torch.zeros(n, dtype=torch.float32, device=fields[0].device)
+            pc = torch.zeros(n, 5, dtype=torch.float32, device=fields[0].device)
+            _sync_producers([st] + list(fields))    # the zero fills above run on torch's stream, the reduction on the library's
             self.check(L.arc_rad_domain_stats(C.byref(d), ms, n, ptrs, C.c_void_p(int(st.data_ptr()))))
             if morans:
                 self.check(L.arc_rad_morans_i(C.byref(d), ms, n, ptrs, C.c_void_p(int(mi.data_ptr()))))
-            st, mi = st.cpu().numpy(), mi.cpu().numpy()
+            if percentiles:
+                self.check(L.arc_rad_percentiles(C.byref(d), ms, n, ptrs, 5, abi.fptr(perc), C.c_void_p(int(pc.data_ptr()))))
+            st, mi, pc = st.cpu().numpy(), mi.cpu().numpy(), pc.cpu().numpy()
         else:
-            st, mi = np.zeros((n, 5)), np.zeros(n, np.float32)
+            st, mi, pc = np.zeros((n, 5)), np.zeros(n, np.float32), np.zeros((n, 5), np.float32)
             self.check(L.arc_rad_domain_stats(C.byref(d), ms, n, ptrs, C.c_void_p(st.ctypes.data)))
             if morans:
                 self.check(L.arc_rad_morans_i(C.byref(d), ms, n, ptrs, C.c_void_p(mi.ctypes.data)))
-        return decomposition.stats_from_sums(st, names=names, morans_i=mi if morans else None)
+            if percentiles:
+                self.check(L.arc_rad_percentiles(C.byref(d), ms, n, ptrs, 5, abi.fptr(perc), C.c_void_p(pc.ctypes.data)))
+        return decomposition.stats_from_sums(st, names=names, morans_i=mi if morans else None, percentiles=pc if percentiles else None)
+
+    def cal_cldfra1(self, dims, CLDFRA, QV, QC, QI, QS, t_phy, p_phy, F_QV=True, F_QC=True, F_QI=True, F_QS=True, F_ICE_PHY=None,
+                    mp_physics=0, cldfra1_flag=None):
+        """cal_cldfra1 of module_radiation_driver.F:2886-3122 (icloud = 1) with the Fortran dummy names; F_Qx = None means the
+        OPTIONAL argument is not PRESENT.  CLDFRA (and cldfra1_flag, int32) are written for the tile levels kts..kte."""
+        d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        arrays = [CLDFRA, QV, QC, QI, QS, t_phy, p_phy, F_ICE_PHY, cldfra1_flag]
+        dev = [_is_device(v) for v in arrays if v is not None]
+        if any(dev) and not all(dev):
+            raise ValueError("mix of host and device arrays")
+        ms = abi.ARC_MEM_DEVICE if dev[0] else abi.ARC_MEM_HOST
+        flag = lambda f: -1 if f is None else int(bool(f))
+        pname = "arc_rad_cal_cldfra1" if self.prefix == "arc_rad_" else "arc_oracle_cal_cldfra1"
+        fn = getattr(self.lib, pname)
+        fn.restype = C.c_int
+        iptr = None
+        if cldfra1_flag is not None:
+            iptr = C.cast(int(cldfra1_flag.data_ptr()) if hasattr(cldfra1_flag, "data_ptr") else cldfra1_flag.ctypes.data, C.c_void_p)
+        common = [_ptr(QV), _ptr(QC), _ptr(QI), _ptr(QS), flag(F_QV), flag(F_QC), flag(F_QI), flag(F_QS), _ptr(t_phy), _ptr(p_phy), _ptr(F_ICE_PHY),
+                  int(mp_physics), _ptr(CLDFRA), iptr]
+        if self.prefix == "arc_rad_":
+            fn.argtypes = [C.POINTER(abi.ArcDims), C.c_int] + [abi.c_fp] * 4 + [C.c_int] * 4 + [abi.c_fp] * 3 + [C.c_int, abi.c_fp, C.c_void_p]
+            _sync_producers(arrays)
+            self.check(fn(C.byref(d), ms, *common))
+        else:
+            fn.argtypes = [C.POINTER(abi.ArcDims)] + [abi.c_fp] * 4 + [C.c_int] * 4 + [abi.c_fp] * 3 + [C.c_int, abi.c_fp, C.c_void_p]
+            rc = fn(C.byref(d), *common)
+            if rc:
+                raise RadiationError(rc, "oracle cal_cldfra1")
 
     def optical_averaging(self, dims, mode, bins, alt, dz8w, outs, sigmag=None):
         """bins: list (one per size section, or per mode) of dicts {species_name: array, ..., "num": array}; a species name
@@ -233,6 +289,7 @@ class RadLib:
         fn = getattr(self.lib, ("arc_aer_optics" if self.prefix == "arc_rad_" else "arc_oracle_aer_optics"))
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(abi.ArcDims), C.POINTER(abi.ArcAerIn), C.POINTER(abi.ArcAerOut)]
+        _sync_producers(arrays + list(outs.values()))
         rc = fn(C.byref(d), C.byref(ai), C.byref(ao))
         if rc != 0:
             err = getattr(self.lib, "arc_rad_last_error" if self.prefix == "arc_rad_" else "arc_oracle_aer_last_error")
