@@ -49,7 +49,14 @@ def compare_outputs(dom, og, oo):
                 worst_rel = max(worst_rel, float((err[big] / np.maximum(np.abs(b[big]), 1e-30)).max()))
         ok = within(a, b)
         bad |= ~(ok if ok.ndim == 1 else ok.all(axis=1))
-    return dict(columns=int(bad.size), out_of_tolerance=int(bad.sum()), worst_abs=worst_abs, worst_rel=worst_rel, worst_hr=worst_hr)
+    nbits = 0
+    for k in og:
+        a, b = per_column(dom, og[k]), per_column(dom, oo[k])
+        if a.ndim == 2:
+            a, b = a[:, :nz + (0 if k.startswith("rthraten") else 2)], b[:, :nz + (0 if k.startswith("rthraten") else 2)]
+        nbits += int((np.ascontiguousarray(a).view(np.uint32) != np.ascontiguousarray(b).view(np.uint32)).sum())
+    return dict(columns=int(bad.size), out_of_tolerance=int(bad.sum()), worst_abs=worst_abs, worst_rel=worst_rel, worst_hr=worst_hr,
+                cells_not_bit_exact=nbits)
 
 
 def run_case(case, lib, orc_mt, ktab, run_pair, init):

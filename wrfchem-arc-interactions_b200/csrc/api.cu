@@ -154,6 +154,7 @@ void carve_sw(SwWs &w, char *base, size_t &bytes) {
   w.zinc = c.take<float>((size_t)2 * NGSW * pcap);
   w.bpart = c.take<float>((size_t)sw_sweep_groups() * (nl + 1) * w.nk * pcap);
   w.dirs = c.take<float>((size_t)2 * NGSW * pcap);
+  w.uvni = c.take<float>((size_t)sw_sweep_groups() * 2 * pcap);
   bytes = c.off;
 }
 void carve_lw(LwWs &w, char *base, size_t &bytes) {

@@ -102,6 +102,7 @@ struct SwWs {
   float *bpart;            // [sweep group][nlay+1][nk][pcap]  per-group sums of the fluxes; nk = kinds in use, slot of kind k = kslot[k]
   int nk; int kslot[NKIND];
   float *dirs;             // [NGSW][cap]          surface direct beam without delta scaling (x incident flux)
+  float *uvni;             // [sweep group][2][pcap] running sums of the FULL surface downward flux over the UV/visible and the near-IR g-points
 };
 
 struct SwArgs {

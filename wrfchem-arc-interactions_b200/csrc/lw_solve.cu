@@ -435,37 +435,40 @@ __device__ __forceinline__ void lw_setup(const float (&fv)[LWC_N], const LwSmem 
 struct LwRT { float atrans, bbd, bbu, X, srcd, Zd, Yu; };
 // clear layer (no sub-column of the column is cloudy in it): series below 0.06, table above; both are evaluated and selected
 // (the table index of a small optical depth is valid), no divergence
+// The per-stream arithmetic below spells out every rounding (explicit fmaf / __fmul_rn / __fadd_rn): the full and the clean
+// stream are two inlined copies of the same source, and left to itself the compiler contracts them differently, so that a
+// clean stream with zero aerosol would no longer equal the full one bit for bit (the reference runs the same code twice).
 __device__ __forceinline__ void lw_rt_clear(const float2 *__restrict__ s_et, const float bpade, const float odepth, const float plfrac,
                                             const float blay, const float dplankdn, const float dplankup, float &atrans, float &bbd, float &bbu) {
   const float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
   const int itr = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
   const float2 et = s_et[itr];
   const bool ser = odepth <= 0.06f;
-  atrans = ser ? odepth - 0.5f * odepth * odepth : 1.f - et.x;
-  const float tf = ser ? 0.166667f * odepth : et.y;
-  bbd = plfrac * (blay + tf * dplankdn);
-  bbu = plfrac * (blay + tf * dplankup);
+  atrans = ser ? fmaf(-__fmul_rn(0.5f, odepth), odepth, odepth) : __fsub_rn(1.f, et.x);
+  const float tf = ser ? __fmul_rn(0.166667f, odepth) : et.y;
+  bbd = __fmul_rn(plfrac, fmaf(tf, dplankdn, blay));
+  bbu = __fmul_rn(plfrac, fmaf(tf, dplankup, blay));
 }
 // layer in which the column has cloud in some sub-column (icldlyr, LW:3218-3290): three optical-depth regimes, gas-only and
 // gas + cloud quantities
 __device__ __forceinline__ void lw_rt_cloudy(const float2 *__restrict__ s_et, const float bpade, float odepth, const float odcld,
                                              const float efclfrac, const float cldfmc, const float plfrac, const float blay, const float dplankdn,
                                              const float dplankup, LwRT &o) {
-  float odtot = odepth + odcld;
+  float odtot = __fadd_rn(odepth, odcld);
   float tf, tftot, atot;
   bool table_gas = false;
   if (odtot < 0.06f) {
-    o.atrans = odepth - 0.5f * odepth * odepth;
-    tf = 0.166667f * odepth;
-    atot = odtot - 0.5f * odtot * odtot;
-    tftot = 0.166667f * odtot;
+    o.atrans = fmaf(-__fmul_rn(0.5f, odepth), odepth, odepth);
+    tf = __fmul_rn(0.166667f, odepth);
+    atot = fmaf(-__fmul_rn(0.5f, odtot), odtot, odtot);
+    tftot = __fmul_rn(0.166667f, odtot);
   } else if (odepth <= 0.06f) {
-    o.atrans = odepth - 0.5f * odepth * odepth;
-    tf = 0.166667f * odepth;
+    o.atrans = fmaf(-__fmul_rn(0.5f, odepth), odepth, odepth);
+    tf = __fmul_rn(0.166667f, odepth);
     const float tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
     const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
     const float2 et = s_et[ittot];
-    tftot = et.y; atot = 1.f - et.x;
+    tftot = et.y; atot = __fsub_rn(1.f, et.x);
   } else {
     float tblind = div_rn(odepth, __fadd_rn(bpade, odepth));
     const int itgas = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
@@ -473,23 +476,23 @@ __device__ __forceinline__ void lw_rt_cloudy(const float2 *__restrict__ s_et, co
     if (itgas >= 10000) odepth = 1.e10f;
     else { const float tfn = div_rn((float)itgas, 10000.0f); odepth = div_rn(__fmul_rn(bpade, tfn), __fsub_rn(1.0f, tfn)); }
     const float2 eg = s_et[itgas];
-    o.atrans = 1.f - eg.x;
+    o.atrans = __fsub_rn(1.f, eg.x);
     tf = eg.y;
     table_gas = true;
-    odtot = odepth + odcld;
+    odtot = __fadd_rn(odepth, odcld);
     tblind = div_rn(odtot, __fadd_rn(bpade, odtot));
     const int ittot = (int)__fadd_rn(__fmul_rn(10000.0f, tblind), 0.5f);
     const float2 et = s_et[ittot];
-    tftot = et.y; atot = 1.f - et.x;
+    tftot = et.y; atot = __fsub_rn(1.f, et.x);
   }
-  o.bbd = plfrac * (blay + tf * dplankdn);
-  o.bbu = plfrac * (blay + tf * dplankup);
-  const float bbdtot = plfrac * (blay + tftot * dplankdn), bbutot = plfrac * (blay + tftot * dplankup);
-  o.srcd = table_gas ? o.atrans * plfrac * (blay + tf * dplankdn) : o.bbd * o.atrans;
-  const float srcu = o.bbu * o.atrans;
-  o.X = o.atrans + efclfrac * (1.f - o.atrans);
-  o.Zd = cldfmc * (bbdtot * atot - o.srcd);
-  o.Yu = srcu + cldfmc * (bbutot * atot - srcu);
+  o.bbd = __fmul_rn(plfrac, fmaf(tf, dplankdn, blay));
+  o.bbu = __fmul_rn(plfrac, fmaf(tf, dplankup, blay));
+  const float bbdtot = __fmul_rn(plfrac, fmaf(tftot, dplankdn, blay)), bbutot = __fmul_rn(plfrac, fmaf(tftot, dplankup, blay));
+  o.srcd = table_gas ? __fmul_rn(__fmul_rn(o.atrans, plfrac), fmaf(tf, dplankdn, blay)) : __fmul_rn(o.bbd, o.atrans);
+  const float srcu = __fmul_rn(o.bbu, o.atrans);
+  o.X = fmaf(efclfrac, __fsub_rn(1.f, o.atrans), o.atrans);
+  o.Zd = __fmul_rn(cldfmc, fmaf(bbdtot, atot, -o.srcd));
+  o.Yu = fmaf(cldfmc, fmaf(bbutot, atot, -srcu), srcu);
 }
 
 // One (column, band group): the ng consecutive g-points of band BAND that start at g-point g0 (absolute index).
@@ -660,15 +663,15 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
       float r[2] = {ST(i, 0), ST(i, 2)}, rcl[2] = {ST(i, 1), ST(i, 3)};
       float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
       float od[2];
-      od[0] = fmaxf(secdiff * (taug + taua), 0.f); od[1] = fmaxf(secdiff * taug, 0.f);
+      od[0] = fmaxf(__fmul_rn(secdiff, __fadd_rn(taug, taua)), 0.f); od[1] = fmaxf(__fmul_rn(secdiff, taug), 0.f);
       if (!icldlyr) {
 #pragma unroll
         for (int v = 0; v < 2; v++) {
           if (v == 1 && !do_clean) break;
           float atrans, bbd, bbu;
           lw_rt_clear(s_et, bpade, od[v], fracs, blay, dplankdn, dplankup, atrans, bbd, bbu);
-          r[v] = r[v] + (bbd - r[v]) * atrans;
-          if (iclddn == 1) rcl[v] = rcl[v] + (bbd - rcl[v]) * atrans;
+          r[v] = fmaf(__fsub_rn(bbd, r[v]), atrans, r[v]);
+          if (iclddn == 1) rcl[v] = fmaf(__fsub_rn(bbd, rcl[v]), atrans, rcl[v]);
           else rcl[v] = r[v];
           if (v == 0) { q4.x = atrans; q4.y = bbu; } else { q4.z = atrans; q4.w = bbu; }
         }
@@ -679,8 +682,8 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
           if (v == 1 && !do_clean) break;
           LwRT t;
           lw_rt_cloudy(s_et, bpade, od[v], odcld, efclfrac, cldfmc, fracs, blay, dplankdn, dplankup, t);
-          r[v] = r[v] - r[v] * t.X + t.srcd + t.Zd;
-          rcl[v] = rcl[v] + (t.bbd - rcl[v]) * t.atrans;          // iclddn == 1 here
+          r[v] = __fadd_rn(__fadd_rn(fmaf(-r[v], t.X, r[v]), t.srcd), t.Zd);
+          rcl[v] = fmaf(__fsub_rn(t.bbd, rcl[v]), t.atrans, rcl[v]);          // iclddn == 1 here
           if (v == 0) { q4.x = t.atrans; q4.y = t.bbu; c4.x = t.X; c4.y = t.Yu; }
           else { q4.z = t.atrans; q4.w = t.bbu; c4.z = t.X; c4.w = t.Yu; }
         }
@@ -692,7 +695,7 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
       if (lay == 0) {
         const float rad0 = fracs * plankbnd;            // fracs of the lowest layer (LW:3305)
 #pragma unroll
-        for (int v = 0; v < 2; v++) { r[v] = rad0 + reflect * r[v]; rcl[v] = rad0 + reflect * rcl[v]; }
+        for (int v = 0; v < 2; v++) { r[v] = fmaf(reflect, r[v], rad0); rcl[v] = fmaf(reflect, rcl[v], rad0); }
         z0 = z0 + r[0]; z1 = z1 + rcl[0]; z2 = z2 + r[1]; z3 = z3 + rcl[1];
       }
       ST(i, 0) = r[0]; ST(i, 1) = rcl[0]; ST(i, 2) = r[1]; ST(i, 3) = rcl[1];
@@ -739,17 +742,17 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
       const float4 *p = rlC;
 #pragma unroll
       for (int i = 0; i < LW_GMAX; i++) {
-        if (i < ng) { const float4 c4 = __ldcs(p); ru[i][0] = ru[i][0] - ru[i][0] * c4.x + c4.y; ru[i][1] = ru[i][1] - ru[i][1] * c4.z + c4.w; }
+        if (i < ng) { const float4 c4 = __ldcs(p); ru[i][0] = __fadd_rn(fmaf(-ru[i][0], c4.x, ru[i][0]), c4.y); ru[i][1] = __fadd_rn(fmaf(-ru[i][1], c4.z, ru[i][1]), c4.w); }
         p += pcap;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < LW_GMAX; i++) { ru[i][0] = ru[i][0] + (q4[i].y - ru[i][0]) * q4[i].x; ru[i][1] = ru[i][1] + (q4[i].w - ru[i][1]) * q4[i].z; }
+      for (int i = 0; i < LW_GMAX; i++) { ru[i][0] = fmaf(__fsub_rn(q4[i].y, ru[i][0]), q4[i].x, ru[i][0]); ru[i][1] = fmaf(__fsub_rn(q4[i].w, ru[i][1]), q4[i].z, ru[i][1]); }
     }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // upward radiances at the top of the layer; g-points beyond ng hold zeros
     if (iclddn == 1) {      // iclddn as the downward sweep left it: any cloud in the column
 #pragma unroll
-      for (int i = 0; i < LW_GMAX; i++) { rcu[i][0] = rcu[i][0] + (q4[i].y - rcu[i][0]) * q4[i].x; rcu[i][1] = rcu[i][1] + (q4[i].w - rcu[i][1]) * q4[i].z; }
+      for (int i = 0; i < LW_GMAX; i++) { rcu[i][0] = fmaf(__fsub_rn(q4[i].y, rcu[i][0]), q4[i].x, rcu[i][0]); rcu[i][1] = fmaf(__fsub_rn(q4[i].w, rcu[i][1]), q4[i].z, rcu[i][1]); }
     } else {
 #pragma unroll
       for (int i = 0; i < LW_GMAX; i++) { rcu[i][0] = ru[i][0]; rcu[i][1] = ru[i][1]; }

@@ -19,11 +19,6 @@
 
 namespace arc {
 
-#ifdef ARC_STRICT
-#define RCP(x) (1.0f / (x))
-#else
-#define RCP(x) __fdividef(1.0f, (x))
-#endif
 
 static __constant__ SwBandDesc c_sw[14];
 static __constant__ int c_sw_ngb[NGSW];    // band index 0..13 of each SW g-point
@@ -330,7 +325,10 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
     reinterpret_cast<float2 *>(rec + slot[s] * (NGSW * SW_REC) + SW_REC_R)[lane] = make_float2(albp, albd);
   }
   float sfluxzen = 0.f;
-  float tdir_nodel = 1.f;     // product of the un-delta-scaled direct transmittances of the FULL stream
+  // un-delta-scaled direct transmittance of every layer of the FULL stream (thread-private, 4 B per layer): the reference
+  // multiplies them from the top down (ztdbt_nodel, SW:8560-8575) while this loop runs bottom-up, and the product is rounded
+  // at every step - so they are kept and multiplied in the reference's order after the loop
+  float enod[NL];
 
   // all workspace words of a layer are requested together at the top of the iteration (one wait per layer)
   const float *coef = ws.coef + coef_index(0, 0, c, cap, SWC_N);
@@ -380,7 +378,7 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
         zomcc = D_(zomcc, ztauc);
         // direct beam without delta scaling (diagnostic surface direct flux of the FULL stream)
         const float tauorig = cloudy ? A_(ztauc, taormc) : ztauc;
-        tdir_nodel = tdir_nodel * sw_expt(s_exp, D_(tauorig, prmu0), bpade);
+        enod[lay] = sw_expt(s_exp, D_(tauorig, prmu0), bpade);
         const float zf = M_(zgcc, zgcc);
         const float zwf = M_(zomcc, zf);
         ztauc = M_(S_(1.0f, zwf), ztauc);
@@ -414,11 +412,12 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
       else if (s == 1) { P = cloudy ? pcld[0] : pclr[0]; e = cloudy ? ecld[0] : eclr[0]; }
       else if (s == 2) { P = cloudy ? pcld[1] : pclr[1]; e = cloudy ? ecld[1] : eclr[1]; }
       else { P = pclr[1]; e = eclr[1]; }
-      // explicit operation order: every stream gets the identical instruction sequence, so streams with identical
-      // inputs (zero aerosol: clean == full; no cloud: clear == full) stay bit-identical like in the reference
-      const float zreflect = RCP(fmaf(-rupd[s], P.y, 1.f));
-      const float nrup = fmaf(__fmul_rn(P.w, fmaf(e, rup[s], __fmul_rn(__fsub_rn(P.z, e), rupd[s]))), zreflect, P.x);
-      const float nrupd = fmaf(__fmul_rn(__fmul_rn(P.w, P.w), rupd[s]), zreflect, P.y);
+      // vrtqdr_sw's bottom-up recurrence (SW:7997-8005) in the reference's own operation order and rounding (unfused, IEEE
+      // reciprocal): with reftra_sw's operands bit-exact the whole shortwave chain reproduces the reference bit for bit,
+      // and streams with identical inputs (zero aerosol: clean == full; no cloud: clear == full) stay identical
+      const float zreflect = D_(1.f, S_(1.f, M_(rupd[s], P.y)));
+      const float nrup = A_(P.x, M_(M_(P.w, A_(M_(S_(P.z, e), rupd[s]), M_(e, rup[s]))), zreflect));
+      const float nrupd = A_(P.y, M_(M_(M_(P.w, P.w), rupd[s]), zreflect));
       rup[s] = nrup; rupd[s] = nrupd;
       float *q = rec + (size_t)((unsigned)(lay + 1) * lvstride) + slot[s] * (NGSW * SW_REC);
       // (where its layer is not cloudy the FULL stream's two-stream solution IS the CLEAR one: k_sw_sweep reads it there)
@@ -429,6 +428,8 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
   if (a.dbg.sfluxzen) a.dbg.sfluxzen[(size_t)ws.cols[c] * NGSW + g] = sfluxzen;
 
   // incident flux of this g-point and the un-delta-scaled direct beam at the surface; the top-down sweep runs in k_sw_sweep
+  float tdir_nodel = 1.f;
+  for (int lay = nlay - 1; lay >= 0; lay--) tdir_nodel = M_(enod[lay], tdir_nodel);
   const float zincflx = ws.colf[(size_t)SWF_ADJFLUX * cap + c] * sfluxzen * prmu0;
   ws.zinc[(size_t)g * pcap + c] = zincflx;
   ws.dirs[(size_t)g * pcap + c] = __fmul_rn(zincflx, tdir_nodel);
@@ -480,6 +481,9 @@ __global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0, int
   const int ku = ws.kslot[s == 0 ? K_CU : s == 1 ? K_FU : s == 2 ? K_NU : K_XU];
   const int kd = ws.kslot[s == 0 ? K_CD : s == 1 ? K_FD : s == 2 ? K_ND : K_XD];
   float *__restrict__ bpart = ws.bpart + (size_t)grp * (nlay + 1) * nk * pcap + c;
+  const float *__restrict__ prev = bpart - (size_t)(nlay + 1) * nk * pcap;       // the previous group's running totals (grp > 0)
+  const int band = c_sw_grp_band[grp];
+  const bool uvband = band >= 9 && band <= 12;
 
   float zinc[NG], tdbt[NG], tdn[NG], rdnd[NG];
 #pragma unroll
@@ -503,31 +507,39 @@ __global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0, int
         e[i] = __ldcs(qs + SW_REC_E + lane);
       }
     }
-    float su = 0.f, sd = 0.f;
+    // running sums over ALL g-points in index order, exactly the reference's accumulation (SW:8617-8650): a group starts from
+    // the totals the previous group left (the groups' launches follow one another on the stream)
+    float su = grp > 0 ? prev[((size_t)lev * nk + ku) * pcap] : 0.f;
+    float sd = grp > 0 ? prev[((size_t)lev * nk + kd) * pcap] : 0.f;
+    float suv = 0.f, sni = 0.f;
+    if (isfull && lev == 0 && grp > 0) { suv = ws.uvni[((size_t)(grp - 1) * 2 + 0) * pcap + c]; sni = ws.uvni[((size_t)(grp - 1) * 2 + 1) * pcap + c]; }
 #pragma unroll
     for (int i = 0; i < NG; i++) {
-      // flux at interface lev (SW:8036-8045); same operation order as the bottom-up sweep of k_sw_solve, so streams
-      // with identical inputs stay bit-identical
+      // flux at interface lev (SW:8036-8045), the reference's operation order and rounding
       const float ru = R[i].x, rud = R[i].y;
-      const float zreflect = RCP(fmaf(-rdnd[i], rud, 1.f));
-      const float dif = __fsub_rn(tdn[i], tdbt[i]);
-      const float fu = __fmul_rn(fmaf(tdbt[i], ru, __fmul_rn(dif, rud)), zreflect);
-      const float fd = fmaf(fmaf(__fmul_rn(tdbt[i], ru), rdnd[i], dif), zreflect, tdbt[i]);
-      su = su + __fmul_rn(zinc[i], fu);
-      sd = sd + __fmul_rn(zinc[i], fd);
+      const float zreflect = D_(1.f, S_(1.f, M_(rdnd[i], rud)));
+      const float dif = S_(tdn[i], tdbt[i]);
+      const float fu = M_(A_(M_(tdbt[i], ru), M_(dif, rud)), zreflect);
+      const float fd = A_(tdbt[i], M_(A_(dif, M_(M_(tdbt[i], ru), rdnd[i])), zreflect));
+      su = A_(su, M_(zinc[i], fu));
+      sd = A_(sd, M_(zinc[i], fd));
+      if (isfull && lev == 0) { if (uvband) suv = A_(suv, M_(zinc[i], fd)); else sni = A_(sni, M_(zinc[i], fd)); }
     }
     __stcs(bpart + ((size_t)lev * nk + ku) * pcap, su);
     __stcs(bpart + ((size_t)lev * nk + kd) * pcap, sd);
-    if (lev == 0) break;
+    if (lev == 0) {
+      if (isfull) { ws.uvni[((size_t)grp * 2 + 0) * pcap + c] = suv; ws.uvni[((size_t)grp * 2 + 1) * pcap + c] = sni; }
+      break;
+    }
 #pragma unroll
     for (int i = 0; i < NG; i++) {
-      // transmittances through the layer below the interface (SW:8007-8034)
-      const float zr = RCP(fmaf(-P[i].y, rdnd[i], 1.f));
-      const float ntdn = fmaf(__fmul_rn(P[i].w, fmaf(__fmul_rn(tdbt[i], P[i].x), rdnd[i], __fsub_rn(tdn[i], tdbt[i]))), zr,
-                              __fmul_rn(tdbt[i], P[i].z));
-      const float nrdnd = fmaf(__fmul_rn(__fmul_rn(P[i].w, P[i].w), rdnd[i]), zr, P[i].y);
+      // transmittances through the layer below the interface (SW:8007-8034); with tdn = tdbt = 1, rdnd = 0 at the top the
+      // general step reproduces the reference's special first step (tdn = tra, rdnd = refd) exactly
+      const float zr = D_(1.f, S_(1.f, M_(P[i].y, rdnd[i])));
+      const float ntdn = A_(M_(tdbt[i], P[i].z), M_(M_(P[i].w, A_(S_(tdn[i], tdbt[i]), M_(M_(tdbt[i], P[i].x), rdnd[i]))), zr));
+      const float nrdnd = A_(P[i].y, M_(M_(M_(P[i].w, P[i].w), rdnd[i]), zr));
       tdn[i] = ntdn; rdnd[i] = nrdnd;
-      tdbt[i] = __fmul_rn(e[i], tdbt[i]);
+      tdbt[i] = M_(e[i], tdbt[i]);
     }
   }
 }
@@ -574,22 +586,14 @@ __global__ void __launch_bounds__(RED_CX * RED_LY, 4) k_sw_reduce(SwArgs a) {
     for (int k = 0; k < NKIND; k++) f[k] = 0.f;
     float uvfd = 0.f, nifd = 0.f;
     const int nk = ws.nk;
-    const float *p = ws.bpart + ((size_t)lev * nk) * cap + c;     // band sums from k_sw_sweep
+    // the last sweep group holds the sums over all 112 g-points, accumulated in index order by k_sw_sweep
     const size_t gstride = (size_t)(nlay + 1) * nk * cap;
+    const float *p = ws.bpart + (size_t)(a.ngroups - 1) * gstride + ((size_t)lev * nk) * cap + c;
     const unsigned ucap = (unsigned)cap;       // 32-bit kind offsets: nk * pcap < 2^31
-    const unsigned oFU = ws.kslot[K_FU] * ucap, oFD = ws.kslot[K_FD] * ucap, oCU = ws.kslot[K_CU] * ucap, oCD = ws.kslot[K_CD] * ucap,
-                   oNU = ws.kslot[K_NU] * ucap, oND = ws.kslot[K_ND] * ucap, oXU = ws.kslot[K_XU] * ucap, oXD = ws.kslot[K_XD] * ucap;
-    for (int q = 0; q < a.ngroups; q++, p += gstride) {
-      const int b = c_sw_grp_band[q];
-      f[K_FU] = f[K_FU] + p[oFU];
-      const float fd = p[oFD];
-      f[K_FD] = f[K_FD] + fd;
-      f[K_CU] = f[K_CU] + p[oCU];
-      f[K_CD] = f[K_CD] + p[oCD];
-      if (do_clean) { f[K_NU] = f[K_NU] + p[oNU]; f[K_ND] = f[K_ND] + p[oND]; }
-      if (do_clnc) { f[K_XU] = f[K_XU] + p[oXU]; f[K_XD] = f[K_XD] + p[oXD]; }
-      if (lev == 0) { if (b >= 9 && b <= 12) uvfd = uvfd + fd; else nifd = nifd + fd; }
-    }
+    f[K_FU] = p[ws.kslot[K_FU] * ucap]; f[K_FD] = p[ws.kslot[K_FD] * ucap]; f[K_CU] = p[ws.kslot[K_CU] * ucap]; f[K_CD] = p[ws.kslot[K_CD] * ucap];
+    if (do_clean) { f[K_NU] = p[ws.kslot[K_NU] * ucap]; f[K_ND] = p[ws.kslot[K_ND] * ucap]; }
+    if (do_clnc) { f[K_XU] = p[ws.kslot[K_XU] * ucap]; f[K_XD] = p[ws.kslot[K_XD] * ucap]; }
+    if (lev == 0) { uvfd = ws.uvni[((size_t)(a.ngroups - 1) * 2 + 0) * cap + c]; nifd = ws.uvni[((size_t)(a.ngroups - 1) * 2 + 1) * cap + c]; }
     s_net[lev][cx] = f[K_FD] - f[K_FU];
     if (a.swupflx) {        // lev <= nz + 1 always
       const size_t q = G.atp(i, G.kts + lev, j);
