@@ -24,8 +24,9 @@ for rp in sys.argv[5:]:
         rd = val("dram__bytes_read.sum") * scale.get(unit.get("dram__bytes_read.sum", "byte"), 1.0)
         wr = val("dram__bytes_write.sum") * scale.get(unit.get("dram__bytes_write.sum", "byte"), 1.0)
         sw = name.startswith("k_sw")
-        cols = nsun if sw else ncols
-        cells = cols * (112.0 * (nk + 1) if sw else 140.0 * nlay_lw)
+        aer = name.startswith("k_aer")
+        cols = nsun if sw else (int(os.environ.get("AER_COLS", "8192")) if aer else ncols)
+        cells = cols * (112.0 * (nk + 1) if sw else (8.0 * 20 * nk if aer else 140.0 * nlay_lw))     # aerosol: per (section, wavelength, level)
         winst = val("smsp__inst_executed.sum")
         lanes = val("smsp__thread_inst_executed_per_inst_executed.ratio")
         out[name] = {"columns_in_launch": cols, "duration_ms_under_ncu": val("gpu__time_duration.sum") / (1e6 if rr[1][h.index("gpu__time_duration.sum")] == "ns" else 1e3 if rr[1][h.index("gpu__time_duration.sum")] == "us" else 1.0),
@@ -33,13 +34,14 @@ for rp in sys.argv[5:]:
                      "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                      "warps_active_pct": val("sm__warps_active.avg.pct_of_peak_sustained_active"),
                      "registers": val("launch__registers_per_thread"),
-                     "thread_instructions_per_column_g_layer": winst * lanes / cells if winst and lanes else None,
-                     "issued_warp_instructions_x32_per_column_g_layer": winst * 32.0 / cells if winst else None,
+                     "thread_instructions_per_cell": winst * lanes / cells if winst and lanes else None,
+                     "issued_warp_instructions_x32_per_cell": winst * 32.0 / cells if winst else None,
                      "active_lanes_of_32": lanes, "report": os.path.basename(rp)}
 try:
     commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
 except Exception:
     commit = None
+out["_cell"] = "cell = (column, g-point, layer) for the RRTMG kernels, (column, section, wavelength, level) for the aerosol kernels; k_sw_sweep: one of the 21 sweep-group launches"
 out["_source"] = "profiles/r2_ncu_metrics.json (ncu --set full --clock-control none, tile %d columns x %d levels, at commit %s)" % (ncols, nk, commit)
 json.dump(out, open(os.path.join(ROOT, "profiles", "r2_ncu_metrics.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -185,13 +185,29 @@ template <class WS> void set_kinds(WS &w, int variants) {
   w.nk = n;
 }
 
+// Workspace arena allocation with an error that tells the caller which knobs bound it
+int arena_alloc(void **p, size_t need, const char *what) {
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  cudaError_t e = need <= fr ? cudaMalloc(p, need) : cudaErrorMemoryAllocation;
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char msg[320];
+    snprintf(msg, sizeof(msg), "%s workspace: %.1f GB needed, %.1f GB free on the device; lower ARC_RAD_CHUNK / ARC_RAD_LW_CHUNK (inner chunk, "
+             "columns), ARC_RAD_REC_GB (shortwave level-record budget) or ARC_RAD_OUTER", what, need / 1e9, fr / 1e9);
+    g.err = msg;
+    return ARC_ERR_CUDA;
+  }
+  return 0;
+}
+
 int ensure_sw_ws(int nlay, size_t cap, size_t pcap, int variants) {
   SwWs w{}; w.cap = (int)cap; w.pcap = (int)pcap; w.nlay = nlay; w.W = (nlay + 31) / 32; set_kinds(w, variants);
   size_t need; carve_sw(w, nullptr, need);
   if (need > g.sw_bytes) {
     if (g.sw_arena) cudaFree(g.sw_arena);
     g.sw_arena = nullptr; g.sw_bytes = 0;
-    CK(cudaMalloc(&g.sw_arena, need));
+    if (int rc = arena_alloc(&g.sw_arena, need, "shortwave")) return rc;
     g.sw_bytes = need;
   }
   carve_sw(w, (char *)g.sw_arena, need);
@@ -204,7 +220,7 @@ int ensure_lw_ws(int nlay, size_t cap, size_t pcap, int variants) {
   if (need > g.lw_bytes) {
     if (g.lw_arena) cudaFree(g.lw_arena);
     g.lw_arena = nullptr; g.lw_bytes = 0;
-    CK(cudaMalloc(&g.lw_arena, need));
+    if (int rc = arena_alloc(&g.lw_arena, need, "longwave")) return rc;
     g.lw_bytes = need;
   }
   carve_lw(w, (char *)g.lw_arena, need);

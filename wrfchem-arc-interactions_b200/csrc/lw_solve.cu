@@ -648,7 +648,7 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
     }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;          // upward radiances leaving the surface (lay == 0 only)
-    float4 *rl = rec + (size_t)lay * rls, *rlC = recC + (size_t)lay * rls;
+    float4 *rl = rec + (size_t)lay * rls, *rlC = recC + (size_t)lay * rls;        // running record pointers: + pcap per g-point
 #pragma unroll UG
     for (int i = 0; i < ng; i++) {
       float taug, fracs;
@@ -687,9 +687,10 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
           if (v == 0) { q4.x = t.atrans; q4.y = t.bbu; c4.x = t.X; c4.y = t.Yu; }
           else { q4.z = t.atrans; q4.w = t.bbu; c4.z = t.X; c4.w = t.Yu; }
         }
-        __stcs(rlC + (size_t)i * pcap, c4);
+        __stcs(rlC, c4);
       }
-      __stcs(rl + (size_t)i * pcap, q4);
+      __stcs(rl, q4);
+      rl += pcap; rlC += pcap;
       // downward radiances at the lower interface of the layer, summed over the group's g-points in index order
       s0 = s0 + r[0]; s1 = s1 + rcl[0]; s2 = s2 + r[1]; s3 = s3 + rcl[1];
       if (lay == 0) {
