@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(128) k_aer_prep(AerArgs a) {
   }
 }
 
+#ifndef AER_UNROLL_J
+#define AER_UNROLL_J 1
+#endif
+constexpr int AER_UNROLL = AER_UNROLL_J;
 constexpr int AER_TAB_FLOATS = AER_NQ * AER_NREFR * AER_NREFI * AER_NCOEF_PAD;     // 7644 floats = 30,576 B per wavelength
 
 __global__ void __launch_bounds__(256) k_aer_mie(AerArgs a, AerDev d) {
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(256) k_aer_mie(AerArgs a, AerDev d) {
     const float *cell = tab + (ir * AER_NREFI + ii) * AER_NCOEF_PAD;
     float tjm1 = 1.f, tj = x;          // T_0, T_1
     const float x2 = 2.f * x;
-#pragma unroll 1
+#pragma unroll AER_UNROLL
     for (int j4 = 0; j4 < AER_NCOEF_PAD; j4 += 4) {
       float T0, T1, T2, T3;
       if (j4 == 0) {

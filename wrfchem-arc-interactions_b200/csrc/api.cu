@@ -1424,44 +1424,61 @@ int arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const floa
 // i.e. every ordered pair of edge-sharing cells once - deviations from the float mean, sums in double, normalised by
 // W_sum * stddev^2 with the N-1 stddev.  calc_standard_stats multiplies the standard error by it (its "corrected SE").
 // One block per field, fixed-order tree: reproducible.
-__global__ void __launch_bounds__(1024) k_morans_i(Geo G, int nfields, const float *const *__restrict__ fields, float *__restrict__ out) {
-  const int f = blockIdx.x;
+// STAT_NB blocks per field, each over a contiguous range of cells; block partials are combined in block order: reproducible.
+constexpr int STAT_NB = 32;
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) { if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(1024) k_morans_sum(Geo G, const float *const *__restrict__ fields, double *__restrict__ part) {
+  const int f = blockIdx.x, nb = gridDim.y, b = blockIdx.y;
   const float *x = fields[f];
-  __shared__ double sh[2][1024];
-  __shared__ float s_mean, s_var;
-  const int ni = G.nci, nj = G.ncol_tile / G.nci;
+  __shared__ double sh[1024];
+  const int per = (G.ncol_tile + nb - 1) / nb, lo = b * per, hi = min(G.ncol_tile, lo + per);
   double s = 0.0;
-  for (int tc = threadIdx.x; tc < G.ncol_tile; tc += blockDim.x) { int i, j; G.ij(tc, i, j); s += (double)x[G.at2(i, j)]; }
-  sh[0][threadIdx.x] = s;
-  __syncthreads();
-  for (int off = 512; off > 0; off >>= 1) { if (threadIdx.x < off) sh[0][threadIdx.x] += sh[0][threadIdx.x + off]; __syncthreads(); }
-  if (threadIdx.x == 0) s_mean = (float)(sh[0][0] / (double)G.ncol_tile);
-  __syncthreads();
-  const float mean = s_mean;
+  for (int tc = lo + threadIdx.x; tc < hi; tc += blockDim.x) { int i, j; G.ij(tc, i, j); s += (double)x[G.at2(i, j)]; }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) part[f * nb + b] = s;
+}
+__global__ void __launch_bounds__(1024) k_morans_pairs(Geo G, const float *const *__restrict__ fields, const double *__restrict__ part,
+                                                        double *__restrict__ part2) {
+  const int f = blockIdx.x, nb = gridDim.y, b = blockIdx.y;
+  const float *x = fields[f];
+  __shared__ double sh[1024];
+  double tot = 0.0;
+  for (int q = 0; q < nb; q++) tot += part[f * nb + q];
+  const float mean = (float)(tot / (double)G.ncol_tile);
+  const int per = (G.ncol_tile + nb - 1) / nb, lo = b * per, hi = min(G.ncol_tile, lo + per);
   // deviations are formed in single precision from the single-precision mean (X_diff = data - X_mean), products in double
   double ss = 0.0, au = 0.0;
-  for (int tc = threadIdx.x; tc < G.ncol_tile; tc += blockDim.x) {
+  for (int tc = lo + threadIdx.x; tc < hi; tc += blockDim.x) {
     int i, j; G.ij(tc, i, j);
     const float d0 = x[G.at2(i, j)] - mean;
     ss += (double)d0 * (double)d0;
-    double nb = 0.0;
-    if (i < G.ite) nb += (double)(x[G.at2(i + 1, j)] - mean);
-    if (j < G.jte) nb += (double)(x[G.at2(i, j + 1)] - mean);
-    au += 2.0 * (double)d0 * nb;               // each edge-sharing pair counts in both directions
+    double nbr = 0.0;
+    if (i < G.ite) nbr += (double)(x[G.at2(i + 1, j)] - mean);
+    if (j < G.jte) nbr += (double)(x[G.at2(i, j + 1)] - mean);
+    au += 2.0 * (double)d0 * nbr;               // each edge-sharing pair counts in both directions
   }
-  sh[0][threadIdx.x] = ss; sh[1][threadIdx.x] = au;
-  __syncthreads();
-  for (int off = 512; off > 0; off >>= 1) {
-    if (threadIdx.x < off) { sh[0][threadIdx.x] += sh[0][threadIdx.x + off]; sh[1][threadIdx.x] += sh[1][threadIdx.x + off]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double n = (double)G.ncol_tile;
-    const float sd = (float)sqrt(sh[0][0] / fmax(n - 1.0, 1.0));           // NCL stddev: N-1
-    const double wsum = 2.0 * ((double)nj * (ni - 1) + (double)ni * (nj - 1));
-    s_var = sd * sd;
-    out[f] = (sh[0][0] == 0.0 || wsum == 0.0) ? 0.f : (float)(sh[1][0] / (wsum * (double)s_var));
-  }
+  ss = block_sum(ss, sh);
+  au = block_sum(au, sh);
+  if (threadIdx.x == 0) { part2[(f * nb + b) * 2] = ss; part2[(f * nb + b) * 2 + 1] = au; }
+}
+__global__ void k_morans_final(Geo G, int nfields, int nb, const double *__restrict__ part2, float *__restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nfields) return;
+  double ss = 0.0, au = 0.0;
+  for (int q = 0; q < nb; q++) { ss += part2[(f * nb + q) * 2]; au += part2[(f * nb + q) * 2 + 1]; }
+  const int ni = G.nci, nj = G.ncol_tile / G.nci;
+  const double n = (double)G.ncol_tile;
+  const float sd = (float)sqrt(ss / fmax(n - 1.0, 1.0));           // NCL stddev: N-1
+  const double wsum = 2.0 * ((double)nj * (ni - 1) + (double)ni * (nj - 1));
+  const float var = sd * sd;
+  out[f] = (ss == 0.0 || wsum == 0.0) ? 0.f : (float)(au / (wsum * (double)var));
 }
 
 int arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *const *fields, float *out) {
@@ -1481,8 +1498,12 @@ int arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *c
   CK(cudaMemcpyAsync(dptrs, dev, sizeof(float *) * nfields, cudaMemcpyHostToDevice, g.stream));
   float *dout = out;
   if (memspace != ARC_MEM_DEVICE) { void *p; if ((rc = stage_slot(sizeof(float) * 64, &p))) return rc; dout = (float *)p; }
-  k_morans_i<<<nfields, 1024, 0, g.stream>>>(G, nfields, (const float *const *)dptrs, dout);
-  count_launch();
+  void *part; if ((rc = stage_slot(sizeof(double) * 64 * STAT_NB * 3, &part))) return rc;
+  double *p1 = (double *)part, *p2 = p1 + 64 * STAT_NB;
+  k_morans_sum<<<dim3(nfields, STAT_NB), 1024, 0, g.stream>>>(G, (const float *const *)dptrs, p1);
+  k_morans_pairs<<<dim3(nfields, STAT_NB), 1024, 0, g.stream>>>(G, (const float *const *)dptrs, p1, p2);
+  k_morans_final<<<1, 64, 0, g.stream>>>(G, nfields, STAT_NB, p2, dout);
+  count_launch(3);
   if (memspace != ARC_MEM_DEVICE) CK(cudaMemcpyAsync(out, dout, sizeof(float) * nfields, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());
@@ -1526,32 +1547,48 @@ int arc_rad_cal_cldfra1(const ArcDims *d, int memspace, const float *qv, const f
 // the result is exactly the value the reference's qsort + index gives.
 __device__ __forceinline__ uint32_t f2key(float x) { const uint32_t u = __float_as_uint(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
-__global__ void __launch_bounds__(1024) k_percentiles(Geo G, int nperc, const float *const *__restrict__ fields, const int *__restrict__ ranks,
-                                                       float *__restrict__ out) {
-  const int f = blockIdx.x, q = blockIdx.y;
+// Selection state per (field, percentile): the key prefix fixed so far and the rank inside the cells that share it.  Each of
+// the four passes is a histogram kernel (STAT_NB blocks per field; shared-memory histograms for all percentiles in ONE scan of
+// the block's cells, added to the global histogram with integer atomics - order-independent, reproducible) and a selection kernel.
+struct PercState { uint32_t prefix, rank; };
+__global__ void __launch_bounds__(1024) k_perc_hist(Geo G, int nperc, int pass, const float *const *__restrict__ fields,
+                                                     const PercState *__restrict__ st, unsigned *__restrict__ ghist) {
+  const int f = blockIdx.x, nb = gridDim.y, b = blockIdx.y;
   const float *x = fields[f];
-  __shared__ unsigned hist[256];
-  __shared__ uint32_t s_prefix; __shared__ unsigned s_rank;
-  if (threadIdx.x == 0) { s_prefix = 0u; s_rank = (unsigned)ranks[q]; }
-  for (int pass = 0; pass < 4; pass++) {
-    const int shift = 24 - 8 * pass;
-    if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
-    __syncthreads();
-    const uint32_t prefix = s_prefix;
-    for (int tc = threadIdx.x; tc < G.ncol_tile; tc += blockDim.x) {
-      int i, j; G.ij(tc, i, j);
-      const uint32_t k = f2key(x[G.at2(i, j)]);
-      if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+  __shared__ unsigned hist[16 * 256];
+  __shared__ uint32_t pre[16];
+  const int nh = pass == 0 ? 1 : nperc;                 // the first pass' histogram is common to all percentiles
+  for (int t = threadIdx.x; t < nh * 256; t += blockDim.x) hist[t] = 0u;
+  if (threadIdx.x < nperc) pre[threadIdx.x] = st[f * nperc + threadIdx.x].prefix;
+  __syncthreads();
+  const int shift = 24 - 8 * pass;
+  const int per = (G.ncol_tile + nb - 1) / nb, lo = b * per, hi = min(G.ncol_tile, lo + per);
+  for (int tc = lo + threadIdx.x; tc < hi; tc += blockDim.x) {
+    int i, j; G.ij(tc, i, j);
+    const uint32_t k = f2key(x[G.at2(i, j)]);
+    const uint32_t dgt = (k >> shift) & 255u;
+    if (pass == 0) atomicAdd(&hist[dgt], 1u);
+    else {
+      const uint32_t hi8 = k >> (shift + 8);
+      for (int q = 0; q < nperc; q++) if (hi8 == pre[q]) atomicAdd(&hist[q * 256 + dgt], 1u);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned r = s_rank, cum = 0u; int dsel = 255;
-      for (int dgt = 0; dgt < 256; dgt++) { if (r < cum + hist[dgt]) { dsel = dgt; break; } cum += hist[dgt]; }
-      s_rank = r - cum; s_prefix = (prefix << 8) | (uint32_t)dsel;
-    }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) out[f * nperc + q] = key2f(s_prefix);
+  __syncthreads();
+  for (int t = threadIdx.x; t < nh * 256; t += blockDim.x) if (hist[t]) atomicAdd(&ghist[(size_t)f * 16 * 256 + t], hist[t]);
+}
+__global__ void k_perc_select(int nfields, int nperc, int pass, PercState *__restrict__ st, unsigned *__restrict__ ghist, float *__restrict__ out) {
+  const int f = blockIdx.x, q = threadIdx.x;
+  if (q < nperc) {
+    const unsigned *h = ghist + (size_t)f * 16 * 256 + (pass == 0 ? 0 : q * 256);
+    PercState s = st[f * nperc + q];
+    unsigned cum = 0u; int dsel = 255;
+    for (int dgt = 0; dgt < 256; dgt++) { if (s.rank < cum + h[dgt]) { dsel = dgt; break; } cum += h[dgt]; }
+    s.rank -= cum; s.prefix = (s.prefix << 8) | (uint32_t)dsel;
+    st[f * nperc + q] = s;
+    if (pass == 3) out[f * nperc + q] = key2f(s.prefix);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 16 * 256; t += blockDim.x) ghist[(size_t)f * 16 * 256 + t] = 0u;     // ready for the next pass
 }
 
 int arc_rad_percentiles(const ArcDims *d, int memspace, int nfields, const float *const *fields, int nperc, const float *perc, float *out) {
@@ -1577,12 +1614,19 @@ int arc_rad_percentiles(const ArcDims *d, int memspace, int nfields, const float
   }
   void *dptrs; if ((rc = stage_slot(sizeof(float *) * 64, &dptrs))) return rc;
   CK(cudaMemcpyAsync(dptrs, dev, sizeof(float *) * nfields, cudaMemcpyHostToDevice, g.stream));
-  void *dranks; if ((rc = stage_slot(sizeof(int) * 16, &dranks))) return rc;
-  CK(cudaMemcpyAsync(dranks, ranks, sizeof(int) * nperc, cudaMemcpyHostToDevice, g.stream));
+  std::vector<PercState> hst((size_t)nfields * nperc);
+  for (int f = 0; f < nfields; f++) for (int q = 0; q < nperc; q++) hst[(size_t)f * nperc + q] = PercState{0u, (uint32_t)ranks[q]};
+  void *dst; if ((rc = stage_slot(sizeof(PercState) * 64 * 16, &dst))) return rc;
+  CK(cudaMemcpyAsync(dst, hst.data(), sizeof(PercState) * hst.size(), cudaMemcpyHostToDevice, g.stream));
+  void *dh; if ((rc = stage_slot(sizeof(unsigned) * 64 * 16 * 256, &dh))) return rc;
+  CK(cudaMemsetAsync(dh, 0, sizeof(unsigned) * (size_t)nfields * 16 * 256, g.stream));
   float *dout = out;
   if (memspace != ARC_MEM_DEVICE) { void *p; if ((rc = stage_slot(sizeof(float) * 64 * 16, &p))) return rc; dout = (float *)p; }
-  k_percentiles<<<dim3(nfields, nperc), 1024, 0, g.stream>>>(G, nperc, (const float *const *)dptrs, (const int *)dranks, dout);
-  count_launch();
+  for (int pass = 0; pass < 4; pass++) {
+    k_perc_hist<<<dim3(nfields, STAT_NB), 1024, 0, g.stream>>>(G, nperc, pass, (const float *const *)dptrs, (const PercState *)dst, (unsigned *)dh);
+    k_perc_select<<<nfields, 256, 0, g.stream>>>(nfields, nperc, pass, (PercState *)dst, (unsigned *)dh, dout);
+  }
+  count_launch(8);
   if (memspace != ARC_MEM_DEVICE) CK(cudaMemcpyAsync(out, dout, sizeof(float) * nfields * nperc, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());
