@@ -245,6 +245,9 @@ int  arc_rad_selftest_pt(const float *p, const float *t, int n, int *packed);
 int  arc_rad_selftest_libm(int which, const float *x, const float *y, int n, float *out, int on_device);
 /* Self-test (GPU): mismatches of the kernels' branch-free division against IEEE division over n random operand pairs */
 int  arc_rad_selftest_div(int n, unsigned seed);
+/* Self-test (GPU): mismatches of the kernels' reciprocal against the IEEE reciprocal for EVERY float with bit pattern in
+ * [lo_bits, hi_bits], both signs (normal range: 0x0D800000 = 2^-100 .. 0x71800000 = 2^100) */
+long long arc_rad_selftest_rcp(unsigned lo_bits, unsigned hi_bits);
 /* FP32 FMA throughput of the device in TFLOP/s (microbenchmark; roofline denominator of the solver kernels) */
 float arc_rad_measure_fp32_tflops(void);
 

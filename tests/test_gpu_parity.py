@@ -279,11 +279,19 @@ def test_chunking_and_determinism(lib, ktab):
     init(lib, dom, ktab)
     a_sw, a_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
     b_sw, b_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
-    os.environ["ARC_RAD_CHUNK"] = "256"; os.environ["ARC_RAD_OUTER"] = "512"
+    os.environ["ARC_RAD_CHUNK"] = "256"; os.environ["ARC_RAD_LW_CHUNK"] = "256"; os.environ["ARC_RAD_OUTER"] = "512"
     try:
         c_sw, c_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
     finally:
-        del os.environ["ARC_RAD_CHUNK"]; del os.environ["ARC_RAD_OUTER"]
+        del os.environ["ARC_RAD_CHUNK"]; del os.environ["ARC_RAD_LW_CHUNK"]; del os.environ["ARC_RAD_OUTER"]
+    # plain tile order instead of the cloud-bucketed column lists: columns are independent, so nothing may change
+    os.environ["ARC_RAD_BUCKET"] = "0"
+    try:
+        lib.init(dom["p_top"], dom["dims"]["kme"], ktab[0], ktab[1])          # the switch is read at init
+        e_sw, e_lw = run_pair("sw", lib, dom), run_pair("lw", lib, dom)
+    finally:
+        del os.environ["ARC_RAD_BUCKET"]
+        lib.init(dom["p_top"], dom["dims"]["kme"], ktab[0], ktab[1])
     # the level-record budget shrinks the inner chunk (here to 256 columns: 3 SW + 4 LW chunks of two buffers each)
     os.environ["ARC_RAD_REC_GB"] = "0.25"
     try:
@@ -291,9 +299,9 @@ def test_chunking_and_determinism(lib, ktab):
     finally:
         del os.environ["ARC_RAD_REC_GB"]
     for k in a_sw:
-        assert np.array_equal(a_sw[k], b_sw[k]) and np.array_equal(a_sw[k], c_sw[k]) and np.array_equal(a_sw[k], d_sw[k]), k
+        assert np.array_equal(a_sw[k], b_sw[k]) and np.array_equal(a_sw[k], c_sw[k]) and np.array_equal(a_sw[k], d_sw[k]) and np.array_equal(a_sw[k], e_sw[k]), k
     for k in a_lw:
-        assert np.array_equal(a_lw[k], b_lw[k]) and np.array_equal(a_lw[k], c_lw[k]) and np.array_equal(a_lw[k], d_lw[k]), k
+        assert np.array_equal(a_lw[k], b_lw[k]) and np.array_equal(a_lw[k], c_lw[k]) and np.array_equal(a_lw[k], d_lw[k]) and np.array_equal(a_lw[k], e_lw[k]), k
 
 
 @pytest.mark.parametrize("halo", [0, 2])
@@ -456,8 +464,14 @@ def test_branch_free_division_is_ieee(lib, ktab):
     lib.lib.arc_rad_selftest_div.restype = C.c_int
     lib.lib.arc_rad_selftest_div.argtypes = [C.c_int, C.c_uint]
     n = 1 << 24
-    bad = lib.lib.arc_rad_selftest_div(n, 12345)
-    assert bad == 0, "%d of %d quotients differ from IEEE" % (bad, n)
+    for seed in range(64):                          # 2^30 operand pairs
+        bad = lib.lib.arc_rad_selftest_div(n, 12345 + 7919 * seed)
+        assert bad == 0, "%d of %d quotients differ from IEEE (seed %d)" % (bad, n, seed)
+    # the reciprocal (1 / exp(-x) and the adding method's 1 / (1 - r r')): every float in [2^-100, 2^100], both signs
+    lib.lib.arc_rad_selftest_rcp.restype = C.c_longlong
+    lib.lib.arc_rad_selftest_rcp.argtypes = [C.c_uint, C.c_uint]
+    bad = lib.lib.arc_rad_selftest_rcp(0x0D800000, 0x71800000)
+    assert bad == 0, "%d reciprocals differ from IEEE" % bad
 
 
 def test_driver_post_and_domain_stats(lib, ktab):

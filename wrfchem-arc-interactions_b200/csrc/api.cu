@@ -767,7 +767,7 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
   {
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // hi = numerically lowest = greatest priority
-    if (const char *eb = getenv("ARC_RAD_BUCKET")) g.bucket = atoi(eb) != 0;
+    { const char *eb = getenv("ARC_RAD_BUCKET"); g.bucket = !(eb && atoi(eb) == 0); }
     const char *e = getenv("ARC_RAD_OVERLAP");
     g.overlap = !(e && atoi(e) == 0);
     const char *pr = getenv("ARC_RAD_SWEEP_PRIO");
@@ -1714,6 +1714,29 @@ __global__ void k_selftest_div(int n, unsigned seed, int *bad) {
   const float q0 = __fdiv_rn(a, b), q1 = div_rn(a, b);
   const bool normal = q0 == 0.f || (fabsf(q0) > 1e-37f && fabsf(q0) < 1e37f);
   if (normal && !(q0 == q1)) atomicAdd(bad, 1);     // value comparison: -0/b gives +0 here, -0 in IEEE
+}
+// rcp_rn against __frcp_rn for every float whose bit pattern lies in [lo_bits, hi_bits] (both signs).  Returns mismatches.
+__global__ void k_selftest_rcp(unsigned lo_bits, unsigned count, unsigned long long *bad) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2ull * count) return;
+  const unsigned bits = lo_bits + (unsigned)(t >> 1);
+  const float x = __uint_as_float(bits | ((t & 1ull) ? 0x80000000u : 0u));
+  if (!(__frcp_rn(x) == rcp_rn(x))) atomicAdd(bad, 1ull);
+}
+long long arc_rad_selftest_rcp(unsigned lo_bits, unsigned hi_bits) {
+  if (!g.ready || hi_bits < lo_bits) return -1;
+  cudaSetDevice(g.device);
+  unsigned long long *d; if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
+  cudaMemsetAsync(d, 0, 8, g.stream);
+  const unsigned count = hi_bits - lo_bits + 1u;
+  const unsigned long long nthreads = 2ull * count;
+  k_selftest_rcp<<<(unsigned)((nthreads + 255) / 256), 256, 0, g.stream>>>(lo_bits, count, d);
+  count_launch();
+  unsigned long long h = ~0ull;
+  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g.stream);
+  cudaStreamSynchronize(g.stream);
+  cudaFree(d);
+  return (long long)h;
 }
 int arc_rad_selftest_div(int n, unsigned seed) {
   if (!g.ready) return -1;

@@ -179,6 +179,7 @@ __device__ __forceinline__ float sw_expt(const float *__restrict__ exp_tbl, floa
 #define A_(a, b) __fadd_rn((a), (b))
 #define S_(a, b) __fsub_rn((a), (b))
 #define D_(a, b) div_rn((a), (b))
+#define R_(b) rcp_rn(b)
 
 // reftra_sw (kmodts = 2, PIFM) for one layer, SW:2540-2690.  Returns (ref, refd, tra, trad) and, because both branches
 // evaluate it anyway, e = exp(-tau/mu0) through the table: the direct-beam transmittance spcvmc_sw computes again from the
@@ -239,8 +240,8 @@ __device__ SW_REFTRA_INLINE SwLayerRT sw_reftra(const float *__restrict__ exp_tb
     const float zt3 = M_(zrk2, A_(zgamma4, M_(za1, prmuz)));
     const float zbeta = D_(S_(zgamma1, zrk), zrkg);
     const float ze1 = fminf(M_(zrk, zto1), 500.f);
-    const float zem1 = sw_expt(exp_tbl, ze1, bpade), zep1 = D_(1.f, zem1);
-    const float zem2 = zexp, zep2 = D_(1.f, zem2);
+    const float zem1 = sw_expt(exp_tbl, ze1, bpade), zep1 = R_(zem1);
+    const float zem2 = zexp, zep2 = R_(zem2);
     const float zdenr = A_(M_(zr4, zep1), M_(zr5, zem1));
     const float zdent = zdenr;   // zt4 = zr4, zt5 = zr5
     if (zdenr >= -eps && zdenr <= eps) { o.x = eps; o.z = zem2; }
@@ -249,7 +250,7 @@ __device__ SW_REFTRA_INLINE SwLayerRT sw_reftra(const float *__restrict__ exp_tb
       o.z = S_(zem2, D_(M_(M_(zem2, zw), S_(S_(M_(zt1, zep1), M_(zt2, zem1)), M_(zt3, zep2))), zdent));
     }
     const float zemm = M_(zem1, zem1);
-    const float zdend = D_(1.f, M_(S_(1.f, M_(zbeta, zemm)), zrkg));
+    const float zdend = R_(M_(S_(1.f, M_(zbeta, zemm)), zrkg));
     o.y = M_(M_(zgamma2, S_(1.f, zemm)), zdend);
     o.w = M_(M_(zrk2, zem1), zdend);
   }
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
       // vrtqdr_sw's bottom-up recurrence (SW:7997-8005) in the reference's own operation order and rounding (unfused, IEEE
       // reciprocal): with reftra_sw's operands bit-exact the whole shortwave chain reproduces the reference bit for bit,
       // and streams with identical inputs (zero aerosol: clean == full; no cloud: clear == full) stay identical
-      const float zreflect = D_(1.f, S_(1.f, M_(rupd[s], P.y)));
+      const float zreflect = R_(S_(1.f, M_(rupd[s], P.y)));
       const float nrup = A_(P.x, M_(M_(P.w, A_(M_(S_(P.z, e), rupd[s]), M_(e, rup[s]))), zreflect));
       const float nrupd = A_(P.y, M_(M_(M_(P.w, P.w), rupd[s]), zreflect));
       rup[s] = nrup; rupd[s] = nrupd;
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0, int
     for (int i = 0; i < NG; i++) {
       // flux at interface lev (SW:8036-8045), the reference's operation order and rounding
       const float ru = R[i].x, rud = R[i].y;
-      const float zreflect = D_(1.f, S_(1.f, M_(rdnd[i], rud)));
+      const float zreflect = R_(S_(1.f, M_(rdnd[i], rud)));
       const float dif = S_(tdn[i], tdbt[i]);
       const float fu = M_(A_(M_(tdbt[i], ru), M_(dif, rud)), zreflect);
       const float fd = A_(tdbt[i], M_(A_(dif, M_(M_(tdbt[i], ru), rdnd[i])), zreflect));
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(128) k_sw_sweep(SwArgs a, int grp, int g0, int
     for (int i = 0; i < NG; i++) {
       // transmittances through the layer below the interface (SW:8007-8034); with tdn = tdbt = 1, rdnd = 0 at the top the
       // general step reproduces the reference's special first step (tdn = tra, rdnd = refd) exactly
-      const float zr = D_(1.f, S_(1.f, M_(P[i].y, rdnd[i])));
+      const float zr = R_(S_(1.f, M_(P[i].y, rdnd[i])));
       const float ntdn = A_(M_(tdbt[i], P[i].z), M_(M_(P[i].w, A_(S_(tdn[i], tdbt[i]), M_(M_(tdbt[i], P[i].x), rdnd[i]))), zr));
       const float nrdnd = A_(P[i].y, M_(M_(M_(P[i].w, P[i].w), rdnd[i]), zr));
       tdn[i] = ntdn; rdnd[i] = nrdnd;
