@@ -191,10 +191,10 @@ struct SwLayerRT { float4 p; float e; };
 #define SW_REFTRA_INLINE __forceinline__
 #endif
 template <bool ZG0>
-__device__ SW_REFTRA_INLINE SwLayerRT sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float zto1, float zw) {
+__device__ SW_REFTRA_INLINE SwLayerRT sw_reftra(const float *__restrict__ exp_tbl, float bpade, float zg, float prmuz, float rmuz, float zto1, float zw) {
   const float eps = 1.e-08f, zwcrit = 0.9999995f;
   float4 o;
-  const float zx = D_(zto1, prmuz);
+  const float zx = div_rn_r(zto1, prmuz, rmuz);        // rmuz = rcp_rn(prmuz), hoisted out of the layer loop
   const float zexp = sw_expt(exp_tbl, fminf(zx, 500.f), bpade);
   float zgamma1, zgamma2, zgamma3, zgamma4, zwo;
   if (ZG0) {
@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
   const bool noaer = do_clean || do_clnc;
 
   const float prmu0 = ws.colf[(size_t)SWF_MU0 * cap + c];
+  const float rmu0 = rcp_rn(prmu0);
   const bool uv = (b >= 9 && b <= 12);
   const float albp = ws.colf[(size_t)(uv ? SWF_ALBDIR_UV : SWF_ALBDIR_NIR) * cap + c];
   const float albd = ws.colf[(size_t)(uv ? SWF_ALBDIF_UV : SWF_ALBDIF_NIR) * cap + c];
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
         zomcc = D_(zomcc, ztauc);
         // direct beam without delta scaling (diagnostic surface direct flux of the FULL stream)
         const float tauorig = cloudy ? A_(ztauc, taormc) : ztauc;
-        enod[lay] = sw_expt(s_exp, D_(tauorig, prmu0), bpade);
+        enod[lay] = sw_expt(s_exp, div_rn_r(tauorig, prmu0, rmu0), bpade);
         const float zf = M_(zgcc, zgcc);
         const float zwf = M_(zomcc, zf);
         ztauc = M_(S_(1.0f, zwf), ztauc);
@@ -391,15 +392,15 @@ __global__ void __launch_bounds__(256, SW_MINBLOCKS) k_sw_solve(SwArgs a) {
         zomcc = D_(taur, ztauc);
         zgcc = 0.f;
       }
-      const SwLayerRT rt = v == 0 ? sw_reftra<false>(s_exp, bpade, zgcc, prmu0, ztauc, zomcc)
-                                  : sw_reftra<true>(s_exp, bpade, 0.f, prmu0, ztauc, zomcc);
+      const SwLayerRT rt = v == 0 ? sw_reftra<false>(s_exp, bpade, zgcc, prmu0, rmu0, ztauc, zomcc)
+                                  : sw_reftra<true>(s_exp, bpade, 0.f, prmu0, rmu0, ztauc, zomcc);
       pclr[v] = rt.p; eclr[v] = rt.e;
       if (cloudy) {
         const float ztauo = A_(ztauc, taucmc);
         float zomco = A_(M_(ztauc, zomcc), M_(taucmc, ssacmc));
         const float zgco = D_(A_(M_(M_(taucmc, ssacmc), asmcmc), M_(M_(ztauc, zomcc), zgcc)), zomco);
         zomco = D_(zomco, ztauo);
-        const SwLayerRT rc = sw_reftra<false>(s_exp, bpade, zgco, prmu0, ztauo, zomco);
+        const SwLayerRT rc = sw_reftra<false>(s_exp, bpade, zgco, prmu0, rmu0, ztauo, zomco);
         pcld[v] = rc.p; ecld[v] = rc.e;
       }
     }
