@@ -24,7 +24,8 @@
 
 namespace arc {
 
-// workspace per (section, point): radius (cm), weight = number * pi r^2 (1/cm), volume fractions of the 9 classes
+// workspace per (section, point): Chebyshev argument x(ln r) of the wet radius, weight = number * pi r^2 (1/cm), volume
+// fractions of the 9 classes
 enum { AWS_R = 0, AWS_W, AWS_VF, AER_WS_N = 2 + AER_NCLASS };
 
 __constant__ float c_dens[AER_NCLASS] = {1.8f, 1.8f, 2.2f, 1.8f, 2.2f, 2.6f, 1.0f, 1.7f, 1.0f};   // g/cm3: so4 no3 cl nh4 na oin oc bc water
@@ -44,7 +45,7 @@ __device__ inline void section_edges(int nsec, int s, float &dlo, float &dhi) {
   dhi = lo * expf(r * (float)(s + 1));
 }
 
-__global__ void __launch_bounds__(128) k_aer_prep(AerArgs a) {
+__global__ void __launch_bounds__(128) k_aer_prep(AerArgs a, float rmin, float rmax, float xrmin, float xrmax) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.npts) return;
   const AerSpecList &sl = *a.sl;
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(128) k_aer_prep(AerArgs a) {
     }
     const float dp_wet = dp_dry * cbrtf(vwet / vdry);
     const float r = 0.5f * dp_wet;
-    w[(size_t)AWS_R * np] = r;
+    // the series argument depends on the radius only: evaluated here once instead of once per wavelength
+    w[(size_t)AWS_R * np] = (2.f * logf(fminf(fmaxf(r, rmin), rmax)) - xrmax - xrmin) / (xrmax - xrmin);
     w[(size_t)AWS_W * np] = n * 3.14159265f * r * r;
     const float inv = 1.0f / vwet;
     for (int c = 0; c < AER_NCLASS; c++) w[(size_t)(AWS_VF + c) * np] = vol[s][c] * inv;
@@ -129,64 +131,152 @@ __global__ void __launch_bounds__(128) k_aer_prep(AerArgs a) {
 #endif
 constexpr int AER_UNROLL = AER_UNROLL_J;
 constexpr int AER_TAB_FLOATS = AER_NQ * AER_NREFR * AER_NREFI * AER_NCOEF_PAD;     // 7644 floats = 30,576 B per wavelength
+constexpr int AER_PTS = 256;                                   // points per block
+constexpr int AER_ITEMS = AER_MAXBIN * AER_PTS;                // (section, point) items per block
+constexpr int AER_NCELL = (AER_NREFR - 1) * (AER_NREFI - 1);   // refractive-index cells; one more bucket holds the empty items
 
-__global__ void __launch_bounds__(256) k_aer_mie(AerArgs a, AerDev d) {
+// Block = 256 (column, level) points x one wavelength.  The 12 coefficient rows an item needs (4 corners of its
+// refractive-index cell x 3 quantities) are picked by the item's composition, so neighbouring points read different rows and a
+// warp's 16-byte shared-memory loads cost 3 wavefronts each - which is what bounded the first version of this kernel.  Here
+// the block's items are first counting-sorted by cell in shared memory (buckets padded to an even length); a thread of the
+// evaluation loop then takes TWO neighbouring items of one bucket, so every coefficient it loads feeds both, and a warp
+// holds items of one cell (two at a bucket edge): the loads are broadcasts.  A broadcast 16-byte load still costs two
+// wavefronts (ncu), hence the pairing.  Each item's arithmetic is unchanged and the section sum runs in section order per
+// point afterwards, so the result does not depend on the order inside a bucket.
+constexpr int AER_PERM = AER_ITEMS + 2 * AER_NCELL;            // sorted list with the padding slots
+constexpr int AER_NONE = 0xFFFF;
+
+__global__ void __launch_bounds__(AER_PTS, 3) k_aer_mie(AerArgs a, AerDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *tab = reinterpret_cast<float *>(smem_raw);
   uint64_t *bar = reinterpret_cast<uint64_t *>(tab + AER_TAB_FLOATS);
-  const int wl = blockIdx.y;
-  {
-    StageReq req[1] = {{tab, d.coef + (size_t)wl * AER_TAB_FLOATS, AER_TAB_FLOATS * 4}};
-    stage_tables(bar, req, 1);
+  float *it_x = reinterpret_cast<float *>(bar + 2);            // x, then Q_ext
+  float *it_t = it_x + AER_ITEMS;                              // t, then Q_sca
+  float *it_u = it_t + AER_ITEMS;                              // u, then g
+  unsigned short *perm = reinterpret_cast<unsigned short *>(it_u + AER_ITEMS);
+  unsigned char *it_cell = reinterpret_cast<unsigned char *>(perm + AER_PERM);
+  int *cnt = reinterpret_cast<int *>(it_cell + AER_ITEMS);     // [AER_NCELL + 1] bucket counts
+  int *off = cnt + AER_NCELL + 1;                              // [AER_NCELL] bucket starts
+  __shared__ int s_total;
+  // the 20 wavelengths of a point tile are neighbours in launch order: the tile's workspace lines are read from L2
+  const int wl = blockIdx.x % AER_NWL;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid <= AER_NCELL) cnt[tid] = 0;
+  // the wavelength's coefficient table arrives by one bulk copy while phases A and B run; it is waited for before phase C
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, AER_TAB_FLOATS * 4);
+    tma_bulk_g2s(tab, d.coef + (size_t)wl * AER_TAB_FLOATS, AER_TAB_FLOATS * 4, bar);
   }
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.npts) return;
+  const int p = (blockIdx.x / AER_NWL) * AER_PTS + tid;
+  const bool live = p < a.npts;
   const size_t np = (size_t)a.npts;
-  float ext = 0.f, sca = 0.f, gsc = 0.f;
-  const float xrmin = d.xrmin, xrmax = d.xrmax;
-  const float r_lo = d.refr_lo[wl], r_hi = d.refr_hi[wl], li_lo = d.lnrefi_lo[wl], li_hi = d.lnrefi_hi[wl];
-  for (int s = 0; s < a.nsec; s++) {
-    const float *w = a.ws + (size_t)s * AER_WS_N * np + p;
-    const float weight = w[(size_t)AWS_W * np];
-    if (!(weight > 0.f)) continue;
-    float r = w[(size_t)AWS_R * np];
-    r = fminf(fmaxf(r, d.rmin), d.rmax);
-    float refr = 0.f, refi = 0.f;
+  const int nsec = a.nsec;
+  const float r_lo = d.refr_lo[wl], li_lo = d.lnrefi_lo[wl];
+  const float r_scale = (float)(AER_NREFR - 1) / (d.refr_hi[wl] - r_lo), li_scale = (float)(AER_NREFI - 1) / (d.lnrefi_hi[wl] - li_lo);
+  float nrw[AER_NCLASS], niw[AER_NCLASS];
 #pragma unroll
-    for (int c = 0; c < AER_NCLASS; c++) {
-      const float vf = w[(size_t)(AWS_VF + c) * np];
-      refr = fmaf(vf, d.nr[c][wl], refr);
-      refi = fmaf(vf, d.ni[c][wl], refi);
-    }
-    // bilinear cell in (n_r linear, n_i geometric)
-    float tr = (refr - r_lo) / (r_hi - r_lo) * (float)(AER_NREFR - 1);
-    tr = fminf(fmaxf(tr, 0.f), (float)(AER_NREFR - 1));
-    int ir = min((int)tr, AER_NREFR - 2);
-    const float t = tr - (float)ir;
-    float ti = (logf(fmaxf(refi, 1.e-30f)) - li_lo) / (li_hi - li_lo) * (float)(AER_NREFI - 1);
-    ti = fminf(fmaxf(ti, 0.f), (float)(AER_NREFI - 1));
-    int ii = min((int)ti, AER_NREFI - 2);
-    const float u = ti - (float)ii;
-    const float w00 = (1.f - t) * (1.f - u), w10 = t * (1.f - u), w01 = (1.f - t) * u, w11 = t * u;
-    const float x = (2.f * logf(r) - xrmax - xrmin) / (xrmax - xrmin);
-    // series sum_j c_j T_j(x), c_0 halved (chebev), evaluated at the four refractive-index corners (12 accumulators), then
-    // blended bilinearly.  The coefficient rows are zero-padded from 50 to 52, so the padding needs no special case.
-    float a4[AER_NQ][4];
+  for (int c = 0; c < AER_NCLASS; c++) { nrw[c] = d.nr[c][wl]; niw[c] = d.ni[c][wl]; }
+  float wgt[AER_MAXBIN];
+  int cid[AER_MAXBIN], rank[AER_MAXBIN];
+
+  // ---- A: refractive index, cell and interpolation weights of every (section, point) item
 #pragma unroll
-    for (int qn = 0; qn < AER_NQ; qn++) { a4[qn][0] = 0.f; a4[qn][1] = 0.f; a4[qn][2] = 0.f; a4[qn][3] = 0.f; }
-    const float *cell = tab + (ir * AER_NREFI + ii) * AER_NCOEF_PAD;
-    float tjm1 = 1.f, tj = x;          // T_0, T_1
-    const float x2 = 2.f * x;
-#pragma unroll AER_UNROLL
-    for (int j4 = 0; j4 < AER_NCOEF_PAD; j4 += 4) {
-      float T0, T1, T2, T3;
-      if (j4 == 0) {
-        T0 = 0.5f; T1 = x;
-        T2 = fmaf(x2, tj, -tjm1); T3 = fmaf(x2, T2, -tj);
-      } else {
-        T0 = fmaf(x2, tj, -tjm1); T1 = fmaf(x2, T0, -tj); T2 = fmaf(x2, T1, -T0); T3 = fmaf(x2, T2, -T1);
+  for (int s = 0; s < AER_MAXBIN; s++) {
+    wgt[s] = 0.f;
+    cid[s] = AER_NCELL;
+    if (s < nsec && live) {
+      const float *w = a.ws + (size_t)s * AER_WS_N * np + p;
+      const float weight = w[(size_t)AWS_W * np];
+      const float x = w[(size_t)AWS_R * np];
+      float refr = 0.f, refi = 0.f;
+#pragma unroll
+      for (int c = 0; c < AER_NCLASS; c++) {
+        const float vf = w[(size_t)(AWS_VF + c) * np];
+        refr = fmaf(vf, nrw[c], refr);
+        refi = fmaf(vf, niw[c], refi);
       }
-      tjm1 = T2; tj = T3;
+      if (weight > 0.f) {
+        wgt[s] = weight;
+        // bilinear cell in (n_r linear, n_i geometric)
+        float tr = (refr - r_lo) * r_scale;
+        tr = fminf(fmaxf(tr, 0.f), (float)(AER_NREFR - 1));
+        const int ir = min((int)tr, AER_NREFR - 2);
+        float ti = (logf(fmaxf(refi, 1.e-30f)) - li_lo) * li_scale;
+        ti = fminf(fmaxf(ti, 0.f), (float)(AER_NREFI - 1));
+        const int ii = min((int)ti, AER_NREFI - 2);
+        cid[s] = ir * (AER_NREFI - 1) + ii;
+        const int item = s * AER_PTS + tid;
+        it_t[item] = tr - (float)ir;
+        it_u[item] = ti - (float)ii;
+        it_x[item] = x;
+      }
+    }
+  }
+  // rank of every item inside its bucket (the order inside a bucket is arbitrary and does not reach the result)
+#pragma unroll
+  for (int s = 0; s < AER_MAXBIN; s++) {
+    if (s < nsec) {
+      it_cell[s * AER_PTS + tid] = (unsigned char)cid[s];
+      const unsigned m = __match_any_sync(0xffffffffu, cid[s]);
+      const int leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&cnt[cid[s]], __popc(m));
+      rank[s] = __shfl_sync(0xffffffffu, base, leader) + __popc(m & ((1u << lane) - 1u));
+    }
+  }
+  __syncthreads();
+  // ---- B: bucket offsets (even; an odd bucket gets one padding slot), then the item list in bucket order
+  if (tid < 32) {
+    int incl[2], n[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int c = tid + 32 * h;
+      n[h] = c < AER_NCELL ? cnt[c] : 0;
+      int v = n[h] + (n[h] & 1);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+      incl[h] = v;
+    }
+    const int tot0 = __shfl_sync(0xffffffffu, incl[0], 31);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int c = tid + 32 * h;
+      if (c < AER_NCELL) {
+        const int start = (h ? tot0 : 0) + incl[h] - (n[h] + (n[h] & 1));
+        off[c] = start;
+        if (n[h] & 1) perm[start + n[h]] = AER_NONE;
+      }
+    }
+    if (tid == 31) s_total = tot0 + incl[1];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < AER_MAXBIN; s++)
+    if (s < nsec && cid[s] < AER_NCELL) perm[off[cid[s]] + rank[s]] = (unsigned short)(s * AER_PTS + tid);
+  __syncthreads();
+  mbar_wait(bar, 0);
+  // ---- C: the Chebyshev series of the sorted items, two per thread
+  const int total = s_total;
+  for (int pos = 2 * tid; pos < total; pos += 2 * AER_PTS) {
+    const int item0 = perm[pos];
+    const int item1raw = perm[pos + 1];
+    const int item1 = item1raw == AER_NONE ? item0 : item1raw;        // padding slot: the pair's first item again
+    const int cellid = it_cell[item0];
+    const int ir = cellid / (AER_NREFI - 1), ii = cellid - ir * (AER_NREFI - 1);
+    const float x[2] = {it_x[item0], it_x[item1]};
+    // series sum_j c_j T_j(x), c_0 halved (chebev), evaluated at the four refractive-index corners (12 accumulators per
+    // item), then blended bilinearly.  The coefficient rows are zero-padded from 50 to 52: the padding needs no special case.
+    float a4[2][AER_NQ][4];
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+      for (int qn = 0; qn < AER_NQ; qn++) { a4[e][qn][0] = 0.f; a4[e][qn][1] = 0.f; a4[e][qn][2] = 0.f; a4[e][qn][3] = 0.f; }
+    const float *cell = tab + (ir * AER_NREFI + ii) * AER_NCOEF_PAD;
+    const float x2[2] = {2.f * x[0], 2.f * x[1]};
+    float T[2][4];
+    auto accumulate = [&](int j4) {
 #pragma unroll
       for (int qn = 0; qn < AER_NQ; qn++) {
         const float *base = cell + qn * (AER_NREFR * AER_NREFI * AER_NCOEF_PAD) + j4;
@@ -194,21 +284,59 @@ __global__ void __launch_bounds__(256) k_aer_mie(AerArgs a, AerDev d) {
         const float4 c01 = *reinterpret_cast<const float4 *>(base + AER_NCOEF_PAD);
         const float4 c10 = *reinterpret_cast<const float4 *>(base + AER_NREFI * AER_NCOEF_PAD);
         const float4 c11 = *reinterpret_cast<const float4 *>(base + (AER_NREFI + 1) * AER_NCOEF_PAD);
-        a4[qn][0] = fmaf(c00.w, T3, fmaf(c00.z, T2, fmaf(c00.y, T1, fmaf(c00.x, T0, a4[qn][0]))));
-        a4[qn][1] = fmaf(c01.w, T3, fmaf(c01.z, T2, fmaf(c01.y, T1, fmaf(c01.x, T0, a4[qn][1]))));
-        a4[qn][2] = fmaf(c10.w, T3, fmaf(c10.z, T2, fmaf(c10.y, T1, fmaf(c10.x, T0, a4[qn][2]))));
-        a4[qn][3] = fmaf(c11.w, T3, fmaf(c11.z, T2, fmaf(c11.y, T1, fmaf(c11.x, T0, a4[qn][3]))));
-      }
-    }
-    float acc[AER_NQ];
 #pragma unroll
-    for (int qn = 0; qn < AER_NQ; qn++) acc[qn] = w00 * a4[qn][0] + w01 * a4[qn][1] + w10 * a4[qn][2] + w11 * a4[qn][3];
-    const float pext = expf(acc[0]);
-    const float pscat = fminf(expf(acc[1]), pext);
-    const float pasm = expf(acc[2]);
-    ext += weight * pext;
-    sca += weight * pscat;
-    gsc += weight * pscat * pasm;
+        for (int e = 0; e < 2; e++) {
+          a4[e][qn][0] = fmaf(c00.w, T[e][3], fmaf(c00.z, T[e][2], fmaf(c00.y, T[e][1], fmaf(c00.x, T[e][0], a4[e][qn][0]))));
+          a4[e][qn][1] = fmaf(c01.w, T[e][3], fmaf(c01.z, T[e][2], fmaf(c01.y, T[e][1], fmaf(c01.x, T[e][0], a4[e][qn][1]))));
+          a4[e][qn][2] = fmaf(c10.w, T[e][3], fmaf(c10.z, T[e][2], fmaf(c10.y, T[e][1], fmaf(c10.x, T[e][0], a4[e][qn][2]))));
+          a4[e][qn][3] = fmaf(c11.w, T[e][3], fmaf(c11.z, T[e][2], fmaf(c11.y, T[e][1], fmaf(c11.x, T[e][0], a4[e][qn][3]))));
+        }
+      }
+    };
+    // j = 0..3: T_0 halved, T_1 = x
+#pragma unroll
+    for (int e = 0; e < 2; e++) { T[e][0] = 0.5f; T[e][1] = x[e]; T[e][2] = fmaf(x2[e], x[e], -1.f); T[e][3] = fmaf(x2[e], T[e][2], -x[e]); }
+    accumulate(0);
+#pragma unroll AER_UNROLL
+    for (int j4 = 4; j4 < AER_NCOEF_PAD; j4 += 4) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float t0 = fmaf(x2[e], T[e][3], -T[e][2]);
+        const float t1 = fmaf(x2[e], t0, -T[e][3]);
+        const float t2 = fmaf(x2[e], t1, -t0);
+        const float t3 = fmaf(x2[e], t2, -t1);
+        T[e][0] = t0; T[e][1] = t1; T[e][2] = t2; T[e][3] = t3;
+      }
+      accumulate(j4);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      if (e == 1 && item1raw == AER_NONE) break;                      // padding slot: nothing to store
+      const int item = e == 0 ? item0 : item1;
+      const float t = it_t[item], u = it_u[item];
+      const float w00 = (1.f - t) * (1.f - u), w10 = t * (1.f - u), w01 = (1.f - t) * u, w11 = t * u;
+      float acc[AER_NQ];
+#pragma unroll
+      for (int qn = 0; qn < AER_NQ; qn++) acc[qn] = w00 * a4[e][qn][0] + w01 * a4[e][qn][1] + w10 * a4[e][qn][2] + w11 * a4[e][qn][3];
+      const float pext = expf(acc[0]);
+      it_x[item] = pext;
+      it_t[item] = fminf(expf(acc[1]), pext);
+      it_u[item] = expf(acc[2]);
+    }
+  }
+  __syncthreads();
+  // ---- D: section sums of each point, in section order
+  if (!live) return;
+  float ext = 0.f, sca = 0.f, gsc = 0.f;
+#pragma unroll
+  for (int s = 0; s < AER_MAXBIN; s++) {
+    if (s < nsec && wgt[s] > 0.f) {
+      const int item = s * AER_PTS + tid;
+      const float weight = wgt[s], pext = it_x[item], pscat = it_t[item], pasm = it_u[item];
+      ext += weight * pext;
+      sca += weight * pscat;
+      gsc += weight * pscat * pasm;
+    }
   }
   int i, k, j; point_ijk(a.geo, p, i, k, j);
   const size_t q = a.geo.at3(i, k, j);
@@ -223,6 +351,8 @@ __global__ void __launch_bounds__(256) k_aer_mie(AerArgs a, AerDev d) {
     if (a.extaerlw[wl - AER_NSW]) a.extaerlw[wl - AER_NSW][q] = absb * 1.0e5f;       // 1/cm -> 1/km
   }
 }
+
+static int aer_mie_smem() { return AER_TAB_FLOATS * 4 + 16 + AER_ITEMS * (3 * 4 + 1) + AER_PERM * 2 + (2 * AER_NCELL + 1) * 4 + 16; }
 
 // ---- host side --------------------------------------------------------------------------------------------------
 static AerTables g_T;
@@ -249,7 +379,7 @@ int aer_init(const float *nr, const float *ni, std::string &err) {
   }
   g_D.rmin = (float)g_T.rmin; g_D.rmax = (float)g_T.rmax;
   g_D.xrmin = logf(g_D.rmin); g_D.xrmax = logf(g_D.rmax);
-  cudaFuncSetAttribute(k_aer_mie, cudaFuncAttributeMaxDynamicSharedMemorySize, AER_TAB_FLOATS * 4 + 16);
+  cudaFuncSetAttribute(k_aer_mie, cudaFuncAttributeMaxDynamicSharedMemorySize, aer_mie_smem());
   g_aer_ready = true;
   return 0;
 }
@@ -273,9 +403,8 @@ int aer_run(AerArgs &a, const AerSpecList &sl, cudaStream_t s, std::string &err)
   a.ws = g_ws;
   a.sl = g_sl;
   cudaMemcpyAsync(g_sl, &sl, sizeof(AerSpecList), cudaMemcpyHostToDevice, s);
-  k_aer_prep<<<(a.npts + 127) / 128, 128, 0, s>>>(a);
-  dim3 grid((a.npts + 255) / 256, AER_NWL);
-  k_aer_mie<<<grid, 256, AER_TAB_FLOATS * 4 + 16, s>>>(a, g_D);
+  k_aer_prep<<<(a.npts + 127) / 128, 128, 0, s>>>(a, g_D.rmin, g_D.rmax, g_D.xrmin, g_D.xrmax);
+  k_aer_mie<<<((a.npts + AER_PTS - 1) / AER_PTS) * AER_NWL, AER_PTS, aer_mie_smem(), s>>>(a, g_D);
   count_launch(2);
   return 0;
 }
