@@ -226,6 +226,17 @@ int  arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *
 int  arc_rad_cal_cldfra1(const ArcDims *d, int memspace, const float *qv, const float *qc, const float *qi, const float *qs, int f_qv,
                          int f_qc, int f_qi, int f_qs, const float *t_phy, const float *p_phy, const float *f_ice_phy, int mp_physics,
                          float *cldfra, int *cldfra1_flag);
+/* cal_cldfra2 (module_radiation_driver.F:2801-2874; icloud = 2, DRV:1205): CLDFRA = 1 where QC + QI > 1e-6 (QC alone when
+ * F_QI is false; 0 everywhere when F_QC is false), tile levels kts..kte. */
+int  arc_rad_cal_cldfra2(const ArcDims *d, int memspace, const float *qc, const float *qi, int f_qc, int f_qi, float *cldfra);
+/* ozn_time_int (module_radiation_driver.F:3993-4098; o3input = 2, DRV:1250): ozmixm(ims:ime, levsiz, jms:jme, num_months) ->
+ * ozmixt(ims:ime, levsiz, jms:jme), linear in time between the mid-month days that bracket JULIAN + 1 (December-January wraps). */
+int  arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, const float *ozmixm,
+                          float *ozmixt);
+/* ozn_p_int (module_radiation_driver.F:4100-4234; DRV:1256): ozmixt on the data levels pin(levsiz) (HOST array in either
+ * memspace; Pa, top down, strictly increasing, levsiz <= 128) -> o3vmr(i,k,j) at the model pressures p(i,k,j): linear in
+ * pressure inside the data range, scaled by p / pin(1) above it, held below it.  kts must be 1.  Bit-exact (unfused, IEEE /). */
+int  arc_rad_ozn_p_int(const ArcDims *d, int memspace, const float *p, const float *pin, int levsiz, const float *ozmixt, float *o3vmr);
 /* Order statistics of `nfields` 2-D (i,j) fields over the tile: out[f * nperc + q] = sorted(field f)[round(0.01 * perc[q] * (N - 1))],
  * the element calc_boxplot_stats picks (misc_stats_library.ncl:145-189); perc = {50, 25, 75, 5, 95} gives calc_standard_stats'
  * median, lower / upper quartile, 5th / 95th percentile (ncl:439-445).  Exact (radix selection, no interpolation).  The 5-cell

@@ -143,6 +143,114 @@ int arc_oracle_cal_cldfra1(const ArcDims *d, const float *QV, const float *QC, c
   return 0;
 }
 
+// cal_cldfra2, module_radiation_driver.F:2801-2874
+int arc_oracle_cal_cldfra2(const ArcDims *d, const float *QC, const float *QI, int F_QC, int F_QI, float *CLDFRA) {
+  const float thresh = 1.0e-6f;
+  const int ni = d->ime - d->ims + 1, nk = d->kme - d->kms + 1;
+  for (int j = d->jts; j <= d->jte; j++)
+    for (int k = d->kts; k <= d->kte; k++)
+      for (int i = d->its; i <= d->ite; i++) {
+        const size_t q = (size_t)(i - d->ims) + (size_t)ni * ((size_t)(k - d->kms) + (size_t)nk * (size_t)(j - d->jms));
+        if (F_QI && F_QC) { if (QC[q] + QI[q] > thresh) CLDFRA[q] = 1.f; else CLDFRA[q] = 0.f; }
+        else if (F_QC) { if (QC[q] > thresh) CLDFRA[q] = 1.f; else CLDFRA[q] = 0.f; }
+        else CLDFRA[q] = 0.f;
+      }
+  return 0;
+}
+
+// ozn_time_int, module_radiation_driver.F:3993-4098 (line by line; ozncyc = .true.)
+int arc_oracle_ozn_time_int(const ArcDims *d, int julday, float JULIAN, int levsiz, int num_months, const float *ozmixm, float *ozmixt) {
+  (void)julday; (void)num_months;
+  static const int date_oz[12] = {16, 45, 75, 105, 136, 166, 197, 228, 258, 289, 319, 350};
+  const float daysperyear = 365.f;
+  volatile float intJULIAN = JULIAN + 1.0f;
+  int IJUL = (int)intJULIAN;
+  intJULIAN = intJULIAN - (float)IJUL;
+  IJUL = IJUL % 365;
+  if (IJUL == 0) IJUL = 365;
+  intJULIAN = intJULIAN + IJUL;
+  int np1 = 1; bool finddate = false;
+  for (int m = 1; m <= 12; m++)
+    if (date_oz[m - 1] > intJULIAN && !finddate) { np1 = m; finddate = true; }
+  float cdayozp = date_oz[np1 - 1], cdayozm;
+  int np, nm;
+  if (np1 > 1) { cdayozm = date_oz[np1 - 2]; np = np1; nm = np - 1; }
+  else { cdayozm = date_oz[11]; np = np1; nm = 12; }
+  volatile float deltat, fact1, fact2;
+  if (np1 == 1) {
+    deltat = cdayozp + daysperyear - cdayozm;
+    if (intJULIAN > cdayozp) { fact1 = (cdayozp + daysperyear - intJULIAN) / deltat; fact2 = (intJULIAN - cdayozm) / deltat; }
+    else { fact1 = (cdayozp - intJULIAN) / deltat; fact2 = (intJULIAN + daysperyear - cdayozm) / deltat; }
+  } else {
+    deltat = cdayozp - cdayozm;
+    fact1 = (cdayozp - intJULIAN) / deltat;
+    fact2 = (intJULIAN - cdayozm) / deltat;
+  }
+  const int ni = d->ime - d->ims + 1, nj = d->jme - d->jms + 1;
+  const size_t nlev = (size_t)ni * levsiz * nj;
+  for (int j = d->jts; j <= d->jte; j++)
+    for (int k = 1; k <= levsiz; k++)
+      for (int i = d->its; i <= d->ite; i++) {
+        const size_t q = (size_t)(i - d->ims) + (size_t)ni * ((size_t)(k - 1) + (size_t)levsiz * (size_t)(j - d->jms));
+        const float a = ozmixm[q + nlev * (nm - 1)] * fact1, b = ozmixm[q + nlev * (np - 1)] * fact2;
+        ozmixt[q] = a + b;
+      }
+  return 0;
+}
+
+// ozn_p_int, module_radiation_driver.F:4100-4234 (line by line, including the row-wide kkstart / kount bookkeeping)
+int arc_oracle_ozn_p_int(const ArcDims *d, const float *p, const float *pin, int levsiz, const float *ozmixt, float *o3vmr) {
+  const int its = d->its, ite = d->ite, kts = d->kts, kte = d->kte;
+  const int ni = d->ime - d->ims + 1, nk = d->kme - d->kms + 1;
+  const int ncol = ite - its + 1, pver = kte - kts + 1;
+  auto P3 = [&](int i, int k, int j) { return (size_t)(i - d->ims) + (size_t)ni * ((size_t)(k - d->kms) + (size_t)nk * (size_t)(j - d->jms)); };
+  auto OZ = [&](int i, int k, int j) { return ozmixt[(size_t)(i - d->ims) + (size_t)ni * ((size_t)(k - 1) + (size_t)levsiz * (size_t)(j - d->jms))]; };
+  auto PIN = [&](int k) { return pin[k - 1]; };
+  std::vector<float> pmid((size_t)ncol * (pver + 1));
+  std::vector<int> kupper(ncol);
+  auto PM = [&](int i, int k) -> float & { return pmid[(size_t)(i - its) + (size_t)ncol * k]; };   // k = 1..pver
+  for (int j = d->jts; j <= d->jte; j++) {
+    for (int i = its; i <= ite; i++) kupper[i - its] = 1;
+    for (int k = kts; k <= kte; k++) {
+      const int kk = kte - k + kts;
+      for (int i = its; i <= ite; i++) PM(i, kk) = p[P3(i, k, j)];
+    }
+    for (int k = 1; k <= pver; k++) {
+      const int kout = pver - k + 1;
+      int kkstart = levsiz;
+      for (int i = its; i <= ite; i++) kkstart = std::min(kkstart, kupper[i - its]);
+      int kount = 0;
+      bool done = false;
+      for (int kk = kkstart; kk <= levsiz - 1 && !done; kk++) {
+        for (int i = its; i <= ite; i++)
+          if (PIN(kk) < PM(i, k) && PM(i, k) <= PIN(kk + 1)) { kupper[i - its] = kk; kount = kount + 1; }
+        if (kount == ncol) {
+          for (int i = its; i <= ite; i++) {
+            const int ku = kupper[i - its];
+            const float dpu = PM(i, k) - PIN(ku), dpl = PIN(ku + 1) - PM(i, k);
+            const float a = OZ(i, ku, j) * dpl, b = OZ(i, ku + 1, j) * dpu;
+            o3vmr[P3(i, kout, j)] = (a + b) / (dpl + dpu);
+          }
+          done = true;
+        }
+      }
+      if (done) continue;
+      for (int i = its; i <= ite; i++) {
+        const int ku = kupper[i - its];
+        if (PM(i, k) < PIN(1)) { const float a = OZ(i, 1, j) * PM(i, k); o3vmr[P3(i, kout, j)] = a / PIN(1); }
+        else if (PM(i, k) > PIN(levsiz)) o3vmr[P3(i, kout, j)] = OZ(i, levsiz, j);
+        else {
+          const float dpu = PM(i, k) - PIN(ku), dpl = PIN(ku + 1) - PM(i, k);
+          const float a = OZ(i, ku, j) * dpl, b = OZ(i, ku + 1, j) * dpu;
+          o3vmr[P3(i, kout, j)] = (a + b) / (dpl + dpu);
+        }
+      }
+      if (kount > ncol) return -1;       // 'OZN_P_INT: Bad ozone data: non-monotonicity suspected'
+    }
+  }
+  return 0;
+}
+
 // The C library's own logf / expf / powf (what gfortran's LOG / EXP / ** call): which = 0 logf(x), 1 expf(x), 2 powf(x, y).
 // Checker for the product's glibc-compatible device functions (csrc/glibc_math.cuh).
 int arc_oracle_libm(int which, const float *x, const float *y, int n, float *out) {

@@ -88,3 +88,73 @@ def test_cal_cldfra1_oracle_known_answers(orc):
     cf3 = np.zeros(shp, np.float32)
     orc.cal_cldfra1(dom["dims"], cf3, dom["qv3d"], dom["qc3d"], None, None, t, p, F_QI=False, F_QS=False)
     assert (cf3[tile] > 0).any()
+
+
+def test_cal_cldfra2_oracle(orc):
+    """cal_cldfra2 (module_radiation_driver.F:2801-2874): 1 where QC + QI > 1e-6; QC alone when F_QI is false; 0 when F_QC is false."""
+    from wrfchem_arc_interactions_b200 import synth
+    dom = synth.make_domain(12, 5, 40, seed=4, cloudy_frac=1.0)
+    qc, qi = dom["qc3d"], dom["qi3d"]
+    tile = (slice(None), slice(0, 40), slice(None))
+    cf = np.full(qc.shape, -9.0, np.float32)
+    orc.cal_cldfra2(dom["dims"], cf, qc, qi)
+    assert np.all(cf[:, 40, :] == -9.0)
+    assert np.array_equal(cf[tile], ((qc + qi)[tile] > np.float32(1e-6)).astype(np.float32)) and 0 < cf[tile].mean() < 1
+    orc.cal_cldfra2(dom["dims"], cf, qc, qi, F_QI=False)
+    assert np.array_equal(cf[tile], (qc[tile] > np.float32(1e-6)).astype(np.float32))
+    orc.cal_cldfra2(dom["dims"], cf, qc, qi, F_QC=False)
+    assert np.all(cf[tile] == 0)
+
+
+def ozone_case(ni=14, nj=6, nk=40, levsiz=59, seed=11):
+    """Synthetic CAM-style ozone climatology: 12 months on `levsiz` pressure levels (top down), and a model pressure field that
+    reaches above the data top and below the data bottom in some columns."""
+    from wrfchem_arc_interactions_b200 import synth
+    rng = np.random.default_rng(seed)
+    dom = synth.make_domain(ni, nj, nk, seed=seed)
+    pin = np.geomspace(30.0, 99000.0, levsiz).astype(np.float32)                  # Pa, top down
+    prof = (8e-6 * np.exp(-((np.log(pin) - np.log(1000.0)) / 1.2) ** 2) + 3e-8).astype(np.float32)
+    ozmixm = (prof[None, None, :, None] * (1 + 0.2 * rng.random((12, nj, levsiz, ni)))).astype(np.float32)
+    p = dom["p3d"].copy()
+    p[:, :, 0] *= np.float32(1.08)                                                 # one column row-edge below the data bottom
+    p[0, nk - 1, :] = 20.0                                                         # above the data top
+    p[1, nk - 1, 3] = pin[0]                                                       # exactly on the top data level
+    return dom, pin, ozmixm, np.ascontiguousarray(p)
+
+
+def test_ozn_time_int_oracle(orc):
+    """ozn_time_int (DRV:3993-4098): on a mid-month day the field is that month's; between two mid-month days it is the linear
+    blend; the December-January wrap uses both ends of the year."""
+    dom, pin, ozmixm, p = ozone_case()
+    nj, levsiz, ni = ozmixm.shape[1:]
+    ozt = np.zeros((nj, levsiz, ni), np.float32)
+    orc.ozn_time_int(dom["dims"], 0, 44.0, ozmixm, ozt, levsiz, 12)               # JULIAN + 1 = 45 = date_oz(2): all of February
+    assert np.array_equal(ozt, ozmixm[1])
+    orc.ozn_time_int(dom["dims"], 0, 59.0, ozmixm, ozt, levsiz, 12)               # day 60: half way between 45 and 75
+    assert np.allclose(ozt, 0.5 * (ozmixm[1] + ozmixm[2]), rtol=1e-6)
+    orc.ozn_time_int(dom["dims"], 0, 359.5, ozmixm, ozt, levsiz, 12)              # day 360.5: December -> January wrap
+    f2 = (360.5 - 350.0) / 31.0
+    assert np.allclose(ozt, (1 - f2) * ozmixm[11] + f2 * ozmixm[0], rtol=2e-6)
+    orc.ozn_time_int(dom["dims"], 0, 4.25, ozmixm, ozt, levsiz, 12)               # day 5.25: January side of the wrap
+    f2 = (5.25 + 365.0 - 350.0) / 31.0
+    assert np.allclose(ozt, (1 - f2) * ozmixm[11] + f2 * ozmixm[0], rtol=2e-6)
+
+
+def test_ozn_p_int_oracle(orc):
+    """ozn_p_int (DRV:4100-4234) against numpy's linear interpolation in pressure inside the data range, the p / pin(1) scaling
+    above the top data level and the held value below the bottom one."""
+    dom, pin, ozmixm, p = ozone_case()
+    nj, levsiz, ni = ozmixm.shape[1:]
+    nk = dom["nk"]
+    ozt = np.ascontiguousarray(ozmixm[4])
+    o3 = np.full(p.shape, -1.0, np.float32)
+    orc.ozn_p_int(dom["dims"], p, pin, levsiz, ozt, o3)
+    assert np.all(o3[:, nk, :] == -1.0) and np.all(o3[:, :nk, :] > 0)
+    for j in range(nj):
+        for i in range(ni):
+            pm = p[j, :nk, i].astype(np.float64)
+            want = np.interp(pm, pin.astype(np.float64), ozt[j, :, i].astype(np.float64))
+            top = pm < pin[0]
+            want[top] = ozt[j, 0, i] * pm[top] / pin[0]
+            assert np.allclose(o3[j, :nk, i], want, rtol=3e-6, atol=0), (j, i)
+    assert (p[:, :nk, :] < pin[0]).any() and (p[:, :nk, :] > pin[-1]).any()

@@ -639,6 +639,50 @@ def test_cal_cldfra1_bit_exact(lib, orc, ktab):
     assert (interior(dom, b[0])[:, :40] == 0).all()               # the last case: an OPTIONAL flag absent -> no cloud
 
 
+def test_cal_cldfra2_and_ozone_interpolation_bit_exact(lib, orc, ktab):
+    """SURVEY 8 row (f)4, the rest of radiation_driver's pre-processing that the WRF-Chem path can select: cal_cldfra2
+    (DRV:2801-2874, icloud = 2), ozn_time_int (DRV:3993-4098) and ozn_p_int (DRV:4100-4234, o3input = 2).  Device vs oracle,
+    bit for bit, host and device arrays, halo and level kme untouched, model pressures above / below / on the data levels."""
+    import torch
+    from test_driver_cpu import ozone_case
+    dom = synth.make_domain(40, 9, 40, seed=33, cloudy_frac=0.7, halo=1)
+    init(lib, dom, ktab)
+    shp = dom["t3d"].shape
+    for kw in (dict(), dict(F_QI=False), dict(F_QC=False)):
+        a, b = np.full(shp, -7.0, np.float32), np.full(shp, -7.0, np.float32)
+        lib.cal_cldfra2(dom["dims"], a, dom["qc3d"], dom["qi3d"], **kw)
+        orc.cal_cldfra2(dom["dims"], b, dom["qc3d"], dom["qi3d"], **kw)
+        assert np.array_equal(a, b), kw
+        assert np.all(a[0] == -7.0) and np.all(a[:, 40] == -7.0) and np.all(a[:, :, 0] == -7.0)
+        dc = torch.full(shp, -7.0, dtype=torch.float32, device="cuda")
+        lib.cal_cldfra2(dom["dims"], dc, torch.from_numpy(dom["qc3d"]).cuda(), torch.from_numpy(dom["qi3d"]).cuda(), **kw)
+        assert np.array_equal(dc.cpu().numpy(), b), kw
+
+    odom, pin, ozmixm, p = ozone_case(ni=37, nj=11, nk=50, levsiz=59, seed=12)
+    init(lib, odom, ktab)
+    nj, levsiz, ni = ozmixm.shape[1:]
+    for julian in (44.0, 59.0, 100.3, 359.5, 4.25, 364.99, 729.6):
+        ta, tb = np.zeros((nj, levsiz, ni), np.float32), np.zeros((nj, levsiz, ni), np.float32)
+        lib.ozn_time_int(odom["dims"], 0, julian, ozmixm, ta, levsiz, 12)
+        orc.ozn_time_int(odom["dims"], 0, julian, ozmixm, tb, levsiz, 12)
+        assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32)), julian
+        oa, ob = np.full(p.shape, -1.0, np.float32), np.full(p.shape, -1.0, np.float32)
+        lib.ozn_p_int(odom["dims"], p, pin, levsiz, ta, oa)
+        orc.ozn_p_int(odom["dims"], p, pin, levsiz, tb, ob)
+        assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32)), julian
+        assert np.all(oa[:, 50] == -1.0)
+    # device arrays end to end: the time-interpolated field never leaves the GPU
+    dm, dpp = torch.from_numpy(ozmixm).cuda(), torch.from_numpy(p).cuda()
+    dt = torch.zeros((nj, levsiz, ni), dtype=torch.float32, device="cuda"); do = torch.full(p.shape, -1.0, dtype=torch.float32, device="cuda")
+    lib.ozn_time_int(odom["dims"], 0, 729.6, dm, dt, levsiz, 12)
+    lib.ozn_p_int(odom["dims"], dpp, pin, levsiz, dt, do)
+    assert np.array_equal(do.cpu().numpy().view(np.uint32), ob.view(np.uint32))
+    # a non-monotonic data axis is the reference's fatal error
+    bad = pin.copy(); bad[7] = bad[6]
+    with pytest.raises(Exception):
+        lib.ozn_p_int(odom["dims"], p, bad, levsiz, ta, oa)
+
+
 def test_full_size_properties(lib, ktab):
     """BASELINE config C2 at full size (127,500 columns x 50 levels), checked through size-independent properties:
     energy bounds, clean == full where the aerosol is zero, clear == full in cloud-free columns, night gate."""

@@ -1540,6 +1540,105 @@ int arc_rad_cal_cldfra1(const ArcDims *d, int memspace, const float *qv, const f
   return 0;
 }
 
+// cal_cldfra2 (module_radiation_driver.F:2801-2874, called for icloud = 2 at DRV:1205): binary cloud fraction.
+int arc_rad_cal_cldfra2(const ArcDims *d, int memspace, const float *qc, const float *qi, int f_qc, int f_qi, float *cldfra) {
+  if (!g.ready) { g.err = "arc_rad_cal_cldfra2: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !cldfra) { g.err = "arc_rad_cal_cldfra2: null argument"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if ((f_qc && !qc) || (f_qc && f_qi && !qi)) { g.err = "arc_rad_cal_cldfra2: F_QC / F_QI set but array missing"; return ARC_ERR_BAD_ARG; }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const size_t n3 = G.n3();
+  const float *dqc = nullptr, *dqi = nullptr;
+  if (f_qc && (rc = in_arr(memspace, qc, n3, &dqc))) return rc;
+  if (f_qc && f_qi && (rc = in_arr(memspace, qi, n3, &dqi))) return rc;
+  float *dcf;
+  if ((rc = out_arr(memspace, cldfra, n3, &dcf))) return rc;
+  launch_cal_cldfra2(G, dqc, dqi, f_qc != 0, f_qi != 0, dcf, g.stream);
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ozn_time_int (module_radiation_driver.F:3993-4098; o3input = 2, DRV:1250): the monthly CAM ozone climatology interpolated in
+// time to the model day.  The date arithmetic (which two months, which weights) is the reference's scalar code in single
+// precision, on the host; the blend of the two months runs on the device.
+int arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, const float *ozmixm, float *ozmixt) {
+  (void)julday;                                              // as in the reference: only JULIAN is used
+  if (!g.ready) { g.err = "arc_rad_ozn_time_int: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !ozmixm || !ozmixt) { g.err = "arc_rad_ozn_time_int: null argument"; return ARC_ERR_BAD_ARG; }
+  if (levsiz < 2 || num_months < 12) { g.err = "arc_rad_ozn_time_int: needs levsiz >= 2 and the 12 monthly fields"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  static const int date_oz[12] = {16, 45, 75, 105, 136, 166, 197, 228, 258, 289, 319, 350};
+  const float daysperyear = 365.f;
+  volatile float intjulian = julian + 1.0f;                  // offset by one day (volatile: every step rounded to single)
+  int ijul = (int)intjulian;
+  intjulian = intjulian - (float)ijul;
+  ijul = ijul % 365;
+  if (ijul == 0) ijul = 365;
+  intjulian = intjulian + (float)ijul;
+  int np1 = 1; bool found = false;
+  for (int m = 1; m <= 12; m++)
+    if ((float)date_oz[m - 1] > intjulian && !found) { np1 = m; found = true; }
+  const float cdayozp = (float)date_oz[np1 - 1];
+  float cdayozm; int np, nm;
+  if (np1 > 1) { cdayozm = (float)date_oz[np1 - 2]; np = np1; nm = np - 1; }
+  else { cdayozm = (float)date_oz[11]; np = np1; nm = 12; }
+  volatile float deltat, fact1, fact2;
+  if (np1 == 1) {                                            // December - January
+    deltat = cdayozp + daysperyear - cdayozm;
+    if (intjulian > cdayozp) { fact1 = (cdayozp + daysperyear - intjulian) / deltat; fact2 = (intjulian - cdayozm) / deltat; }
+    else { fact1 = (cdayozp - intjulian) / deltat; fact2 = (intjulian + daysperyear - cdayozm) / deltat; }
+  } else {
+    deltat = cdayozp - cdayozm;
+    fact1 = (cdayozp - intjulian) / deltat;
+    fact2 = (intjulian - cdayozm) / deltat;
+  }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const size_t nlev = (size_t)G.ni * (size_t)levsiz * (size_t)(G.jme - G.jms + 1);
+  const float *m0, *m1;
+  if ((rc = in_arr(memspace, ozmixm + nlev * (size_t)(nm - 1), nlev, &m0)) || (rc = in_arr(memspace, ozmixm + nlev * (size_t)(np - 1), nlev, &m1))) return rc;
+  float *dt;
+  if ((rc = out_arr(memspace, ozmixt, nlev, &dt))) return rc;
+  launch_ozn_time_int(G, levsiz, m0, m1, fact1, fact2, dt, g.stream);
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ozn_p_int (module_radiation_driver.F:4100-4234; DRV:1256): ozone on the data pressure levels `pin` (HOST array, Pa, top
+// down, strictly increasing) interpolated to the model mid-level pressures p(i,k,j) -> o3vmr(i,k,j), the O3RAD that
+// RRTMG_SWRAD / RRTMG_LWRAD read with o3input = 2.
+int arc_rad_ozn_p_int(const ArcDims *d, int memspace, const float *p, const float *pin, int levsiz, const float *ozmixt, float *o3vmr) {
+  if (!g.ready) { g.err = "arc_rad_ozn_p_int: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !p || !pin || !ozmixt || !o3vmr) { g.err = "arc_rad_ozn_p_int: null argument"; return ARC_ERR_BAD_ARG; }
+  if (levsiz < 2 || levsiz > ARC_OZN_MAXLEV) { g.err = "arc_rad_ozn_p_int: levsiz must be 2.." + std::to_string(ARC_OZN_MAXLEV); return ARC_ERR_BAD_ARG; }
+  for (int k = 1; k < levsiz; k++)
+    if (!(pin[k] > pin[k - 1])) { g.err = "OZN_P_INT: Bad ozone data: non-monotonicity suspected"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if (d->kts != 1) { g.err = "arc_rad_ozn_p_int: kts must be 1 (the reference indexes its work arrays from 1)"; return ARC_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const size_t nlev = (size_t)G.ni * (size_t)levsiz * (size_t)(G.jme - G.jms + 1);
+  const float *dp, *dt; float *dv;
+  if ((rc = in_arr(memspace, p, G.n3(), &dp)) || (rc = in_arr(memspace, ozmixt, nlev, &dt))) return rc;
+  if ((rc = out_arr(memspace, o3vmr, G.n3(), &dv))) return rc;
+  launch_ozn_p_int(G, levsiz, pin, dp, dt, dv, g.stream);
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // Order statistics of 2-D diagnostic fields over the tile: calc_boxplot_stats picks sorted(x)[round(0.01 * p * (N - 1))] for
 // p = 5, 25, 50, 75, 95 (misc_stats_library.ncl:145-189; calc_standard_stats stores them as median, quartiles and 5th / 95th
 // percentile, ncl:439-445).  No sort: one block per (field, percentile) selects the element of that rank by four 8-bit radix

@@ -678,6 +678,81 @@ void launch_cal_cldfra1(const Geo &G, const float *qv, const float *qc, const fl
   count_launch();
 }
 
+// cal_cldfra2 (module_radiation_driver.F:2801-2874; icloud = 2): cloud fraction 1 where QC + QI (or QC alone) exceeds 1e-6, else 0.
+__global__ void __launch_bounds__(256) k_cal_cldfra2(Geo G, const float *__restrict__ qc, const float *__restrict__ qi, int f_qc, int f_qi,
+                                                     float *__restrict__ cldfra) {
+  const int nz = G.kte - G.kts + 1;
+  const long n = (long)G.ncol_tile * nz;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int ii = (int)(t % G.nci), k = G.kts + (int)((t / G.nci) % nz), j = G.jts + (int)(t / ((long)G.nci * nz));
+  const size_t q = G.at3(G.its + ii, k, j);
+  const float thresh = 1.0e-6f;
+  float cf = 0.f;
+  if (f_qi && f_qc) cf = __fadd_rn(qc[q], qi[q]) > thresh ? 1.f : 0.f;
+  else if (f_qc) cf = qc[q] > thresh ? 1.f : 0.f;
+  cldfra[q] = cf;
+}
+void launch_cal_cldfra2(const Geo &G, const float *qc, const float *qi, int f_qc, int f_qi, float *cldfra, cudaStream_t s) {
+  const long n = (long)G.ncol_tile * (G.kte - G.kts + 1);
+  k_cal_cldfra2<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(G, qc, qi, f_qc, f_qi, cldfra);
+  count_launch();
+}
+
+// ozn_time_int (module_radiation_driver.F:3993-4098): ozmixt(i,k,j) = ozmixm(i,k,j,nm) * fact1 + ozmixm(i,k,j,np) * fact2 for the
+// tile's (i, j) and all levsiz data levels; the month indices and weights come from the host (scalar date arithmetic).
+__global__ void __launch_bounds__(256) k_ozn_time_int(Geo G, int levsiz, const float *__restrict__ m0, const float *__restrict__ m1, float fact1,
+                                                      float fact2, float *__restrict__ ozmixt) {
+  const long n = (long)G.ncol_tile * levsiz;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int ii = (int)(t % G.nci), k = (int)((t / G.nci) % levsiz), j = G.jts + (int)(t / ((long)G.nci * levsiz));
+  const size_t q = (size_t)(G.its + ii - G.ims) + (size_t)G.ni * ((size_t)k + (size_t)levsiz * (size_t)(j - G.jms));
+  ozmixt[q] = __fadd_rn(__fmul_rn(m0[q], fact1), __fmul_rn(m1[q], fact2));
+}
+void launch_ozn_time_int(const Geo &G, int levsiz, const float *m0, const float *m1, float fact1, float fact2, float *ozmixt, cudaStream_t s) {
+  const long n = (long)G.ncol_tile * levsiz;
+  k_ozn_time_int<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(G, levsiz, m0, m1, fact1, fact2, ozmixt);
+  count_launch();
+}
+
+// ozn_p_int (module_radiation_driver.F:4100-4234): the data-level ozone interpolated linearly in pressure to the model levels,
+// top level first.  The reference walks a tile row with a shared starting level (kkstart = the smallest kupper of the row);
+// because the model pressure rises monotonically towards the surface every column finds the same bracket it would find from
+// its own kupper, so one thread per column carrying its own kupper reproduces it.  Above the data top the mixing ratio is
+// scaled by p / pin(1), below the data bottom it is held.  Unfused arithmetic, IEEE division.
+struct OznPin { float pin[ARC_OZN_MAXLEV]; };
+__global__ void __launch_bounds__(128) k_ozn_p_int(Geo G, int levsiz, OznPin P, const float *__restrict__ p, const float *__restrict__ ozmixt,
+                                                   float *__restrict__ o3vmr) {
+  const int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tc >= G.ncol_tile) return;
+  int i, j; G.ij(tc, i, j);
+  const size_t ob = (size_t)(i - G.ims) + (size_t)G.ni * (size_t)levsiz * (size_t)(j - G.jms);     // ozmixt(i, 1, j)
+  int kupper = 1;                                                                                     // 1-based, as in the reference
+  for (int k = G.kte; k >= G.kts; k--) {
+    const size_t q = G.at3(i, k, j);
+    const float pm = p[q];
+    for (int kk = kupper; kk <= levsiz - 1; kk++)
+      if (P.pin[kk - 1] < pm && pm <= P.pin[kk]) { kupper = kk; break; }
+    float o3;
+    if (pm < P.pin[0]) o3 = div_rn(__fmul_rn(ozmixt[ob], pm), P.pin[0]);
+    else if (pm > P.pin[levsiz - 1]) o3 = ozmixt[ob + (size_t)G.ni * (levsiz - 1)];
+    else {
+      const float dpu = __fsub_rn(pm, P.pin[kupper - 1]);
+      const float dpl = __fsub_rn(P.pin[kupper], pm);
+      o3 = div_rn(__fadd_rn(__fmul_rn(ozmixt[ob + (size_t)G.ni * (kupper - 1)], dpl), __fmul_rn(ozmixt[ob + (size_t)G.ni * kupper], dpu)),
+                  __fadd_rn(dpl, dpu));
+    }
+    o3vmr[q] = o3;
+  }
+}
+void launch_ozn_p_int(const Geo &G, int levsiz, const float *pin_host, const float *p, const float *ozmixt, float *o3vmr, cudaStream_t s) {
+  OznPin P;
+  for (int k = 0; k < ARC_OZN_MAXLEV; k++) P.pin[k] = k < levsiz ? pin_host[k] : 0.f;
+  k_ozn_p_int<<<(G.ncol_tile + 127) / 128, 128, 0, s>>>(G, levsiz, P, p, ozmixt, o3vmr);
+  count_launch();
+}
+
 // ------------------------------------------------------------------------------------------------------
 // LW column preparation.  One thread per column (all columns; LW has no day/night gate).
 __global__ void __launch_bounds__(128) k_lw_prep(LwArgs a) {

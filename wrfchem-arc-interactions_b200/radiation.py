@@ -259,6 +259,46 @@ class RadLib:
             if rc:
                 raise RadiationError(rc, "oracle cal_cldfra1")
 
+    def _driver_call(self, name, dims, arrays, args_lib, args_orc, types_lib, types_orc):
+        """Common plumbing of the radiation_driver pre-processing entry points: one memory space for all arrays, the product
+        library takes (dims, memspace, ...), the oracle (dims, ...)."""
+        d = abi.make_dims(dims) if isinstance(dims, dict) else dims
+        dev = [_is_device(v) for v in arrays if v is not None]
+        if any(dev) and not all(dev):
+            raise ValueError("mix of host and device arrays")
+        ms = abi.ARC_MEM_DEVICE if dev[0] else abi.ARC_MEM_HOST
+        fn = getattr(self.lib, ("arc_rad_" if self.prefix == "arc_rad_" else "arc_oracle_") + name)
+        fn.restype = C.c_int
+        if self.prefix == "arc_rad_":
+            fn.argtypes = [C.POINTER(abi.ArcDims), C.c_int] + types_lib
+            _sync_producers(arrays)
+            self.check(fn(C.byref(d), ms, *args_lib))
+        else:
+            fn.argtypes = [C.POINTER(abi.ArcDims)] + types_orc
+            rc = fn(C.byref(d), *args_orc)
+            if rc:
+                raise RadiationError(rc, "oracle " + name)
+
+    def cal_cldfra2(self, dims, CLDFRA, QC, QI, F_QC=True, F_QI=True):
+        """cal_cldfra2 of module_radiation_driver.F:2801-2874 (icloud = 2): CLDFRA = 1 where QC + QI > 1e-6, tile levels kts..kte."""
+        a = [_ptr(QC), _ptr(QI), int(bool(F_QC)), int(bool(F_QI)), _ptr(CLDFRA)]
+        t = [abi.c_fp, abi.c_fp, C.c_int, C.c_int, abi.c_fp]
+        self._driver_call("cal_cldfra2", dims, [CLDFRA, QC, QI], a, a, t, t)
+
+    def ozn_time_int(self, dims, julday, julian, ozmixm, ozmixt, levsiz, num_months):
+        """ozn_time_int of module_radiation_driver.F:3993-4098: ozmixm (num_months, jms:jme, levsiz, ims:ime in C order) ->
+        ozmixt (jms:jme, levsiz, ims:ime), linear in time between the bracketing mid-month days."""
+        a = [int(julday), float(julian), int(levsiz), int(num_months), _ptr(ozmixm), _ptr(ozmixt)]
+        t = [C.c_int, C.c_float, C.c_int, C.c_int, abi.c_fp, abi.c_fp]
+        self._driver_call("ozn_time_int", dims, [ozmixm, ozmixt], a, a, t, t)
+
+    def ozn_p_int(self, dims, p, pin, levsiz, ozmixt, o3vmr):
+        """ozn_p_int of module_radiation_driver.F:4100-4234: ozone on the data levels pin (host float32 array) -> o3vmr at p."""
+        pin = np.ascontiguousarray(pin, dtype=np.float32)
+        a = [_ptr(p), abi.fptr(pin), int(levsiz), _ptr(ozmixt), _ptr(o3vmr)]
+        t = [abi.c_fp, abi.c_fp, C.c_int, abi.c_fp, abi.c_fp]
+        self._driver_call("ozn_p_int", dims, [p, ozmixt, o3vmr], a, a, t, t)
+
     def optical_averaging(self, dims, mode, bins, alt, dz8w, outs, sigmag=None):
         """bins: list (one per size section, or per mode) of dicts {species_name: array, ..., "num": array}; a species name
         starts with its class (so4, no3, cl, nh4, na, oin, oc, bc, water), e.g. "oc_orgaro1j".  outs: dict with
