@@ -59,6 +59,9 @@ static constexpr LwK LWK[16] = {
     {888, 600, 848, 860, 864, 876, 884, NONE6, NONE6}};
 #undef NONE6
 constexpr int LW_SLICE_MAX = 2096;
+#ifndef LW_PF
+#define LW_PF 3
+#endif
 
 void upload_band_descs_lw(const HostTables &T) {
   cudaMemcpyToSymbol(c_lw, T.lw, sizeof(LwBandDesc) * 16);
@@ -739,6 +742,20 @@ __device__ __forceinline__ void lw_band_body(const LwArgs &a, const LwSmem &sm, 
 #pragma unroll
       for (int i = 0; i < LW_GMAX; i++) { if (i < ng) qn[i] = __ldcs(p); p += pcap; }
     }
+#if LW_PF > 0
+    // the records were written a whole downward sweep ago and come from HBM: lines LW_PF layers ahead are pulled into L2 so
+    // that the register prefetch above (one layer ahead) finds them there
+    if (lay + LW_PF < nlay) {
+      const float4 *p = rl + (size_t)LW_PF * rls;
+#pragma unroll
+      for (int i = 0; i < LW_GMAX; i++) { if (i < ng) asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); p += pcap; }
+    }
+    if (((lay + 1) & 31) != 0 && ((awc >> ((lay + 1) & 31)) & 1u)) {
+      const float4 *p = rlC + rls;
+#pragma unroll
+      for (int i = 0; i < LW_GMAX; i++) { if (i < ng) asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); p += pcap; }
+    }
+#endif
     if (icldlyr) {          // rad' = rad - rad X + Y
       const float4 *p = rlC;
 #pragma unroll
