@@ -57,6 +57,33 @@ def test_modal_vs_oracle(lib, orc, ktab):
     compare(og, oo, 30, loose=10.0)      # single-precision erf differences of neighbouring section edges
 
 
+def test_empty_and_ragged_sections(lib, orc, ktab):
+    """Edge cases of the sectional input: whole sections empty, points without any aerosol, one populated section, a single
+    species per section, and a tile whose point count is not a multiple of the 256-point block - against the oracle, and
+    tau = 0, omega = 1, g = 0 where nothing is there.  (The block's counting sort sees empty, single and odd-length buckets.)"""
+    dom = synth.make_domain(13, 7, 23, seed=43)                     # 2,093 points: 8 full blocks + a ragged one
+    setup(lib, orc, ktab, dom)
+    bins, alt, _ = synth.make_aerosol(dom, nbin=8)
+    for name in bins[2]:
+        bins[2][name] = np.zeros_like(bins[2][name])                 # an empty section
+    for name in bins[5]:
+        if name not in ("num", "so4"):
+            bins[5][name] = np.zeros_like(bins[5][name])             # a single-species section
+    for b in bins:
+        for name in b:
+            b[name][:, :, 3] = 0.0                                   # a column without aerosol
+            b[name][2, 5:9, :] = 0.0                                 # a slab of empty points
+    for b in bins[1:]:
+        for name in b:
+            b[name][:, :, 7] = 0.0                                   # a column with one populated section
+    og, oo = R.alloc_aer_outputs(dom, ext=True), R.alloc_aer_outputs(dom, ext=True)
+    lib.optical_averaging(dom["dims"], "sectional", bins, alt, dom["dz8w"], og)
+    orc.optical_averaging(dom["dims"], "sectional", bins, alt, dom["dz8w"], oo)
+    compare(og, oo, 23)
+    assert not og["tauaer400"][:, :23, 3].any() and np.all(og["waer400"][:, :23, 3] == 1.0) and not og["gaer400"][:, :23, 3].any()
+    assert not og["tauaerlw7"][2, 5:9, :].any() and og["tauaer400"][:, :23, 7].max() > 0
+
+
 def test_tables_vs_direct_mie(lib, orc, ktab):
     """Chebyshev-interpolated efficiencies against direct Mie sums at random sizes / refractive indices inside the table."""
     dom = synth.make_domain(4, 2, 10, seed=43)

@@ -683,6 +683,53 @@ def test_cal_cldfra2_and_ozone_interpolation_bit_exact(lib, orc, ktab):
         lib.ozn_p_int(odom["dims"], p, bad, levsiz, ta, oa)
 
 
+def extreme_domain():
+    """A 48 x 8 tile whose column groups sit on the edges of the input space: grazing and overhead sun, black and white
+    surfaces, conservative / absorbing / forward-peaked and very thick aerosol, no spectral slope, overcast decks with large
+    water paths and near-zero cloud fractions, very cold / very warm and very dry / saturated profiles, low emissivity."""
+    dom = synth.make_domain(48, 8, 40, seed=77, cloudy_frac=0.5, night_frac=0.0, all_day=True)
+    f32 = np.float32
+    col = lambda a, i: a[:, i] if a.ndim == 2 else a[:, :, i]            # (nj[, nk]) view of tile column i
+    for i, cz in enumerate((1e-4, 1e-3, 0.01, 1.0, 0.99999994, 0.5)):
+        dom["xcoszen"][:, i] = f32(cz)
+    dom["albedo"][:, 6] = 0.0; dom["albedo"][:, 7] = 1.0; dom["albedo"][:, 8] = f32(0.999)
+    aer = [k for k in dom if k.startswith("tauaer") and not k.startswith("tauaerlw")]
+    for k in aer:
+        dom[k][:, :, 9] *= f32(60.0)                                       # column AOD in the tens
+    for wl in (300, 400, 600, 999):
+        dom["waer%d" % wl][:, :, 10] = 1.0; dom["waer%d" % wl][:, :, 11] = 0.0
+        dom["gaer%d" % wl][:, :, 12] = f32(0.99); dom["gaer%d" % wl][:, :, 13] = 0.0
+        dom["tauaer%d" % wl][:, :, 14] = dom["tauaer400"][:, :, 14]       # Angstrom exponent 0
+        dom["tauaer%d" % wl][:, :20, 15] = 0.0                            # aerosol-free lower half
+    dom["tauaer300"][:, :, 16] = 0.0                                       # one wavelength without aerosol
+    for i in (17, 18):
+        dom["cldfra3d"][:, 2:30, i] = 1.0
+        dom["qc3d"][:, 2:15, i] = f32(2e-3 if i == 17 else 1e-6); dom["qi3d"][:, 15:30, i] = f32(5e-4 if i == 17 else 1e-7)
+        dom["qs3d"][:, 15:30, i] = f32(2e-4 if i == 17 else 0.0)
+    dom["cldfra3d"][:, 5:12, 19] = f32(1e-6); dom["qc3d"][:, 5:12, 19] = f32(1e-4)
+    dom["cldfra3d"][:, 5:12, 20] = f32(0.999999); dom["qc3d"][:, 5:12, 20] = f32(1e-4)
+    nk = dom["nk"]
+    for i, dt in ((21, -38.0), (22, 28.0)):                                # cold / warm: temperatures near the Planck table's ends
+        dom["t3d"][:, :nk, i] += f32(dt); dom["t8w"][:, :, i] += f32(dt); dom["tsk"][:, i] += f32(dt)
+    dom["qv3d"][:, :nk, 23] = f32(1e-9); dom["qv3d"][:, :nk, 24] *= f32(3.0)
+    dom["emiss"][:, 25] = f32(0.5); dom["emiss"][:, 26] = 1.0
+    dom["tsk"][:, 27] = f32(339.0); dom["tsk"][:, 28] = f32(161.0)
+    return dom
+
+
+def test_extreme_columns(lib, orc, ktab):
+    """Edge cases of the input space (the reference ships no tests; these are the domain's own corners): shortwave bit-exact,
+    longwave inside the tolerance, every output finite."""
+    dom = extreme_domain()
+    og, oo, tg, to = both("sw", lib, orc, dom, ktab, clean_atm_diag=1)
+    check_sw(dom, og, oo, tg, to)
+    assert all(np.isfinite(interior(dom, v)[..., :dom["nk"], :] if v.ndim == 3 else v).all() for v in og.values())
+    assert interior(dom, og["swdnb"])[:, 0].max() < 1.0                    # grazing sun: next to nothing arrives
+    og, oo, tg, to = both("lw", lib, orc, dom, ktab, clean_atm_diag=1)
+    check_lw(dom, lib, og, oo, tg, to)
+    assert all(np.isfinite(interior(dom, v)[..., :dom["nk"], :] if v.ndim == 3 else v).all() for v in og.values())
+
+
 def test_full_size_properties(lib, ktab):
     """BASELINE config C2 at full size (127,500 columns x 50 levels), checked through size-independent properties:
     energy bounds, clean == full where the aerosol is zero, clear == full in cloud-free columns, night gate."""
