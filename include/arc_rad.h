@@ -229,6 +229,13 @@ int  arc_rad_cal_cldfra1(const ArcDims *d, int memspace, const float *qv, const 
 /* cal_cldfra2 (module_radiation_driver.F:2801-2874; icloud = 2, DRV:1205): CLDFRA = 1 where QC + QI > 1e-6 (QC alone when
  * F_QI is false; 0 everywhere when F_QC is false), tile levels kts..kte. */
 int  arc_rad_cal_cldfra2(const ArcDims *d, int memspace, const float *qc, const float *qi, int f_qc, int f_qi, float *cldfra);
+/* cal_cldfra3 (module_radiation_driver.F:3140-3274 with find_cloudLayers / adjust_cloud* :3281-3599; icloud = 3, DRV:1228):
+ * CLDFRA(i,k,j) from relative humidity against a grid-size (gridkm) and land / ocean (XLAND) dependent threshold, fractional
+ * clouds removed above the diagnosed tropopause and in the well-mixed layer, then per cloud layer a made-up condensate
+ * profile ADDED to qc / qi (INOUT, as in the reference; the caller saves and restores qs, DRV:1217-1225).  rslf / rsif come from
+ * module_mp_thompson, which the reference repository does not contain: the published Flatau polynomials are used (unpinned). */
+int  arc_rad_cal_cldfra3(const ArcDims *d, int memspace, float *cldfra, const float *qv, float *qc, float *qi, const float *qs,
+                         const float *p, const float *t, const float *rho, const float *xland, float gridkm);
 /* ozn_time_int (module_radiation_driver.F:3993-4098; o3input = 2, DRV:1250): ozmixm(ims:ime, levsiz, jms:jme, num_months) ->
  * ozmixt(ims:ime, levsiz, jms:jme), linear in time between the mid-month days that bracket JULIAN + 1 (December-January wraps). */
 int  arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, const float *ozmixm,

@@ -158,6 +158,205 @@ int arc_oracle_cal_cldfra2(const ArcDims *d, const float *QC, const float *QI, i
   return 0;
 }
 
+// rslf / rsif of module_mp_thompson (WRF v3.9.1 phys/module_mp_thompson.F) - NOT in the reference repository: the published
+// Flatau et al. (1992) 8th-order polynomials of the saturation vapour pressure over water / ice as the Thompson scheme
+// codes them (X = MAX(-80, T - 273.16); e capped at 15 % of p; r = 0.622 e / (p - e)).  PARITY UNPINNED for these two
+// functions; cal_cldfra3 below is a line-by-line restatement of what IS in the reference.
+static float thompson_rslf(float P, float T) {
+  const float C0 = .611583699E03f, C1 = .444606896E02f, C2 = .143177157E01f, C3 = .264224321E-1f, C4 = .299291081E-3f, C5 = .203154182E-5f,
+              C6 = .702620698E-8f, C7 = .379534310E-11f, C8 = -.321582393E-13f;
+  const float X = std::max(-80.f, T - 273.16f);
+  float ESL = C0 + X * (C1 + X * (C2 + X * (C3 + X * (C4 + X * (C5 + X * (C6 + X * (C7 + X * C8)))))));
+  ESL = std::min(ESL, P * 0.15f);
+  return .622f * ESL / (P - ESL);
+}
+static float thompson_rsif(float P, float T) {
+  const float C0 = .609868993E03f, C1 = .499320233E02f, C2 = .184672631E01f, C3 = .402737184E-1f, C4 = .565392987E-3f, C5 = .521693933E-5f,
+              C6 = .307839583E-7f, C7 = .105785160E-9f, C8 = .161444444E-12f;
+  const float X = std::max(-80.f, T - 273.16f);
+  float ESI = C0 + X * (C1 + X * (C2 + X * (C3 + X * (C4 + X * (C5 + X * (C6 + X * (C7 + X * C8)))))));
+  ESI = std::min(ESI, P * 0.15f);
+  return .622f * ESI / (P - ESI);
+}
+
+namespace {
+// 1-based views (kts..kte) as the Fortran declares its 1-D work arrays
+struct Col1D {
+  std::vector<float> v; int kts;
+  Col1D(int kts_, int kte) : v(kte - kts_ + 1, 0.f), kts(kts_) {}
+  float &operator()(int k) { return v[k - kts]; }
+};
+// adjust_cloudIce, module_radiation_driver.F:3472-3512 (kmid and iwp_exists are computed there and never used)
+void adjust_cloudIce(Col1D &cfr, Col1D &qi, Col1D &qs, Col1D &qvs, Col1D &T, Col1D &Rho, Col1D &dz, float entr, int k1, int k2) {
+  (void)qs; (void)Rho;
+  float tdz = 0.f;
+  for (int k = k1; k <= k2; k++) tdz = tdz + dz(k);
+  const float max_iwc = std::fabs(qvs(k2 - 1) - qvs(k1));
+  float this_dz = 0.0f;
+  for (int k = k1; k <= k2; k++) {
+    if (k == k1) this_dz = this_dz + 0.5f * dz(k); else this_dz = this_dz + dz(k);
+    const float this_iwc = max_iwc * this_dz / tdz;
+    const float iwc = std::max(1.E-6f, this_iwc * (1.f - entr));
+    if (cfr(k) > 0.01f && cfr(k) < 0.99f && T(k) >= 203.16f) qi(k) = qi(k) + 0.1f * cfr(k) * iwc;
+    else if (qi(k) < 1.E-5f && cfr(k) >= 0.99f && T(k) >= 203.16f) qi(k) = qi(k) + 0.01f * iwc;
+  }
+}
+// adjust_cloudH2O, module_radiation_driver.F:3516-3555
+void adjust_cloudH2O(Col1D &cfr, Col1D &qc, Col1D &qvs, Col1D &T, Col1D &dz, float entr, int k1, int k2) {
+  float tdz = 0.f;
+  for (int k = k1; k <= k2; k++) tdz = tdz + dz(k);
+  const float max_lwc = std::fabs(qvs(k2 - 1) - qvs(k1));
+  float this_dz = 0.0f;
+  for (int k = k1; k <= k2; k++) {
+    if (k == k1) this_dz = this_dz + 0.5f * dz(k); else this_dz = this_dz + dz(k);
+    const float this_lwc = max_lwc * this_dz / tdz;
+    const float lwc = std::max(1.E-6f, this_lwc * (1.f - entr));
+    if (cfr(k) > 0.01f && cfr(k) < 0.99f && T(k) < 298.16f && T(k) >= 253.16f) qc(k) = qc(k) + cfr(k) * cfr(k) * lwc;
+    else if (cfr(k) >= 0.99f && qc(k) < 1.E-5f && T(k) < 298.16f && T(k) >= 253.16f) qc(k) = qc(k) + 0.1f * lwc;
+  }
+}
+// adjust_cloudFinal, module_radiation_driver.F:3562-3599
+void adjust_cloudFinal(Col1D &cfr, Col1D &qc, Col1D &qi, Col1D &Rho, Col1D &dz, int kts, int k_tropo) {
+  float lwp = 0.f, iwp = 0.f;
+  for (int k = kts; k <= k_tropo; k++)
+    if (cfr(k) > 0.0f) { lwp = lwp + qc(k) * Rho(k) * dz(k); iwp = iwp + qi(k) * Rho(k) * dz(k); }
+  if (lwp > 1.5f) { const float xfac = 1.f / lwp; for (int k = kts; k <= k_tropo; k++) if (cfr(k) > 0.01f && cfr(k) < 0.99f) qc(k) = qc(k) * xfac; }
+  if (iwp > 1.5f) { const float xfac = 1.f / iwp; for (int k = kts; k <= k_tropo; k++) if (cfr(k) > 0.01f && cfr(k) < 0.99f) qi(k) = qi(k) * xfac; }
+}
+// find_cloudLayers, module_radiation_driver.F:3281-3468.  The second search starts at k_m12C + 2, which the Fortran does not
+// bound by kte; a level above kte is read as cloud-free here (the product does the same).
+void find_cloudLayers(Col1D &qvs1d, Col1D &cfr1d, Col1D &T1d, Col1D &P1d, Col1D &R1d, float entrmnt, Col1D &qc1d, Col1D &qi1d, Col1D &qs1d,
+                      int kts, int kte) {
+  Col1D theta(kts, kte), dz(kts, kte);
+  int k, k2, k_tropo, k_m12C = 0, k_m40C = 0, k_cldb, k_cldt, kbot;
+  bool in_cloud;
+  for (k = kte; k >= kts; k--) {
+    theta(k) = T1d(k) * powf(100000.0f / P1d(k), 287.05f / 1004.f);
+    if (T1d(k) - 273.16f > -40.0f && P1d(k) > 7000.0f) k_m40C = std::max(k_m40C, k);
+    if (T1d(k) - 273.16f > -12.0f && P1d(k) > 10000.0f) k_m12C = std::max(k_m12C, k);
+  }
+  if (k_m40C <= kts) k_m40C = kts;
+  if (k_m12C <= kts) k_m12C = kts;
+  float Z2 = 44307.692f * (1.0f - powf(P1d(kte) / 101325.f, 0.190f));
+  for (k = kte - 1; k >= kts; k--) {
+    const float Z1 = 44307.692f * (1.0f - powf(P1d(k) / 101325.f, 0.190f));
+    dz(k + 1) = Z2 - Z1;
+    Z2 = Z1;
+  }
+  dz(kts) = dz(kts + 1);
+  for (k = kte - 3; k >= kts; k--) {
+    const float theta1 = theta(k), theta2 = theta(k + 2);
+    const float ht1 = 44307.692f * (1.0f - powf(P1d(k) / 101325.f, 0.190f));
+    const float ht2 = 44307.692f * (1.0f - powf(P1d(k + 2) / 101325.f, 0.190f));
+    if ((((theta2 - theta1) / (ht2 - ht1)) < 10.f / 1500.f) && (ht1 < 19000.f) && (ht1 > 4000.f)) break;
+  }
+  k_tropo = std::max(kts + 2, k + 2);
+  for (k = k_tropo + 1; k <= kte; k++)
+    if (cfr1d(k) > 0.0f && cfr1d(k) < 0.999f) cfr1d(k) = 0.f;
+  kbot = kts + 2;
+  for (k = kbot; k <= k_m12C; k++)
+    if ((theta(k) - theta(k - 1)) > 0.05E-3f * dz(k)) break;
+  kbot = std::max(kts + 1, k - 2);
+  for (k = kts; k <= kbot; k++)
+    if (cfr1d(k) > 0.0f && cfr1d(k) < 0.999f) cfr1d(k) = 0.f;
+  auto CFR = [&](int kk) { return kk <= kte ? cfr1d(kk) : 0.f; };
+  k_cldb = k_tropo;
+  in_cloud = false;
+  k = k_tropo;
+  while (!in_cloud && k > k_m12C) {
+    k_cldt = 0;
+    if (CFR(k) >= 0.01f) { in_cloud = true; k_cldt = std::max(k_cldt, k); }
+    if (in_cloud) {
+      for (k2 = k_cldt - 1; k2 >= k_m12C; k2--)
+        if (cfr1d(k2) < 0.01f || k2 == k_m12C) { k_cldb = k2 + 1; break; }
+      in_cloud = false;
+    }
+    if ((k_cldt - k_cldb + 1) >= 2) {
+      adjust_cloudIce(cfr1d, qi1d, qs1d, qvs1d, T1d, R1d, dz, entrmnt, k_cldb, k_cldt);
+      k = k_cldb;
+    } else {
+      if (cfr1d(k_cldb) > 0.f && qi1d(k_cldb) < 1.E-6f) qi1d(k_cldb) = 1.E-5f * cfr1d(k_cldb);
+    }
+    k = k - 1;
+  }
+  k_cldb = k_tropo;
+  in_cloud = false;
+  k = k_m12C + 2;
+  while (!in_cloud && k > kbot) {
+    k_cldt = 0;
+    if (CFR(k) >= 0.01f) { in_cloud = true; k_cldt = std::max(k_cldt, k); }
+    if (in_cloud) {
+      for (k2 = k_cldt - 1; k2 >= kbot; k2--)
+        if (cfr1d(k2) < 0.01f || k2 == kbot) { k_cldb = k2 + 1; break; }
+      in_cloud = false;
+    }
+    if ((k_cldt - k_cldb + 1) >= 2) {
+      adjust_cloudH2O(cfr1d, qc1d, qvs1d, T1d, dz, entrmnt, k_cldb, k_cldt);
+      k = k_cldb;
+    } else {
+      if (cfr1d(k_cldb) > 0.f && qc1d(k_cldb) < 1.E-6f) qc1d(k_cldb) = 1.E-5f * cfr1d(k_cldb);
+    }
+    k = k - 1;
+  }
+  adjust_cloudFinal(cfr1d, qc1d, qi1d, R1d, dz, kts, k_tropo);
+}
+}  // namespace
+
+// cal_cldfra3, module_radiation_driver.F:3140-3274 (icloud = 3; G. Thompson's Sundqvist-type scheme); qc and qi are INOUT
+int arc_oracle_cal_cldfra3(const ArcDims *d, float *CLDFRA, const float *qv, float *qc, float *qi, const float *qs, const float *p, const float *t,
+                           const float *rho, const float *XLAND, float gridkm) {
+  const int ni = d->ime - d->ims + 1, nk = d->kme - d->kms + 1;
+  const int kts = d->kts, kte = d->kte;
+  if (kte - kts < 4) return -1;
+  auto Q3 = [&](int i, int k, int j) { return (size_t)(i - d->ims) + (size_t)ni * ((size_t)(k - d->kms) + (size_t)nk * (size_t)(j - d->jms)); };
+  auto Q2 = [&](int i, int j) { return (size_t)(i - d->ims) + (size_t)ni * (size_t)(j - d->jms); };
+  const float RH_00L = 0.7f + sqrtf(1.f / (25.0f + gridkm * gridkm * gridkm));
+  const float RH_00O = 0.81f + sqrtf(1.f / (50.0f + gridkm * gridkm * gridkm));
+  std::vector<float> qvsat((size_t)ni * nk * (d->jme - d->jms + 1), 0.f);
+  for (int j = d->jts; j <= d->jte; j++)
+    for (int k = kts; k <= kte; k++)
+      for (int i = d->its; i <= d->ite; i++) {
+        const size_t q = Q3(i, k, j);
+        CLDFRA[q] = 0.0f;
+        if (qc[q] > 1.E-6f || qi[q] >= 1.E-7f || qs[q] > 1.E-5f) {
+          CLDFRA[q] = 1.0f;
+          qvsat[q] = qv[q];
+        } else {
+          const float TK = t[q], TC = TK - 273.16f;
+          const float qvsw = thompson_rslf(p[q], TK), qvsi = thompson_rsif(p[q], TK);
+          if (TC >= -12.0f) qvsat[q] = qvsw;
+          else if (TC < -20.0f) qvsat[q] = qvsi;
+          else qvsat[q] = qvsw - (qvsw - qvsi) * (-12.0f - TC) / (-12.0f + 20.f);
+          float RHUM = std::max(0.01f, std::min(qv[q] / qvsat[q], 0.9999f));
+          const float RH_00 = (XLAND[Q2(i, j)] - 1.5f) > 0.f ? RH_00O : RH_00L;
+          if (TC >= -12.0f) {
+            RHUM = std::min(0.999f, RHUM);
+            CLDFRA[q] = std::max(0.0f, 1.0f - sqrtf((1.0f - RHUM) / (1.f - RH_00)));
+          } else if (TC < -12.f && TC > -70.f && RHUM > RH_00L) {
+            RHUM = std::max(0.01f, std::min(qv[q] / qvsat[q], 1.0f - 1.E-6f));
+            CLDFRA[q] = std::max(0.f, 1.0f - sqrtf((1.0f - RHUM) / (1.0f - RH_00L)));
+          }
+          CLDFRA[q] = std::min(0.90f, CLDFRA[q]);
+        }
+      }
+  Col1D qvs1d(kts, kte), cfr1d(kts, kte), T1d(kts, kte), P1d(kts, kte), R1d(kts, kte), qc1d(kts, kte), qi1d(kts, kte), qs1d(kts, kte);
+  for (int j = d->jts; j <= d->jte; j++)
+    for (int i = d->its; i <= d->ite; i++) {
+      const float entrmnt = 0.5f;
+      for (int k = kts; k <= kte; k++) {
+        const size_t q = Q3(i, k, j);
+        qvs1d(k) = qvsat[q]; cfr1d(k) = CLDFRA[q]; T1d(k) = t[q]; P1d(k) = p[q]; R1d(k) = rho[q];
+        qc1d(k) = qc[q]; qi1d(k) = qi[q]; qs1d(k) = qs[q];
+      }
+      find_cloudLayers(qvs1d, cfr1d, T1d, P1d, R1d, entrmnt, qc1d, qi1d, qs1d, kts, kte);
+      for (int k = kts; k <= kte; k++) {
+        const size_t q = Q3(i, k, j);
+        CLDFRA[q] = cfr1d(k); qc[q] = qc1d(k); qi[q] = qi1d(k);
+      }
+    }
+  return 0;
+}
+
 // ozn_time_int, module_radiation_driver.F:3993-4098 (line by line; ozncyc = .true.)
 int arc_oracle_ozn_time_int(const ArcDims *d, int julday, float JULIAN, int levsiz, int num_months, const float *ozmixm, float *ozmixt) {
   (void)julday; (void)num_months;

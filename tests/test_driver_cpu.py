@@ -158,3 +158,56 @@ def test_ozn_p_int_oracle(orc):
             want[top] = ozt[j, 0, i] * pm[top] / pin[0]
             assert np.allclose(o3[j, :nk, i], want, rtol=3e-6, atol=0), (j, i)
     assert (p[:, :nk, :] < pin[0]).any() and (p[:, :nk, :] > pin[-1]).any()
+
+
+def cldfra3_case(ni=24, nj=6, nk=40, seed=21):
+    from wrfchem_arc_interactions_b200 import synth
+    dom = synth.make_domain(ni, nj, nk, seed=seed, cloudy_frac=0.4)
+    rng = np.random.default_rng(seed)
+    qv = dom["qv3d"].copy()
+    qv[:, :, 5] = np.float32(1e-9)                                  # a dry column
+    qv[:, 8:20, 6] *= np.float32(1.6)                               # a deep moist layer: fractional cloud decks
+    qv[:, 3:30, 7] *= np.float32(1.25)
+    return dom, np.ascontiguousarray(qv)
+
+
+def test_cal_cldfra3_oracle(orc):
+    """cal_cldfra3 (module_radiation_driver.F:3140-3274, find_cloudLayers / adjust_cloud* :3281-3599) restated in the oracle:
+    resolved condensate -> 1; elsewhere 1 - sqrt((1 - RH) / (1 - RH_00)) capped at 0.9 with the grid-size and land / ocean
+    dependent threshold, checked in closed form with the Flatau saturation polynomials; no fractional cloud in the two lowest
+    levels; qc / qi only ever gain (sub-grid condensate of the cloud layers found), qs untouched; a dry column stays clear."""
+    dom, qv = cldfra3_case()
+    nk = dom["nk"]
+    qc, qi, qs = dom["qc3d"].copy(), dom["qi3d"].copy(), dom["qs3d"].copy()
+    cf = np.full(qc.shape, -3.0, np.float32)
+    gridkm = 12.0
+    orc.cal_cldfra3(dom["dims"], cf, qv, qc, qi, qs, dom["p3d"], dom["t3d"], dom["rho3d"], dom["xland"], gridkm)
+    tile = (slice(None), slice(0, nk), slice(None))
+    c = cf[tile]
+    assert np.all(cf[:, nk, :] == -3.0) and np.array_equal(qs, dom["qs3d"])
+    resolved = (dom["qc3d"][tile] > 1e-6) | (dom["qi3d"][tile] >= 1e-7) | (dom["qs3d"][tile] > 1e-5)
+    assert np.all(c[resolved] == 1.0) and np.all((c == 0) | (c == 1) | ((c > 0) & (c <= np.float32(0.9))))
+    frac = (c > 0) & (c < 1)
+    assert frac.sum() > 50 and not frac[:, :2, :].any()            # kbot >= kts + 1: the two lowest levels never hold fractional cloud
+    assert np.all(qc[tile] >= dom["qc3d"][tile]) and np.all(qi[tile] >= dom["qi3d"][tile])
+    assert (qc[tile] > dom["qc3d"][tile]).any() and (qi[tile] > dom["qi3d"][tile]).any()
+    grew = (qc[tile] > dom["qc3d"][tile]) | (qi[tile] > dom["qi3d"][tile])
+    assert np.all(c[grew] > 0)                                      # condensate is only made up where there is cloud fraction
+    assert not c[:, :, 5][~resolved[:, :, 5]].any()                 # the dry column
+
+    def flatau(tk, ice):
+        w = [.611583699E03, .444606896E02, .143177157E01, .264224321E-1, .299291081E-3, .203154182E-5, .702620698E-8, .379534310E-11, -.321582393E-13]
+        i = [.609868993E03, .499320233E02, .184672631E01, .402737184E-1, .565392987E-3, .521693933E-5, .307839583E-7, .105785160E-9, .161444444E-12]
+        x = max(-80.0, tk - 273.16)
+        return sum(cc * x ** n for n, cc in enumerate(i if ice else w))
+    assert abs(flatau(293.16, False) - 2339.0) < 5.0 and abs(flatau(253.16, True) - 103.2) < 0.5       # Pa, textbook values
+    rh00 = {1.0: 0.7 + np.sqrt(1.0 / (25.0 + gridkm ** 3)), 2.0: 0.81 + np.sqrt(1.0 / (50.0 + gridkm ** 3))}
+    checked = 0
+    for jj, kk, ii in zip(*np.nonzero(frac & (dom["t3d"][tile] > 262.0))):
+        tk, pp = float(dom["t3d"][jj, kk, ii]), float(dom["p3d"][jj, kk, ii])
+        es = min(flatau(tk, False), 0.15 * pp)
+        rh = min(max(float(qv[jj, kk, ii]) / (0.622 * es / (pp - es)), 0.01), 0.999)
+        want = min(0.9, max(0.0, 1.0 - np.sqrt((1.0 - rh) / (1.0 - rh00[float(dom["xland"][jj, ii])]))))
+        assert abs(float(c[jj, kk, ii]) - want) < 3e-4, (jj, kk, ii)
+        checked += 1
+    assert checked > 20

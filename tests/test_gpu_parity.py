@@ -683,6 +683,40 @@ def test_cal_cldfra2_and_ozone_interpolation_bit_exact(lib, orc, ktab):
         lib.ozn_p_int(odom["dims"], p, bad, levsiz, ta, oa)
 
 
+def test_cal_cldfra3_bit_exact(lib, orc, ktab):
+    """cal_cldfra3 on the device (DRV:3140-3274 + find_cloudLayers / adjust_cloud* DRV:3281-3599, icloud = 3)
+    against the oracle's line-by-line restatement: CLDFRA and the INOUT qc / qi bit-exact, host and device arrays, several
+    grid sizes (the RH threshold depends on it)."""
+    import torch
+    from test_driver_cpu import cldfra3_case
+    for seed, gridkm in ((21, 12.0), (22, 3.0), (23, 36.0)):
+        dom, qv = cldfra3_case(ni=40, nj=9, nk=40, seed=seed)
+        init(lib, dom, ktab)
+        args = lambda qc, qi, cf: (dom["dims"], cf, qv, qc, qi, dom["qs3d"], dom["p3d"], dom["t3d"], dom["rho3d"], dom["xland"], gridkm)
+        a = [dom["qc3d"].copy(), dom["qi3d"].copy(), np.full(qv.shape, -3.0, np.float32)]
+        b = [dom["qc3d"].copy(), dom["qi3d"].copy(), np.full(qv.shape, -3.0, np.float32)]
+        lib.cal_cldfra3(*args(*a)); orc.cal_cldfra3(*args(*b))
+        for x, y, name in zip(a, b, ("qc", "qi", "cldfra")):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (name, gridkm, int((x != y).sum()))
+        assert np.all(a[2][:, 40] == -3.0) and (a[0] > dom["qc3d"]).any() and (a[1] > dom["qi3d"]).any()
+        dv = {k: torch.from_numpy(v).cuda() for k, v in dom.items() if isinstance(v, np.ndarray) and v.ndim >= 2}
+        dqc, dqi, dcf = dv["qc3d"].clone(), dv["qi3d"].clone(), torch.full(qv.shape, -3.0, dtype=torch.float32, device="cuda")
+        lib.cal_cldfra3(dom["dims"], dcf, torch.from_numpy(qv).cuda(), dqc, dqi, dv["qs3d"], dv["p3d"], dv["t3d"], dv["rho3d"], dv["xland"], gridkm)
+        for x, y in zip((dqc, dqi, dcf), b):
+            assert np.array_equal(x.cpu().numpy().view(np.uint32), y.view(np.uint32))
+    # halo: memory cells outside the tile keep the caller's values
+    dom = synth.make_domain(20, 7, 40, seed=24, halo=2)
+    init(lib, dom, ktab)
+    qc, qi, cf = dom["qc3d"].copy(), dom["qi3d"].copy(), np.full(dom["t3d"].shape, -3.0, np.float32)
+    qc2, qi2, cf2 = qc.copy(), qi.copy(), cf.copy()
+    fin = lambda x: np.nan_to_num(x, nan=1.0)                     # the synthetic halo holds NaN
+    common = (dom["qs3d"], dom["p3d"], dom["t3d"], dom["rho3d"], dom["xland"], 9.0)
+    lib.cal_cldfra3(dom["dims"], cf, dom["qv3d"], qc, qi, *common)
+    orc.cal_cldfra3(dom["dims"], cf2, dom["qv3d"], qc2, qi2, *common)
+    assert np.array_equal(fin(cf).view(np.uint32), fin(cf2).view(np.uint32)) and np.array_equal(fin(qc).view(np.uint32), fin(qc2).view(np.uint32))
+    assert np.array_equal(fin(qi).view(np.uint32), fin(qi2).view(np.uint32)) and np.all(cf[:2] == -3.0) and np.all(cf[:, :, :2] == -3.0)
+
+
 def extreme_domain():
     """A 48 x 8 tile whose column groups sit on the edges of the input space: grazing and overhead sun, black and white
     surfaces, conservative / absorbing / forward-peaked and very thick aerosol, no spectral slope, overcast decks with large

@@ -1563,6 +1563,36 @@ int arc_rad_cal_cldfra2(const ArcDims *d, int memspace, const float *qc, const f
   return 0;
 }
 
+// cal_cldfra3 (module_radiation_driver.F:3140-3274, called for icloud = 3 at DRV:1228): G. Thompson's cloud-fraction scheme.
+// CLDFRA is written, QC and QI are INOUT (the scheme adds sub-grid condensate to the fractional layers it finds), QS is read.
+int arc_rad_cal_cldfra3(const ArcDims *d, int memspace, float *cldfra, const float *qv, float *qc, float *qi, const float *qs, const float *p,
+                        const float *t, const float *rho, const float *xland, float gridkm) {
+  if (!g.ready) { g.err = "arc_rad_cal_cldfra3: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !cldfra || !qv || !qc || !qi || !qs || !p || !t || !rho || !xland) {
+    g.err = "Can not use icloud = 3 option, missing QC or QI field.";       // the reference's message (DRV:1236) covers the null case
+    return ARC_ERR_BAD_ARG;
+  }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if (d->kte - d->kts < 4) { g.err = "arc_rad_cal_cldfra3: needs at least 5 levels"; return ARC_ERR_BAD_ARG; }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const size_t n3 = G.n3(), n2 = G.n2();
+  const float *dqv, *dqs, *dp, *dt, *drho, *dxl;
+  float *dcf, *dqc, *dqi;
+  if ((rc = in_arr(memspace, qv, n3, &dqv)) || (rc = in_arr(memspace, qs, n3, &dqs)) || (rc = in_arr(memspace, p, n3, &dp)) ||
+      (rc = in_arr(memspace, t, n3, &dt)) || (rc = in_arr(memspace, rho, n3, &drho)) || (rc = in_arr(memspace, xland, n2, &dxl))) return rc;
+  if ((rc = out_arr(memspace, cldfra, n3, &dcf)) || (rc = out_arr(memspace, qc, n3, &dqc)) || (rc = out_arr(memspace, qi, n3, &dqi))) return rc;
+  void *w[3];
+  for (int q = 0; q < 3; q++) if ((rc = stage_slot(n3 * 4, &w[q]))) return rc;
+  launch_cal_cldfra3(G, dcf, dqv, dqc, dqi, dqs, dp, dt, drho, dxl, gridkm, (float *)w[0], (float *)w[1], (float *)w[2], g.stream);
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ozn_time_int (module_radiation_driver.F:3993-4098; o3input = 2, DRV:1250): the monthly CAM ozone climatology interpolated in
 // time to the model day.  The date arithmetic (which two months, which weights) is the reference's scalar code in single
 // precision, on the host; the blend of the two months runs on the device.

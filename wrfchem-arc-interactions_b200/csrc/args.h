@@ -199,6 +199,8 @@ void launch_lw_prep(const LwArgs &a, cudaStream_t s);
 void launch_cal_cldfra1(const Geo &G, const float *qv, const float *qc, const float *qi, const float *qs, int f_qv, int f_qc, int f_qi, int f_qs,
                         const float *t_phy, const float *p_phy, const float *f_ice_phy, int mp_physics, float *cldfra, int *flag, cudaStream_t s);
 constexpr int ARC_OZN_MAXLEV = 128;      // data levels of the ozone climatology passed by value to the kernel (CAM: 59)
+void launch_cal_cldfra3(const Geo &G, float *cldfra, const float *qv, float *qc, float *qi, const float *qs, const float *p, const float *t,
+                        const float *rho, const float *xland, float gridkm, float *qvsat, float *theta, float *dz, cudaStream_t s);
 void launch_cal_cldfra2(const Geo &G, const float *qc, const float *qi, int f_qc, int f_qi, float *cldfra, cudaStream_t s);
 void launch_ozn_time_int(const Geo &G, int levsiz, const float *m0, const float *m1, float fact1, float fact2, float *ozmixt, cudaStream_t s);
 void launch_ozn_p_int(const Geo &G, int levsiz, const float *pin_host, const float *p, const float *ozmixt, float *o3vmr, cudaStream_t s);

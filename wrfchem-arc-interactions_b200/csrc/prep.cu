@@ -699,6 +699,174 @@ void launch_cal_cldfra2(const Geo &G, const float *qc, const float *qi, int f_qc
   count_launch();
 }
 
+// cal_cldfra3 (module_radiation_driver.F:3140-3274; icloud = 3, G. Thompson's Sundqvist-type scheme) in two kernels.
+//   k_cldfra3_cell    one thread per cell: first-guess cloud fraction from RH against a grid-size dependent threshold (land /
+//                     ocean), the saturation mixing ratio qvsat it used, and theta of find_cloudLayers.
+//   k_cldfra3_column  one thread per column: find_cloudLayers (DRV:3281-3468) with adjust_cloudIce / adjust_cloudH2O /
+//                     adjust_cloudFinal (DRV:3472-3599), working in place on CLDFRA, qc, qi (INOUT in the reference) with the
+//                     1-D work arrays theta, dz, qvsat in global scratch, lanes = neighbouring columns.
+// rslf / rsif belong to module_mp_thompson, which is not in the reference repository: the published Flatau et al. (1992)
+// polynomials as the Thompson scheme codes them (parity unpinned for these two functions).  Unfused arithmetic, glibc **.
+__device__ __forceinline__ float thompson_rs(float P, float T, bool ice) {
+  const float W[9] = {.611583699E03f, .444606896E02f, .143177157E01f, .264224321E-1f, .299291081E-3f, .203154182E-5f, .702620698E-8f,
+                      .379534310E-11f, -.321582393E-13f};
+  const float I[9] = {.609868993E03f, .499320233E02f, .184672631E01f, .402737184E-1f, .565392987E-3f, .521693933E-5f, .307839583E-7f,
+                      .105785160E-9f, .161444444E-12f};
+  const float X = fmaxf(-80.f, T - 273.16f);
+  float es = ice ? I[8] : W[8];
+#pragma unroll
+  for (int n = 7; n >= 0; n--) es = (ice ? I[n] : W[n]) + X * es;
+  es = fminf(es, P * 0.15f);
+  return .622f * es / (P - es);
+}
+struct Cldfra3Args {
+  Geo geo;
+  const float *qv, *qs, *p, *t, *rho, *xland;
+  float *qc, *qi, *cldfra;
+  float *qvsat, *theta, *dz;          // scratch, (i,k,j) like the fields
+  float rh_00l, rh_00o;
+};
+__global__ void __launch_bounds__(256) k_cldfra3_cell(Cldfra3Args a) {
+  const Geo &G = a.geo;
+  const int nz = G.kte - G.kts + 1;
+  const long n = (long)G.ncol_tile * nz;
+  const long tq = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tq >= n) return;
+  const int ii = (int)(tq % G.nci), k = G.kts + (int)((tq / G.nci) % nz), j = G.jts + (int)(tq / ((long)G.nci * nz));
+  const size_t q = G.at3(G.its + ii, k, j);
+  const float TK = a.t[q], P = a.p[q], qv = a.qv[q];
+  a.theta[q] = TK * glm::powf_(100000.0f / P, 287.05f / 1004.f);
+  float cf = 0.0f, qvs;
+  if (a.qc[q] > 1.E-6f || a.qi[q] >= 1.E-7f || a.qs[q] > 1.E-5f) { cf = 1.0f; qvs = qv; }
+  else {
+    const float TC = TK - 273.16f;
+    const float qvsw = thompson_rs(P, TK, false), qvsi = thompson_rs(P, TK, true);
+    if (TC >= -12.0f) qvs = qvsw;
+    else if (TC < -20.0f) qvs = qvsi;
+    else qvs = qvsw - (qvsw - qvsi) * (-12.0f - TC) / (-12.0f + 20.f);
+    float RHUM = fmaxf(0.01f, fminf(qv / qvs, 0.9999f));
+    const float RH_00 = (a.xland[G.at2(G.its + ii, j)] - 1.5f) > 0.f ? a.rh_00o : a.rh_00l;
+    if (TC >= -12.0f) {
+      RHUM = fminf(0.999f, RHUM);
+      cf = fmaxf(0.0f, 1.0f - sqrtf((1.0f - RHUM) / (1.f - RH_00)));
+    } else if (TC < -12.f && TC > -70.f && RHUM > a.rh_00l) {
+      RHUM = fmaxf(0.01f, fminf(qv / qvs, 1.0f - 1.E-6f));
+      cf = fmaxf(0.f, 1.0f - sqrtf((1.0f - RHUM) / (1.0f - a.rh_00l)));
+    }
+    cf = fminf(0.90f, cf);
+  }
+  a.cldfra[q] = cf;
+  a.qvsat[q] = qvs;
+}
+__global__ void __launch_bounds__(128) k_cldfra3_column(Cldfra3Args a) {
+  const Geo &G = a.geo;
+  const int tc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tc >= G.ncol_tile) return;
+  int i, j; G.ij(tc, i, j);
+  const int kts = G.kts, kte = G.kte;
+  const size_t q0 = G.at3(i, kts, j), ks = (size_t)G.ni;          // level stride
+  auto at = [&](int k) { return q0 + (size_t)(k - kts) * ks; };
+#define CFR(k) a.cldfra[at(k)]
+#define QC1(k) a.qc[at(k)]
+#define QI1(k) a.qi[at(k)]
+#define QVS(k) a.qvsat[at(k)]
+#define T1(k) a.t[at(k)]
+#define P1(k) a.p[at(k)]
+#define R1(k) a.rho[at(k)]
+#define TH(k) a.theta[at(k)]
+#define DZ(k) a.dz[at(k)]
+  const float entr = 0.5f;
+  auto height = [&](int k) { return 44307.692f * (1.0f - glm::powf_(P1(k) / 101325.f, 0.190f)); };
+  int k, k2, k_m12C = 0, k_m40C = 0, k_cldb, k_cldt, kbot;
+  for (k = kte; k >= kts; k--) {
+    if (T1(k) - 273.16f > -40.0f && P1(k) > 7000.0f) k_m40C = max(k_m40C, k);
+    if (T1(k) - 273.16f > -12.0f && P1(k) > 10000.0f) k_m12C = max(k_m12C, k);
+  }
+  if (k_m40C <= kts) k_m40C = kts;
+  if (k_m12C <= kts) k_m12C = kts;
+  float Z2 = height(kte);
+  for (k = kte - 1; k >= kts; k--) { const float Z1 = height(k); DZ(k + 1) = Z2 - Z1; Z2 = Z1; }
+  DZ(kts) = DZ(kts + 1);
+  for (k = kte - 3; k >= kts; k--) {      // tropopause: d(theta)/dz below 10 K per 1500 m over three levels, between 4 and 19 km
+    const float ht1 = height(k), ht2 = height(k + 2);
+    if ((((TH(k + 2) - TH(k)) / (ht2 - ht1)) < 10.f / 1500.f) && (ht1 < 19000.f) && (ht1 > 4000.f)) break;
+  }
+  const int k_tropo = max(kts + 2, k + 2);
+  for (k = k_tropo + 1; k <= kte; k++) { const float c = CFR(k); if (c > 0.0f && c < 0.999f) CFR(k) = 0.f; }
+  kbot = kts + 2;
+  for (k = kbot; k <= k_m12C; k++)
+    if ((TH(k) - TH(k - 1)) > 0.05E-3f * DZ(k)) break;
+  kbot = max(kts + 1, k - 2);
+  for (k = kts; k <= kbot; k++) { const float c = CFR(k); if (c > 0.0f && c < 0.999f) CFR(k) = 0.f; }
+  auto cfr_at = [&](int kk) { return kk <= kte ? CFR(kk) : 0.f; };       // the Fortran does not bound k_m12C + 2 by kte
+  // the two layer searches: ice clouds from the tropopause down to the -12 C level, water clouds from there to kbot
+  for (int pass = 0; pass < 2; pass++) {
+    const int klow = pass == 0 ? k_m12C : kbot;
+    k_cldb = k_tropo;
+    k = pass == 0 ? k_tropo : k_m12C + 2;
+    while (k > klow) {
+      k_cldt = 0;
+      if (cfr_at(k) >= 0.01f) {
+        k_cldt = k;
+        for (k2 = k_cldt - 1; k2 >= klow; k2--)
+          if (CFR(k2) < 0.01f || k2 == klow) { k_cldb = k2 + 1; break; }
+      }
+      if ((k_cldt - k_cldb + 1) >= 2) {
+        // adjust_cloudIce / adjust_cloudH2O: an adiabatic-like condensate profile over the layer's depth, entrainment-reduced
+        float tdz = 0.f;
+        for (int kk = k_cldb; kk <= k_cldt; kk++) tdz = tdz + DZ(kk);
+        const float max_wc = fabsf(QVS(k_cldt - 1) - QVS(k_cldb));
+        float this_dz = 0.0f;
+        for (int kk = k_cldb; kk <= k_cldt; kk++) {
+          this_dz = kk == k_cldb ? this_dz + 0.5f * DZ(kk) : this_dz + DZ(kk);
+          const float wc = fmaxf(1.E-6f, (max_wc * this_dz / tdz) * (1.f - entr));
+          const float c = CFR(kk), T = T1(kk);
+          if (pass == 0) {
+            const float qi = QI1(kk);
+            if (c > 0.01f && c < 0.99f && T >= 203.16f) QI1(kk) = qi + 0.1f * c * wc;
+            else if (qi < 1.E-5f && c >= 0.99f && T >= 203.16f) QI1(kk) = qi + 0.01f * wc;
+          } else {
+            const float qc = QC1(kk);
+            if (c > 0.01f && c < 0.99f && T < 298.16f && T >= 253.16f) QC1(kk) = qc + c * c * wc;
+            else if (c >= 0.99f && qc < 1.E-5f && T < 298.16f && T >= 253.16f) QC1(kk) = qc + 0.1f * wc;
+          }
+        }
+        k = k_cldb;
+      } else {
+        const float c = CFR(k_cldb);
+        if (pass == 0) { if (c > 0.f && QI1(k_cldb) < 1.E-6f) QI1(k_cldb) = 1.E-5f * c; }
+        else { if (c > 0.f && QC1(k_cldb) < 1.E-6f) QC1(k_cldb) = 1.E-5f * c; }
+      }
+      k = k - 1;
+    }
+  }
+  // adjust_cloudFinal: more than 1.5 kg m-2 of made-up condensate below the tropopause is scaled back
+  float lwp = 0.f, iwp = 0.f;
+  for (k = kts; k <= k_tropo; k++)
+    if (CFR(k) > 0.0f) { const float m = R1(k); lwp = lwp + QC1(k) * m * DZ(k); iwp = iwp + QI1(k) * m * DZ(k); }
+  if (lwp > 1.5f) { const float xfac = 1.f / lwp; for (k = kts; k <= k_tropo; k++) { const float c = CFR(k); if (c > 0.01f && c < 0.99f) QC1(k) = QC1(k) * xfac; } }
+  if (iwp > 1.5f) { const float xfac = 1.f / iwp; for (k = kts; k <= k_tropo; k++) { const float c = CFR(k); if (c > 0.01f && c < 0.99f) QI1(k) = QI1(k) * xfac; } }
+#undef CFR
+#undef QC1
+#undef QI1
+#undef QVS
+#undef T1
+#undef P1
+#undef R1
+#undef TH
+#undef DZ
+}
+void launch_cal_cldfra3(const Geo &G, float *cldfra, const float *qv, float *qc, float *qi, const float *qs, const float *p, const float *t,
+                        const float *rho, const float *xland, float gridkm, float *qvsat, float *theta, float *dz, cudaStream_t s) {
+  Cldfra3Args a{G, qv, qs, p, t, rho, xland, qc, qi, cldfra, qvsat, theta, dz, 0.f, 0.f};
+  a.rh_00l = 0.7f + sqrtf(1.f / (25.0f + gridkm * gridkm * gridkm));
+  a.rh_00o = 0.81f + sqrtf(1.f / (50.0f + gridkm * gridkm * gridkm));
+  const long n = (long)G.ncol_tile * (G.kte - G.kts + 1);
+  k_cldfra3_cell<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+  k_cldfra3_column<<<(G.ncol_tile + 127) / 128, 128, 0, s>>>(a);
+  count_launch(2);
+}
+
 // ozn_time_int (module_radiation_driver.F:3993-4098): ozmixt(i,k,j) = ozmixm(i,k,j,nm) * fact1 + ozmixm(i,k,j,np) * fact2 for the
 // tile's (i, j) and all levsiz data levels; the month indices and weights come from the host (scalar date arithmetic).
 __global__ void __launch_bounds__(256) k_ozn_time_int(Geo G, int levsiz, const float *__restrict__ m0, const float *__restrict__ m1, float fact1,

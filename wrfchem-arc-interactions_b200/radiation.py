@@ -285,6 +285,12 @@ class RadLib:
         t = [abi.c_fp, abi.c_fp, C.c_int, C.c_int, abi.c_fp]
         self._driver_call("cal_cldfra2", dims, [CLDFRA, QC, QI], a, a, t, t)
 
+    def cal_cldfra3(self, dims, CLDFRA, qv, qc, qi, qs, p, t, rho, XLAND, gridkm):
+        """cal_cldfra3 of module_radiation_driver.F:3140-3274 (icloud = 3): CLDFRA out, qc / qi INOUT."""
+        a = [_ptr(CLDFRA), _ptr(qv), _ptr(qc), _ptr(qi), _ptr(qs), _ptr(p), _ptr(t), _ptr(rho), _ptr(XLAND), float(gridkm)]
+        t_ = [abi.c_fp] * 9 + [C.c_float]
+        self._driver_call("cal_cldfra3", dims, [CLDFRA, qv, qc, qi, qs, p, t, rho, XLAND], a, a, t_, t_)
+
     def ozn_time_int(self, dims, julday, julian, ozmixm, ozmixt, levsiz, num_months):
         """ozn_time_int of module_radiation_driver.F:3993-4098: ozmixm (num_months, jms:jme, levsiz, ims:ime in C order) ->
         ozmixt (jms:jme, levsiz, ims:ime), linear in time between the bracketing mid-month days."""
