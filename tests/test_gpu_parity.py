@@ -331,6 +331,29 @@ def test_pipelined_host_path_is_bit_identical(lib, ktab, halo):
     assert (ref["sw"]["swupt"] == -555.0).any() == (halo > 0)
 
 
+def test_ramped_slab_schedule_is_bit_identical(lib, ktab):
+    """The host path's slabs ramp up (a quarter, a half, full slabs, a longer and a shorter last piece) once a tile holds three
+    slabs of >= 8 rows; uniform slabs (ARC_RAD_SLAB_RAMP=0), ramped slabs and the unpipelined call give identical results."""
+    dom = synth.make_domain(16, 43, 30, seed=25, halo=1)
+    init(lib, dom, ktab)
+
+    def run(slab_cols, ramp):
+        os.environ["ARC_RAD_SLAB_COLUMNS"] = str(slab_cols); os.environ["ARC_RAD_SLAB_RAMP"] = str(ramp)
+        try:
+            o_lw, o_sw = R.alloc_outputs(dom, "lw"), R.alloc_outputs(dom, "sw")
+            for o in (o_lw, o_sw):
+                for k in o:
+                    o[k][:] = -555.0
+            flags = R.common_flags(dom)
+            lib.RRTMG_LWSW(dom["dims"], R.lw_kwargs(dom, o_lw, **flags), R.sw_kwargs(dom, o_sw, **flags))
+            return {**o_lw, **o_sw}
+        finally:
+            del os.environ["ARC_RAD_SLAB_COLUMNS"], os.environ["ARC_RAD_SLAB_RAMP"]
+    ref, uni, ramp = run(0, 1), run(16 * 8, 0), run(16 * 8, 1)      # 43 rows, 8-row slabs: 2 + 4 + 8 + 8 + 8 + 8 + 3 + 2 rows when ramped
+    for k in ref:
+        assert np.array_equal(ref[k], uni[k], equal_nan=True) and np.array_equal(ref[k], ramp[k], equal_nan=True), k
+
+
 def test_combined_lwsw_step_equals_separate_calls(lib, ktab):
     """arc_rad_lwsw (LW then SW in one slab pipeline, shared inputs uploaded once) == the two separate calls, bit for bit."""
     dom = synth.make_domain(24, 12, 40, seed=20, halo=1)

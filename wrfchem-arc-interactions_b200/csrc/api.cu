@@ -512,21 +512,27 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
   const int ni = d.ime - d.ims + 1, nk = d.kme - d.kms + 1;
   const int rows_per = slab_rows_default(nrows, d.ite - d.its + 1);
   if (rows_per >= nrows) return -1;
-  // Slab boundaries: a short first slab (the pipeline cannot compute before its upload has finished) and a short last slab
-  // (nothing hides its download) of ARC_RAD_SLAB_EDGE columns each can be requested (default 0 = uniform slabs: measured no gain).
+  // Slab boundaries.  The pipeline cannot compute before the first upload has finished and nothing hides the last download, so
+  // the slabs ramp up (a quarter, a half, then full slabs of `rows_per` rows: an upload is ~2x faster than the compute of the
+  // same rows, so each upload still finishes under the previous slab's compute) and the last 1.5 slabs' worth is cut into a
+  // longer and a shorter piece.  Measured on C2 (device timestamps, ARC_RAD_PIPE_TRACE): uniform slabs fill for 5.2 ms and
+  // drain for 2.0 ms; ramped ones for 1.5 / 0.9 ms, but six slabs instead of four cost 3.3 ms more compute (every slab pays the
+  // latency-bound column kernels and partial waves once): 55.2 -> 54.1 ms per step.  ARC_RAD_SLAB_RAMP=0 restores uniform slabs.
   std::vector<int> slab_j0;      // first row of every slab (relative to jts), plus the end
   {
-    const char *e = getenv("ARC_RAD_SLAB_EDGE");
-    const long edge_cols = e ? atol(e) : 0;
-    int edge = (int)std::min<long>(rows_per, std::max<long>(0, edge_cols / std::max(d.ite - d.its + 1, 1)));
-    if (nrows < 2 * edge + rows_per) edge = 0;
+    const char *e = getenv("ARC_RAD_SLAB_RAMP");
+    const bool ramp = !(e && atoi(e) == 0) && nrows >= 3 * rows_per && rows_per >= 8;
     int j = 0;
-    if (edge > 0) { slab_j0.push_back(0); j = edge; }
-    const int mid_end = nrows - edge;
-    const int nmid = (mid_end - j + rows_per - 1) / rows_per;
-    const int each = (mid_end - j + nmid - 1) / nmid;
-    while (j < mid_end) { slab_j0.push_back(j); j = std::min(mid_end, j + each); }
-    if (edge > 0) slab_j0.push_back(mid_end);
+    if (ramp) {
+      for (int r : {rows_per / 4, rows_per / 2}) { slab_j0.push_back(j); j += r; }
+      while (nrows - j > rows_per + rows_per / 2) { slab_j0.push_back(j); j += rows_per; }
+      const int left = nrows - j, a = std::min(rows_per, (int)(0.65 * left));
+      if (a > 0 && left - a > 0) { slab_j0.push_back(j); j += a; }
+      slab_j0.push_back(j);
+    } else {
+      const int n = (nrows + rows_per - 1) / rows_per, each = (nrows + n - 1) / n;
+      while (j < nrows) { slab_j0.push_back(j); j = std::min(nrows, j + each); }
+    }
     slab_j0.push_back(nrows);
   }
   const int nslab = (int)slab_j0.size() - 1;
@@ -606,13 +612,20 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
     return 0;
   };
 
+  // ARC_RAD_PIPE_TRACE=1: device timestamps of every slab's upload end, last compute kernel and download end (developer aid)
+  const bool trace = getenv("ARC_RAD_PIPE_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  mark(g.h2d);
   int rc = upload(0);
   if (rc) return rc;
+  mark(g.h2d);
   int status = 0;
   std::vector<std::vector<char>> din(nparts), dout(nparts);
   for (int s = 0; s < nslab; s++) {
     const int set = s & 1;
     if (s + 1 < nslab && (rc = upload(s + 1))) return rc;
+    mark(g.h2d);
     const int j0 = d.jts + slab_j0[s], j1 = d.jts + slab_j0[s + 1] - 1;
     ArcDims ds = d;
     ds.jms = j0; ds.jme = j1; ds.jts = j0; ds.jte = j1;
@@ -645,7 +658,9 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
       CK(cudaStreamWaitEvent(g.d2h, g.ev_pre, 0));
     }
     if (status) break;            // a failed slab leaves the caller's arrays as they were (nothing of it is copied back)
+    mark(g.stream); mark(g.stream2);
     if ((rc = download(s))) return rc;
+    mark(g.d2h);
   }
   if (!status && nparts == 2 && g.overlap && parts[0].call == call_lw_ptr && parts[1].call == call_sw_ptr) {
     // end of the asynchronous pipeline: drain the compute streams, fetch the device status word, collect the kernel times
@@ -659,6 +674,17 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
   }
   CK(cudaStreamSynchronize(g.d2h));
   CK(cudaStreamSynchronize(g.h2d));
+  if (trace && tev.size() >= 2) {
+    // order of marks: t0, upload(0) end, then per slab: upload(s+1) end, main-stream end, stream2 end, download end
+    fprintf(stderr, "pipe trace (ms since the first upload started): upload0 end %.2f", [&] { float m; cudaEventElapsedTime(&m, tev[0], tev[1]); return m; }());
+    for (size_t q = 2; q + 3 < tev.size() + 0 && q < tev.size(); q += 4) {
+      float m[4] = {0, 0, 0, 0};
+      for (int r = 0; r < 4 && q + r < tev.size(); r++) cudaEventElapsedTime(&m[r], tev[0], tev[q + r]);
+      fprintf(stderr, " | slab %zu: next upload end %.2f, main stream %.2f, sweep stream %.2f, download end %.2f", (q - 2) / 4, m[0], m[1], m[2], m[3]);
+    }
+    fprintf(stderr, "\n");
+    for (auto e : tev) cudaEventDestroy(e);
+  }
   return status;
 }
 
