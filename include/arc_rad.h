@@ -105,7 +105,7 @@ typedef struct ArcSwIn {
   const float *tauaer300, *tauaer400, *tauaer600, *tauaer999;
   const float *gaer300, *gaer400, *gaer600, *gaer999;
   const float *waer300, *waer400, *waer600, *waer999;
-  const float *aerod;                                   /* (i,k,j,no_src), aer_opt=1: unsupported */
+  const float *aerod;                                   /* (i,k,j,no_src >= 6), aer_opt=1: the six ECMWF aerosol types (iaer = 6); not with clean_atm_diag */
   const float *tauaer3d_sw, *ssaaer3d_sw, *asyaer3d_sw; /* (i,k,j,14) pointers, aer_opt=2,3  */
   /* 2-D (i,j) */
   const float *xcoszen, *albedo, *tsk, *xland, *xice, *snow;
@@ -244,6 +244,14 @@ int  arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float juli
  * memspace; Pa, top down, strictly increasing, levsiz <= 128) -> o3vmr(i,k,j) at the model pressures p(i,k,j): linear in
  * pressure inside the data range, scaled by p / pin(1) above it, held below it.  kts must be 1.  Bit-exact (unfused, IEEE /). */
 int  arc_rad_ozn_p_int(const ArcDims *d, int memspace, const float *p, const float *pin, int levsiz, const float *ozmixt, float *o3vmr);
+/* aer_time_int / aer_p_int (module_radiation_driver.F:4236-4343, 4345-4506; aer_opt = 1): the monthly Tegen aerosol climatology
+ * aerodm(ims:ime, levsiz, jms:jme, num_months, no_src) interpolated in time (as ozn_time_int, per aerosol type) and then to the model
+ * pressures: AEROD(i,k,j,1:no_src) = interpolated value x (pf(k) - pf(k+1)), TOTAOD(i,j) = their sum over types and levels.  `pin`
+ * is a HOST array (hPa, top down, strictly increasing); p and pf (= p8w) in Pa; kts must be 1.  Bit-exact. */
+int  arc_rad_aer_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, int no_src,
+                          const float *aerodm, float *aerodt);
+int  arc_rad_aer_p_int(const ArcDims *d, int memspace, const float *p, const float *pin, int levsiz, const float *aerodt, float *aerod,
+                       int no_src, const float *pf, float *totaod);
 /* Order statistics of `nfields` 2-D (i,j) fields over the tile: out[f * nperc + q] = sorted(field f)[round(0.01 * perc[q] * (N - 1))],
  * the element calc_boxplot_stats picks (misc_stats_library.ncl:145-189); perc = {50, 25, 75, 5, 95} gives calc_standard_stats'
  * median, lower / upper quartile, 5th / 95th percentile (ncl:439-445).  Exact (radix selection, no interpolation).  The 5-cell

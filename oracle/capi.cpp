@@ -397,6 +397,91 @@ int arc_oracle_ozn_time_int(const ArcDims *d, int julday, float JULIAN, int levs
   return 0;
 }
 
+// aer_time_int, module_radiation_driver.F:4236-4343: ozn_time_int per aerosol type
+int arc_oracle_aer_time_int(const ArcDims *d, int julday, float JULIAN, int levsiz, int num_months, int no_src, const float *aerodm, float *aerodt) {
+  const int ni = d->ime - d->ims + 1, nj = d->jme - d->jms + 1;
+  const size_t nlev = (size_t)ni * levsiz * nj;
+  for (int s = 0; s < no_src; s++) {
+    int rc = arc_oracle_ozn_time_int(d, julday, JULIAN, levsiz, num_months, aerodm + nlev * (size_t)num_months * s, aerodt + nlev * (size_t)s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// aer_p_int, module_radiation_driver.F:4345-4506 (line by line)
+int arc_oracle_aer_p_int(const ArcDims *d, const float *p, const float *pin, int levsiz, const float *aerodt, float *aerod, int no_src,
+                         const float *pf, float *totaod) {
+  const int its = d->its, ite = d->ite, kts = d->kts, kte = d->kte;
+  const int ni = d->ime - d->ims + 1, nk = d->kme - d->kms + 1, nj = d->jme - d->jms + 1;
+  const int ncol = ite - its + 1, pver = kte - kts + 1;
+  const size_t n3 = (size_t)ni * nk * nj, nlev = (size_t)ni * levsiz * nj;
+  auto P3 = [&](int i, int k, int j) { return (size_t)(i - d->ims) + (size_t)ni * ((size_t)(k - d->kms) + (size_t)nk * (size_t)(j - d->jms)); };
+  auto PIN = [&](int k) { return pin[k - 1]; };
+  std::vector<float> pmid((size_t)ncol * (pver + 1));
+  std::vector<int> kupper(ncol);
+  auto PM = [&](int i, int k) -> float & { return pmid[(size_t)(i - its) + (size_t)ncol * k]; };
+  for (int s = 1; s <= no_src; s++) {
+    auto AT = [&](int i, int k, int j) { return aerodt[(size_t)(i - d->ims) + (size_t)ni * ((size_t)(k - 1) + (size_t)levsiz * (size_t)(j - d->jms)) + nlev * (size_t)(s - 1)]; };
+    float *ao = aerod + n3 * (size_t)(s - 1);
+    for (int j = d->jts; j <= d->jte; j++) {
+      for (int i = its; i <= ite; i++) kupper[i - its] = 1;
+      for (int k = kts; k <= kte; k++) {
+        const int kk = kte - k + kts;
+        for (int i = its; i <= ite; i++) PM(i, kk) = p[P3(i, k, j)] * 0.01f;
+      }
+      for (int k = 1; k <= pver; k++) {
+        const int kout = pver - k + 1;
+        int kkstart = levsiz;
+        for (int i = its; i <= ite; i++) kkstart = std::min(kkstart, kupper[i - its]);
+        int kount = 0;
+        bool done = false;
+        for (int kk = kkstart; kk <= levsiz - 1 && !done; kk++) {
+          for (int i = its; i <= ite; i++)
+            if (PIN(kk) < PM(i, k) && PM(i, k) <= PIN(kk + 1)) { kupper[i - its] = kk; kount = kount + 1; }
+          if (kount == ncol) {
+            for (int i = its; i <= ite; i++) {
+              const int ku = kupper[i - its];
+              const float dpu = PM(i, k) - PIN(ku), dpl = PIN(ku + 1) - PM(i, k);
+              const float dpm = pf[P3(i, kout, j)] - pf[P3(i, kout + 1, j)];
+              const float a = AT(i, ku, j) * dpl, b = AT(i, ku + 1, j) * dpu;
+              float v = (a + b) / (dpl + dpu);
+              v = v * dpm;
+              ao[P3(i, kout, j)] = v;
+            }
+            done = true;
+          }
+        }
+        if (done) continue;
+        for (int i = its; i <= ite; i++) {
+          const int ku = kupper[i - its];
+          const float dpm = pf[P3(i, kout, j)] - pf[P3(i, kout + 1, j)];
+          float v;
+          if (PM(i, k) < PIN(1)) { const float a = AT(i, 1, j) * PM(i, k); v = a / PIN(1); }
+          else if (PM(i, k) > PIN(levsiz)) v = AT(i, levsiz, j);
+          else {
+            const float dpu = PM(i, k) - PIN(ku), dpl = PIN(ku + 1) - PM(i, k);
+            const float a = AT(i, ku, j) * dpl, b = AT(i, ku + 1, j) * dpu;
+            v = (a + b) / (dpl + dpu);
+          }
+          v = v * dpm;
+          ao[P3(i, kout, j)] = v;
+        }
+        if (kount > ncol) return -1;       // 'AER_P_INT: Bad aerosol data: non-monotonicity suspected'
+      }
+    }
+  }
+  for (int j = d->jts; j <= d->jte; j++)
+    for (int i = its; i <= ite; i++) totaod[(size_t)(i - d->ims) + (size_t)ni * (size_t)(j - d->jms)] = 0.f;
+  for (int s = 1; s <= no_src; s++)
+    for (int j = d->jts; j <= d->jte; j++)
+      for (int k = 1; k <= pver; k++)
+        for (int i = its; i <= ite; i++) {
+          float &t = totaod[(size_t)(i - d->ims) + (size_t)ni * (size_t)(j - d->jms)];
+          t = t + aerod[P3(i, k, j) + n3 * (size_t)(s - 1)];
+        }
+  return 0;
+}
+
 // ozn_p_int, module_radiation_driver.F:4100-4234 (line by line, including the row-wide kkstart / kount bookkeeping)
 int arc_oracle_ozn_p_int(const ArcDims *d, const float *p, const float *pin, int levsiz, const float *ozmixt, float *o3vmr) {
   const int its = d->its, ite = d->ite, kts = d->kts, kte = d->kte;

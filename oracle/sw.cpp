@@ -895,7 +895,12 @@ int oracle_swrad(const ArcDims &d, const ArcSwIn &in, ArcSwOut &out, ArcDebug *d
       err = "Warning: missing fields required for aerosol radiation"; return ARC_ERR_MISSING_FIELD;
     }
   }
-  if (in.aer_opt == 1) { err = "aer_opt=1 (Tegen climatology, iaer=6) not supported"; return ARC_ERR_UNSUPPORTED; }
+  if (in.aer_opt == 1) {
+    // iaer = 6 (SW:9201-9205): the six ECMWF aerosol types with the optical depths AEROD(i,k,j,1:6).  The reference's second
+    // ("clean") spcvmc_sw call reads ztauacln, which only the iaer = 10 branch defines (SW:9343-9352): undefined there, refused here.
+    if (!in.aerod || in.no_src < 6) { err = "aer_opt=1 needs aerod(i,k,j,1:6) (no_src >= 6)"; return ARC_ERR_MISSING_FIELD; }
+    if (in.clean_atm_diag > 0) { err = "aer_opt=1 with clean_atm_diag: the reference leaves the clean call's aerosol optical depth undefined"; return ARC_ERR_UNSUPPORTED; }
+  }
   const int clean = in.clean_atm_diag;
   const Idx ix(d);
   const int kts = d.kts, kte = d.kte, nz = kte - kts + 1;
@@ -1020,6 +1025,27 @@ int oracle_swrad(const ArcDims &d, const ArcSwIn &in, ArcSwOut &out, ArcDebug *d
             for (int k = 1; k <= nz; k++) slope = slope + W.taua[nb][k];
             if (slope < 0.f) { err = "ERROR: Negative total optical depth"; return ARC_ERR_NEG_AOD; }
             else if (slope > 6.f) { for (int k = 1; k <= nz; k++) W.taua[nb][k] = W.taua[nb][k] * 6.0f / slope; }
+          }
+        }
+        if (in.aer_opt == 1) {
+          // ecaer of the adapter (SW:11083-11100: model layers from AEROD, 0 in the extra top layer) and the iaer = 6 mixing of
+          // rrtmg_sw (SW:9313-9341), which replaces taua / ssaa / asma
+          const FArr &rsrtaua = T.in.get("sw_rsrtaua"), &rsrpiza = T.in.get("sw_rsrpiza"), &rsrasya = T.in.get("sw_rsrasya");
+          const size_t n3 = (size_t)(d.ime - d.ims + 1) * (d.kme - d.kms + 1) * (d.jme - d.jms + 1);
+          for (int k = 1; k <= nz + 1; k++) {
+            float ecaer[7];
+            for (int na = 1; na <= 6; na++) ecaer[na] = k <= nz ? in.aerod[ix.at3(i, kts + k - 1, j) + n3 * (size_t)(na - 1)] : 0.f;
+            for (int ib = 1; ib <= NBSW; ib++) {
+              float ztaua = 0.f, zasya = 0.f, zomga = 0.f;
+              for (int ia = 1; ia <= 6; ia++) {
+                ztaua = ztaua + rsrtaua(ib, ia) * ecaer[ia];
+                zomga = zomga + rsrtaua(ib, ia) * ecaer[ia] * rsrpiza(ib, ia);
+                zasya = zasya + rsrtaua(ib, ia) * ecaer[ia] * rsrpiza(ib, ia) * rsrasya(ib, ia);
+              }
+              if (zomga != 0.f) zasya = zasya / zomga;
+              if (ztaua != 0.f) zomga = zomga / ztaua;
+              W.taua[ib][k] = ztaua; W.ssaa[ib][k] = zomga; W.asma[ib][k] = zasya;
+            }
           }
         }
         SwColumnOut co;

@@ -211,3 +211,40 @@ def test_cal_cldfra3_oracle(orc):
         assert abs(float(c[jj, kk, ii]) - want) < 3e-4, (jj, kk, ii)
         checked += 1
     assert checked > 20
+
+
+def tegen_case(ni=14, nj=6, nk=40, levsiz=12, seed=31):
+    """Synthetic Tegen-style climatology: 12 months x 6 aerosol types on `levsiz` pressure levels (hPa, top down)."""
+    from wrfchem_arc_interactions_b200 import synth
+    rng = np.random.default_rng(seed)
+    dom = synth.make_domain(ni, nj, nk, seed=seed)
+    pin = np.linspace(20.0, 985.0, levsiz).astype(np.float32)                      # hPa
+    prof = (1e-5 * np.exp(-(1000.0 - pin) / 250.0)).astype(np.float32)             # optical depth per Pa of layer thickness
+    aerodm = (prof[None, None, None, :, None] * rng.uniform(0.2, 1.0, (6, 12, nj, levsiz, ni))).astype(np.float32)
+    return dom, pin, np.ascontiguousarray(aerodm)
+
+
+def test_aer_time_and_p_int_oracle(orc):
+    """aer_time_int / aer_p_int (DRV:4236-4506): per aerosol type the time blend of ozn_time_int; then linear interpolation in
+    pressure (model p in hPa) x the layer's interface-pressure difference, held below the data bottom, scaled by p / pin(1) above
+    the data top; TOTAOD is the sum over types and levels."""
+    dom, pin, aerodm = tegen_case()
+    nk = dom["nk"]
+    no_src, _, nj, levsiz, ni = aerodm.shape
+    aerodt = np.zeros((no_src, nj, levsiz, ni), np.float32)
+    orc.aer_time_int(dom["dims"], 0, 59.0, aerodm, aerodt, levsiz, 12, no_src)     # day 60: half way between mid-February and mid-March
+    assert np.allclose(aerodt, 0.5 * (aerodm[:, 1] + aerodm[:, 2]), rtol=1e-6)
+    aerod = np.full((no_src,) + dom["p3d"].shape, -1.0, np.float32); tot = np.full(dom["xland"].shape, -1.0, np.float32)
+    orc.aer_p_int(dom["dims"], dom["p3d"], pin, levsiz, aerodt, aerod, no_src, dom["p8w"], tot)
+    assert np.all(aerod[:, :, nk, :] == -1.0) and np.all(aerod[:, :, :nk, :] >= 0)
+    for s in (0, 3, 5):
+        for j in (0, nj - 1):
+            for i in (0, ni // 2):
+                pm = dom["p3d"][j, :nk, i].astype(np.float64) * 0.01
+                want = np.interp(pm, pin.astype(np.float64), aerodt[s, j, :, i].astype(np.float64))
+                top = pm < pin[0]
+                want[top] = aerodt[s, j, 0, i] * pm[top] / pin[0]
+                want *= dom["p8w"][j, :nk, i].astype(np.float64) - dom["p8w"][j, 1:nk + 1, i]
+                assert np.allclose(aerod[s, j, :nk, i], want, rtol=5e-6, atol=0), (s, j, i)
+    assert np.allclose(tot, aerod[:, :, :nk, :].astype(np.float64).sum(axis=(0, 2)), rtol=2e-6)
+    assert 0.01 < tot.mean() < 5.0

@@ -740,6 +740,70 @@ def test_cal_cldfra3_bit_exact(lib, orc, ktab):
     assert np.array_equal(fin(qi).view(np.uint32), fin(qi2).view(np.uint32)) and np.all(cf[:2] == -3.0) and np.all(cf[:, :, :2] == -3.0)
 
 
+def test_aer_opt_1_ecmwf_aerosol_types(lib, orc, ktab):
+    """aer_opt = 1 (iaer = 6: six ECMWF aerosol types mixed from AEROD, SW:9313-9341, 11083-11100) on the device against the
+    oracle: every shortwave output bit-exact, host and device arrays; the clean diagnostic (undefined in the reference for this
+    option) and a missing AEROD are refused with the oracle's codes."""
+    import torch
+    from test_oracle_cpu import tegen_aerod
+    dom = synth.make_domain(24, 7, 40, seed=26, halo=1)
+    aerod = tegen_aerod(dom)
+    over = dict(clean_atm_diag=0, aer_opt=1, no_src=6, aerod=aerod)
+    og, oo, tg, to = both("sw", lib, orc, dom, ktab, **over)
+    check_sw(dom, og, oo, tg, to)
+    plain = run_pair("sw", lib, dom, clean_atm_diag=0, aer_ra_feedback=0)
+    assert (interior(dom, og["swdnb"]) != interior(dom, plain["swdnb"])).any()
+    ddom = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in dom.items()}
+    od = R.alloc_outputs(dom, "sw", like=ddom["xcoszen"])
+    flags = R.common_flags(dom); flags.update(over); flags["aerod"] = torch.from_numpy(aerod).cuda()
+    lib.RRTMG_SWRAD(dom["dims"], **R.sw_kwargs(ddom, od, **flags))
+    for k in og:
+        assert np.array_equal(od[k].cpu().numpy(), og[k], equal_nan=True), k
+    for bad in (dict(over, clean_atm_diag=1), dict(clean_atm_diag=0, aer_opt=1, no_src=6)):
+        codes = []
+        for rad in (lib, orc):
+            with pytest.raises(R.RadiationError) as e:
+                run_pair("sw", rad, dom, **bad)
+            codes.append(e.value.code)
+        assert codes[0] == codes[1]
+
+
+def test_tegen_climatology_to_radiation_chain(lib, orc, ktab):
+    """aer_time_int + aer_p_int on the device (DRV:4236-4506) bit-exact against the oracle, host and device arrays; then the
+    chain the reference runs for aer_opt = 1: climatology -> AEROD -> RRTMG_SWRAD with the six ECMWF aerosol types, all on the
+    device, equal to the oracle's chain bit for bit."""
+    import torch
+    from test_driver_cpu import tegen_case
+    dom, pin, aerodm = tegen_case(ni=33, nj=9, nk=40)
+    init(lib, dom, ktab); init(orc, dom, ktab)
+    no_src, _, nj, levsiz, ni = aerodm.shape
+    res = {}
+    for name, rad in (("gpu", lib), ("cpu", orc)):
+        aerodt = np.zeros((no_src, nj, levsiz, ni), np.float32)
+        rad.aer_time_int(dom["dims"], 0, 200.7, aerodm, aerodt, levsiz, 12, no_src)
+        aerod = np.full((no_src,) + dom["p3d"].shape, -1.0, np.float32); tot = np.full(dom["xland"].shape, -1.0, np.float32)
+        rad.aer_p_int(dom["dims"], dom["p3d"], pin, levsiz, aerodt, aerod, no_src, dom["p8w"], tot)
+        res[name] = (aerodt, aerod, tot)
+    for a, b in zip(res["gpu"], res["cpu"]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    dt, dv, dtot = cu(np.zeros_like(res["cpu"][0])), cu(np.full_like(res["cpu"][1], -1.0)), cu(np.full_like(res["cpu"][2], -1.0))
+    lib.aer_time_int(dom["dims"], 0, 200.7, cu(aerodm), dt, levsiz, 12, no_src)
+    lib.aer_p_int(dom["dims"], cu(dom["p3d"]), pin, levsiz, dt, dv, no_src, cu(dom["p8w"]), dtot)
+    assert np.array_equal(dv.cpu().numpy().view(np.uint32), res["cpu"][1].view(np.uint32)) and np.array_equal(dtot.cpu().numpy(), res["cpu"][2])
+    # radiation with the device-resident AEROD
+    ddom = {k: (cu(v) if isinstance(v, np.ndarray) and v.ndim >= 2 else v) for k, v in dom.items()}
+    od = R.alloc_outputs(dom, "sw", like=ddom["xcoszen"])
+    flags = R.common_flags(dom, clean_atm_diag=0); flags.update(aer_opt=1, no_src=6, aerod=dv)
+    lib.RRTMG_SWRAD(dom["dims"], **R.sw_kwargs(ddom, od, **flags))
+    oo = run_pair("sw", orc, dom, clean_atm_diag=0, aer_opt=1, no_src=6, aerod=res["cpu"][1])
+    for k in oo:
+        a, b = od[k].cpu().numpy(), oo[k]
+        if a.ndim == 3:
+            a, b = a[:, :dom["nk"] + (2 if k in SWPROF else 0)], b[:, :dom["nk"] + (2 if k in SWPROF else 0)]
+        assert bits_equal(a, b), k
+
+
 def extreme_domain():
     """A 48 x 8 tile whose column groups sit on the edges of the input space: grazing and overhead sun, black and white
     surfaces, conservative / absorbing / forward-peaked and very thick aerosol, no spectral slope, overcast decks with large

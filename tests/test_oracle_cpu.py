@@ -176,3 +176,60 @@ def test_kissvec_known_answers():
     # the generator is a pure function of its state: same seeds, same stream
     s2 = [123456789, 362436069, 521288629, 916191069]
     assert [kiss(s2) for _ in range(5)] == draws[:5]
+
+
+def inline_table(name):
+    """One table of data/rrtmg_inline_tables.bin (layout: tools/extract_inline_tables.py), flat, Fortran element order."""
+    import struct
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "wrfchem-arc-interactions_b200", "data", "rrtmg_inline_tables.bin")
+    blob = open(path, "rb").read()
+    assert blob[:8] == b"ARCTBL1\0"
+    n = struct.unpack_from("<I", blob, 8)[0]
+    for e in range(n):
+        off = 12 + 76 * e
+        if blob[off:off + 32].split(b"\0")[0].decode() == name:
+            ndim = struct.unpack_from("<I", blob, off + 32)[0]
+            dims = struct.unpack_from("<4I", blob, off + 36)[:ndim]
+            return np.frombuffer(blob, "<f4", int(np.prod(dims)) if ndim else 1, struct.unpack_from("<Q", blob, off + 68)[0]).copy()
+    raise KeyError(name)
+
+
+def tegen_aerod(dom, seed=5, types=(0, 1, 2, 3, 4, 5)):
+    """AEROD(i,k,j,1:6) in C order (6, nj, nkm, ni): layer optical depths at 0.55 um of the ECMWF aerosol types."""
+    rng = np.random.default_rng(seed)
+    nj, nkm, ni = dom["t3d"].shape
+    prof = np.exp(-np.arange(nkm) / 6.0)[None, :, None]
+    a = np.zeros((6, nj, nkm, ni), np.float32)
+    for t in types:
+        a[t] = (rng.uniform(0.0, 0.03, (nj, 1, ni)) * prof).astype(np.float32)
+    return a
+
+
+def test_aer_opt_1_ecmwf_aerosol_types(orc, ktab):
+    """aer_opt = 1 -> iaer = 6 (SW:9201-9205, 9313-9341, 11083-11100): zero AEROD is the aerosol-free atmosphere bit for bit; one
+    aerosol type alone equals the direct specification (the tauaer3d_sw input) of rsrtaua * AEROD, rsrpiza, rsrasya per band;
+    more aerosol dims the surface; the clean diagnostic, undefined in the reference for this option, is refused."""
+    from wrfchem_arc_interactions_b200 import radiation as R
+    dom = synth.make_domain(8, 3, 40, seed=16, all_day=True)
+    init(orc, dom, ktab)
+    nj, nkm, ni = dom["t3d"].shape
+    base = run_pair("sw", orc, dom, clean_atm_diag=0, aer_ra_feedback=0)
+    zero = run_pair("sw", orc, dom, clean_atm_diag=0, aer_ra_feedback=0, aer_opt=1, no_src=6, aerod=np.zeros((6, nj, nkm, ni), np.float32))
+    for k in base:
+        assert np.array_equal(base[k], zero[k]), k
+    aerod = tegen_aerod(dom)
+    mix = run_pair("sw", orc, dom, clean_atm_diag=0, aer_ra_feedback=0, aer_opt=1, no_src=6, aerod=aerod)
+    assert np.all(mix["swdnb"] < base["swdnb"]) and np.all(mix["swdnbc"] < base["swdnbc"])
+    one = tegen_aerod(dom, types=(1,))
+    rsr = {n: inline_table("sw_" + n).reshape(6, 14) for n in ("rsrtaua", "rsrpiza", "rsrasya")}      # [type][band]
+    tau = np.stack([rsr["rsrtaua"][1, b] * one[1] for b in range(14)]).astype(np.float32)
+    ssa = np.stack([np.full_like(one[1], rsr["rsrpiza"][1, b]) for b in range(14)]); asy = np.stack([np.full_like(one[1], rsr["rsrasya"][1, b]) for b in range(14)])
+    a = run_pair("sw", orc, dom, clean_atm_diag=0, aer_ra_feedback=0, aer_opt=1, no_src=6, aerod=one)
+    b = run_pair("sw", orc, dom, clean_atm_diag=0, aer_ra_feedback=0, aer_opt=2, tauaer3d_sw=tau, ssaaer3d_sw=ssa, asyaer3d_sw=asy)
+    for k in ("swdnb", "swupt", "swdnbc", "swddir", "gsw"):
+        assert np.allclose(a[k], b[k], rtol=2e-5, atol=2e-3), k
+    with pytest.raises(R.RadiationError) as e:
+        run_pair("sw", orc, dom, clean_atm_diag=1, aer_opt=1, no_src=6, aerod=aerod)
+    assert "undefined" in str(e.value)
+    with pytest.raises(R.RadiationError):
+        run_pair("sw", orc, dom, clean_atm_diag=0, aer_ra_feedback=0, aer_opt=1, no_src=6)

@@ -9,7 +9,7 @@ repo because ``/root/reference`` does not exist on the GPU box.
 
 Sources (``/root/reference/WRF-Chem_code/v3.9.1/phys``):
   module_ra_rrtmg_sw.F : swcldpr 6068-7891, swatmref 2993-3047, swcmbdat 4793-4916,
-                         swdatinit 4701-4790, wavemin/wavemax 10117-10122
+                         swdatinit 4701-4790, swaerpr 4918-5020, wavemin/wavemax 10117-10122
   module_ra_rrtmg_lw.F : lwcldpr 9858-10496, lwatmref 3812-3973, lwavplank 3975-4678,
                          lwcmbdat 8124-8204, lwdatinit 8012-8122, rtrnmc a0/a1/a2 2958-2969,
                          retab 11424-11441, o3data 12747-12770, PPROF/TPROF 11794-11815
@@ -49,6 +49,8 @@ SW_SHAPES = {
     "wavenum1": ((14,), (16,)), "wavenum2": ((14,), (16,)), "delwave": ((14,), (16,)),
     "nspa": ((14,), (16,)), "nspb": ((14,), (16,)),
     "wavemin": ((14,), (1,)), "wavemax": ((14,), (1,)),
+    # swaerpr (SW:4918-5020): optical-depth ratio, single-scattering albedo and asymmetry of the six ECMWF aerosol types (iaer = 6)
+    "rsrtaua": ((14, 6), (1, 1)), "rsrpiza": ((14, 6), (1, 1)), "rsrasya": ((14, 6), (1, 1)),
 }
 LW_SHAPES = {
     "absliq1": ((58, 16), (1, 1)), "absice0": ((2,), (1,)), "absice1": ((2, 5), (1, 1)),

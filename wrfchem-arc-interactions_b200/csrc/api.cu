@@ -859,6 +859,12 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
     if ((rc = upload_vec(o3ann, &D.o3wrk))) return rc;
     if ((rc = upload_vec(ppwrkh, &D.ppwrkh))) return rc;
   }
+  {   // swaerpr (SW:4918-5020): ratio / omega / g of the six ECMWF aerosol types per band, [quantity][type][band]
+    std::vector<float> rsr;
+    for (const char *n : {"sw_rsrtaua", "sw_rsrpiza", "sw_rsrasya"}) { const std::vector<float> &v = H.get(n); rsr.insert(rsr.end(), v.begin(), v.end()); }
+    if (rsr.size() != 3 * 6 * 14) { g.err = "inline tables: swaerpr arrays missing"; return ARC_ERR_IO; }
+    if ((rc = upload_vec(rsr, &D.sw_rsr))) return rc;
+  }
   if ((rc = upload_vec(H.get("lw_retab"), &D.retab))) return rc;
   if ((rc = upload_vec(H.get("lw_pprof"), &D.pprof))) return rc;
   if ((rc = upload_vec(H.get("lw_tprof"), &D.tprof))) return rc;
@@ -883,7 +889,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   if (!d || !in || !out) { g.err = "arc_rad_sw: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
   if (rc) return rc;
-  if (in->memspace == ARC_MEM_HOST && !dbg && !in->tauaer3d_sw) {
+  if (in->memspace == ARC_MEM_HOST && !dbg && !in->tauaer3d_sw && in->aer_opt != 1) {
     const PipePart part = sw_part(in, out);
     rc = run_pipelined(*d, &part, 1);
     if (rc != -1) return rc;
@@ -898,7 +904,14 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   if (in->clean_atm_diag > 0 && in->aer_ra_feedback <= 0) {
     g.err = "clean_atm_diag > 0 requires aer_ra_feedback > 0 (chemics_init.F:406-408)"; return ARC_ERR_CONFIG;
   }
-  if (in->aer_opt == 1) { g.err = "aer_opt=1 (Tegen climatology, iaer=6) not supported"; return ARC_ERR_UNSUPPORTED; }
+  if (in->aer_opt == 1) {
+    // iaer = 6 (SW:9201-9205): the six ECMWF aerosol types with the optical depths AEROD(i,k,j,1:6).  The reference's second
+    // ("clean") spcvmc_sw call reads ztauacln, which only the iaer = 10 branch defines (SW:9343-9352): undefined there, refused here.
+    if (!in->aerod || in->no_src < 6) { g.err = "aer_opt=1 needs aerod(i,k,j,1:6) (no_src >= 6)"; return ARC_ERR_MISSING_FIELD; }
+    if (in->clean_atm_diag > 0) {
+      g.err = "aer_opt=1 with clean_atm_diag: the reference leaves the clean call's aerosol optical depth undefined"; return ARC_ERR_UNSUPPORTED;
+    }
+  }
   if (!in->xcoszen || !in->albedo || !in->t3d || !in->t8w || !in->p3d || !in->p8w || !in->pi3d || !in->qv3d || !in->xland ||
       !in->xice || !in->snow || !out->rthratensw || !out->gsw || !out->swcf || !out->coszr || !out->swddir || !out->swddni ||
       !out->swddif) {
@@ -955,6 +968,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
   IN3(t8w); IN3(p3d); IN3(p8w); IN3(pi3d); IN3(o33d);
   IN2(tsk);
   if (in->aer_ra_feedback == 1) { IN3(tauaer300); IN3(tauaer400); IN3(tauaer600); IN3(tauaer999); IN3(gaer400); IN3(gaer600); IN3(waer400); IN3(waer600); }
+  if (in->aer_opt == 1 && (rc = in_arr(ms, in->aerod, n3 * 6, &a.aerod))) return rc;
   if (in->tauaer3d_sw && in->ssaaer3d_sw && in->asyaer3d_sw) {
     if ((rc = in_arr(ms, in->tauaer3d_sw, n3 * 14, &a.tauaer3d_sw))) return rc;
     if ((rc = in_arr(ms, in->ssaaer3d_sw, n3 * 14, &a.ssaaer3d_sw))) return rc;
@@ -1239,7 +1253,7 @@ int arc_rad_lwsw(const ArcDims *d, const ArcLwIn *lwin, ArcLwOut *lwout, const A
   if (!d || !lwin || !lwout || !swin || !swout) { g.err = "arc_rad_lwsw: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
   if (rc) return rc;
-  if (lwin->memspace == ARC_MEM_HOST && swin->memspace == ARC_MEM_HOST && !swin->tauaer3d_sw) {
+  if (lwin->memspace == ARC_MEM_HOST && swin->memspace == ARC_MEM_HOST && !swin->tauaer3d_sw && swin->aer_opt != 1) {
     const PipePart parts[2] = {lw_part(lwin, lwout), sw_part(swin, swout)};
     rc = run_pipelined(*d, parts, 2);
     if (rc != -1) return rc;
@@ -1619,16 +1633,9 @@ int arc_rad_cal_cldfra3(const ArcDims *d, int memspace, float *cldfra, const flo
   return 0;
 }
 
-// ozn_time_int (module_radiation_driver.F:3993-4098; o3input = 2, DRV:1250): the monthly CAM ozone climatology interpolated in
-// time to the model day.  The date arithmetic (which two months, which weights) is the reference's scalar code in single
-// precision, on the host; the blend of the two months runs on the device.
-int arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, const float *ozmixm, float *ozmixt) {
-  (void)julday;                                              // as in the reference: only JULIAN is used
-  if (!g.ready) { g.err = "arc_rad_ozn_time_int: not initialised"; return ARC_ERR_NOT_INIT; }
-  if (!d || !ozmixm || !ozmixt) { g.err = "arc_rad_ozn_time_int: null argument"; return ARC_ERR_BAD_ARG; }
-  if (levsiz < 2 || num_months < 12) { g.err = "arc_rad_ozn_time_int: needs levsiz >= 2 and the 12 monthly fields"; return ARC_ERR_BAD_ARG; }
-  int rc = check_dims(*d);
-  if (rc) return rc;
+// The date arithmetic ozn_time_int and aer_time_int share (DRV:4023-4082 = DRV:4268-4327): the two mid-month days that bracket
+// JULIAN + 1 and their linear weights, December - January wrapping; the reference's scalar code in single precision.
+static void clim_time_weights(float julian, int &nm_out, int &np_out, float &fact1_out, float &fact2_out) {
   static const int date_oz[12] = {16, 45, 75, 105, 136, 166, 197, 228, 258, 289, 319, 350};
   const float daysperyear = 365.f;
   volatile float intjulian = julian + 1.0f;                  // offset by one day (volatile: every step rounded to single)
@@ -1654,6 +1661,21 @@ int arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float julia
     fact1 = (cdayozp - intjulian) / deltat;
     fact2 = (intjulian - cdayozm) / deltat;
   }
+  nm_out = nm; np_out = np; fact1_out = fact1; fact2_out = fact2;
+}
+
+// ozn_time_int (module_radiation_driver.F:3993-4098; o3input = 2, DRV:1250): the monthly CAM ozone climatology interpolated in
+// time to the model day.  The date arithmetic (which two months, which weights) is the reference's scalar code in single
+// precision, on the host; the blend of the two months runs on the device.
+int arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, const float *ozmixm, float *ozmixt) {
+  (void)julday;                                              // as in the reference: only JULIAN is used
+  if (!g.ready) { g.err = "arc_rad_ozn_time_int: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !ozmixm || !ozmixt) { g.err = "arc_rad_ozn_time_int: null argument"; return ARC_ERR_BAD_ARG; }
+  if (levsiz < 2 || num_months < 12) { g.err = "arc_rad_ozn_time_int: needs levsiz >= 2 and the 12 monthly fields"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  int nm, np; float fact1, fact2;
+  clim_time_weights(julian, nm, np, fact1, fact2);
   CK(cudaSetDevice(g.device));
   g.pool_next = 0; g.backs.clear();
   Geo G = make_geo(*d);
@@ -1689,6 +1711,62 @@ int arc_rad_ozn_p_int(const ArcDims *d, int memspace, const float *p, const floa
   if ((rc = in_arr(memspace, p, G.n3(), &dp)) || (rc = in_arr(memspace, ozmixt, nlev, &dt))) return rc;
   if ((rc = out_arr(memspace, o3vmr, G.n3(), &dv))) return rc;
   launch_ozn_p_int(G, levsiz, pin, dp, dt, dv, g.stream);
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// aer_time_int (module_radiation_driver.F:4236-4343; aer_opt = 1): the monthly Tegen aerosol climatology
+// aerodm(ims:ime, levsiz, jms:jme, num_months, no_src) -> aerodt(ims:ime, levsiz, jms:jme, no_src), as ozn_time_int per aerosol type.
+int arc_rad_aer_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, int no_src, const float *aerodm,
+                         float *aerodt) {
+  (void)julday;
+  if (!g.ready) { g.err = "arc_rad_aer_time_int: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !aerodm || !aerodt) { g.err = "arc_rad_aer_time_int: null argument"; return ARC_ERR_BAD_ARG; }
+  if (levsiz < 2 || num_months < 12 || no_src < 1) { g.err = "arc_rad_aer_time_int: needs levsiz >= 2, 12 monthly fields, no_src >= 1"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  int nm, np; float fact1, fact2;
+  clim_time_weights(julian, nm, np, fact1, fact2);
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const size_t nlev = (size_t)G.ni * (size_t)levsiz * (size_t)(G.jme - G.jms + 1);
+  for (int s = 0; s < no_src; s++) {
+    const float *m0, *m1; float *dt;
+    const float *base = aerodm + nlev * (size_t)num_months * (size_t)s;
+    if ((rc = in_arr(memspace, base + nlev * (size_t)(nm - 1), nlev, &m0)) || (rc = in_arr(memspace, base + nlev * (size_t)(np - 1), nlev, &m1))) return rc;
+    if ((rc = out_arr(memspace, aerodt + nlev * (size_t)s, nlev, &dt))) return rc;
+    launch_ozn_time_int(G, levsiz, m0, m1, fact1, fact2, dt, g.stream);
+  }
+  if ((rc = copy_back())) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// aer_p_int (module_radiation_driver.F:4345-4506): the climatology on its pressure levels `pin` (HOST array, hPa, top down) ->
+// layer optical depths AEROD(i,k,j,1:no_src) at the model pressures p (Pa; compared as p * 0.01), each multiplied by the layer's
+// interface-pressure difference pf(k) - pf(k+1), and their column total TOTAOD(i,j).  AEROD is what RRTMG_SWRAD reads with aer_opt = 1.
+int arc_rad_aer_p_int(const ArcDims *d, int memspace, const float *p, const float *pin, int levsiz, const float *aerodt, float *aerod, int no_src,
+                      const float *pf, float *totaod) {
+  if (!g.ready) { g.err = "arc_rad_aer_p_int: not initialised"; return ARC_ERR_NOT_INIT; }
+  if (!d || !p || !pin || !aerodt || !aerod || !pf || !totaod) { g.err = "arc_rad_aer_p_int: null argument"; return ARC_ERR_BAD_ARG; }
+  if (levsiz < 2 || levsiz > ARC_OZN_MAXLEV || no_src < 1) { g.err = "arc_rad_aer_p_int: levsiz must be 2.." + std::to_string(ARC_OZN_MAXLEV) + ", no_src >= 1"; return ARC_ERR_BAD_ARG; }
+  for (int k = 1; k < levsiz; k++)
+    if (!(pin[k] > pin[k - 1])) { g.err = "AER_P_INT: Bad aerosol data: non-monotonicity suspected"; return ARC_ERR_BAD_ARG; }
+  int rc = check_dims(*d);
+  if (rc) return rc;
+  if (d->kts != 1) { g.err = "arc_rad_aer_p_int: kts must be 1 (the reference indexes its work arrays from 1)"; return ARC_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(g.device));
+  g.pool_next = 0; g.backs.clear();
+  Geo G = make_geo(*d);
+  const size_t nlev = (size_t)G.ni * (size_t)levsiz * (size_t)(G.jme - G.jms + 1);
+  const float *dp, *dt, *dpf; float *dv, *dtot;
+  if ((rc = in_arr(memspace, p, G.n3(), &dp)) || (rc = in_arr(memspace, pf, G.n3(), &dpf)) || (rc = in_arr(memspace, aerodt, nlev * no_src, &dt))) return rc;
+  if ((rc = out_arr(memspace, aerod, G.n3() * no_src, &dv)) || (rc = out_arr(memspace, totaod, G.n2(), &dtot))) return rc;
+  launch_clim_p_int(G, levsiz, pin, dp, 0.01f, no_src, dt, dv, dpf, dtot, g.stream);
   if ((rc = copy_back())) return rc;
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());

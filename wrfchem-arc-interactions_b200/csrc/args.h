@@ -118,6 +118,7 @@ struct SwArgs {
   const float *t8w, *p3d, *p8w, *pi3d, *o33d, *tsk;
   const float *tauaer300, *tauaer400, *tauaer600, *tauaer999, *gaer400, *gaer600, *waer400, *waer600;
   const float *tauaer3d_sw, *ssaaer3d_sw, *asyaer3d_sw;
+  const float *aerod;       // (i,k,j,1:6), non-null = aer_opt 1 (iaer = 6)
   const float *xcoszen, *albedo, *alswvisdir, *alswvisdif, *alswnirdir, *alswnirdif;
   // outputs
   float *rthratensw, *gsw, *swcf, *coszr;
@@ -203,6 +204,8 @@ void launch_cal_cldfra3(const Geo &G, float *cldfra, const float *qv, float *qc,
                         const float *rho, const float *xland, float gridkm, float *qvsat, float *theta, float *dz, cudaStream_t s);
 void launch_cal_cldfra2(const Geo &G, const float *qc, const float *qi, int f_qc, int f_qi, float *cldfra, cudaStream_t s);
 void launch_ozn_time_int(const Geo &G, int levsiz, const float *m0, const float *m1, float fact1, float fact2, float *ozmixt, cudaStream_t s);
+void launch_clim_p_int(const Geo &G, int levsiz, const float *pin_host, const float *p, float pscale, int nsrc, const float *data, float *out,
+                       const float *pf, float *total, cudaStream_t s);
 void launch_ozn_p_int(const Geo &G, int levsiz, const float *pin_host, const float *p, const float *ozmixt, float *o3vmr, cudaStream_t s);
 void launch_lw_band(const LwArgs &a, cudaStream_t s);
 bool lw_layout_ok();

@@ -547,8 +547,23 @@ __global__ void __launch_bounds__(128) k_sw_prep(SwArgs a) {
         if (asma < 0.5f) asma = 0.5f;
         if (asma >= 1.0f) asma = 1.0f;
       }
-      AER(b, 0, l) = taua; AER(b, 1, l) = ssaa; AER(b, 2, l) = asma;
       if (model) aersum[b] = aersum[b] + taua;
+      if (a.aerod) {
+        // aer_opt = 1, iaer = 6: rrtmg_sw ignores taua / ssaa / asma and mixes the six ECMWF aerosol types from their optical
+        // depths ecaer (SW:9313-9341; the adapter copies AEROD for the model layers and 0 for the extra top layer, SW:11083-11100)
+        float zt = 0.f, zo = 0.f, za = 0.f;
+        for (int ia = 0; ia < 6; ia++) {
+          const float ec = model ? a.aerod[G.at3(i, k, j) + G.n3() * (size_t)ia] : 0.f;
+          const float re = tb.sw_rsr[ia * 14 + b] * ec;
+          zt = zt + re;
+          zo = zo + re * tb.sw_rsr[84 + ia * 14 + b];
+          za = za + re * tb.sw_rsr[84 + ia * 14 + b] * tb.sw_rsr[168 + ia * 14 + b];
+        }
+        if (zo != 0.f) za = za / zo;
+        if (zt != 0.f) zo = zo / zt;
+        taua = zt; ssaa = zo; asma = za;
+      }
+      AER(b, 0, l) = taua; AER(b, 1, l) = ssaa; AER(b, 2, l) = asma;
     }
     // ---- cloud physical properties and band optics (only where some sub-column is cloudy)
     const bool anycld = (ws.anyc[(size_t)(l >> 5) * cap + c] >> (l & 31)) & 1u;
@@ -574,7 +589,7 @@ __global__ void __launch_bounds__(128) k_sw_prep(SwArgs a) {
     for (int b = 0; b < NBSW; b++) {
       const float slope = aersum[b];
       if (slope < 0.f) { if (!err) err = ARC_ERR_NEG_AOD; }
-      else if (slope > 6.f) {
+      else if (slope > 6.f && !a.aerod) {            // (with iaer = 6 the capped array is the one rrtmg_sw ignores)
         for (int l = 0; l < nz; l++) AER(b, 0, l) = AER(b, 0, l) * 6.0f / slope;
       }
     }
@@ -890,35 +905,53 @@ void launch_ozn_time_int(const Geo &G, int levsiz, const float *m0, const float 
 // its own kupper, so one thread per column carrying its own kupper reproduces it.  Above the data top the mixing ratio is
 // scaled by p / pin(1), below the data bottom it is held.  Unfused arithmetic, IEEE division.
 struct OznPin { float pin[ARC_OZN_MAXLEV]; };
-__global__ void __launch_bounds__(128) k_ozn_p_int(Geo G, int levsiz, OznPin P, const float *__restrict__ p, const float *__restrict__ ozmixt,
-                                                   float *__restrict__ o3vmr) {
+// One kernel serves ozn_p_int and aer_p_int (DRV:4345-4506), which is the same interpolation per aerosol type with the model
+// pressure in hPa (p * 0.01), the result multiplied by the layer's interface-pressure difference pf(k) - pf(k+1), and the column
+// total over types and levels (types outer, levels inner, as the reference accumulates).
+__global__ void __launch_bounds__(128) k_clim_p_int(Geo G, int levsiz, OznPin P, const float *__restrict__ p, float pscale, int nsrc,
+                                                    const float *__restrict__ data, float *__restrict__ out, const float *__restrict__ pf,
+                                                    float *__restrict__ total) {
   const int tc = blockIdx.x * blockDim.x + threadIdx.x;
   if (tc >= G.ncol_tile) return;
   int i, j; G.ij(tc, i, j);
-  const size_t ob = (size_t)(i - G.ims) + (size_t)G.ni * (size_t)levsiz * (size_t)(j - G.jms);     // ozmixt(i, 1, j)
-  int kupper = 1;                                                                                     // 1-based, as in the reference
-  for (int k = G.kte; k >= G.kts; k--) {
-    const size_t q = G.at3(i, k, j);
-    const float pm = p[q];
-    for (int kk = kupper; kk <= levsiz - 1; kk++)
-      if (P.pin[kk - 1] < pm && pm <= P.pin[kk]) { kupper = kk; break; }
-    float o3;
-    if (pm < P.pin[0]) o3 = div_rn(__fmul_rn(ozmixt[ob], pm), P.pin[0]);
-    else if (pm > P.pin[levsiz - 1]) o3 = ozmixt[ob + (size_t)G.ni * (levsiz - 1)];
-    else {
-      const float dpu = __fsub_rn(pm, P.pin[kupper - 1]);
-      const float dpl = __fsub_rn(P.pin[kupper], pm);
-      o3 = div_rn(__fadd_rn(__fmul_rn(ozmixt[ob + (size_t)G.ni * (kupper - 1)], dpl), __fmul_rn(ozmixt[ob + (size_t)G.ni * kupper], dpu)),
-                  __fadd_rn(dpl, dpu));
+  const size_t nlev = (size_t)G.ni * (size_t)levsiz * (size_t)(G.jme - G.jms + 1), n3 = G.n3();
+  float tot = 0.f;
+  for (int s = 0; s < nsrc; s++) {
+    const float *__restrict__ dt = data + nlev * (size_t)s;
+    float *__restrict__ o = out + n3 * (size_t)s;
+    const size_t ob = (size_t)(i - G.ims) + (size_t)G.ni * (size_t)levsiz * (size_t)(j - G.jms);   // data(i, 1, j)
+    int kupper = 1;                                                                                   // 1-based, as in the reference
+    for (int k = G.kte; k >= G.kts; k--) {
+      const size_t q = G.at3(i, k, j);
+      const float pm = __fmul_rn(p[q], pscale);
+      for (int kk = kupper; kk <= levsiz - 1; kk++)
+        if (P.pin[kk - 1] < pm && pm <= P.pin[kk]) { kupper = kk; break; }
+      float v;
+      if (pm < P.pin[0]) v = div_rn(__fmul_rn(dt[ob], pm), P.pin[0]);
+      else if (pm > P.pin[levsiz - 1]) v = dt[ob + (size_t)G.ni * (levsiz - 1)];
+      else {
+        const float dpu = __fsub_rn(pm, P.pin[kupper - 1]);
+        const float dpl = __fsub_rn(P.pin[kupper], pm);
+        v = div_rn(__fadd_rn(__fmul_rn(dt[ob + (size_t)G.ni * (kupper - 1)], dpl), __fmul_rn(dt[ob + (size_t)G.ni * kupper], dpu)),
+                   __fadd_rn(dpl, dpu));
+      }
+      if (pf) v = __fmul_rn(v, __fsub_rn(pf[q], pf[G.at3(i, k + 1, j)]));
+      o[q] = v;
     }
-    o3vmr[q] = o3;
+    if (total)
+      for (int k = G.kts; k <= G.kte; k++) tot = __fadd_rn(tot, o[G.at3(i, k, j)]);
   }
+  if (total) total[G.at2(i, j)] = tot;
 }
-void launch_ozn_p_int(const Geo &G, int levsiz, const float *pin_host, const float *p, const float *ozmixt, float *o3vmr, cudaStream_t s) {
+void launch_clim_p_int(const Geo &G, int levsiz, const float *pin_host, const float *p, float pscale, int nsrc, const float *data, float *out,
+                       const float *pf, float *total, cudaStream_t s) {
   OznPin P;
   for (int k = 0; k < ARC_OZN_MAXLEV; k++) P.pin[k] = k < levsiz ? pin_host[k] : 0.f;
-  k_ozn_p_int<<<(G.ncol_tile + 127) / 128, 128, 0, s>>>(G, levsiz, P, p, ozmixt, o3vmr);
+  k_clim_p_int<<<(G.ncol_tile + 127) / 128, 128, 0, s>>>(G, levsiz, P, p, pscale, nsrc, data, out, pf, total);
   count_launch();
+}
+void launch_ozn_p_int(const Geo &G, int levsiz, const float *pin_host, const float *p, const float *ozmixt, float *o3vmr, cudaStream_t s) {
+  launch_clim_p_int(G, levsiz, pin_host, p, 1.0f, 1, ozmixt, o3vmr, nullptr, nullptr, s);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -305,6 +305,20 @@ class RadLib:
         t = [abi.c_fp, abi.c_fp, C.c_int, abi.c_fp, abi.c_fp]
         self._driver_call("ozn_p_int", dims, [p, ozmixt, o3vmr], a, a, t, t)
 
+    def aer_time_int(self, dims, julday, julian, aerodm, aerodt, levsiz, num_months, no_src):
+        """aer_time_int of module_radiation_driver.F:4236-4343: aerodm (no_src, num_months, jms:jme, levsiz, ims:ime in C order) ->
+        aerodt (no_src, jms:jme, levsiz, ims:ime)."""
+        a = [int(julday), float(julian), int(levsiz), int(num_months), int(no_src), _ptr(aerodm), _ptr(aerodt)]
+        t = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, abi.c_fp, abi.c_fp]
+        self._driver_call("aer_time_int", dims, [aerodm, aerodt], a, a, t, t)
+
+    def aer_p_int(self, dims, p, pin, levsiz, aerodt, aerod, no_src, pf, totaod):
+        """aer_p_int of module_radiation_driver.F:4345-4506: -> AEROD (no_src, jms:jme, kms:kme, ims:ime) and TOTAOD (jms:jme, ims:ime)."""
+        pin = np.ascontiguousarray(pin, dtype=np.float32)
+        a = [_ptr(p), abi.fptr(pin), int(levsiz), _ptr(aerodt), _ptr(aerod), int(no_src), _ptr(pf), _ptr(totaod)]
+        t = [abi.c_fp, abi.c_fp, C.c_int, abi.c_fp, abi.c_fp, C.c_int, abi.c_fp, abi.c_fp]
+        self._driver_call("aer_p_int", dims, [p, aerodt, aerod, pf, totaod], a, a, t, t)
+
     def optical_averaging(self, dims, mode, bins, alt, dz8w, outs, sigmag=None):
         """bins: list (one per size section, or per mode) of dicts {species_name: array, ..., "num": array}; a species name
         starts with its class (so4, no3, cl, nh4, na, oin, oc, bc, water), e.g. "oc_orgaro1j".  outs: dict with
