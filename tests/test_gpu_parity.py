@@ -568,6 +568,14 @@ def test_percentiles_and_trim_match_the_ncl_statistics(lib, ktab):
     lib.check(L.arc_rad_percentiles(C.byref(d1), 0, 1, ptr, 3, abi.fptr(perc), C.c_void_p(out.ctypes.data)))
     row = np.sort(interior(dom, lw["olr"])[2])
     assert out[0] == row[0] and out[2] == row[-1] and out[1] == row[N.ncl_round(np.float32(np.float32(0.01) * np.float32(33.0)) * np.float32(row.size - 1))]
+    # a region box, as calculate_domain_stats' region_select branch cuts it (0-based inclusive lon / lat index ranges)
+    box = (3, 17, 2, 9)
+    reg = lib.domain_statistics(dom["dims"], [fields[n] for n in names], names=names, region=box)
+    for n in names:
+        ref = N.calc_standard_stats(interior(dom, fields[n])[box[2]:box[3] + 1, box[0]:box[1] + 1])
+        for k in ("median", "p05", "p95", "min", "max", "N"):
+            assert reg[n][k] == ref[k], (n, k)
+        assert np.isclose(reg[n]["avg"], ref["avg"], rtol=1e-12) and abs(reg[n]["morans_i"] - ref["morans_i"]) <= 2e-6 * max(1.0, abs(ref["morans_i"]))
 
 
 def test_four_scenario_decomposition_from_device_statistics(lib, ktab):

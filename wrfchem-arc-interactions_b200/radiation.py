@@ -185,15 +185,22 @@ class RadLib:
 
 
     # optical_averaging (WRF-Chem chem/module_optical_averaging.F; restated)
-    def domain_statistics(self, dims, fields, names=None, morans=True, percentiles=True, trim=0):
+    def domain_statistics(self, dims, fields, names=None, morans=True, percentiles=True, trim=0, region=None):
         """The 13 statistics of calc_standard_stats (misc_stats_library.ncl:396-461) for 2-D fields, reduced on the device:
         avg, stddev (N-1), min, max, median, lower_quartile, upper_quartile, p05, p95 (with `percentiles`), standard_error,
         morans_i and corrected_standard_error = SE * I (with `morans`), N.  `trim` cells are cut from every edge of the tile
-        first, as calculate_domain_stats does with domain_trim@trim = 5 (data_extraction_library.ncl:318-322).
+        first, as calculate_domain_stats does with domain_trim@trim = 5 (data_extraction_library.ncl:318-322); `region` =
+        (lon_start, lon_end, lat_start, lat_end), the 0-based inclusive index box of its region_select branch (ncl:291-316, from
+        wrf_user_ll_to_ij), takes precedence over `trim` as in the reference.
         `fields`: list of numpy arrays (host) or torch CUDA tensors (device); returns decomposition.stats_from_sums(...)."""
         from . import decomposition
         d = abi.make_dims(dims) if isinstance(dims, dict) else abi.ArcDims.from_buffer_copy(dims)
-        if trim:
+        if region is not None:
+            i0, i1, j0, j1 = (int(x) for x in region)
+            if not (0 <= i0 <= i1 <= d.ite - d.its and 0 <= j0 <= j1 <= d.jte - d.jts):
+                raise ValueError("region outside the tile")
+            d.ite = d.its + i1; d.its = d.its + i0; d.jte = d.jts + j1; d.jts = d.jts + j0
+        elif trim:
             d.its += trim; d.ite -= trim; d.jts += trim; d.jte -= trim
         dev = [_is_device(f) for f in fields]
         if any(dev) and not all(dev):
