@@ -612,20 +612,22 @@ def test_four_scenario_decomposition_from_device_statistics(lib, ktab):
     ds = mean(fa["SWUPT"]) - mean(fb["SWUPT"])
     assert np.isclose(out["Delta_S"][0], ds, rtol=1e-9, atol=1e-9)
     assert np.isclose(out["SW_DIRECT"][0] + out["SW_SEMIDIRECT"][0] + (mean(fan["SWUPT"]) - mean(fbn["SWUPT"])), ds, rtol=1e-9, atol=1e-9)
-    # ... and through the reference's text files: device statistics -> <var>_domain_stats.txt per scenario (write_stats_data,
-    # data_extraction_library.ncl:428-574) -> load_Files (RadDecomp_functions.py:95-112) -> the same decomposition to the files' 4 decimals
+    # ... and through the reference's text files: EXTRACT_domain_averages.ncl's loop on the in-memory fields (device statistics ->
+    # <var>_domain_stats.txt per scenario; *CLN of the runs without aerosol-radiation interaction = the all-aerosol field) ->
+    # load_Files (RadDecomp_functions.py:95-112) -> the same decomposition to the files' 4 decimals
     import datetime
     import tempfile
     from wrfchem_arc_interactions_b200 import stats_files as SF
     root = tempfile.mkdtemp()
     t = [datetime.datetime(2012, 7, 21, 12)]
-    for scen, st in (("BASE", b), ("BASE_nA", bn), ("ALT", a), ("ALT_nA", an)):
-        for var in SF.VAR_LIST:
-            SF.write_stats_data(os.path.join(root, scen), var, SF.create_local_time_strings(t), SF.calc_runtime_in_hours(t), [st[var]], units="W m-2")
+    drop = lambda f: {k: v for k, v in f.items() if "CLN" not in k}
+    scen = {"BASE": (True, [fb]), "BASE_nA": (False, [drop(fbn)]), "ALT": (True, [fa]), "ALT_nA": (False, [drop(fan)])}
+    SF.extract_domain_averages(lib, dom["dims"], scen, root, t, plot_variables=SF.VAR_LIST, trim=0)
     Bf, Af = SF.load_Files(root, "BASE", "_nA", "domain"), SF.load_Files(root, "ALT", "_nA", "domain")
     eff, err = D.calc_SW_DIRECT(Bf, Af, "SE_corr")
     assert abs(float(eff.iloc[0]) - outc["SW_DIRECT"][0]) < 4e-4 and abs(float(err.iloc[0]) - outc["SW_DIRECT"][1]) < 4e-4
     assert float(Bf["SWUPT"]["N"].iloc[0]) == 24 * 16
+    assert float(Bf["SWUPTCLN_nA"]["avg"].iloc[0]) == float(Bf["SWUPT_nA"]["avg"].iloc[0])
 
 
 def test_coszen_and_accumulation(lib, orc, ktab):

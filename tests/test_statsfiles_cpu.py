@@ -69,3 +69,38 @@ def test_device_statistics_dicts_feed_the_writer(tmp_path):
     assert abs(row["SE_corr"][0] - 0.8 * row["SE"][0]) < 1e-4
     with pytest.raises(ValueError):
         SF.write_stats_data(str(tmp_path), "SWUPT", ["a", "b"], [0.0], [st])
+
+
+class _HostStats:
+    """Stand-in for Radiation.domain_statistics on the CPU: the restated NCL statistics of oracle/ncl_stats.py."""
+    def domain_statistics(self, dims, fields, names=None, morans=True, percentiles=True, trim=0, region=None):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ncl_stats as N
+        out = {}
+        for n, f in zip(names, fields):
+            x = f if region is None else f[region[2]:region[3] + 1, region[0]:region[1] + 1]
+            out[n] = N.calc_standard_stats(x, trim=0 if region is not None else trim)
+        return out
+
+
+def test_extract_domain_averages_driver(tmp_path):
+    """EXTRACT_domain_averages.ncl's loop: every variable of every scenario to its file; a scenario without clean-sky output gets
+    the all-aerosol field for *CLN (ncl:160-165); 5-cell trim; region boxes name their files <var>_<region>_domain_stats.txt."""
+    rng = np.random.default_rng(3)
+    times = [datetime.datetime(2012, 7, 21, 0), datetime.datetime(2012, 7, 21, 3)]
+    mk = lambda names: [{n: rng.normal(200.0, 20.0, (24, 30)).astype(np.float32) for n in names} for _ in times]
+    full = mk(SF.PLOT_VARIABLES)
+    nocln = mk([v for v in SF.PLOT_VARIABLES if "CLN" not in v])
+    out = SF.extract_domain_averages(_HostStats(), None, {"Basecase": (True, full), "Basecase_nA": (False, nocln)}, str(tmp_path), times)
+    assert len(out["Basecase"]) == 24 and os.path.basename(out["Basecase"][("SWUPTCLN", None)]) == "SWUPTCLN_domain_stats.txt"
+    a = SF.read_stats_file(out["Basecase_nA"][("SWUPTCLN", None)]); b = SF.read_stats_file(out["Basecase_nA"][("SWUPT", None)])
+    assert np.array_equal(a["avg"], b["avg"]) and a["Time"] == ["(Jul-21) 00", "(Jul-21) 03"] and list(a["Hour"]) == [0.0, 3.0]
+    assert a["N"][0] == (24 - 10) * (30 - 10)                                   # domain_trim@trim = 5
+    want = float(np.float64(full[1]["LWDNB"][5:-5, 5:-5].astype(np.float64).mean()))
+    assert abs(SF.read_stats_file(out["Basecase"][("LWDNB", None)])["avg"][1] - want) < 6e-5
+    reg = SF.extract_domain_averages(_HostStats(), None, {"Basecase": (True, full)}, str(tmp_path / "r"), times, plot_variables=("SWUPT",),
+                                     regions={"ENG": (4, 11, 2, 9)})
+    r = SF.read_stats_file(reg["Basecase"][("SWUPT", "ENG")])
+    assert os.path.basename(reg["Basecase"][("SWUPT", "ENG")]) == "SWUPT_ENG_domain_stats.txt" and r["N"][0] == 64
+    with pytest.raises(KeyError):
+        SF.extract_domain_averages(_HostStats(), None, {"x": (True, nocln)}, str(tmp_path / "e"), times)

@@ -97,3 +97,47 @@ def load_Files(DATADir, scen, alt_end, dom):
             df = pd.DataFrame({k: v for k, v in cols.items() if k != "Hour"}, index=pd.Index(cols["Hour"], name="Hour"))
             out[var + suffix] = df
     return out
+
+
+PLOT_VARIABLES = ("SWUPT", "SWUPTC", "SWUPTCLN", "SWDNT", "SWDNTC", "SWDNTCLN", "SWUPB", "SWUPBC", "SWUPBCLN", "SWDNB", "SWDNBC", "SWDNBCLN",
+                  "LWUPT", "LWUPTC", "LWUPTCLN", "LWDNT", "LWDNTC", "LWDNTCLN", "LWUPB", "LWUPBC", "LWUPBCLN", "LWDNB", "LWDNBC", "LWDNBCLN")
+
+
+def extract_name(var, clean_flag):
+    """The variable actually read for `var`: a scenario without clean-sky output (clean_flag False: the runs without
+    aerosol-radiation interaction) gets the all-aerosol variable in place of every *CLN one
+    (load_2D_3D_variable_and_sample_at_given_altitudes, data_extraction_library.ncl:160-165)."""
+    return var.replace("CLN", "") if (not clean_flag and "CLN" in var) else var
+
+
+def extract_domain_averages(rad, dims, scenarios, output_root_directory, times, plot_variables=PLOT_VARIABLES, trim=5, regions=None,
+                            local_time_offset=None, units="W m-2"):
+    """The main loop of EXTRACT_domain_averages.ncl on in-memory fields instead of wrfout files: for every scenario and variable
+    the 13 domain statistics of every output time (reduced on the device by `rad.domain_statistics`, 5-cell trim or region
+    boxes as calculate_domain_stats cuts them) written to `<output_root>/<scenario>/<var>[_<region>]_domain_stats.txt`.
+
+    scenarios: {name: (clean_flag, [ {wrf variable name: 2-D field} per output time ])} - host arrays or CUDA tensors;
+    regions:   None, or {region name: (lon_start, lon_end, lat_start, lat_end)} index boxes (wrf_user_ll_to_ij results - 1).
+    Returns {scenario: {(var, region or None): path}}."""
+    labels = create_local_time_strings(times, local_time_offset or 0.0)
+    hours = calc_runtime_in_hours(times)
+    written = {}
+    for scen, (clean_flag, per_time) in scenarios.items():
+        if len(per_time) != len(times):
+            raise ValueError("extract_domain_averages: scenario %s has %d times, expected %d" % (scen, len(per_time), len(times)))
+        written[scen] = {}
+        for region, box in (regions.items() if regions else [(None, None)]):
+            rows = {v: [] for v in plot_variables}
+            for fields in per_time:
+                src = [extract_name(v, clean_flag) for v in plot_variables]
+                missing = [n for n in src if n not in fields]
+                if missing:
+                    raise KeyError("extract_domain_averages: scenario %s lacks %s" % (scen, ", ".join(sorted(set(missing)))))
+                uniq = sorted(set(src))
+                st = rad.domain_statistics(dims, [fields[n] for n in uniq], names=uniq, trim=0 if box else trim, region=box)
+                for v, n in zip(plot_variables, src):
+                    rows[v].append(st[n])
+            for v in plot_variables:
+                written[scen][(v, region)] = write_stats_data(os.path.join(output_root_directory, scen), v, labels, hours, rows[v], units=units,
+                                                              region=region)
+    return written
