@@ -428,6 +428,28 @@ def test_device_memspace_equals_host_memspace(lib, ktab):
             assert np.array_equal(h[k], o[k].cpu().numpy()), k
 
 
+def test_calls_from_several_host_threads_are_serialised(lib, ktab):
+    """One context per process: the entry points take a process-wide lock, so WRF's OpenMP tiles - here four
+    Python threads whose ctypes calls run concurrently - get the results of serial calls, bit for bit."""
+    import threading
+    doms = [synth.make_domain(20, 6, 40, seed=60 + t) for t in range(4)]
+    init(lib, doms[0], ktab)
+    serial = [(run_pair("sw", lib, d), run_pair("lw", lib, d)) for d in doms]
+    got = [None] * 4
+
+    def work(t):
+        got[t] = (run_pair("sw", lib, doms[t]), run_pair("lw", lib, doms[t]))
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for t in range(4):
+        for a, b in zip(got[t], serial[t]):
+            for k in a:
+                assert np.array_equal(a[k], b[k], equal_nan=True), (t, k)
+
+
 def test_errors(lib, ktab):
     dom = synth.make_domain(8, 4, 40, seed=15, all_day=True)
     init(lib, dom, ktab)

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -701,6 +702,11 @@ static PipePart lw_part(const ArcLwIn *in, ArcLwOut *out) {
 
 }  // namespace
 
+// One context (streams, workspaces, status word) per process: the public entry points serialise on a recursive mutex, so calls
+// from several host threads (WRF's OpenMP tiles) are safe - they run one after the other (arc_rad_lwsw re-enters arc_rad_lw / _sw).
+static std::recursive_mutex g_api_mu;
+#define API_LOCK std::lock_guard<std::recursive_mutex> api_lock_(g_api_mu)
+
 extern "C" {
 
 const char *arc_rad_last_error(void) { return g.err.c_str(); }
@@ -719,13 +725,14 @@ int arc_rad_test_sweep_groups(const int *ng, int nbands, int gmax, int *band, in
 long long arc_rad_test_coef_index(int field, int layer, long long column, long long cap, int nfields) {
   return (long long)coef_index(field, layer, (size_t)column, (size_t)cap, nfields);
 }
-int arc_rad_set_overlap(int on) { const int prev = g.overlap ? 1 : 0; g.overlap = on != 0; return prev; }
+int arc_rad_set_overlap(int on) { API_LOCK; const int prev = g.overlap ? 1 : 0; g.overlap = on != 0; return prev; }
 float arc_rad_last_kernel_ms(const char *name) {
   auto it = g.last_ms.find(name ? name : "");
   return it == g.last_ms.end() ? -1.f : it->second;
 }
 
 void arc_rad_finalize(void) {
+  API_LOCK;
   if (!g.ready) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
@@ -774,6 +781,7 @@ void arc_rad_finalize(void) {
 }
 
 int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_data_path) {
+  API_LOCK;
   if (!cfg || !sw_data_path || !lw_data_path) { g.err = "arc_rad_init: null argument"; return ARC_ERR_BAD_ARG; }
   if (g.ready) arc_rad_finalize();
   std::string inl;
@@ -885,6 +893,7 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
 
 // ---------------------------------------------------------------------------------------------------------
 int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebug *dbg) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_sw: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !in || !out) { g.err = "arc_rad_sw: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1078,6 +1087,7 @@ int arc_rad_sw(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out) { return arc_
 
 // ---------------------------------------------------------------------------------------------------------
 int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebug *dbg) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_lw: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !in || !out) { g.err = "arc_rad_lw: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1249,6 +1259,7 @@ int arc_rad_lw(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out) { return arc_
 // With host arrays both run inside ONE slab pipeline: the arrays the two adapters share are uploaded once and the
 // pipeline fills and drains once; otherwise this is simply the two calls.
 int arc_rad_lwsw(const ArcDims *d, const ArcLwIn *lwin, ArcLwOut *lwout, const ArcSwIn *swin, ArcSwOut *swout) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_lwsw: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !lwin || !lwout || !swin || !swout) { g.err = "arc_rad_lwsw: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1289,6 +1300,7 @@ __global__ void k_driver_post(Geo G, const float *__restrict__ lw, const float *
 
 int arc_rad_driver_post(const ArcDims *d, int memspace, const float *rthratenlw, const float *rthratensw, float *rthraten,
                         const float *gsw, const float *albedo, float *swdown) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_driver_post: not initialised"; return ARC_ERR_NOT_INIT; }
   int rc = check_dims(*d);
   if (rc) return rc;
@@ -1343,6 +1355,7 @@ __global__ void k_calc_coszen(Geo G, float xt24, float gmt, float declin, float 
 
 int arc_rad_calc_coszen(const ArcDims *d, int memspace, float julian, float xtime, float gmt, float declin, float degrad,
                         const float *xlon, const float *xlat, float *coszen, float *hrang) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_calc_coszen: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !xlon || !xlat || !coszen) { g.err = "arc_rad_calc_coszen: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1376,6 +1389,7 @@ __global__ void k_accumulate(Geo G, float dt, int nf, const float *const *__rest
 }
 
 int arc_rad_accumulate(const ArcDims *d, int memspace, float dtaccum, int nfields, const float *const *flux, float *const *acc) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_accumulate: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !flux || !acc || nfields < 1 || nfields > 32) { g.err = "arc_rad_accumulate: bad argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1434,6 +1448,7 @@ __global__ void __launch_bounds__(1024) k_domain_stats(Geo G, int nfields, const
 }
 
 int arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const float *const *fields, double *out) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_domain_stats: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !fields || !out || nfields < 1 || nfields > 64) { g.err = "arc_rad_domain_stats: bad argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1522,6 +1537,7 @@ __global__ void k_morans_final(Geo G, int nfields, int nb, const double *__restr
 }
 
 int arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *const *fields, float *out) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_morans_i: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !fields || !out || nfields < 1 || nfields > 64) { g.err = "arc_rad_morans_i: bad argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1555,6 +1571,7 @@ int arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *c
 int arc_rad_cal_cldfra1(const ArcDims *d, int memspace, const float *qv, const float *qc, const float *qi, const float *qs, int f_qv, int f_qc,
                         int f_qi, int f_qs, const float *t_phy, const float *p_phy, const float *f_ice_phy, int mp_physics, float *cldfra,
                         int *cldfra1_flag) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_cal_cldfra1: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !qv || !t_phy || !p_phy || !cldfra) { g.err = "arc_rad_cal_cldfra1: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1582,6 +1599,7 @@ int arc_rad_cal_cldfra1(const ArcDims *d, int memspace, const float *qv, const f
 
 // cal_cldfra2 (module_radiation_driver.F:2801-2874, called for icloud = 2 at DRV:1205): binary cloud fraction.
 int arc_rad_cal_cldfra2(const ArcDims *d, int memspace, const float *qc, const float *qi, int f_qc, int f_qi, float *cldfra) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_cal_cldfra2: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !cldfra) { g.err = "arc_rad_cal_cldfra2: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1607,6 +1625,7 @@ int arc_rad_cal_cldfra2(const ArcDims *d, int memspace, const float *qc, const f
 // CLDFRA is written, QC and QI are INOUT (the scheme adds sub-grid condensate to the fractional layers it finds), QS is read.
 int arc_rad_cal_cldfra3(const ArcDims *d, int memspace, float *cldfra, const float *qv, float *qc, float *qi, const float *qs, const float *p,
                         const float *t, const float *rho, const float *xland, float gridkm) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_cal_cldfra3: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !cldfra || !qv || !qc || !qi || !qs || !p || !t || !rho || !xland) {
     g.err = "Can not use icloud = 3 option, missing QC or QI field.";       // the reference's message (DRV:1236) covers the null case
@@ -1668,6 +1687,7 @@ static void clim_time_weights(float julian, int &nm_out, int &np_out, float &fac
 // time to the model day.  The date arithmetic (which two months, which weights) is the reference's scalar code in single
 // precision, on the host; the blend of the two months runs on the device.
 int arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, const float *ozmixm, float *ozmixt) {
+  API_LOCK;
   (void)julday;                                              // as in the reference: only JULIAN is used
   if (!g.ready) { g.err = "arc_rad_ozn_time_int: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !ozmixm || !ozmixt) { g.err = "arc_rad_ozn_time_int: null argument"; return ARC_ERR_BAD_ARG; }
@@ -1695,6 +1715,7 @@ int arc_rad_ozn_time_int(const ArcDims *d, int memspace, int julday, float julia
 // down, strictly increasing) interpolated to the model mid-level pressures p(i,k,j) -> o3vmr(i,k,j), the O3RAD that
 // RRTMG_SWRAD / RRTMG_LWRAD read with o3input = 2.
 int arc_rad_ozn_p_int(const ArcDims *d, int memspace, const float *p, const float *pin, int levsiz, const float *ozmixt, float *o3vmr) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_ozn_p_int: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !p || !pin || !ozmixt || !o3vmr) { g.err = "arc_rad_ozn_p_int: null argument"; return ARC_ERR_BAD_ARG; }
   if (levsiz < 2 || levsiz > ARC_OZN_MAXLEV) { g.err = "arc_rad_ozn_p_int: levsiz must be 2.." + std::to_string(ARC_OZN_MAXLEV); return ARC_ERR_BAD_ARG; }
@@ -1721,6 +1742,7 @@ int arc_rad_ozn_p_int(const ArcDims *d, int memspace, const float *p, const floa
 // aerodm(ims:ime, levsiz, jms:jme, num_months, no_src) -> aerodt(ims:ime, levsiz, jms:jme, no_src), as ozn_time_int per aerosol type.
 int arc_rad_aer_time_int(const ArcDims *d, int memspace, int julday, float julian, int levsiz, int num_months, int no_src, const float *aerodm,
                          float *aerodt) {
+  API_LOCK;
   (void)julday;
   if (!g.ready) { g.err = "arc_rad_aer_time_int: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !aerodm || !aerodt) { g.err = "arc_rad_aer_time_int: null argument"; return ARC_ERR_BAD_ARG; }
@@ -1751,6 +1773,7 @@ int arc_rad_aer_time_int(const ArcDims *d, int memspace, int julday, float julia
 // interface-pressure difference pf(k) - pf(k+1), and their column total TOTAOD(i,j).  AEROD is what RRTMG_SWRAD reads with aer_opt = 1.
 int arc_rad_aer_p_int(const ArcDims *d, int memspace, const float *p, const float *pin, int levsiz, const float *aerodt, float *aerod, int no_src,
                       const float *pf, float *totaod) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_aer_p_int: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !p || !pin || !aerodt || !aerod || !pf || !totaod) { g.err = "arc_rad_aer_p_int: null argument"; return ARC_ERR_BAD_ARG; }
   if (levsiz < 2 || levsiz > ARC_OZN_MAXLEV || no_src < 1) { g.err = "arc_rad_aer_p_int: levsiz must be 2.." + std::to_string(ARC_OZN_MAXLEV) + ", no_src >= 1"; return ARC_ERR_BAD_ARG; }
@@ -1825,6 +1848,7 @@ __global__ void k_perc_select(int nfields, int nperc, int pass, PercState *__res
 }
 
 int arc_rad_percentiles(const ArcDims *d, int memspace, int nfields, const float *const *fields, int nperc, const float *perc, float *out) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_percentiles: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !fields || !out || !perc || nfields < 1 || nfields > 64 || nperc < 1 || nperc > 16) { g.err = "arc_rad_percentiles: bad argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -1889,6 +1913,7 @@ int arc_rad_host_table(const char *inline_tables, const char *sw_data_path, cons
 
 // Self-test (GPU): jp | jt << 8 | jt1 << 12 of setcoef for n host (p [hPa], T [K]) pairs, through the prep kernels' own code
 int arc_rad_selftest_pt(const float *p, const float *t, int n, int *packed) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_rad_selftest_pt: not initialised"; return ARC_ERR_NOT_INIT; }
   CK(cudaSetDevice(g.device));
   g.pool_next = 0; g.backs.clear();
@@ -1912,6 +1937,7 @@ __global__ void k_selftest_libm(int which, const float *__restrict__ x, const fl
   out[t] = which == 0 ? glm::logf_(x[t]) : which == 1 ? glm::expf_(x[t]) : glm::powf_(x[t], y[t]);
 }
 int arc_rad_selftest_libm(int which, const float *x, const float *y, int n, float *out, int on_device) {
+  API_LOCK;
   if (which < 0 || which > 2 || !x || !out || (which == 2 && !y) || n < 0) { g.err = "arc_rad_selftest_libm: bad argument"; return ARC_ERR_BAD_ARG; }
   if (!on_device) {
     for (int t = 0; t < n; t++) out[t] = which == 0 ? glm::logf_(x[t]) : which == 1 ? glm::expf_(x[t]) : glm::powf_(x[t], y[t]);
@@ -1957,6 +1983,7 @@ __global__ void k_selftest_rcp(unsigned lo_bits, unsigned count, unsigned long l
   if (!(__frcp_rn(x) == rcp_rn(x))) atomicAdd(bad, 1ull);
 }
 long long arc_rad_selftest_rcp(unsigned lo_bits, unsigned hi_bits) {
+  API_LOCK;
   if (!g.ready || hi_bits < lo_bits) return -1;
   cudaSetDevice(g.device);
   unsigned long long *d; if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
@@ -1972,6 +1999,7 @@ long long arc_rad_selftest_rcp(unsigned lo_bits, unsigned hi_bits) {
   return (long long)h;
 }
 int arc_rad_selftest_div(int n, unsigned seed) {
+  API_LOCK;
   if (!g.ready) return -1;
   cudaSetDevice(g.device);
   int *d; if (cudaMalloc(&d, 4) != cudaSuccess) return -1;
@@ -1994,12 +2022,14 @@ void arc_aer_default_refindex(float *refr, float *refi) {
 }
 
 int arc_aer_init(const float *refr, const float *refi) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_aer_init: call arc_rad_init first"; return ARC_ERR_NOT_INIT; }
   CK(cudaSetDevice(g.device));
   return aer_init(refr, refi, g.err);
 }
 
 int arc_aer_optics(const ArcDims *d, const ArcAerIn *in, ArcAerOut *out) {
+  API_LOCK;
   if (!g.ready) { g.err = "arc_aer_optics: not initialised"; return ARC_ERR_NOT_INIT; }
   if (!d || !in || !out) { g.err = "arc_aer_optics: null argument"; return ARC_ERR_BAD_ARG; }
   int rc = check_dims(*d);
@@ -2113,6 +2143,7 @@ __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters) {
   if (s == 12345.678f) out[0] = s;
 }
 float arc_rad_measure_fp32_tflops(void) {
+  API_LOCK;
   if (!g.ready) return -1.f;
   cudaSetDevice(g.device);
   float *dout; if (cudaMalloc(&dout, 4) != cudaSuccess) return -1.f;
