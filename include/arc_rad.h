@@ -219,6 +219,10 @@ int  arc_rad_domain_stats(const ArcDims *d, int memspace, int nfields, const flo
  * for calc_standard_stats (neighbour + manhattan options: ordered pairs of edge-sharing cells, N-1 variance;
  * misc_stats_library.ncl:196-371).  corrected SE = SE * I (misc_stats_library.ncl:449). */
 int  arc_rad_morans_i(const ArcDims *d, int memspace, int nfields, const float *const *fields, float *out);
+/* Counts of the reference's aerosol warnings in the most recent call (or LW + SW pair): (column, band) pairs whose chem-aerosol
+ * column optical depth exceeded 6 in the shortwave and was rescaled to 6 (SW:11034-11069), or exceeded 5 in the longwave (warning
+ * only, LW:12616-12627).  Either pointer may be NULL. */
+void arc_rad_warning_counts(int *sw_aod_capped, int *lw_aod_large);
 /* cal_cldfra1 (module_radiation_driver.F:2886-3122; radiation_driver calls it for icloud = 1, DRV:1104-1118): cloud fraction
  * CLDFRA(i,k,j) from QV, QC, QI, QS, T, p, tile levels kts..kte.  f_q*: 1 = .TRUE., 0 = .FALSE., < 0 = argument not PRESENT;
  * f_ice_phy and cldfra1_flag (INTEGER(i,k,j): 1 no condensate, 2 saturated, 3 partial) may be NULL.  Bit-exact with the

@@ -450,6 +450,40 @@ def test_calls_from_several_host_threads_are_serialised(lib, ktab):
                 assert np.array_equal(a[k], b[k], equal_nan=True), (t, k)
 
 
+def test_aerosol_warning_counts(lib, ktab):
+    """The reference warns for every (column, band) with a column AOD above 6 (SW, where it rescales to 6, SW:11034-11069) or above 5
+    (LW, LW:12616-12627); the library counts these events instead of printing (arc_rad_warning_counts)."""
+    L = lib.lib
+    L.arc_rad_warning_counts.restype = None
+    L.arc_rad_warning_counts.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+
+    def counts():
+        a, b = C.c_int(-1), C.c_int(-1)
+        L.arc_rad_warning_counts(C.byref(a), C.byref(b))
+        return a.value, b.value
+    dom = synth.make_domain(20, 6, 40, seed=71)
+    init(lib, dom, ktab)
+    run_pair("sw", lib, dom); sw0 = counts()[0]
+    run_pair("lw", lib, dom); lw0 = counts()[1]
+    thick = dict(dom)
+    lwfac = 6.0 / float(np.median(dom["tauaerlw16"][:, :dom["nk"], :].sum(axis=1)))      # half the columns of the last band above 5
+    for k in dom:
+        if k.startswith("tauaer"):
+            thick[k] = (dom[k] * np.float32(lwfac if k.startswith("tauaerlw") else 60.0)).astype(np.float32)
+    nsun = int((interior(dom, dom["xcoszen"]) > 0).sum())
+    run_pair("sw", lib, thick); sw1 = counts()[0]
+    run_pair("lw", lib, thick); lw1 = counts()[1]
+    assert sw0 == 0 and 0 < sw1 <= 14 * nsun
+    want = 0                                                            # LW: sum over the model levels in single precision, k ascending
+    for b in range(16):
+        acc = np.zeros(interior(dom, dom["xcoszen"]).shape, np.float32)
+        t = thick["tauaerlw%d" % (b + 1)]
+        for k in range(dom["nk"]):
+            acc = acc + t[:, k, :]
+        want += int((acc > np.float32(5.0)).sum())
+    assert lw0 == 0 and lw1 == want and want > 0
+
+
 def test_errors(lib, ktab):
     dom = synth.make_domain(8, 4, 40, seed=15, all_day=True)
     init(lib, dom, ktab)

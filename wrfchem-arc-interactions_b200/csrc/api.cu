@@ -51,6 +51,7 @@ struct Ctx {
   DevTables D;
   std::vector<void *> table_allocs;
   int *d_status = nullptr, *d_count = nullptr;
+  int warn_sw = 0, warn_lw = 0;        // warning counts of the last call (see arc_rad_warning_counts)
   int *d_cols = nullptr; size_t cols_cap = 0;
   int *d_cols_lw = nullptr; size_t cols_lw_cap = 0;      // LW column list (every column, cloud-bucketed)
   // workspaces (grow-only)
@@ -386,12 +387,13 @@ int finish_call(std::vector<std::pair<void *, std::pair<void *, size_t>>> &dbgli
   for (auto &e : dbglist) CK(cudaMemcpyAsync(e.first, e.second.first, e.second.second, cudaMemcpyDeviceToHost, g.stream));
   int rc = copy_back();
   if (rc) return rc;
-  int status = 0;
-  CK(cudaMemcpyAsync(&status, g.d_status, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  int st[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(st, g.d_status, sizeof(int) * 4, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());
   collect_times();
-  if (status) { g.err = code_msg(status); return status; }
+  g.warn_sw = st[1]; g.warn_lw = st[2];
+  if (st[0]) { g.err = code_msg(st[0]); return st[0]; }
   return 0;
 }
 
@@ -665,13 +667,14 @@ static int run_pipelined(const ArcDims &d, const PipePart *parts, int nparts) {
   }
   if (!status && nparts == 2 && g.overlap && parts[0].call == call_lw_ptr && parts[1].call == call_sw_ptr) {
     // end of the asynchronous pipeline: drain the compute streams, fetch the device status word, collect the kernel times
-    int dev_status = 0;
+    int st[4] = {0, 0, 0, 0};
     CK(cudaStreamSynchronize(g.stream3)); CK(cudaStreamSynchronize(g.stream2));
-    CK(cudaMemcpyAsync(&dev_status, g.d_status, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(st, g.d_status, sizeof(int) * 4, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaGetLastError());
     collect_times();
-    if (dev_status) { g.err = code_msg(dev_status); status = dev_status; }
+    g.warn_sw = st[1]; g.warn_lw = st[2];
+    if (st[0]) { g.err = code_msg(st[0]); status = st[0]; }
   }
   CK(cudaStreamSynchronize(g.d2h));
   CK(cudaStreamSynchronize(g.h2d));
@@ -724,6 +727,14 @@ int arc_rad_test_sweep_groups(const int *ng, int nbands, int gmax, int *band, in
 }
 long long arc_rad_test_coef_index(int field, int layer, long long column, long long cap, int nfields) {
   return (long long)coef_index(field, layer, (size_t)column, (size_t)cap, nfields);
+}
+// The reference prints a warning block for every (column, band) whose chem-aerosol column optical depth exceeds 6 in the shortwave
+// (where it also rescales the profile to 6, SW:11034-11069) or 5 in the longwave (LW:12616-12627).  Nothing is printed from the
+// device: the events of the most recent call (pair) are counted and returned here.
+void arc_rad_warning_counts(int *sw_aod_capped, int *lw_aod_large) {
+  API_LOCK;
+  if (sw_aod_capped) *sw_aod_capped = g.warn_sw;
+  if (lw_aod_large) *lw_aod_large = g.warn_lw;
 }
 int arc_rad_set_overlap(int on) { API_LOCK; const int prev = g.overlap ? 1 : 0; g.overlap = on != 0; return prev; }
 float arc_rad_last_kernel_ms(const char *name) {
@@ -818,7 +829,8 @@ int arc_rad_init(const ArcConfig *cfg, const char *sw_data_path, const char *lw_
   CK(cudaStreamCreateWithFlags(&g.h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&g.d2h, cudaStreamNonBlocking));
   for (int q = 0; q < 2; q++) { CK(cudaEventCreateWithFlags(&g.ev_in[q], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.ev_out[q], cudaEventDisableTiming)); }
-  CK(cudaMalloc(&g.d_status, sizeof(int)));
+  CK(cudaMalloc(&g.d_status, sizeof(int) * 4));       // [0] first error, [1] SW (column, band) AOD capped at 6, [2] LW (column, band) AOD > 5
+  CK(cudaMemset(g.d_status, 0, sizeof(int) * 4));
   CK(cudaMalloc(&g.d_count, 2 * sizeof(int)));
 
   const HostTables &H = g.H;
@@ -959,7 +971,7 @@ int arc_rad_sw_debug(const ArcDims *d, const ArcSwIn *in, ArcSwOut *out, ArcDebu
 
   const bool chained = g.chain == 2;
   cudaStream_t sp = chained ? g.stream3 : g.stream;       // stream of the column-parallel pre-kernels of the first outer chunk
-  if (!chained) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
+  if (!chained) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int) * 4, g.stream));
   if (chained && g.async_pair) CK(cudaStreamWaitEvent(g.stream3, g.ev_sw_done, 0));    // the SW workspace of the previous slab is free
   {
     const int fq[7] = {in->f_qv, in->f_qc, in->f_qr, in->f_qi, in->f_qs, in->f_qg, in->f_qndrop};
@@ -1143,7 +1155,7 @@ int arc_rad_lw_debug(const ArcDims *d, const ArcLwIn *in, ArcLwOut *out, ArcDebu
   const int nlay = g.H.lw_nlayers;
   if (nlay > 159 || nlay < nz + 1) { g.err = "arc_rad_lw: bad LW layer count (nlayers from init vs kte)"; return ARC_ERR_BAD_ARG; }
 
-  if (!(g.chain == 1 && g.async_pair && g.slab_index > 0)) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int), g.stream));
+  if (!(g.chain == 1 && g.async_pair && g.slab_index > 0)) CK(cudaMemsetAsync(g.d_status, 0, sizeof(int) * 4, g.stream));
   // Slab pipeline: from the second slab on the LW column kernels (McICA, prep) run on stream3 beside the SW solver of the
   // previous slab (at one slab's worth of columns they are latency-bound and would otherwise sit exposed on the main stream)
   cudaStream_t spl = (g.chain == 1 && g.async_pair && g.slab_index > 0) ? g.stream3 : g.stream;

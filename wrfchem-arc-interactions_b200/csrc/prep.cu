@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(128) k_sw_prep(SwArgs a) {
       const float slope = aersum[b];
       if (slope < 0.f) { if (!err) err = ARC_ERR_NEG_AOD; }
       else if (slope > 6.f && !a.aerod) {            // (with iaer = 6 the capped array is the one rrtmg_sw ignores)
+        atomicAdd(a.status + 1, 1);                   // the reference's "WARNING: Large total sw optical depth" (SW:11049-11066)
         for (int l = 0; l < nz; l++) AER(b, 0, l) = AER(b, 0, l) * 6.0f / slope;
       }
     }
@@ -1157,7 +1158,10 @@ __global__ void __launch_bounds__(128) k_lw_prep(LwArgs a) {
     plev_b = plev_t; tlev_b = tlev_t;
   }
   if (a.aer_ra_feedback == 1)
-    for (int b = 0; b < NBLW; b++) if (aersum[b] < 0.f && !err) err = ARC_ERR_NEG_AOD;
+    for (int b = 0; b < NBLW; b++) {
+      if (aersum[b] < 0.f && !err) err = ARC_ERR_NEG_AOD;
+      else if (aersum[b] > 5.f) atomicAdd(a.status + 2, 1);        // "WARNING: Large total lw optical depth" (LW:12616-12627)
+    }
   ws.laytrop[c] = laytrop;
   if (a.dbg.laytrop) a.dbg.laytrop[tc] = laytrop;
   // precipitable water and the diffusivity angle per band (inatm LW:11397-11399, rtrnmc LW:3170-3183)
